@@ -1,0 +1,1027 @@
+// api.cu -- host side of the C ABI declared in include/chronoclust_b200.h: device-resident
+// structure-of-arrays microcluster stores, chunk orchestration of the ordered kernels, the offline
+// pipeline, import/export.  One handle = one device + one stream.  No CPU fallback anywhere: every
+// numeric result is produced by the kernels in nearest.cuh / online.cuh / offline.cuh.
+#include "../../include/chronoclust_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nearest.cuh"
+#include "offline.cuh"
+#include "online.cuh"
+
+using namespace ccb;
+
+namespace {
+
+thread_local std::string g_err;
+
+const int kDPs[] = {4, 8, 12, 16, 24, 32, 40, 48, 64};
+int round_dp(int D) {
+    for (int v : kDPs)
+        if (D <= v) return v;
+    return -1;
+}
+#define CCB_DISPATCH_DP(dp, ...)                    \
+    switch (dp) {                                   \
+    case 4: { constexpr int kDP = 4; __VA_ARGS__ } break;  \
+    case 8: { constexpr int kDP = 8; __VA_ARGS__ } break;  \
+    case 12: { constexpr int kDP = 12; __VA_ARGS__ } break; \
+    case 16: { constexpr int kDP = 16; __VA_ARGS__ } break; \
+    case 24: { constexpr int kDP = 24; __VA_ARGS__ } break; \
+    case 32: { constexpr int kDP = 32; __VA_ARGS__ } break; \
+    case 40: { constexpr int kDP = 40; __VA_ARGS__ } break; \
+    case 48: { constexpr int kDP = 48; __VA_ARGS__ } break; \
+    case 64: { constexpr int kDP = 64; __VA_ARGS__ } break; \
+    default: break;                                 \
+    }
+
+bool is_pow2(double k) {
+    if (!(k > 0.0) || std::isinf(k)) return false;
+    int e;
+    return std::frexp(k, &e) == 0.5;
+}
+
+constexpr int TOPK = 4;
+constexpr int REJ_CAP = 2048;   // rejects per ordered-commit launch (also the dirty-list capacity)
+constexpr int MAX_SLABS = 148;
+constexpr size_t PCORE_SMEM_LIMIT = 200 * 1024;
+
+} // namespace
+
+struct ccb_handle {
+    ccb_params prm{};
+    int D = 0, DP = 0, div_mode = 0, cnt_gt1 = 0, wave = 32;
+    int64_t chunk = 65536;
+    double wsel = 1.0;
+    cudaStream_t stream = nullptr;
+    Store P[2]{}, O[2]{};
+    int pcur = 0, ocur = 0;
+    Ctl *d_ctl = nullptr, *h_ctl = nullptr;
+    double mu = 0, omicron = 0;
+    int64_t pi = 0;
+    bool have_params = false;
+    // ingest buffers
+    double *d_X = nullptr;
+    size_t x_cap = 0;
+    int32_t *d_assign = nullptr;
+    uint8_t *d_stage = nullptr;
+    size_t n_cap = 0;
+    int32_t *d_rej = nullptr;
+    double *d_tk_dist_slab = nullptr, *d_tk_dist = nullptr;
+    int32_t *d_tk_idx_slab = nullptr, *d_tk_idx = nullptr;
+    uint8_t *d_dirty = nullptr;
+    int32_t *d_dirty_list = nullptr;
+    int32_t *d_pnew = nullptr, *d_pfin = nullptr, *d_onew = nullptr;
+    double *d_dist_gmem = nullptr;
+    size_t dist_gmem_cap = 0;
+    // offline results (host copies)
+    int64_t off_M = 0;
+    std::vector<int64_t> cl_off, cl_members;
+    std::vector<double> cl_w, cl_cf1, cl_cf2, cl_cen, cl_pref;
+    std::vector<int32_t> cl_label;
+    std::vector<uint8_t> off_core;
+    std::vector<uint32_t> off_nbr, off_wnbr;
+    std::vector<uint64_t> off_submask;
+    ccb_stats st{};
+    std::string err;
+    void *dnrm2 = nullptr;
+};
+
+namespace {
+
+int fail(ccb_handle *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    g_err = buf;
+    return code;
+}
+#define CK(h, call)                                                                                        \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? CCB_ENOMEM : CCB_ECUDA, "%s:%d %s: %s", __FILE__, \
+                        __LINE__, #call, cudaGetErrorString(e_));                                          \
+    } while (0)
+#define CKL(h) CK(h, cudaGetLastError())
+
+int alloc_store(ccb_handle *h, Store &S, int cap) {
+    const int D = h->D, DP = h->DP;
+    S = Store{};
+    S.cap = cap;
+    const size_t nd = (size_t)cap * D + 2; // + slack for 16-byte rounded bulk copies
+    CK(h, cudaMalloc(&S.cf1, nd * 8));
+    CK(h, cudaMalloc(&S.cf2, nd * 8));
+    CK(h, cudaMalloc(&S.cen, nd * 8));
+    CK(h, cudaMalloc(&S.w, (size_t)cap * 8));
+    CK(h, cudaMalloc(&S.mask, (size_t)cap * 8));
+    CK(h, cudaMalloc(&S.id, (size_t)cap * 8));
+    CK(h, cudaMalloc(&S.uid, (size_t)cap * 4));
+    CK(h, cudaMalloc(&S.cw, (size_t)cap * DP * sizeof(double2)));
+    return CCB_OK;
+}
+void free_store(Store &S) {
+    cudaFree(S.cf1);
+    cudaFree(S.cf2);
+    cudaFree(S.cen);
+    cudaFree(S.w);
+    cudaFree(S.mask);
+    cudaFree(S.id);
+    cudaFree(S.uid);
+    cudaFree(S.cw);
+    S = Store{};
+}
+// grows both ping-pong buffers of a list to >= want entries, preserving the first n of the current one
+int grow_store(ccb_handle *h, Store (&S)[2], int cur, int n, int64_t want) {
+    if (want <= S[cur].cap) return CCB_OK;
+    int64_t cap = S[cur].cap;
+    while (cap < want) cap *= 2;
+    if (cap > (int64_t)1 << 30) return fail(h, CCB_ELIMIT, "microcluster list would exceed 2^30 entries");
+    const int D = h->D, DP = h->DP;
+    Store nw;
+    int rc = alloc_store(h, nw, (int)cap);
+    if (rc) return rc;
+    Store &o = S[cur];
+    cudaStream_t s = h->stream;
+    CK(h, cudaMemcpyAsync(nw.cf1, o.cf1, (size_t)n * D * 8, cudaMemcpyDeviceToDevice, s));
+    CK(h, cudaMemcpyAsync(nw.cf2, o.cf2, (size_t)n * D * 8, cudaMemcpyDeviceToDevice, s));
+    CK(h, cudaMemcpyAsync(nw.cen, o.cen, (size_t)n * D * 8, cudaMemcpyDeviceToDevice, s));
+    CK(h, cudaMemcpyAsync(nw.w, o.w, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    CK(h, cudaMemcpyAsync(nw.mask, o.mask, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    CK(h, cudaMemcpyAsync(nw.id, o.id, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    CK(h, cudaMemcpyAsync(nw.uid, o.uid, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    CK(h, cudaMemcpyAsync(nw.cw, o.cw, (size_t)n * DP * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+    CK(h, cudaStreamSynchronize(s));
+    free_store(S[cur]);
+    free_store(S[1 - cur]);
+    S[cur] = nw;
+    rc = alloc_store(h, S[1 - cur], (int)cap);
+    return rc;
+}
+
+int realloc_aux_for_outlier_cap(ccb_handle *h) {
+    const int cap = h->O[h->ocur].cap;
+    cudaFree(h->d_dirty);
+    cudaFree(h->d_onew);
+    CK(h, cudaMalloc(&h->d_dirty, (size_t)cap));
+    CK(h, cudaMalloc(&h->d_onew, (size_t)cap * 4));
+    return CCB_OK;
+}
+int realloc_aux_for_pcore_cap(ccb_handle *h) {
+    const int cap = h->P[h->pcur].cap;
+    cudaFree(h->d_pnew);
+    cudaFree(h->d_pfin);
+    CK(h, cudaMalloc(&h->d_pnew, (size_t)cap * 4));
+    CK(h, cudaMalloc(&h->d_pfin, (size_t)cap * 4));
+    return CCB_OK;
+}
+
+int sync_ctl(ccb_handle *h) { // device control block -> pinned host mirror
+    CK(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return CCB_OK;
+}
+int push_ctl(ccb_handle *h) {
+    CK(h, cudaMemcpyAsync(h->d_ctl, h->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
+    return CCB_OK;
+}
+
+Num make_num(const ccb_handle *h) {
+    Num nm{};
+    nm.delta2 = h->prm.delta2;
+    nm.k = h->prm.k;
+    nm.wsel = h->wsel;
+    nm.eps2 = h->prm.eps2;
+    nm.beta_mu = h->prm.beta * h->mu; // beta * mu, hddstream.py:413, 524
+    nm.pi = h->pi;
+    nm.D = h->D;
+    nm.DP = h->DP;
+    nm.div_mode = h->div_mode;
+    nm.cnt_gt1 = h->cnt_gt1;
+    // the gate compares count(pref' != 1) with pi; for k == 1 that count is 0 and the gate is vacuous,
+    // as it is whenever pi >= D (hddstream.py:315-321)
+    nm.pi_active = (h->prm.k != 1.0) && (h->pi < (int64_t)h->D);
+    return nm;
+}
+
+// kernel 1 launch over an explicit cw array
+template <int K>
+int launch_nearest(ccb_handle *h, cudaStream_t s, int DP, int div_mode, const double *X, const int32_t *rows,
+                   const int32_t *nrows_dev, int64_t row_off, int64_t nrows_max, int64_t ld, int D, const double2 *cw,
+                   int M, double *slab_dist, int32_t *slab_idx, double *out_dist, int32_t *out_idx, int max_slabs,
+                   int *nslab_out) {
+    int launched = 0;
+    CCB_DISPATCH_DP(DP, {
+        using Cfg = NearestCfg<kDP>;
+        const int gx = (int)((nrows_max + Cfg::CELLS - 1) / Cfg::CELLS);
+        int want = (2 * 148 + gx - 1) / gx;
+        if (want > max_slabs) want = max_slabs;
+        const int tiles = (M + Cfg::TM - 1) / Cfg::TM;
+        if (want > tiles) want = tiles;
+        if (want < 1) want = 1;
+        int slab_mcs = ((tiles + want - 1) / want) * Cfg::TM;
+        const int nslab = (M + slab_mcs - 1) / slab_mcs;
+        dim3 grid(gx, nslab);
+        double *od = nslab == 1 ? out_dist : slab_dist;
+        int32_t *oi = nslab == 1 ? out_idx : slab_idx;
+        if (div_mode)
+            k_nearest<kDP, K, true><<<grid, NEAREST_THREADS, 0, s>>>(X, rows, nrows_dev, row_off, nrows_max, ld, D, cw,
+                                                                     M, slab_mcs, od, oi);
+        else
+            k_nearest<kDP, K, false><<<grid, NEAREST_THREADS, 0, s>>>(X, rows, nrows_dev, row_off, nrows_max, ld, D, cw,
+                                                                      M, slab_mcs, od, oi);
+        launched = 1;
+        if (nslab > 1) {
+            k_topk_merge<K><<<(unsigned)((nrows_max + 255) / 256), 256, 0, s>>>(slab_dist, slab_idx, nrows_dev, row_off,
+                                                                                nrows_max, nslab, out_dist, out_idx);
+            launched = 2;
+        }
+        if (nslab_out) *nslab_out = nslab;
+    })
+    if (!launched) return fail(h, CCB_ELIMIT, "unsupported padded dimensionality %d", DP);
+    if (h) h->st.kernel_launches += launched;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, CCB_ECUDA, "k_nearest launch: %s", cudaGetErrorString(e));
+    return CCB_OK;
+}
+
+int ensure_point_buffers(ccb_handle *h, int64_t N) {
+    if ((size_t)N > h->n_cap) {
+        cudaFree(h->d_assign);
+        cudaFree(h->d_stage);
+        h->n_cap = 0;
+        CK(h, cudaMalloc(&h->d_assign, (size_t)N * 4));
+        CK(h, cudaMalloc(&h->d_stage, (size_t)N));
+        h->n_cap = (size_t)N;
+    }
+    return CCB_OK;
+}
+
+// the ordered loop over cells [0, N) of a device-resident X
+int ingest_core(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t *d_assign, uint8_t *d_stage) {
+    if (!h->have_params) return fail(h, CCB_ESTATE, "ccb_begin_timepoint must precede ccb_ingest");
+    cudaStream_t s = h->stream;
+    const Num nm = make_num(h);
+    int rc;
+    if ((rc = sync_ctl(h))) return rc;
+    int64_t pos = 0;
+    while (pos < N) {
+        Ctl &c = *h->h_ctl;
+        // capacity for this chunk: at most REJ_CAP new outlier MCs and one upgrade
+        if ((int64_t)c.n_outlier + REJ_CAP + 1 > h->O[h->ocur].cap) {
+            if ((rc = grow_store(h, h->O, h->ocur, c.n_outlier, (int64_t)c.n_outlier + REJ_CAP + 1))) return rc;
+            if ((rc = realloc_aux_for_outlier_cap(h))) return rc;
+        }
+        if (c.n_pcore + 1 > h->P[h->pcur].cap) {
+            if ((rc = grow_store(h, h->P, h->pcur, c.n_pcore, c.n_pcore + 1))) return rc;
+            if ((rc = realloc_aux_for_pcore_cap(h))) return rc;
+        }
+        Store &P = h->P[h->pcur], &O = h->O[h->ocur];
+        const int Mp = c.n_pcore, Mo = c.n_outlier;
+
+        k_max_w<<<1, 1024, 0, s>>>(O.w, h->d_ctl);
+        h->st.kernel_launches++;
+
+        PcoreArgs pa{};
+        pa.X = dX;
+        pa.ld = ld;
+        pa.start = pos;
+        pa.end = std::min<int64_t>(N, pos + h->chunk);
+        pa.P = P;
+        pa.nm = nm;
+        pa.ctl = h->d_ctl;
+        pa.assign = d_assign;
+        pa.stage = d_stage;
+        pa.rej_list = h->d_rej;
+        pa.rej_cap = REJ_CAP;
+        pa.wave = h->wave;
+        size_t smem = pcore_smem_bytes(h->D, Mp, true, true);
+        pa.state_in_smem = pa.dist_in_smem = 1;
+        if (smem > PCORE_SMEM_LIMIT) {
+            pa.dist_in_smem = 0;
+            smem = pcore_smem_bytes(h->D, Mp, true, false);
+            if (smem > PCORE_SMEM_LIMIT) {
+                pa.state_in_smem = 0;
+                smem = pcore_smem_bytes(h->D, Mp, false, false);
+            }
+            const size_t need = (size_t)Mp * XS;
+            if (need > h->dist_gmem_cap) {
+                cudaFree(h->d_dist_gmem);
+                h->dist_gmem_cap = 0;
+                CK(h, cudaMalloc(&h->d_dist_gmem, need * 2 * 8));
+                h->dist_gmem_cap = need * 2;
+            }
+        }
+        pa.dist_gmem = h->d_dist_gmem;
+        k_pcore_stage<<<1, PCORE_THREADS, smem, s>>>(pa);
+        CKL(h);
+        h->st.kernel_launches++;
+        h->st.chunks++;
+
+        // outlier stage of the chunk's rejects
+        int q_snap = 0;
+        bool first = true;
+        for (;;) {
+            Store &Oc = h->O[h->ocur];
+            const int mo_snap = first ? Mo : h->h_ctl->n_outlier;
+            CK(h, cudaMemsetAsync(h->d_dirty, 0, (size_t)std::max(mo_snap, 1), s));
+            if (mo_snap > 0) {
+                rc = launch_nearest<TOPK>(h, s, h->DP, h->div_mode, dX, h->d_rej, &h->d_ctl->n_rej, q_snap, REJ_CAP - q_snap,
+                                          ld, h->D, Oc.cw, mo_snap, h->d_tk_dist_slab, h->d_tk_idx_slab, h->d_tk_dist,
+                                          h->d_tk_idx, MAX_SLABS, nullptr);
+                if (rc) return rc;
+            } else {
+                CK(h, cudaMemsetAsync(h->d_tk_idx, 0xff, (size_t)REJ_CAP * TOPK * 4, s));
+            }
+            ResolveArgs ra{};
+            ra.X = dX;
+            ra.ld = ld;
+            ra.O = Oc;
+            ra.P = h->P[h->pcur];
+            ra.nm = nm;
+            ra.ctl = h->d_ctl;
+            ra.rej_list = h->d_rej;
+            ra.q_snap = q_snap;
+            ra.mo_snap = mo_snap;
+            ra.topk = TOPK;
+            ra.tk_dist = h->d_tk_dist;
+            ra.tk_idx = h->d_tk_idx;
+            ra.dirty = h->d_dirty;
+            ra.dirty_list = h->d_dirty_list;
+            ra.assign = d_assign;
+            ra.stage = d_stage;
+            k_resolve<<<1, RES_THREADS, 0, s>>>(ra);
+            CKL(h);
+            h->st.kernel_launches++;
+            h->st.resolver_calls++;
+            if ((rc = sync_ctl(h))) return rc;
+            Ctl &cc = *h->h_ctl;
+            if (first) {
+                h->st.rejects += cc.n_rej;
+                h->st.nearest_pairs += (int64_t)cc.n_rej * mo_snap;
+            } else {
+                h->st.nearest_pairs += (int64_t)(cc.n_rej - q_snap) * mo_snap;
+            }
+            first = false;
+            if (cc.res_reason == RES_CUT || cc.res_reason == RES_OCAP) {
+                if (cc.res_reason == RES_CUT) h->st.resolver_cuts++;
+                if (cc.res_reason == RES_OCAP) {
+                    if ((rc = grow_store(h, h->O, h->ocur, cc.n_outlier, (int64_t)cc.n_outlier + REJ_CAP + 1))) return rc;
+                    if ((rc = realloc_aux_for_outlier_cap(h))) return rc;
+                }
+                q_snap = cc.res_done;
+                // fresh snapshot: nothing is dirty any more
+                cc.n_dirty = 0;
+                CK(h, cudaMemcpyAsync(&h->d_ctl->n_dirty, &cc.n_dirty, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+                continue;
+            }
+            if (cc.res_reason == RES_PCAP) return fail(h, CCB_ESTATE, "internal: pcore list capacity exhausted mid-chunk");
+            if (cc.res_reason == RES_UPGRADE && cc.res_done != cc.n_rej)
+                return fail(h, CCB_ESTATE, "internal: upgrade before the last reject of a chunk (%d of %d)", cc.res_done,
+                            cc.n_rej);
+            break;
+        }
+        pos = h->h_ctl->pos_end;
+    }
+    h->st.points += N;
+    return CCB_OK;
+}
+
+int pcore_ids_host(ccb_handle *h, int n, std::vector<int64_t> &ids) {
+    ids.resize(n);
+    if (n) CK(h, cudaMemcpy(ids.data(), h->P[h->pcur].id, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return CCB_OK;
+}
+
+double builtin_nrm2(const double *x, int n) {
+    // restatement of OpenBLAS' x86-64 dnrm2: squares, sum and square root in x87 extended precision
+    long double s = 0.0L;
+    for (int i = 0; i < n; ++i) s += (long double)x[i] * (long double)x[i];
+    return (double)sqrtl(s);
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+};
+
+int launch_off_neighbours(ccb_handle *h, cudaStream_t s, const double *cen, int M, int D, int r0, int r1, double E2,
+                          uint32_t *nbr, int32_t *cnt, int32_t *border, int border_cap, int32_t *n_border) {
+    const int DP = round_dp(D);
+    int ok = 0;
+    CCB_DISPATCH_DP(DP, {
+        const int gx = (r1 - r0 + OFFN_THREADS - 1) / OFFN_THREADS;
+        if (gx > 0)
+            k_off_neighbours<kDP><<<gx, OFFN_THREADS, 0, s>>>(cen, M, D, r0, r1, E2, nbr, cnt, border, border_cap, n_border);
+        ok = 1;
+    })
+    if (!ok) return fail(h, CCB_ELIMIT, "unsupported dimensionality %d", D);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, CCB_ECUDA, "k_off_neighbours launch: %s", cudaGetErrorString(e));
+    return CCB_OK;
+}
+
+} // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char *ccb_last_error(const ccb_handle *h) { return h ? h->err.c_str() : g_err.c_str(); }
+void *ccb_stream(ccb_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int ccb_create(const ccb_params *p, ccb_handle **out) {
+    if (!p || !out) return fail(nullptr, CCB_EINVAL, "null argument");
+    *out = nullptr;
+    if (p->D < 1 || p->D > CCB_MAX_D) return fail(nullptr, CCB_ELIMIT, "D=%d outside 1..%d", p->D, CCB_MAX_D);
+    if (p->wave < 0 || p->wave > 32) return fail(nullptr, CCB_EINVAL, "wave=%d outside 0..32", p->wave);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, CCB_ECUDA, "no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (p->device < 0 || p->device >= ndev) return fail(nullptr, CCB_EINVAL, "device %d of %d", p->device, ndev);
+    ccb_handle *h = new (std::nothrow) ccb_handle();
+    if (!h) return fail(nullptr, CCB_ENOMEM, "host allocation failed");
+    h->prm = *p;
+    h->D = p->D;
+    h->DP = round_dp(p->D);
+    h->wave = p->wave ? p->wave : 32;
+    h->chunk = p->chunk > 0 ? p->chunk : 65536;
+    const bool p2 = is_pow2(p->k);
+    h->div_mode = p2 ? 0 : 1;
+    h->wsel = p2 ? 1.0 / p->k : p->k; // exact reciprocal of a power of two, else the divisor itself
+    h->cnt_gt1 = p->k > 1.0;
+#define CKC(call)                                                                            \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            int rc_ = fail(nullptr, CCB_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));     \
+            ccb_destroy(h);                                                                  \
+            return rc_;                                                                      \
+        }                                                                                    \
+    } while (0)
+    CKC(cudaSetDevice(p->device));
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKC(cudaMalloc(&h->d_ctl, sizeof(Ctl)));
+    CKC(cudaMemset(h->d_ctl, 0, sizeof(Ctl)));
+    CKC(cudaMallocHost(&h->h_ctl, sizeof(Ctl)));
+    memset(h->h_ctl, 0, sizeof(Ctl));
+    CKC(cudaFuncSetAttribute(k_pcore_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCORE_SMEM_LIMIT + 8192));
+    int rc = 0;
+    for (int i = 0; i < 2 && !rc; ++i) rc = alloc_store(h, h->P[i], 256);
+    for (int i = 0; i < 2 && !rc; ++i) rc = alloc_store(h, h->O[i], 8192);
+    if (!rc) rc = realloc_aux_for_outlier_cap(h);
+    if (!rc) rc = realloc_aux_for_pcore_cap(h);
+    if (rc) {
+        g_err = h->err;
+        ccb_destroy(h);
+        return rc;
+    }
+    CKC(cudaMalloc(&h->d_rej, (size_t)REJ_CAP * 4));
+    CKC(cudaMalloc(&h->d_dirty_list, (size_t)(REJ_CAP + 8) * 4));
+    CKC(cudaMalloc(&h->d_tk_dist_slab, (size_t)REJ_CAP * MAX_SLABS * TOPK * 8));
+    CKC(cudaMalloc(&h->d_tk_idx_slab, (size_t)REJ_CAP * MAX_SLABS * TOPK * 4));
+    CKC(cudaMalloc(&h->d_tk_dist, (size_t)REJ_CAP * TOPK * 8));
+    CKC(cudaMalloc(&h->d_tk_idx, (size_t)REJ_CAP * TOPK * 4));
+#undef CKC
+    *out = h;
+    return CCB_OK;
+}
+
+void ccb_destroy(ccb_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->prm.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < 2; ++i) {
+        free_store(h->P[i]);
+        free_store(h->O[i]);
+    }
+    cudaFree(h->d_ctl);
+    if (h->h_ctl) cudaFreeHost(h->h_ctl);
+    cudaFree(h->d_X);
+    cudaFree(h->d_assign);
+    cudaFree(h->d_stage);
+    cudaFree(h->d_rej);
+    cudaFree(h->d_tk_dist_slab);
+    cudaFree(h->d_tk_idx_slab);
+    cudaFree(h->d_tk_dist);
+    cudaFree(h->d_tk_idx);
+    cudaFree(h->d_dirty);
+    cudaFree(h->d_dirty_list);
+    cudaFree(h->d_pnew);
+    cudaFree(h->d_pfin);
+    cudaFree(h->d_onew);
+    cudaFree(h->d_dist_gmem);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int ccb_get_stats(const ccb_handle *h, ccb_stats *out) {
+    if (!h || !out) return fail(nullptr, CCB_EINVAL, "null argument");
+    *out = h->st;
+    const Ctl &c = *h->h_ctl;
+    out->waves = c.waves;
+    out->wave_rollbacks = c.rollbacks;
+    out->pcore_pairs = c.pcore_pairs;
+    out->upgrades = c.upgrades;
+    out->created = c.created;
+    out->downgraded = c.downgraded;
+    out->deleted = c.deleted;
+    return CCB_OK;
+}
+
+int ccb_set_dnrm2(ccb_handle *h, void *fn) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    h->dnrm2 = fn;
+    return CCB_OK;
+}
+
+int ccb_begin_timepoint(ccb_handle *h, double mu, double omicron, int64_t pi, int32_t decay, double decay_factor) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    CK(h, cudaSetDevice(h->prm.device));
+    h->mu = mu;
+    h->omicron = omicron;
+    h->pi = pi;
+    h->have_params = true;
+    if (!decay) return CCB_OK;
+    cudaStream_t s = h->stream;
+    MaintArgs ma{};
+    ma.P = h->P[h->pcur];
+    ma.O = h->O[h->ocur];
+    ma.P2 = h->P[1 - h->pcur];
+    ma.O2 = h->O[1 - h->ocur];
+    ma.ctl = h->d_ctl;
+    ma.p_new = h->d_pnew;
+    ma.p_fin = h->d_pfin;
+    ma.o_new = h->d_onew;
+    ma.f = decay_factor;
+    ma.beta_mu = h->prm.beta * mu;
+    ma.omicron = omicron;
+    ma.pi = pi;
+    ma.D = h->D;
+    ma.DP = h->DP;
+    ma.cnt_gt1 = h->cnt_gt1;
+    ma.wsel = h->wsel;
+    int rc;
+    if ((rc = sync_ctl(h))) return rc;
+    // every downgraded pcore MC lands in the outlier list: make room first
+    const int64_t need_o = (int64_t)h->h_ctl->n_outlier + h->h_ctl->n_pcore;
+    if (need_o > h->O[h->ocur].cap) {
+        if ((rc = grow_store(h, h->O, h->ocur, h->h_ctl->n_outlier, need_o))) return rc;
+        if ((rc = realloc_aux_for_outlier_cap(h))) return rc;
+        ma.O = h->O[h->ocur];
+        ma.O2 = h->O[1 - h->ocur];
+        ma.o_new = h->d_onew;
+    }
+    k_maint_plan<<<1, MAINT_THREADS, 0, s>>>(ma);
+    CKL(h);
+    const int64_t total = (int64_t)(h->h_ctl->n_pcore + h->h_ctl->n_outlier) * h->DP;
+    const int gx = (int)std::min<int64_t>(std::max<int64_t>((total + 255) / 256, 1), 148 * 8);
+    k_maint_gather<<<gx, 256, 0, s>>>(ma);
+    CKL(h);
+    k_maint_finish<<<1, 1, 0, s>>>(h->d_ctl);
+    CKL(h);
+    h->st.kernel_launches += 3;
+    h->pcur = 1 - h->pcur;
+    h->ocur = 1 - h->ocur;
+    return sync_ctl(h);
+}
+
+int ccb_ingest_device(ccb_handle *h, const double *X_dev, int64_t N, int64_t ld, int32_t *assign_uid_dev,
+                      uint8_t *stage_dev) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    if (N < 0 || ld < h->D || (!X_dev && N > 0) || (!assign_uid_dev && N > 0)) return fail(h, CCB_EINVAL, "bad ingest arguments");
+    CK(h, cudaSetDevice(h->prm.device));
+    return ingest_core(h, X_dev, N, ld, assign_uid_dev, stage_dev);
+}
+
+int ccb_ingest(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *assign_uid, uint8_t *stage) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    if (N < 0 || ld < h->D || (!X && N > 0) || (!assign_uid && N > 0)) return fail(h, CCB_EINVAL, "bad ingest arguments");
+    if (N == 0) return CCB_OK;
+    CK(h, cudaSetDevice(h->prm.device));
+    const size_t need = (size_t)N * ld;
+    if (need > h->x_cap) {
+        cudaFree(h->d_X);
+        h->x_cap = 0;
+        CK(h, cudaMalloc(&h->d_X, (need + 2) * 8));
+        h->x_cap = need;
+    }
+    int rc = ensure_point_buffers(h, N);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(h->d_X, X, need * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = ingest_core(h, h->d_X, N, ld, h->d_assign, h->d_stage);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(assign_uid, h->d_assign, (size_t)N * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (stage) CK(h, cudaMemcpyAsync(stage, h->d_stage, (size_t)N, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return CCB_OK;
+}
+
+int ccb_counts(ccb_handle *h, int64_t out[4]) {
+    if (!h || !out) return fail(nullptr, CCB_EINVAL, "null argument");
+    CK(h, cudaSetDevice(h->prm.device));
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    out[0] = h->h_ctl->n_pcore;
+    out[1] = h->h_ctl->n_outlier_alive;
+    out[2] = h->h_ctl->pcore_last_id;
+    out[3] = h->h_ctl->outlier_last_id;
+    return CCB_OK;
+}
+
+int ccb_export_list(ccb_handle *h, int32_t which, int64_t *ids, int64_t *uids, double *w, double *cf1, double *cf2,
+                    double *cen, double *pref) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    CK(h, cudaSetDevice(h->prm.device));
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    const Store &S = which ? h->O[h->ocur] : h->P[h->pcur];
+    const int n = which ? h->h_ctl->n_outlier : h->h_ctl->n_pcore;
+    const int D = h->D;
+    if (n == 0) return CCB_OK;
+    std::vector<double> hw(n), h1((size_t)n * D), h2((size_t)n * D), hc((size_t)n * D);
+    std::vector<uint64_t> hm(n);
+    std::vector<int64_t> hid(n);
+    std::vector<int32_t> hu(n);
+    CK(h, cudaMemcpy(hw.data(), S.w, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(h1.data(), S.cf1, (size_t)n * D * 8, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(h2.data(), S.cf2, (size_t)n * D * 8, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(hc.data(), S.cen, (size_t)n * D * 8, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(hm.data(), S.mask, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(hid.data(), S.id, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(hu.data(), S.uid, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    int o = 0;
+    for (int j = 0; j < n; ++j) {
+        if (which && hw[j] < 0.0) continue; // tombstone left by an upgrade
+        if (ids) ids[o] = hid[j];
+        if (uids) uids[o] = hu[j];
+        if (w) w[o] = hw[j];
+        for (int d = 0; d < D; ++d) {
+            if (cf1) cf1[(size_t)o * D + d] = h1[(size_t)j * D + d];
+            if (cf2) cf2[(size_t)o * D + d] = h2[(size_t)j * D + d];
+            if (cen) cen[(size_t)o * D + d] = hc[(size_t)j * D + d];
+            if (pref) pref[(size_t)o * D + d] = ((hm[j] >> d) & 1ull) ? h->prm.k : 1.0;
+        }
+        ++o;
+    }
+    return CCB_OK;
+}
+
+int ccb_import_list(ccb_handle *h, int32_t which, int64_t n, const int64_t *ids, const int64_t *uids, const double *w,
+                    const double *cf1, const double *cf2, const double *cen, const double *pref) {
+    if (!h || n < 0) return fail(nullptr, CCB_EINVAL, "bad argument");
+    CK(h, cudaSetDevice(h->prm.device));
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    const int D = h->D;
+    if (which) {
+        if ((rc = grow_store(h, h->O, h->ocur, 0, std::max<int64_t>(n, 1)))) return rc;
+        if ((rc = realloc_aux_for_outlier_cap(h))) return rc;
+    } else {
+        if ((rc = grow_store(h, h->P, h->pcur, 0, std::max<int64_t>(n, 1)))) return rc;
+        if ((rc = realloc_aux_for_pcore_cap(h))) return rc;
+    }
+    Store &S = which ? h->O[h->ocur] : h->P[h->pcur];
+    std::vector<uint64_t> hm(n);
+    std::vector<int32_t> hu(n);
+    for (int64_t j = 0; j < n; ++j) {
+        uint64_t m = 0;
+        for (int d = 0; d < D; ++d)
+            if (pref[(size_t)j * D + d] == h->prm.k && h->prm.k != 1.0) m |= 1ull << d;
+        hm[j] = m;
+        if (uids[j] < 0 || uids[j] >= ((int64_t)1 << 31)) return fail(h, CCB_ELIMIT, "uid outside int32");
+        hu[j] = (int32_t)uids[j];
+    }
+    if (n) {
+        CK(h, cudaMemcpy(S.w, w, (size_t)n * 8, cudaMemcpyHostToDevice));
+        CK(h, cudaMemcpy(S.cf1, cf1, (size_t)n * D * 8, cudaMemcpyHostToDevice));
+        CK(h, cudaMemcpy(S.cf2, cf2, (size_t)n * D * 8, cudaMemcpyHostToDevice));
+        CK(h, cudaMemcpy(S.cen, cen, (size_t)n * D * 8, cudaMemcpyHostToDevice));
+        CK(h, cudaMemcpy(S.mask, hm.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+        CK(h, cudaMemcpy(S.id, ids, (size_t)n * 8, cudaMemcpyHostToDevice));
+        CK(h, cudaMemcpy(S.uid, hu.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+        k_repack_store<<<(unsigned)(((size_t)n * h->DP + 255) / 256), 256, 0, h->stream>>>(S, (int)n, D, h->DP, h->wsel);
+        CKL(h);
+        h->st.kernel_launches++;
+    }
+    if (which) {
+        h->h_ctl->n_outlier = (int32_t)n;
+        h->h_ctl->n_outlier_alive = (int32_t)n;
+    } else {
+        h->h_ctl->n_pcore = (int32_t)n;
+    }
+    if ((rc = push_ctl(h))) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return CCB_OK;
+}
+
+int ccb_set_counters(ccb_handle *h, int64_t pcore_last_id, int64_t outlier_last_id) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    CK(h, cudaSetDevice(h->prm.device));
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    h->h_ctl->pcore_last_id = pcore_last_id;
+    h->h_ctl->outlier_last_id = outlier_last_id;
+    if ((rc = push_ctl(h))) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return CCB_OK;
+}
+
+// ---- offline ------------------------------------------------------------------------------------------
+int ccb_offline(ccb_handle *h, int64_t *n_clusters) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    if (!h->have_params) return fail(h, CCB_ESTATE, "ccb_begin_timepoint must precede ccb_offline");
+    CK(h, cudaSetDevice(h->prm.device));
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    const int M = h->h_ctl->n_pcore, D = h->D;
+    const Store &P = h->P[h->pcur];
+    const int words = (M + 31) / 32;
+    h->off_M = M;
+    h->cl_off.assign(1, 0);
+    h->cl_members.clear();
+    h->cl_w.clear();
+    h->cl_cf1.clear();
+    h->cl_cf2.clear();
+    h->cl_cen.clear();
+    h->cl_pref.clear();
+    h->cl_label.assign(M, -1);
+    h->off_core.assign(M, 0);
+    h->off_nbr.assign((size_t)M * words, 0);
+    h->off_wnbr.assign((size_t)M * words, 0);
+    h->off_submask.assign(M, 0);
+    if (n_clusters) *n_clusters = 0;
+    if (M == 0) return CCB_OK;
+
+    const double E2 = h->prm.upsilon_eps2;
+    DevBuf<uint8_t> core, cls;
+    DevBuf<uint32_t> nbr, wnbr;
+    DevBuf<int32_t> cnt, border, nborder, queue, label, order, cloff, ncl;
+    DevBuf<uint64_t> submask, omask;
+    const int border_cap = 1 << 16;
+    CK(h, core.alloc(M));
+    CK(h, cls.alloc(M));
+    CK(h, nbr.alloc((size_t)M * words));
+    CK(h, wnbr.alloc((size_t)M * words));
+    CK(h, cnt.alloc(M));
+    CK(h, border.alloc(2 * (size_t)border_cap));
+    CK(h, nborder.alloc(1));
+    CK(h, queue.alloc(2 * (size_t)M + 2));
+    CK(h, label.alloc(M));
+    CK(h, order.alloc(M));
+    CK(h, cloff.alloc((size_t)M + 2));
+    CK(h, ncl.alloc(1));
+    CK(h, submask.alloc(M));
+    CK(h, cudaMemsetAsync(nborder.p, 0, 4, s));
+    CK(h, cudaMemsetAsync(submask.p, 0, (size_t)M * 8, s));
+    CK(h, cudaMemsetAsync(cls.p, 0, (size_t)M, s));
+
+    k_off_core<<<(M + 127) / 128, 128, 0, s>>>(P.cf1, P.cf2, P.w, P.mask, M, D, h->prm.k, h->wsel, h->div_mode, h->cnt_gt1,
+                                               h->prm.eps2, h->mu, h->pi, core.p);
+    CKL(h);
+    if ((rc = launch_off_neighbours(h, s, P.cen, M, D, 0, M, E2, nbr.p, cnt.p, border.p, border_cap, nborder.p))) return rc;
+    h->st.kernel_launches += 2;
+    int32_t nb = 0;
+    CK(h, cudaMemcpyAsync(&nb, nborder.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(h, cudaStreamSynchronize(s));
+    if (nb > border_cap) return fail(h, CCB_ELIMIT, "%d borderline neighbour pairs exceed the resolver capacity", nb);
+    if (nb > 0) {
+        // settle the pairs inside the guard band with the BLAS dnrm2 the reference itself calls
+        std::vector<int32_t> pairs(2 * (size_t)nb);
+        std::vector<double> hc((size_t)M * D), x(D);
+        std::vector<uint8_t> dec(nb);
+        CK(h, cudaMemcpy(pairs.data(), border.p, pairs.size() * 4, cudaMemcpyDeviceToHost));
+        CK(h, cudaMemcpy(hc.data(), P.cen, hc.size() * 8, cudaMemcpyDeviceToHost));
+        typedef double (*nrm2_fn)(int *, double *, int *);
+        for (int i = 0; i < nb; ++i) {
+            const int p_ = pairs[2 * i], q_ = pairs[2 * i + 1];
+            for (int d = 0; d < D; ++d) x[d] = hc[(size_t)q_ * D + d] - hc[(size_t)p_ * D + d];
+            double r;
+            if (h->dnrm2) {
+                int n = D, inc = 1;
+                r = ((nrm2_fn)h->dnrm2)(&n, x.data(), &inc);
+            } else {
+                r = builtin_nrm2(x.data(), D);
+            }
+            dec[i] = r <= h->prm.upsilon_eps;
+        }
+        DevBuf<uint8_t> ddec;
+        CK(h, ddec.alloc(nb));
+        CK(h, cudaMemcpy(ddec.p, dec.data(), nb, cudaMemcpyHostToDevice));
+        k_off_patch<<<(nb + 127) / 128, 128, 0, s>>>(nbr.p, cnt.p, border.p, ddec.p, nb, 0, words);
+        CKL(h);
+        CK(h, cudaStreamSynchronize(s));
+        h->st.borderline_pairs += nb;
+        h->st.kernel_launches++;
+    }
+    {
+        const int64_t t = (int64_t)M * D;
+        k_off_subspace<<<(unsigned)((t + 127) / 128), 128, 0, s>>>(P.cen, M, D, 0, M, nbr.p, cnt.p, h->prm.delta, submask.p);
+        CKL(h);
+        const int64_t t2 = (int64_t)M * words;
+        k_off_weighted<<<(unsigned)((t2 + 127) / 128), 128, 0, s>>>(P.cen, M, D, 0, M, nbr.p, submask.p, h->prm.k, E2, wnbr.p);
+        CKL(h);
+        k_off_clusters<<<1, OFFC_THREADS, 0, s>>>(M, wnbr.p, core.p, submask.p, h->cnt_gt1, h->pi, cls.p, queue.p, label.p,
+                                                  order.p, cloff.p, ncl.p);
+        CKL(h);
+        h->st.kernel_launches += 3;
+    }
+    int32_t nc_raw = 0;
+    CK(h, cudaMemcpyAsync(&nc_raw, ncl.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(h, cudaStreamSynchronize(s));
+    std::vector<int32_t> hl(M), ho(M), hoff((size_t)nc_raw + 1);
+    std::vector<double> kw(nc_raw), k1((size_t)nc_raw * D), k2((size_t)nc_raw * D), kc((size_t)nc_raw * D);
+    std::vector<uint64_t> km(nc_raw);
+    if (nc_raw > 0) {
+        DevBuf<double> d1, d2, dc, dw;
+        CK(h, d1.alloc((size_t)nc_raw * D));
+        CK(h, d2.alloc((size_t)nc_raw * D));
+        CK(h, dc.alloc((size_t)nc_raw * D));
+        CK(h, dw.alloc(nc_raw));
+        CK(h, omask.alloc(nc_raw));
+        k_off_cluster_cf<<<nc_raw, 64, 0, s>>>(P.cf1, P.cf2, P.w, D, order.p, cloff.p, h->prm.delta2, d1.p, d2.p, dc.p, omask.p,
+                                               dw.p);
+        CKL(h);
+        h->st.kernel_launches++;
+        CK(h, cudaMemcpyAsync(kw.data(), dw.p, (size_t)nc_raw * 8, cudaMemcpyDeviceToHost, s));
+        CK(h, cudaMemcpyAsync(k1.data(), d1.p, k1.size() * 8, cudaMemcpyDeviceToHost, s));
+        CK(h, cudaMemcpyAsync(k2.data(), d2.p, k2.size() * 8, cudaMemcpyDeviceToHost, s));
+        CK(h, cudaMemcpyAsync(kc.data(), dc.p, kc.size() * 8, cudaMemcpyDeviceToHost, s));
+        CK(h, cudaMemcpyAsync(km.data(), omask.p, (size_t)nc_raw * 8, cudaMemcpyDeviceToHost, s));
+        CK(h, cudaStreamSynchronize(s));
+    }
+    CK(h, cudaMemcpy(hl.data(), label.p, (size_t)M * 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(ho.data(), order.p, (size_t)M * 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(hoff.data(), cloff.p, hoff.size() * 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(h->off_core.data(), core.p, (size_t)M, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(h->off_nbr.data(), nbr.p, h->off_nbr.size() * 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(h->off_wnbr.data(), wnbr.p, h->off_wnbr.size() * 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(h->off_submask.data(), submask.p, (size_t)M * 8, cudaMemcpyDeviceToHost));
+    std::vector<int64_t> ids;
+    if ((rc = pcore_ids_host(h, M, ids))) return rc;
+    // keep clusters whose weight is > 0 (predecon.py:83); relabel
+    std::vector<int32_t> remap(nc_raw, -1);
+    for (int c = 0; c < nc_raw; ++c) {
+        if (!(kw[c] > 0.0)) continue;
+        remap[c] = (int32_t)h->cl_w.size();
+        h->cl_w.push_back(kw[c]);
+        for (int i = hoff[c]; i < hoff[c + 1]; ++i) h->cl_members.push_back(ids[ho[i]]);
+        h->cl_off.push_back((int64_t)h->cl_members.size());
+        for (int d = 0; d < D; ++d) {
+            h->cl_cf1.push_back(k1[(size_t)c * D + d]);
+            h->cl_cf2.push_back(k2[(size_t)c * D + d]);
+            h->cl_cen.push_back(kc[(size_t)c * D + d]);
+            h->cl_pref.push_back(((km[c] >> d) & 1ull) ? h->prm.k : 1.0);
+        }
+    }
+    for (int j = 0; j < M; ++j) h->cl_label[j] = hl[j] >= 0 ? remap[hl[j]] : -1;
+    if (n_clusters) *n_clusters = (int64_t)h->cl_w.size();
+    return CCB_OK;
+}
+
+int ccb_cluster_sizes(ccb_handle *h, int64_t out[3]) {
+    if (!h || !out) return fail(nullptr, CCB_EINVAL, "null argument");
+    out[0] = (int64_t)h->cl_w.size();
+    out[1] = (int64_t)h->cl_members.size();
+    out[2] = h->off_M;
+    return CCB_OK;
+}
+
+int ccb_export_clusters(ccb_handle *h, int64_t *off, int64_t *members, double *w, double *cf1, double *cf2, double *cen,
+                        double *pref, int32_t *label) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    auto cp = [](auto *dst, const auto &v) {
+        if (dst && !v.empty()) memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+    };
+    cp(off, h->cl_off);
+    cp(members, h->cl_members);
+    cp(w, h->cl_w);
+    cp(cf1, h->cl_cf1);
+    cp(cf2, h->cl_cf2);
+    cp(cen, h->cl_cen);
+    cp(pref, h->cl_pref);
+    cp(label, h->cl_label);
+    return CCB_OK;
+}
+
+int ccb_export_offline(ccb_handle *h, uint8_t *core, uint8_t *nbr, uint8_t *wnbr, double *subw) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    const int64_t M = h->off_M;
+    const int D = h->D, words = (int)((M + 31) / 32);
+    for (int64_t p = 0; p < M; ++p) {
+        if (core) core[p] = h->off_core[p];
+        for (int64_t q = 0; q < M; ++q) {
+            if (nbr) nbr[p * M + q] = (h->off_nbr[p * words + (q >> 5)] >> (q & 31)) & 1u;
+            if (wnbr) wnbr[p * M + q] = (h->off_wnbr[p * words + (q >> 5)] >> (q & 31)) & 1u;
+        }
+        if (subw)
+            for (int d = 0; d < D; ++d) subw[p * D + d] = ((h->off_submask[p] >> d) & 1ull) ? h->prm.k : 1.0;
+    }
+    return CCB_OK;
+}
+
+// ---- stateless device-pointer entry points ------------------------------------------------------------
+int ccb_nearest(int32_t device, void *stream, const double *X, int64_t N, int64_t ld, int32_t D, const double *cen,
+                const uint64_t *prefmask, int64_t M, double k, int32_t *slot, double *dist) {
+    if (D < 1 || D > CCB_MAX_D || N < 0 || M < 0 || ld < D) return fail(nullptr, CCB_EINVAL, "bad ccb_nearest arguments");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (N == 0) return CCB_OK;
+    if (M == 0) {
+        cudaMemsetAsync(slot, 0xff, (size_t)N * 4, s);
+        return CCB_OK;
+    }
+    const int DP = round_dp(D);
+    const bool p2 = is_pow2(k);
+    const double wsel = p2 ? 1.0 / k : k;
+    double2 *cw = nullptr;
+    double *sd = nullptr;
+    int32_t *si = nullptr;
+    // scratch: packed rows + per-slab candidates (slabs only matter when N is small)
+    const int max_slabs = N >= (int64_t)148 * 2 * NEAREST_THREADS * 2 ? 1 : MAX_SLABS; // slabs only matter when N is small
+    if ((e = cudaMallocAsync(&cw, (size_t)M * DP * sizeof(double2), s)) != cudaSuccess ||
+        (e = cudaMallocAsync(&sd, (size_t)N * max_slabs * 8, s)) != cudaSuccess ||
+        (e = cudaMallocAsync(&si, (size_t)N * max_slabs * 4, s)) != cudaSuccess)
+        return fail(nullptr, CCB_ENOMEM, "scratch allocation: %s", cudaGetErrorString(e));
+    k_pack_cw<<<(unsigned)(((size_t)M * DP + 255) / 256), 256, 0, s>>>(cen, prefmask, M, D, DP, wsel, cw);
+    int rc = launch_nearest<1>(nullptr, s, DP, p2 ? 0 : 1, X, nullptr, nullptr, 0, N, ld, D, cw, (int)M, sd, si, dist, slot,
+                               max_slabs, nullptr);
+    cudaFreeAsync(cw, s);
+    cudaFreeAsync(sd, s);
+    cudaFreeAsync(si, s);
+    return rc;
+}
+
+int ccb_off_neighbours(int32_t device, void *stream, const double *cen, int64_t M, int32_t D, int64_t r0, int64_t r1,
+                       double E2, uint32_t *nbr, int32_t *cnt, int32_t *border, int32_t border_cap, int32_t *n_border) {
+    if (D < 1 || D > CCB_MAX_D || M < 0 || r0 < 0 || r1 < r0 || r1 > M) return fail(nullptr, CCB_EINVAL, "bad arguments");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return launch_off_neighbours(nullptr, (cudaStream_t)stream, cen, (int)M, D, (int)r0, (int)r1, E2, nbr, cnt, border,
+                                 border_cap, n_border);
+}
+
+int ccb_off_subspace(int32_t device, void *stream, const double *cen, int64_t M, int32_t D, int64_t r0, int64_t r1,
+                     const uint32_t *nbr, const int32_t *cnt, double delta, uint64_t *submask) {
+    if (D < 1 || D > CCB_MAX_D || M < 0 || r0 < 0 || r1 < r0 || r1 > M) return fail(nullptr, CCB_EINVAL, "bad arguments");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (r1 == r0) return CCB_OK;
+    cudaMemsetAsync(submask, 0, (size_t)(r1 - r0) * 8, s);
+    const int64_t t = (r1 - r0) * D;
+    k_off_subspace<<<(unsigned)((t + 127) / 128), 128, 0, s>>>(cen, (int)M, D, (int)r0, (int)r1, nbr, cnt, delta, submask);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "k_off_subspace: %s", cudaGetErrorString(e));
+}
+
+int ccb_off_weighted(int32_t device, void *stream, const double *cen, int64_t M, int32_t D, int64_t r0, int64_t r1,
+                     const uint32_t *nbr, const uint64_t *submask_all, double k, double E2, uint32_t *wnbr) {
+    if (D < 1 || D > CCB_MAX_D || M < 0 || r0 < 0 || r1 < r0 || r1 > M) return fail(nullptr, CCB_EINVAL, "bad arguments");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    if (r1 == r0) return CCB_OK;
+    const int words = (int)((M + 31) / 32);
+    const int64_t t = (r1 - r0) * words;
+    k_off_weighted<<<(unsigned)((t + 127) / 128), 128, 0, (cudaStream_t)stream>>>(cen, (int)M, D, (int)r0, (int)r1, nbr,
+                                                                                  submask_all, k, E2, wnbr);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "k_off_weighted: %s", cudaGetErrorString(e));
+}
+
+int ccb_off_clusters(int32_t device, void *stream, int64_t M, const uint32_t *wnbr, const uint8_t *core,
+                     const uint64_t *submask_all, double k, int64_t pi, int32_t *label, int32_t *order, int32_t *cl_off,
+                     int32_t *n_cl) {
+    if (M < 0) return fail(nullptr, CCB_EINVAL, "bad arguments");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t *cls = nullptr;
+    int32_t *queue = nullptr;
+    if ((e = cudaMallocAsync(&cls, (size_t)std::max<int64_t>(M, 1), s)) != cudaSuccess ||
+        (e = cudaMallocAsync(&queue, (2 * (size_t)M + 2) * 4, s)) != cudaSuccess)
+        return fail(nullptr, CCB_ENOMEM, "scratch allocation: %s", cudaGetErrorString(e));
+    cudaMemsetAsync(cls, 0, (size_t)std::max<int64_t>(M, 1), s);
+    k_off_clusters<<<1, OFFC_THREADS, 0, s>>>((int)M, wnbr, core, submask_all, k > 1.0, pi, cls, queue, label, order, cl_off,
+                                              n_cl);
+    e = cudaGetLastError();
+    cudaFreeAsync(cls, s);
+    cudaFreeAsync(queue, s);
+    return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "k_off_clusters: %s", cudaGetErrorString(e));
+}
+
+} // extern "C"

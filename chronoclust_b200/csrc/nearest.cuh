@@ -1,0 +1,221 @@
+// nearest.cuh -- KERNEL 1: tiled fp64 cell x microcluster preference-weighted projected distance with
+// a top-K (K = 1: argmin) selection.
+//
+// Replaces: Microcluster.get_projected_dist_to_point (objects/microcluster.py:167-181 ->
+// utilities/mc_functions.py:35-43) evaluated for every MC of a list, and the strict-< first-wins
+// argmin of the scans (clustering/hddstream.py:311-328, 371-375).
+//
+// Layout.  Microclusters are packed as cw[M][DP] double2 = (centroid_d, weight_d), row-major, DP = D
+// rounded up to a multiple of 4 with (0.0, 1.0) padding (adds exact zeros).  weight_d is 1/pref_d
+// when k is a power of two (x * 2^-m is bit-identical to x / 2^m for every x, subnormals included)
+// and pref_d itself otherwise (true IEEE division).  A dead slot carries NaN in its first centroid
+// word: its distance is NaN and never wins a strict-< comparison.
+//
+// Mapping.  One thread owns PPT cells whose DP coordinates live in registers for the whole kernel;
+// the MC axis is cut into slabs (blockIdx.y) and each slab is streamed through shared memory in tiles
+// of TM microclusters by 1-D bulk TMA copies (cp.async.bulk + mbarrier, double buffered).  Every lane
+// of a warp reads the same (c, w) pair -> one broadcast LDS.128 per (MC, dim).  The sum over
+// dimensions is a sequential dependent chain per (cell, MC) as parity requires; instruction-level
+// parallelism comes from JU microclusters x PPT cells advancing together.
+//
+// Roofline: FP64 pipe.  Algorithmic work = 4*D flops per evaluated pair (sub, mul, div, add); bytes =
+// 8*D per cell read + 12 B per cell written.
+#pragma once
+#include "common.cuh"
+
+namespace ccb {
+
+constexpr int NEAREST_THREADS = 128;
+constexpr int NEAREST_JU = 4;
+
+template <int DP>
+struct NearestCfg {
+    static constexpr int PPT = (DP <= 40) ? 2 : 1;
+    // tile of TM microclusters, ~12-16 KB per buffer, TM a multiple of JU
+    static constexpr int TM = ((1024 / DP) < 8 ? 8 : (1024 / DP)) / NEAREST_JU * NEAREST_JU;
+    static constexpr int CELLS = NEAREST_THREADS * PPT;
+};
+
+template <int K>
+__device__ __forceinline__ void topk_insert(double (&bd)[K], int (&bi)[K], double d, int j) {
+    // strict <: an equal distance never displaces an earlier (smaller-index) entry
+    if (!(d < bd[K - 1])) return;
+    bd[K - 1] = d;
+    bi[K - 1] = j;
+#pragma unroll
+    for (int s = K - 1; s > 0; --s) {
+        if (bd[s] < bd[s - 1]) {
+            double td = bd[s];
+            bd[s] = bd[s - 1];
+            bd[s - 1] = td;
+            int ti = bi[s];
+            bi[s] = bi[s - 1];
+            bi[s - 1] = ti;
+        }
+    }
+}
+
+// rows == nullptr: cell r is row r of X.  nrows_dev (optional) overrides nrows with a device-side count.
+// out_dist/out_idx: [nrows][nslab][K]; unused entries hold (+inf, -1).
+template <int DP, int K, bool DIV>
+__global__ void __launch_bounds__(NEAREST_THREADS)
+    k_nearest(const double *__restrict__ X, const int32_t *__restrict__ rows, const int32_t *__restrict__ nrows_dev,
+              int64_t row_off, int64_t nrows, int64_t ld, int D, const double2 *__restrict__ cw, int M, int slab_mcs,
+              double *__restrict__ out_dist, int32_t *__restrict__ out_idx) {
+    using Cfg = NearestCfg<DP>;
+    constexpr int PPT = Cfg::PPT, TM = Cfg::TM, JU = NEAREST_JU;
+    __shared__ __align__(128) double2 tile[2][TM * DP];
+    __shared__ __align__(8) uint64_t bar[2];
+
+    if (nrows_dev) nrows = (int64_t)(*nrows_dev) - row_off;
+    const int64_t cell0 = (int64_t)blockIdx.x * Cfg::CELLS;
+    if (cell0 >= nrows) return;
+    const int nslab = gridDim.y;
+    const int j0 = blockIdx.y * slab_mcs;
+    const int j1 = min(M, j0 + slab_mcs);
+
+    // ---- this thread's cells -> registers (row-contiguous 16-byte loads; every fetched sector is used)
+    double p[PPT][DP];
+    int64_t cell[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        cell[u] = cell0 + threadIdx.x + u * NEAREST_THREADS;
+        const bool live = cell[u] < nrows;
+        const int64_t r = live ? (rows ? (int64_t)rows[row_off + cell[u]] : row_off + cell[u]) : 0;
+        const double *xr = X + r * ld;
+        if (live && ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0)) {
+#pragma unroll
+            for (int d = 0; d < DP; d += 2) {
+                if (d + 1 < D) {
+                    double2 v = *reinterpret_cast<const double2 *>(xr + d);
+                    p[u][d] = v.x;
+                    p[u][d + 1] = v.y;
+                } else {
+                    p[u][d] = (d < D) ? xr[d] : 0.0;
+                    p[u][d + 1] = 0.0;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) p[u][d] = (live && d < D) ? xr[d] : 0.0;
+        }
+    }
+    double bd[PPT][K];
+    int bi[PPT][K];
+#pragma unroll
+    for (int u = 0; u < PPT; ++u)
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            bd[u][s] = __longlong_as_double(0x7ff0000000000000LL);
+            bi[u][s] = -1;
+        }
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int ntiles = (j1 - j0 + TM - 1) / TM;
+    auto issue = [&](int t) {
+        const int jt = j0 + t * TM;
+        const int n = min(TM, j1 - jt);
+        const uint32_t bytes = (uint32_t)n * DP * (uint32_t)sizeof(double2);
+        mbar_expect_tx(&bar[t & 1], bytes);
+        tma_load_1d(&tile[t & 1][0], cw + (size_t)jt * DP, bytes, &bar[t & 1]);
+    };
+    if (threadIdx.x == 0 && ntiles > 0) issue(0);
+
+    for (int t = 0; t < ntiles; ++t) {
+        if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1); // buffer (t+1)&1 was released by the barrier below
+        mbar_wait(&bar[t & 1], (t >> 1) & 1);
+        const double2 *tl = tile[t & 1];
+        const int jt = j0 + t * TM;
+        const int n = min(TM, j1 - jt);
+        for (int jj = 0; jj < n; jj += JU) {
+            double acc[PPT][JU];
+#pragma unroll
+            for (int u = 0; u < PPT; ++u)
+#pragma unroll
+                for (int v = 0; v < JU; ++v) acc[u][v] = 0.0;
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+#pragma unroll
+                for (int v = 0; v < JU; ++v) {
+                    const double2 c = tl[(jj + v) * DP + d]; // broadcast LDS.128 (garbage past n is masked below)
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) {
+                        double tt = dsub(p[u][d], c.x);
+                        tt = dmul(tt, tt);
+                        tt = DIV ? ddiv(tt, c.y) : dmul(tt, c.y);
+                        acc[u][v] = dadd(acc[u][v], tt);
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < JU; ++v) {
+                if (jj + v < n) {
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) topk_insert<K>(bd[u], bi[u], acc[u][v], jt + jj + v);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        if (cell[u] < nrows) {
+            const size_t o = ((size_t)cell[u] * nslab + blockIdx.y) * K;
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                out_dist[o + s] = bd[u][s];
+                out_idx[o + s] = bi[u][s];
+            }
+        }
+    }
+}
+
+// Merges the per-slab top-K lists of every cell into one ascending list of K (dist, idx) entries.
+// Slabs cover ascending index ranges, so scanning them in order with strict < keeps ties on the
+// smaller index.
+template <int K>
+__global__ void k_topk_merge(const double *__restrict__ in_dist, const int32_t *__restrict__ in_idx,
+                             const int32_t *__restrict__ nrows_dev, int64_t row_off, int64_t nrows, int nslab,
+                             double *__restrict__ out_dist, int32_t *__restrict__ out_idx) {
+    if (nrows_dev) nrows = (int64_t)(*nrows_dev) - row_off;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nrows) return;
+    double bd[K];
+    int bi[K];
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        bd[s] = __longlong_as_double(0x7ff0000000000000LL);
+        bi[s] = -1;
+    }
+    for (int e = 0; e < nslab * K; ++e) {
+        const int j = in_idx[(size_t)c * nslab * K + e];
+        if (j >= 0) topk_insert<K>(bd, bi, in_dist[(size_t)c * nslab * K + e], j);
+    }
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        out_dist[(size_t)c * K + s] = bd[s];
+        out_idx[(size_t)c * K + s] = bi[s];
+    }
+}
+
+// Builds the packed (centroid, weight) rows from separate centroid / preference-mask arrays.
+__global__ void k_pack_cw(const double *__restrict__ cen, const uint64_t *__restrict__ mask, int64_t M, int D, int DP,
+                          double wsel, double2 *__restrict__ cw) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * DP) return;
+    const int64_t j = i / DP;
+    const int d = (int)(i % DP);
+    double2 v;
+    v.x = d < D ? cen[j * D + d] : 0.0;
+    v.y = (d < D && ((mask[j] >> d) & 1ull)) ? wsel : 1.0;
+    cw[i] = v;
+}
+
+} // namespace ccb

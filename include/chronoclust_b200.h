@@ -1,0 +1,171 @@
+/*
+ * chronoclust_b200.h -- C ABI of the B200-native ChronoClust per-timepoint clustering hot path.
+ *
+ * One shared library (chronoclust_b200/libchronoclust_b200.so), plain pointers and sizes, no C++ or
+ * torch types.  Every entry point returns 0 on success or a negative CCB_E* code; the message is
+ * available from ccb_last_error().  No C++ exception crosses this boundary.  A handle is bound to
+ * one CUDA device and one stream; the caller is single-threaded per handle; independent handles may
+ * live on different devices (parameter sweeps).  There is NO CPU fallback: without a CUDA device
+ * ccb_create fails with CCB_ECUDA.
+ *
+ * What each entry point replaces (file:line relative to the reference, ghar1821/Chronoclust):
+ *
+ *   ccb_create              HDDStream.__init__                      clustering/hddstream.py:30-67
+ *   ccb_begin_timepoint     decay + downgrade + reset               clustering/hddstream.py:199-213,
+ *                                                                    247-286, 512-549
+ *   ccb_ingest[_device]     the ordered per-point loop              clustering/hddstream.py:220-237,
+ *                           (_add_to_pcore, _add_to_outlier,          288-343, 345-395, 397-430, 434-462
+ *                            _upgrade_outlier_microcluster,          objects/microcluster.py:89-153,
+ *                            _create_new_outlier_cluster)             167-197, 213-233
+ *                                                                    utilities/mc_functions.py:14-62
+ *   ccb_offline             HDDStream.offline_clustering            clustering/hddstream.py:464-510
+ *                           + PreDeCon.run                          clustering/predecon.py:49-120,136-267
+ *                                                                    objects/predecon_mc.py:50-80
+ *                                                                    utilities/predeconmc_functions.py:4-62
+ *                                                                    utilities/mc_functions.py:64-77
+ *   ccb_export_list /       the Microcluster objects in             objects/microcluster.py:71-81
+ *   ccb_import_list         HDDStream.pcore_MC / outlier_MC         (state for the Python facade, pickling)
+ *   ccb_export_clusters     HDDStream.final_clusters                clustering/hddstream.py:508
+ *   ccb_nearest             Microcluster.get_projected_dist_to_point objects/microcluster.py:167-181,
+ *                           + the strict-< argmin of the scans       clustering/hddstream.py:311-328,371-375
+ *   ccb_off_*               the row-sharded stages of PreDeCon      clustering/predecon.py:136-217
+ *                           (multi-GPU offline path, config C4)
+ *
+ * The derived constants (epsilon**2, upsilon*epsilon, delta**2, 2**(-lambda*dt), mu*N, omicron*N_prev,
+ * round(pi)) are evaluated by the Python host with Python's own float semantics, exactly where the
+ * reference evaluates them (hddstream.py:44-52, 107-126, 283), and passed in as doubles.
+ */
+#ifndef CHRONOCLUST_B200_H
+#define CHRONOCLUST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCB_OK 0
+#define CCB_EINVAL (-1)  /* bad argument */
+#define CCB_ECUDA (-2)   /* CUDA runtime error / no device */
+#define CCB_ENOMEM (-3)  /* host or device allocation failed */
+#define CCB_ESTATE (-4)  /* call sequence error */
+#define CCB_ELIMIT (-5)  /* a documented limit was exceeded (D > 64, ids >= 2^31) */
+
+#define CCB_MAX_D 64
+
+typedef struct ccb_handle ccb_handle;
+
+typedef struct {
+    int32_t D;           /* markers per cell, 1..CCB_MAX_D */
+    int32_t device;      /* CUDA device ordinal */
+    double eps2;         /* epsilon ** 2                          hddstream.py:45 */
+    double upsilon_eps;  /* float(upsilon) * epsilon              hddstream.py:47 */
+    double upsilon_eps2; /* (upsilon * epsilon) ** 2              predecon.py:40 */
+    double delta;        /*                                       hddstream.py:48 */
+    double delta2;       /* delta ** 2                            hddstream.py:49 */
+    double beta;         /*                                       hddstream.py:50 */
+    double k;            /*                                       hddstream.py:51 */
+    int32_t wave;        /* ordered-commit micro-batch width 1..32; 0 = default (32); 1 = fully serial */
+    int32_t chunk;       /* max points per ordered-commit launch; 0 = default */
+} ccb_params;
+
+/* Counters since ccb_create (monotonic); all int64. */
+typedef struct {
+    int64_t points;          /* cells ingested */
+    int64_t chunks;          /* ordered-commit launches (kernel 2a) */
+    int64_t waves;           /* micro-batches executed inside kernel 2a */
+    int64_t wave_rollbacks;  /* micro-batches cut short by a failed verification */
+    int64_t rejects;         /* cells that went on to the outlier stage */
+    int64_t resolver_calls;  /* kernel 2b launches */
+    int64_t resolver_cuts;   /* times kernel 2b stopped because every snapshot candidate was stale */
+    int64_t nearest_pairs;   /* (cell x outlier MC) distances evaluated by kernel 1 */
+    int64_t pcore_pairs;     /* (cell x pcore MC) distances evaluated by kernel 2a (incl. verification) */
+    int64_t upgrades, created, downgraded, deleted;
+    int64_t kernel_launches; /* every kernel this library launched */
+    int64_t borderline_pairs; /* offline pairs resolved on the host through dnrm2 */
+} ccb_stats;
+
+int ccb_create(const ccb_params *params, ccb_handle **out);
+void ccb_destroy(ccb_handle *h);
+/* h == NULL returns the message of the last failed ccb_create / stateless call of this thread. */
+const char *ccb_last_error(const ccb_handle *h);
+/* cudaStream_t the handle launches on (for CUDA-event timing by the caller). */
+void *ccb_stream(ccb_handle *h);
+int ccb_get_stats(const ccb_handle *h, ccb_stats *out);
+
+/* The BLAS dnrm2 the reference reaches through numba (predeconmc_functions.py:16-17):
+ * double fn(int *n, double *x, int *incx).  Used only for offline pairs whose squared distance is
+ * within a guard band of (upsilon*epsilon)^2; NULL restores the built-in restatement. */
+int ccb_set_dnrm2(ccb_handle *h, void *fn);
+
+/* Timepoint start.  decay != 0 iff t != last_data_timestamp (hddstream.py:199); decay_factor is
+ * 2 ** (-lambda * interval).  mu = float(config mu) * N, omicron = config omicron * N_prev,
+ * pi = D if config pi <= 0 else round(pi)  (hddstream.py:107-126). */
+int ccb_begin_timepoint(ccb_handle *h, double mu, double omicron, int64_t pi, int32_t decay, double decay_factor);
+
+/* The ordered loop over N cells.  X: host, row-major, leading dimension ld (doubles).
+ * assign_uid[r] (host, N) receives the unique creation id (= prev_outlier_id, microcluster.py:83-84)
+ * of the MC that absorbed row r; stage[r] (host, N, may be NULL): 0 pcore absorb, 1 outlier absorb,
+ * 2 outlier absorb + upgrade, 3 new outlier MC. */
+int ccb_ingest(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *assign_uid, uint8_t *stage);
+/* Same with X, assign_uid and stage already resident on the handle's device (stage may be NULL). */
+int ccb_ingest_device(ccb_handle *h, const double *X_dev, int64_t N, int64_t ld, int32_t *assign_uid_dev,
+                      uint8_t *stage_dev);
+
+/* Offline phase over the current pcore list; returns the number of clusters. */
+int ccb_offline(ccb_handle *h, int64_t *n_clusters);
+
+/* out[0] = pcore MCs, out[1] = outlier MCs, out[2] = pcore_MC_last_id, out[3] = outlier_MC_last_id */
+int ccb_counts(ccb_handle *h, int64_t out[4]);
+/* which: 0 pcore, 1 outlier.  Arrays in list order: ids/uids [n], w [n], cf1/cf2/cen/pref [n][D]. */
+int ccb_export_list(ccb_handle *h, int32_t which, int64_t *ids, int64_t *uids, double *w, double *cf1, double *cf2,
+                    double *cen, double *pref);
+/* Replaces a list (restore / white-box tests).  pref entries equal to k become "preferred". */
+int ccb_import_list(ccb_handle *h, int32_t which, int64_t n, const int64_t *ids, const int64_t *uids,
+                    const double *w, const double *cf1, const double *cf2, const double *cen, const double *pref);
+int ccb_set_counters(ccb_handle *h, int64_t pcore_last_id, int64_t outlier_last_id);
+
+/* Result of the last ccb_offline.  out[0] = clusters, out[1] = total members, out[2] = pcore MCs seen. */
+int ccb_cluster_sizes(ccb_handle *h, int64_t out[3]);
+/* off [nc+1], members [out[1]] = pcore ids in claim order (insert into a Python set in this order),
+ * w [nc], cf1/cf2/cen/pref [nc][D]; label [out[2]] = cluster index of every pcore MC in list order, -1 none. */
+int ccb_export_clusters(ccb_handle *h, int64_t *off, int64_t *members, double *w, double *cf1, double *cf2,
+                        double *cen, double *pref, int32_t *label);
+/* White-box: core flags [M], neighbour / weighted-neighbour matrices [M*M] bytes, subspace weights [M][D]. */
+int ccb_export_offline(ccb_handle *h, uint8_t *core, uint8_t *nbr, uint8_t *wnbr, double *subw);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stateless device-pointer entry points (all pointers are device memory on `device`; stream is a
+ * cudaStream_t or NULL).  These are what bench.py times for the roofline and what the multi-GPU
+ * offline path calls between its NCCL all-gathers.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Kernel 1: for every row of X [N][ld] the nearest of M microclusters under the preference-weighted
+ * projected distance sum_d ((x_d - c_d)^2) / pref_d, strict-< first-wins.  cen [M][D]; prefmask [M]
+ * (bit d set <=> pref_d == k, else 1.0).  slot [N] (-1 if M == 0), dist [N]. */
+int ccb_nearest(int32_t device, void *stream, const double *X, int64_t N, int64_t ld, int32_t D, const double *cen,
+                const uint64_t *prefmask, int64_t M, double k, int32_t *slot, double *dist);
+
+/* Offline stage 1 for rows [r0, r1) of M pcore MCs: neighbourhood bit rows nbr [(r1-r0)][words]
+ * (words = ceil(M/32), uint32), neighbour counts cnt [(r1-r0)], and the list of borderline pairs
+ * (row, col) whose squared distance is within the guard band of E2 (border [2*border_cap] int32,
+ * n_border [1] int32, counted even beyond border_cap). */
+int ccb_off_neighbours(int32_t device, void *stream, const double *cen, int64_t M, int32_t D, int64_t r0, int64_t r1,
+                       double E2, uint32_t *nbr, int32_t *cnt, int32_t *border, int32_t border_cap, int32_t *n_border);
+/* Offline stage 2: subspace preference masks submask [(r1-r0)] from the neighbour rows (delta, not delta^2). */
+int ccb_off_subspace(int32_t device, void *stream, const double *cen, int64_t M, int32_t D, int64_t r0, int64_t r1,
+                     const uint32_t *nbr, const int32_t *cnt, double delta, uint64_t *submask);
+/* Offline stage 3: weighted-neighbour bit rows for rows [r0, r1); submask_all [M] is the gathered mask of all rows. */
+int ccb_off_weighted(int32_t device, void *stream, const double *cen, int64_t M, int32_t D, int64_t r0, int64_t r1,
+                     const uint32_t *nbr, const uint64_t *submask_all, double k, double E2, uint32_t *wnbr);
+/* Offline stage 4: ordered cluster growth over the full weighted-neighbour matrix wnbr [M][words].
+ * label [M] (-1 none), order [M] = MC indices in claim order grouped by cluster, cl_off [M+1], n_cl [1].
+ * Clusters whose accumulated weight is not > 0 are dropped by the caller (predecon.py:83). */
+int ccb_off_clusters(int32_t device, void *stream, int64_t M, const uint32_t *wnbr, const uint8_t *core,
+                     const uint64_t *submask_all, double k, int64_t pi, int32_t *label, int32_t *order, int32_t *cl_off,
+                     int32_t *n_cl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHRONOCLUST_B200_H */

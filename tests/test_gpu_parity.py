@@ -1,0 +1,222 @@
+"""GPU suite (-m gpu): the CUDA path behind the C ABI against the golden vectors of the live reference
+and against the CPU oracle on the same seeded inputs.  Bit-exact everywhere: assignments, list order,
+ids, weights, CF1/CF2, centroids, preference vectors, cluster membership / set order / sums."""
+import ctypes as C
+import json
+import logging
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (GOLDEN, STRESS_NAMES, assert_clusters_equal, assert_list_equal, bits_equal, config_of, load,
+                     stress_inputs)
+
+pytestmark = pytest.mark.gpu
+
+LOG = logging.getLogger("test")
+
+
+def make(cfg, **kw):
+    from chronoclust_b200.hddstream import HDDStream
+
+    return HDDStream(dict(cfg), LOG, **kw)
+
+
+def clusters_of(h):
+    return [(c.members_in_claim_order, c.cumulative_weight, c.CF1, c.CF2, c.cluster_centroids,
+             c.preferred_dimension_vector) for c in h.final_clusters]
+
+
+def run_against_golden(z, Xs, what, **kw):
+    h = make(config_of(z), **kw)
+    for i, (t, X) in enumerate(zip(z["timestamps"].tolist(), Xs)):
+        h.online_microcluster_maintenance(X, int(t))
+        P = f"t{i}_"
+        assert (h.last_assignment == z[P + "assign"]).all(), \
+            f"{what} t{i}: {(h.last_assignment != z[P + 'assign']).sum()} assignments differ, first at " \
+            f"{np.flatnonzero(h.last_assignment != z[P + 'assign'])[:5]}"
+        for which, name in ((0, "p_"), (1, "o_")):
+            assert_list_equal(h.export_arrays(which), z, P + name, f"{what} t{i} list{which}")
+        assert h.counts()[2:] == z[P + "counters"].tolist()
+        assert_clusters_equal(clusters_of(h), z, P, f"{what} t{i}")
+    return h
+
+
+@pytest.mark.parametrize("wave", [32, 1, 7])
+@pytest.mark.parametrize("name", STRESS_NAMES)
+def test_stress_matches_reference(name, wave):
+    z = load(f"stress_{name}.npz")
+    run_against_golden(z, stress_inputs(z), f"{name}/wave{wave}", wave=wave)
+
+
+@pytest.mark.parametrize("chunk", [0, 97])
+def test_c1_matches_reference(chunk):
+    z = load("c1.npz")
+    h = run_against_golden(z, [z[f"scaled{t}"] for t in range(5)], "c1", chunk=chunk)
+    st = h.stats()
+    assert st["kernel_launches"] > 0 and st["points"] == sum(z[f"scaled{t}"].shape[0] for t in range(5))
+
+
+def test_points_view_matches_assignment():
+    z = load("c1.npz")
+    h = make(config_of(z))
+    X = z["scaled0"]
+    h.online_microcluster_maintenance(X, 0)
+    seen = 0
+    for mc in h.pcore_MC + h.outlier_MC:
+        keys = list(mc.points.keys())
+        assert keys == sorted(keys)
+        assert (h.last_assignment[keys] == mc.prev_outlier_id).all()
+        assert mc.points[keys[0]] == X[keys[0]].tolist()
+        seen += len(keys)
+    assert seen == X.shape[0]
+
+
+def test_offline_sets_match_predecon():
+    z = load("offline_sets.npz")
+    for s in range(int(z["nset"])):
+        P = f"s{s}_"
+        D, M, k, pi, delta, E = z[P + "params"]
+        D, M, pi = int(D), int(M), int(pi)
+        cen, w, cf1, cf2, ids, core = (z[P + n] for n in ("cen", "w", "cf1", "cf2", "ids", "core"))
+        wc, wn_ = w[core], w[~core]
+        separable = not (len(wc) and len(wn_) and wc.min() <= wn_.max())
+        mu = 0.0
+        if separable:
+            mu = float((wc.min() + wn_.max()) / 2) if len(wc) and len(wn_) else (0.0 if len(wc) else 1e300)
+        cfg = {"beta": 0.0, "delta": float(delta), "epsilon": 1e150, "lambda": 0, "k": float(k), "mu": 0.0, "pi": pi,
+               "omicron": 0.0, "upsilon": float(E) / 1e150}
+        h = make(cfg)
+        assert h.upsilon == float(E), "test construction: upsilon*epsilon must reproduce E exactly"
+        h.dataset_dimensionality = D
+        h._ensure_handle(D)
+        h.pi, h.mu, h.omicron = pi, mu, 0.0
+        from chronoclust_b200 import _lib
+        _lib.check(_lib.lib().ccb_begin_timepoint(h._h, mu, 0.0, pi, 0, 1.0), h._h)
+        h.import_arrays(0, ids, ids, w, cf1, cf2, cen, np.ones((M, D)))
+        h.offline_clustering(0)
+        got_core, nbr, wn, subw = h.offline_intermediates()
+        exp_nbr = np.unpackbits(z[P + "nbr"])[:M * M].reshape(M, M)
+        exp_wn = np.unpackbits(z[P + "wnbr"])[:M * M].reshape(M, M)
+        assert (nbr == exp_nbr).all(), f"set {s}: neighbourhoods differ"
+        assert bits_equal(subw, z[P + "subw"]), f"set {s}: subspace preference vectors differ"
+        assert (wn == exp_wn).all(), f"set {s}: weighted neighbourhoods differ"
+        if separable:
+            assert (got_core.astype(bool) == core).all()
+            assert_clusters_equal(clusters_of(h), z, P, f"offline set {s}")
+
+
+def test_kats_on_device():
+    """The reference's unit-test known answers through the CUDA path."""
+    import torch
+    from chronoclust_b200 import _lib
+
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
+    L = _lib.lib()
+    # projected distance (unittest_microcluster.py:10-32) through kernel 1
+    for case in kat["projdist"]:
+        x = torch.tensor([case["pt"]], dtype=torch.float64, device="cuda")
+        cen = torch.tensor([case["cen"]], dtype=torch.float64, device="cuda")
+        mask = sum(1 << d for d, v in enumerate(case["pref"]) if v == 15.0)
+        m = torch.tensor([mask], dtype=torch.int64, device="cuda")
+        slot = torch.full((1,), -5, dtype=torch.int32, device="cuda")
+        dist = torch.zeros(1, dtype=torch.float64, device="cuda")
+        _lib.check(L.ccb_nearest(0, None, x.data_ptr(), 1, 3, 3, cen.data_ptr(), m.data_ptr(), 1, 15.0, slot.data_ptr(),
+                                 dist.data_ptr()))
+        torch.cuda.synchronize()
+        assert slot.item() == 0 and dist.item() == case["dist"] and round(dist.item(), 2) == case["rounded"]
+    # preference vector / CF / centroid after 10 ordered absorbs (unittest_microcluster.py:34-80)
+    pts = np.ascontiguousarray(kat["prefvec"]["pts"], np.float64)
+    for case in kat["prefvec"]["cases"]:
+        cfg = {"beta": 1.0, "delta": case["delta2"] ** 0.5, "epsilon": 1e6, "lambda": 0, "k": case["k"], "mu": 1e9,
+               "pi": 0, "omicron": 0.0, "upsilon": 1.0}
+        h = make(cfg)
+        h.delta_squared = case["delta2"]
+        h.online_microcluster_maintenance(pts, 0, run_offline=False)
+        ids, uids, w, cf1, cf2, cen, pref = h.export_arrays(1)
+        assert len(ids) == 1 and w[0] == case["w"]
+        assert bits_equal(cf1[0], case["cf1"]) and bits_equal(cf2[0], case["cf2"]) and bits_equal(cen[0], case["cen"])
+        assert pref[0].tolist() == case["pref"]
+    # radius^2 (unittest_microcluster.py:82-104) through the core flag: eps^2 just above / below the answer
+    r = kat["radius2"]
+    for eps2, expect in ((np.nextafter(r["r2"], 1.0), 1), (r["r2"], 1), (np.nextafter(r["r2"], 0.0), 0)):
+        cfg = {"beta": 0.0, "delta": 0.5, "epsilon": float(eps2) ** 0.5, "lambda": 0, "k": 16.0, "mu": 0.0, "pi": 0,
+               "omicron": 0.0, "upsilon": 1.0}
+        h = make(cfg)
+        h.epsilon_squared = float(eps2)
+        h.dataset_dimensionality = 20
+        h._ensure_handle(20)
+        _lib.check(L.ccb_begin_timepoint(h._h, 0.0, 0.0, 20, 0, 1.0), h._h)
+        one = lambda v: np.ascontiguousarray([v], np.float64)
+        h.import_arrays(0, [0], [0], [r["w"]], one(r["cf1"]), one(r["cf2"]), one(r["cf1"]) / r["w"], one(r["pref"]))
+        h.offline_clustering(0)
+        assert h.offline_intermediates()[0][0] == expect
+
+
+@pytest.mark.parametrize("D,M,k", [(3, 5, 4.0), (12, 300, 4.0), (40, 1000, 4.0), (12, 77, 3.0), (7, 4100, 1.0),
+                                   (64, 33, 2.0)])
+def test_kernel1_nearest_bit_exact(D, M, k):
+    """Kernel 1 against a scalar restatement (sequential sum over d, true division, strict-< first wins)."""
+    import torch
+    from chronoclust_b200 import _lib
+    from oracle.oracle import lib as olib, _p
+
+    rng = np.random.default_rng(D * 1000 + M)
+    N = 3000
+    X = rng.random((N, D))
+    cen = rng.random((M, D))
+    cen[M // 2] = cen[0]  # exact tie between two microclusters: the earlier one must win
+    maskbits = rng.random((M, D)) < 0.5
+    maskbits[M // 2] = maskbits[0]
+    pref = np.where(maskbits, k, 1.0)
+    masks = np.array([sum(1 << d for d in range(D) if maskbits[j, d]) for j in range(M)], np.uint64).astype(np.int64)
+    tX, tc = torch.from_numpy(X).cuda(), torch.from_numpy(cen).cuda()
+    tm = torch.from_numpy(masks).cuda()
+    slot = torch.empty(N, dtype=torch.int32, device="cuda")
+    dist = torch.empty(N, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().ccb_nearest(0, None, tX.data_ptr(), N, D, D, tc.data_ptr(), tm.data_ptr(), M, k,
+                                      slot.data_ptr(), dist.data_ptr()))
+    torch.cuda.synchronize()
+    L = olib()
+    exp_slot, exp_dist = np.zeros(N, np.int32), np.zeros(N)
+    for i in range(0, N, 7):  # a sample of rows through the oracle's scalar kernel
+        best, bd = -1, 0.0
+        for j in range(M):
+            d = L.cco_kat_projected_distance(_p(np.ascontiguousarray(cen[j])), _p(np.ascontiguousarray(pref[j])),
+                                             _p(np.ascontiguousarray(X[i])), D)
+            if best < 0 or d < bd:
+                best, bd = j, d
+        assert slot[i].item() == best and dist[i].item() == bd, (i, slot[i].item(), best, dist[i].item(), bd)
+
+
+@pytest.mark.parametrize("cfgname,N,T", [("C2", 60000, 3), ("C3", 20000, 2)])
+def test_online_offline_vs_oracle_mid_size(cfgname, N, T):
+    """CUDA vs the (reference-pinned) oracle at sizes the reference itself cannot reach in test time."""
+    from chronoclust_b200.synth import CONFIGS, config_params, gen
+    from oracle.oracle import OracleHDDStream
+
+    _, D, _, Cn, seed, _, _ = CONFIGS[cfgname]
+    cfg = config_params(cfgname)
+    Xs = gen(N, D, T, Cn, seed)
+    h, o = make(cfg), OracleHDDStream(cfg)
+    for t, X in enumerate(Xs):
+        h.online_microcluster_maintenance(X, t)
+        o.online_microcluster_maintenance(X, t)
+        assert (h.last_assignment == o.assign_uid).all(), f"t{t}: first diff at {np.flatnonzero(h.last_assignment != o.assign_uid)[:5]}"
+        assert (h.last_stage == o.stage).all()
+        for which in (0, 1):
+            e = o.export(which)
+            got = h.export_arrays(which)
+            assert len(got[0]) == len(e)
+            assert (got[0] == e.ids).all() and (got[1] == e.uids).all()
+            for g, x in zip(got[2:], (e.w, e.cf1, e.cf2, e.cen, e.pref)):
+                assert bits_equal(g, x)
+        oc = o.clusters()
+        hc = clusters_of(h)
+        assert len(oc) == len(hc)
+        for (m1, w1, a1, b1, c1, p1), (m2, w2, a2, b2, c2, p2) in zip(hc, oc):
+            assert list(m1) == list(m2) and w1 == w2
+            assert bits_equal(a1, a2) and bits_equal(b1, b2) and bits_equal(c1, c2) and bits_equal(p1, p2)
+    st = h.stats()
+    print(cfgname, st)
