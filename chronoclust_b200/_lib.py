@@ -38,6 +38,10 @@ SYMBOLS = {
     "ccb_last_error": (C.c_char_p, [vp]),
     "ccb_stream": (vp, [vp]),
     "ccb_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
+    "ccb_reset": (C.c_int, [vp]),
+    "ccb_fp64_peak": (C.c_int, [i32, vp, i32, i32, i32, vp, C.POINTER(f64)]),
+    "ccb_enable_timing": (C.c_int, [vp, i32]),
+    "ccb_get_timing": (C.c_int, [vp, C.POINTER(f64 * 8), C.POINTER(i64 * 8), i32]),
     "ccb_set_dnrm2": (C.c_int, [vp, vp]),
     "ccb_begin_timepoint": (C.c_int, [vp, f64, f64, i64, i32, f64]),
     "ccb_ingest": (C.c_int, [vp, vp, i64, i64, vp, vp]),
@@ -56,6 +60,9 @@ SYMBOLS = {
     "ccb_off_weighted": (C.c_int, [i32, vp, vp, i64, i32, i64, i64, vp, vp, f64, f64, vp]),
     "ccb_off_clusters": (C.c_int, [i32, vp, i64, vp, vp, vp, f64, i64, vp, vp, vp, vp]),
 }
+
+
+CATEGORIES = ["pcore_stage", "nearest", "resolve", "maintenance", "offline", "misc", "copy", "reserved"]
 
 
 class CCBError(RuntimeError):

@@ -89,8 +89,16 @@ struct ccb_handle {
     std::vector<uint32_t> off_nbr, off_wnbr;
     std::vector<uint64_t> off_submask;
     ccb_stats st{};
+    ccb_stats st_base{}; // device-side counters folded in by ccb_reset
     std::string err;
     void *dnrm2 = nullptr;
+    // optional per-category GPU timing (CUDA events on the handle's stream)
+    bool timing = false;
+    struct Ev { cudaEvent_t a, b; int cat; };
+    std::vector<Ev> ev_pending;
+    std::vector<cudaEvent_t> ev_pool;
+    double cat_ms[CCB_NCAT] = {0};
+    int64_t cat_n[CCB_NCAT] = {0};
 };
 
 namespace {
@@ -113,6 +121,49 @@ int fail(ccb_handle *h, int code, const char *fmt, ...) {
                         __LINE__, #call, cudaGetErrorString(e_));                                          \
     } while (0)
 #define CKL(h) CK(h, cudaGetLastError())
+
+// RAII bracket: records CUDA events around the launches of one category when timing is enabled
+struct Timed {
+    ccb_handle *h;
+    ccb_handle::Ev e{};
+    bool on;
+    Timed(ccb_handle *h_, int cat) : h(h_), on(h_ && h_->timing) {
+        if (!on) return;
+        auto get = [&]() {
+            cudaEvent_t x;
+            if (!h->ev_pool.empty()) {
+                x = h->ev_pool.back();
+                h->ev_pool.pop_back();
+            } else {
+                cudaEventCreate(&x);
+            }
+            return x;
+        };
+        e.a = get();
+        e.b = get();
+        e.cat = cat;
+        cudaEventRecord(e.a, h->stream);
+    }
+    void stop() {
+        if (!on) return;
+        cudaEventRecord(e.b, h->stream);
+        h->ev_pending.push_back(e);
+        on = false;
+    }
+    ~Timed() { stop(); }
+};
+void drain_timing(ccb_handle *h) { // call after a stream synchronize
+    for (auto &e : h->ev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+            h->cat_ms[e.cat] += ms;
+            h->cat_n[e.cat] += 1;
+        }
+        h->ev_pool.push_back(e.a);
+        h->ev_pool.push_back(e.b);
+    }
+    h->ev_pending.clear();
+}
 
 int alloc_store(ccb_handle *h, Store &S, int cap) {
     const int D = h->D, DP = h->DP;
@@ -188,6 +239,7 @@ int realloc_aux_for_pcore_cap(ccb_handle *h) {
 int sync_ctl(ccb_handle *h) { // device control block -> pinned host mirror
     CK(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    if (h->timing) drain_timing(h);
     return CCB_OK;
 }
 int push_ctl(ccb_handle *h) {
@@ -288,7 +340,10 @@ int ingest_core(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t 
         Store &P = h->P[h->pcur], &O = h->O[h->ocur];
         const int Mp = c.n_pcore, Mo = c.n_outlier;
 
-        k_max_w<<<1, 1024, 0, s>>>(O.w, h->d_ctl);
+        {
+            Timed tm(h, CCB_CAT_MISC);
+            k_max_w<<<1, 1024, 0, s>>>(O.w, h->d_ctl);
+        }
         h->st.kernel_launches++;
 
         PcoreArgs pa{};
@@ -322,7 +377,10 @@ int ingest_core(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t 
             }
         }
         pa.dist_gmem = h->d_dist_gmem;
-        k_pcore_stage<<<1, PCORE_THREADS, smem, s>>>(pa);
+        {
+            Timed tm(h, CCB_CAT_PCORE);
+            k_pcore_stage<<<1, PCORE_THREADS, smem, s>>>(pa);
+        }
         CKL(h);
         h->st.kernel_launches++;
         h->st.chunks++;
@@ -335,6 +393,7 @@ int ingest_core(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t 
             const int mo_snap = first ? Mo : h->h_ctl->n_outlier;
             CK(h, cudaMemsetAsync(h->d_dirty, 0, (size_t)std::max(mo_snap, 1), s));
             if (mo_snap > 0) {
+                Timed tm(h, CCB_CAT_NEAREST);
                 rc = launch_nearest<TOPK>(h, s, h->DP, h->div_mode, dX, h->d_rej, &h->d_ctl->n_rej, q_snap, REJ_CAP - q_snap,
                                           ld, h->D, Oc.cw, mo_snap, h->d_tk_dist_slab, h->d_tk_idx_slab, h->d_tk_dist,
                                           h->d_tk_idx, MAX_SLABS, nullptr);
@@ -359,7 +418,10 @@ int ingest_core(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t 
             ra.dirty_list = h->d_dirty_list;
             ra.assign = d_assign;
             ra.stage = d_stage;
-            k_resolve<<<1, RES_THREADS, 0, s>>>(ra);
+            {
+                Timed tm(h, CCB_CAT_RESOLVE);
+                k_resolve<<<1, RES_THREADS, 0, s>>>(ra);
+            }
             CKL(h);
             h->st.kernel_launches++;
             h->st.resolver_calls++;
@@ -523,21 +585,76 @@ void ccb_destroy(ccb_handle *h) {
     cudaFree(h->d_pfin);
     cudaFree(h->d_onew);
     cudaFree(h->d_dist_gmem);
+    for (auto &e : h->ev_pending) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    for (auto &e : h->ev_pool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
 int ccb_get_stats(const ccb_handle *h, ccb_stats *out) {
     if (!h || !out) return fail(nullptr, CCB_EINVAL, "null argument");
+    // the device-side counters are as of the last control-block read-back (every chunk / ccb_counts)
     *out = h->st;
     const Ctl &c = *h->h_ctl;
-    out->waves = c.waves;
-    out->wave_rollbacks = c.rollbacks;
-    out->pcore_pairs = c.pcore_pairs;
-    out->upgrades = c.upgrades;
-    out->created = c.created;
-    out->downgraded = c.downgraded;
-    out->deleted = c.deleted;
+    out->waves = h->st_base.waves + c.waves;
+    out->wave_rollbacks = h->st_base.wave_rollbacks + c.rollbacks;
+    out->pcore_pairs = h->st_base.pcore_pairs + c.pcore_pairs;
+    out->upgrades = h->st_base.upgrades + c.upgrades;
+    out->created = h->st_base.created + c.created;
+    out->downgraded = h->st_base.downgraded + c.downgraded;
+    out->deleted = h->st_base.deleted + c.deleted;
+    return CCB_OK;
+}
+
+int ccb_reset(ccb_handle *h) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    CK(h, cudaSetDevice(h->prm.device));
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    {
+        const Ctl &c = *h->h_ctl;
+        h->st_base.waves += c.waves;
+        h->st_base.wave_rollbacks += c.rollbacks;
+        h->st_base.pcore_pairs += c.pcore_pairs;
+        h->st_base.upgrades += c.upgrades;
+        h->st_base.created += c.created;
+        h->st_base.downgraded += c.downgraded;
+        h->st_base.deleted += c.deleted;
+    }
+    memset(h->h_ctl, 0, sizeof(Ctl));
+    rc = push_ctl(h);
+    if (rc) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->have_params = false;
+    h->off_M = 0;
+    h->cl_off.assign(1, 0);
+    h->cl_members.clear();
+    h->cl_w.clear();
+    return CCB_OK;
+}
+
+int ccb_enable_timing(ccb_handle *h, int32_t on) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    h->timing = on != 0;
+    return CCB_OK;
+}
+
+int ccb_get_timing(ccb_handle *h, double ms[CCB_NCAT], int64_t launches[CCB_NCAT], int32_t reset) {
+    if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
+    CK(h, cudaSetDevice(h->prm.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    drain_timing(h);
+    for (int i = 0; i < CCB_NCAT; ++i) {
+        if (ms) ms[i] = h->cat_ms[i];
+        if (launches) launches[i] = h->cat_n[i];
+        if (reset) {
+            h->cat_ms[i] = 0;
+            h->cat_n[i] = 0;
+        }
+    }
     return CCB_OK;
 }
 
@@ -584,6 +701,7 @@ int ccb_begin_timepoint(ccb_handle *h, double mu, double omicron, int64_t pi, in
         ma.O2 = h->O[1 - h->ocur];
         ma.o_new = h->d_onew;
     }
+    Timed tm(h, CCB_CAT_MAINT);
     k_maint_plan<<<1, MAINT_THREADS, 0, s>>>(ma);
     CKL(h);
     const int64_t total = (int64_t)(h->h_ctl->n_pcore + h->h_ctl->n_outlier) * h->DP;
@@ -595,6 +713,7 @@ int ccb_begin_timepoint(ccb_handle *h, double mu, double omicron, int64_t pi, in
     h->st.kernel_launches += 3;
     h->pcur = 1 - h->pcur;
     h->ocur = 1 - h->ocur;
+    tm.stop();
     return sync_ctl(h);
 }
 
@@ -620,12 +739,19 @@ int ccb_ingest(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *a
     }
     int rc = ensure_point_buffers(h, N);
     if (rc) return rc;
-    CK(h, cudaMemcpyAsync(h->d_X, X, need * 8, cudaMemcpyHostToDevice, h->stream));
+    {
+        Timed tm(h, CCB_CAT_COPY);
+        CK(h, cudaMemcpyAsync(h->d_X, X, need * 8, cudaMemcpyHostToDevice, h->stream));
+    }
     rc = ingest_core(h, h->d_X, N, ld, h->d_assign, h->d_stage);
     if (rc) return rc;
-    CK(h, cudaMemcpyAsync(assign_uid, h->d_assign, (size_t)N * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (stage) CK(h, cudaMemcpyAsync(stage, h->d_stage, (size_t)N, cudaMemcpyDeviceToHost, h->stream));
+    {
+        Timed tm(h, CCB_CAT_COPY);
+        CK(h, cudaMemcpyAsync(assign_uid, h->d_assign, (size_t)N * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (stage) CK(h, cudaMemcpyAsync(stage, h->d_stage, (size_t)N, cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(h, cudaStreamSynchronize(h->stream));
+    if (h->timing) drain_timing(h);
     return CCB_OK;
 }
 
@@ -767,6 +893,7 @@ int ccb_offline(ccb_handle *h, int64_t *n_clusters) {
     if (M == 0) return CCB_OK;
 
     const double E2 = h->prm.upsilon_eps2;
+    Timed tm_off(h, CCB_CAT_OFFLINE);
     DevBuf<uint8_t> core, cls;
     DevBuf<uint32_t> nbr, wnbr;
     DevBuf<int32_t> cnt, border, nborder, queue, label, order, cloff, ncl;
@@ -863,6 +990,9 @@ int ccb_offline(ccb_handle *h, int64_t *n_clusters) {
         CK(h, cudaMemcpyAsync(km.data(), omask.p, (size_t)nc_raw * 8, cudaMemcpyDeviceToHost, s));
         CK(h, cudaStreamSynchronize(s));
     }
+    tm_off.stop();
+    CK(h, cudaStreamSynchronize(s));
+    if (h->timing) drain_timing(h);
     CK(h, cudaMemcpy(hl.data(), label.p, (size_t)M * 4, cudaMemcpyDeviceToHost));
     CK(h, cudaMemcpy(ho.data(), order.p, (size_t)M * 4, cudaMemcpyDeviceToHost));
     CK(h, cudaMemcpy(hoff.data(), cloff.p, hoff.size() * 4, cudaMemcpyDeviceToHost));
@@ -930,6 +1060,39 @@ int ccb_export_offline(ccb_handle *h, uint8_t *core, uint8_t *nbr, uint8_t *wnbr
         if (subw)
             for (int d = 0; d < D; ++d) subw[p * D + d] = ((h->off_submask[p] >> d) & 1ull) ? h->prm.k : 1.0;
     }
+    return CCB_OK;
+}
+
+// ---- FP64 pipe microbenchmark (roofline denominators; MEASURED_PEAKS.json has no FP64 figure) ----------
+__global__ void k_fp64_peak(int mode, int iters, double *sink) {
+    double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3;
+    double a4 = a0 + 0.4, a5 = a0 + 0.5, a6 = a0 + 0.6, a7 = a0 + 0.7;
+    const double m = 1.0000000001, c = 1e-12;
+    if (mode == 0) { // fused multiply-add stream: 2 flop per instruction
+        for (int i = 0; i < iters; ++i) {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+        }
+    } else { // separate multiply and add, never contracted: 1 flop per instruction (what parity allows)
+        for (int i = 0; i < iters; ++i) {
+            a0 = __dadd_rn(__dmul_rn(a0, m), c); a1 = __dadd_rn(__dmul_rn(a1, m), c);
+            a2 = __dadd_rn(__dmul_rn(a2, m), c); a3 = __dadd_rn(__dmul_rn(a3, m), c);
+            a4 = __dadd_rn(__dmul_rn(a4, m), c); a5 = __dadd_rn(__dmul_rn(a5, m), c);
+            a6 = __dadd_rn(__dmul_rn(a6, m), c); a7 = __dadd_rn(__dmul_rn(a7, m), c);
+        }
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) sink[0] = r;
+}
+
+int ccb_fp64_peak(int32_t device, void *stream, int32_t mode, int32_t iters, int32_t blocks, double *sink,
+                  double *flops_out) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    k_fp64_peak<<<blocks, 256, 0, (cudaStream_t)stream>>>(mode, iters, sink);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "k_fp64_peak: %s", cudaGetErrorString(e));
+    if (flops_out) *flops_out = (double)blocks * 256.0 * (double)iters * 8.0 * 2.0; // 8 chains x (mul + add)
     return CCB_OK;
 }
 

@@ -248,6 +248,46 @@ class HDDStream(object):
         _lib.check(_lib.lib().ccb_get_stats(self._h, C.byref(st)), self._h)
         return st.as_dict()
 
+    def reset(self):
+        """Forgets all microclusters and counters (a new run with the same parameters and device)."""
+        if self._h is not None:
+            _lib.check(_lib.lib().ccb_reset(self._h), self._h)
+        self._views.reset()
+        self._lists = [None, None]
+        self.final_clusters = []
+        self.last_data_timestamp = 0
+        self.dataset_size = 0
+        self.last_assignment = self.last_stage = self.last_cluster_label = None
+
+    @property
+    def stream_ptr(self):
+        return _lib.lib().ccb_stream(self._h)
+
+    def ingest_device(self, x_ptr, N, ld, daystamp, assign_ptr, stage_ptr=None, run_offline=True):
+        """online_microcluster_maintenance for a dataset already resident on the handle's device
+        (raw device pointers; per-row results stay on the device).  Used by bench.py for `value`."""
+        L, h = _lib.lib(), self._h
+        shape = type("S", (), {"shape": (N, self.dataset_dimensionality)})
+        self._set_dataset_dependent_parameters(shape)
+        decay = (self.last_data_timestamp - daystamp) != 0
+        factor = 2 ** (-self.lambbda * (daystamp - self.last_data_timestamp)) if decay else 1.0
+        _lib.check(L.ccb_begin_timepoint(h, float(self.mu), float(self.omicron), int(self.pi), int(decay),
+                                         float(factor)), h)
+        _lib.check(L.ccb_ingest_device(h, x_ptr, N, ld, assign_ptr, stage_ptr), h)
+        self._lists = [None, None]
+        self.last_data_timestamp = daystamp
+        if run_offline:
+            self.offline_clustering(daystamp)
+
+    def enable_timing(self, on=True):
+        _lib.check(_lib.lib().ccb_enable_timing(self._h, int(on)), self._h)
+
+    def timing(self, reset=False):
+        """{category: (gpu milliseconds, bracketed launch groups)} measured with CUDA events."""
+        ms, n = (C.c_double * 8)(), (C.c_int64 * 8)()
+        _lib.check(_lib.lib().ccb_get_timing(self._h, C.byref(ms), C.byref(n), int(reset)), self._h)
+        return {c: (float(ms[i]), int(n[i])) for i, c in enumerate(_lib.CATEGORIES)}
+
     @property
     def pcore_MC_last_id(self):
         return self.counts()[2] if self._h else 0

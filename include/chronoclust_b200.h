@@ -92,6 +92,21 @@ const char *ccb_last_error(const ccb_handle *h);
 /* cudaStream_t the handle launches on (for CUDA-event timing by the caller). */
 void *ccb_stream(ccb_handle *h);
 int ccb_get_stats(const ccb_handle *h, ccb_stats *out);
+/* Forgets every microcluster and both id counters (a new run on the same device / stream). */
+int ccb_reset(ccb_handle *h);
+
+/* Optional GPU timing per kernel category, taken with CUDA events on the handle's stream (this is
+ * what bench.py reads for the live roofline).  ms / launches: arrays of CCB_NCAT. */
+#define CCB_CAT_PCORE 0   /* kernel 2a  k_pcore_stage */
+#define CCB_CAT_NEAREST 1 /* kernel 1   k_nearest (+ k_topk_merge) on the rejected cells */
+#define CCB_CAT_RESOLVE 2 /* kernel 2b  k_resolve */
+#define CCB_CAT_MAINT 3   /* kernel 3   k_maint_plan + k_maint_gather */
+#define CCB_CAT_OFFLINE 4 /* kernel 4   offline pipeline (device part) */
+#define CCB_CAT_MISC 5    /* small helpers */
+#define CCB_CAT_COPY 6    /* host<->device copies of ccb_ingest */
+#define CCB_NCAT 8
+int ccb_enable_timing(ccb_handle *h, int32_t on);
+int ccb_get_timing(ccb_handle *h, double ms[CCB_NCAT], int64_t launches[CCB_NCAT], int32_t reset);
 
 /* The BLAS dnrm2 the reference reaches through numba (predeconmc_functions.py:16-17):
  * double fn(int *n, double *x, int *incx).  Used only for offline pairs whose squared distance is
@@ -145,6 +160,12 @@ int ccb_export_offline(ccb_handle *h, uint8_t *core, uint8_t *nbr, uint8_t *wnbr
  * (bit d set <=> pref_d == k, else 1.0).  slot [N] (-1 if M == 0), dist [N]. */
 int ccb_nearest(int32_t device, void *stream, const double *X, int64_t N, int64_t ld, int32_t D, const double *cen,
                 const uint64_t *prefmask, int64_t M, double k, int32_t *slot, double *dist);
+
+/* FP64 pipe microbenchmark for the roofline denominators: mode 0 = DFMA stream (2 flop/instr), mode 1 =
+ * separate DMUL + DADD (1 flop/instr, the only form the parity contract allows).  Launches `blocks` CTAs of
+ * 256 threads x 8 independent chains x iters; *flops_out = flops executed.  Time it with CUDA events. */
+int ccb_fp64_peak(int32_t device, void *stream, int32_t mode, int32_t iters, int32_t blocks, double *sink,
+                  double *flops_out);
 
 /* Offline stage 1 for rows [r0, r1) of M pcore MCs: neighbourhood bit rows nbr [(r1-r0)][words]
  * (words = ceil(M/32), uint32), neighbour counts cnt [(r1-r0)], and the list of borderline pairs

@@ -1,0 +1,37 @@
+"""Exploratory timing of the CUDA path (not the bench contract): per-timepoint wall time and counters."""
+import logging
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from chronoclust_b200.hddstream import HDDStream
+from chronoclust_b200.synth import CONFIGS, config_params, gen
+
+name = sys.argv[1] if len(sys.argv) > 1 else "C2"
+scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+wave = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+N, D, T, Cn, seed, eps, pi = CONFIGS[name]
+N = int(N * scale)
+t0 = time.time()
+Xs = gen(N, D, T, Cn, seed)
+print(f"gen {time.time()-t0:.1f}s  N={N} D={D} T={T}")
+h = HDDStream(config_params(name), logging.getLogger("q"), wave=wave)
+prev = None
+h._ensure_handle(D)
+h.enable_timing()
+for t, X in enumerate(Xs):
+    t0 = time.time()
+    h.online_microcluster_maintenance(X, t, run_offline=False)
+    t1 = time.time()
+    h.offline_clustering(t)
+    t2 = time.time()
+    st = h.stats()
+    d = {k: st[k] - (prev[k] if prev else 0) for k in st}
+    prev = st
+    c = h.counts()
+    print(f"t={t} online {t1-t0:.3f}s offline {t2-t1:.3f}s  {N/(t2-t0):.0f} cells/s  pcore={c[0]} outlier={c[1]} "
+          f"clusters={len(h.final_clusters)}")
+    print("   ", {k: v for k, v in d.items() if v})
+    print("    gpu ms:", {k: (round(v[0], 2), v[1]) for k, v in h.timing(reset=True).items() if v[1]})
