@@ -39,6 +39,7 @@ SYMBOLS = {
     "ccb_stream": (vp, [vp]),
     "ccb_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
     "ccb_reset": (C.c_int, [vp]),
+    "ccb_debug_phase_cycles": (C.c_int, [vp, C.POINTER(i64 * 8)]),
     "ccb_fp64_peak": (C.c_int, [i32, vp, i32, i32, i32, vp, C.POINTER(f64)]),
     "ccb_enable_timing": (C.c_int, [vp, i32]),
     "ccb_get_timing": (C.c_int, [vp, C.POINTER(f64 * 8), C.POINTER(i64 * 8), i32]),

@@ -379,7 +379,7 @@ int ingest_core(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t 
         pa.dist_gmem = h->d_dist_gmem;
         {
             Timed tm(h, CCB_CAT_PCORE);
-            k_pcore_stage<<<1, PCORE_THREADS, smem, s>>>(pa);
+            CCB_DISPATCH_DP(h->DP, { k_pcore_stage<kDP><<<1, PCORE_THREADS, smem, s>>>(pa); })
         }
         CKL(h);
         h->st.kernel_launches++;
@@ -539,7 +539,10 @@ int ccb_create(const ccb_params *p, ccb_handle **out) {
     CKC(cudaMemset(h->d_ctl, 0, sizeof(Ctl)));
     CKC(cudaMallocHost(&h->h_ctl, sizeof(Ctl)));
     memset(h->h_ctl, 0, sizeof(Ctl));
-    CKC(cudaFuncSetAttribute(k_pcore_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCORE_SMEM_LIMIT + 8192));
+    CCB_DISPATCH_DP(h->DP, {
+        CKC(cudaFuncSetAttribute(k_pcore_stage<kDP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)PCORE_SMEM_LIMIT + 8192));
+    })
     int rc = 0;
     for (int i = 0; i < 2 && !rc; ++i) rc = alloc_store(h, h->P[i], 256);
     for (int i = 0; i < 2 && !rc; ++i) rc = alloc_store(h, h->O[i], 8192);
@@ -606,6 +609,14 @@ int ccb_get_stats(const ccb_handle *h, ccb_stats *out) {
     out->created = h->st_base.created + c.created;
     out->downgraded = h->st_base.downgraded + c.downgraded;
     out->deleted = h->st_base.deleted + c.deleted;
+    return CCB_OK;
+}
+
+int ccb_debug_phase_cycles(ccb_handle *h, int64_t out[8]) {
+    if (!h || !out) return fail(nullptr, CCB_EINVAL, "null argument");
+    int rc = sync_ctl(h);
+    if (rc) return rc;
+    for (int i = 0; i < 8; ++i) out[i] = h->h_ctl->phase_cycles[i];
     return CCB_OK;
 }
 

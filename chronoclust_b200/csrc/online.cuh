@@ -40,6 +40,7 @@ struct Ctl {
     int64_t waves, rollbacks, pcore_pairs, upgrades, created;
     int32_t new_n_pcore, new_n_outlier; // kernel 3 plan output
     int64_t downgraded, deleted;
+    int64_t phase_cycles[8]; // kernel 2a, thread 0: cycles between barriers per phase (diagnostics)
 };
 enum { RES_DONE = 0, RES_UPGRADE = 1, RES_CUT = 2, RES_OCAP = 3, RES_PCAP = 4 };
 
@@ -140,14 +141,13 @@ struct PcoreArgs {
     double *dist_gmem; // [Mp][33] fallback
 };
 
-constexpr int PCORE_THREADS = 512;
+constexpr int PCORE_THREADS = 768;
 constexpr int PCORE_WARPS = PCORE_THREADS / 32;
 constexpr int XS = 33; // padded stride of the transposed wave tile and of the distance matrix
 
 __host__ __device__ inline size_t pcore_smem_bytes(int D, int Mp, bool state, bool dist) {
-    size_t dbl = (size_t)D * XS            // xT
-                 + 3 * (size_t)32 * D + 32 // versions cf1, cf2, cen, w
-                 + (size_t)PCORE_WARPS * CCB_MAX_D;
+    size_t dbl = 2 * (size_t)D * XS          // xT, double buffered
+                 + 3 * (size_t)32 * D + 32;  // versions cf1, cf2, cen, w
     if (dist) dbl += (size_t)Mp * XS;
     if (state) dbl += 3 * (size_t)Mp * D + Mp;
     size_t b = dbl * 8 + (32 + (state ? (size_t)Mp : 0)) * 8; // v_mask, m_mask
@@ -155,6 +155,66 @@ __host__ __device__ inline size_t pcore_smem_bytes(int D, int Mp, bool state, bo
     return b;
 }
 
+// 8-byte asynchronous global->shared copy (LDGSTS); used to prefetch the next wave's cells transposed
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+template <int DP>
+__device__ __forceinline__ double proj_dist_t(const double *x, const double *c, uint64_t mask, const Num &nm) {
+    double acc = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+        if (d < nm.D) {
+            double t = dsub(x[d * XS], c[d]);
+            t = dmul(t, t);
+            if ((mask >> d) & 1ull) t = nm.div_mode ? ddiv(t, nm.k) : dmul(t, nm.wsel);
+            acc = dadd(acc, t);
+        }
+    }
+    return acc;
+}
+
+// Tentative absorb held by one warp, lane d owns dims d and d+32; the D radius terms are summed in index
+// order by every lane redundantly from warp-shuffle broadcasts (no shared memory, no barrier).
+template <int DP>
+__device__ __forceinline__ bool tentative_absorb_t(const LaneMc &m, double w, const double x[2], const Num &nm,
+                                                   LaneMc &o, double &wn, uint64_t &nmask) {
+    const int lane = threadIdx.x & 31;
+    wn = dadd(w, 1.0);
+    uint32_t bits[2] = {0u, 0u};
+    double term[2] = {0.0, 0.0};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (h == 0 || DP > 32) {
+            const int d = lane + 32 * h;
+            // idle lanes (d >= D) carry CF = 1 so that their (discarded) quotients stay on the fast path of the
+            // IEEE division; a zero dividend would drag the whole warp through the slow-path subroutine
+            const bool act = d < nm.D;
+            o.cf1[h] = dadd(m.cf1[h], x[h]);
+            o.cf2[h] = dadd(m.cf2[h], dmul(x[h], x[h]));
+            const double a = ddiv(o.cf2[h], wn);
+            const double c = ddiv(o.cf1[h], wn);
+            o.cen[h] = c;
+            const double var = dsub(a, dmul(c, c));
+            const bool bit = act && (var <= nm.delta2);
+            term[h] = bit ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var;
+            bits[h] = __ballot_sync(0xffffffffu, bit);
+        }
+    }
+    nmask = (uint64_t)bits[0] | ((uint64_t)bits[1] << 32);
+    double s = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+        if (d < nm.D) s = dadd(s, __shfl_sync(0xffffffffu, term[d >> 5], d & 31));
+    }
+    return s <= nm.eps2;
+}
+
+template <int DP>
 __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Num nm = a.nm;
@@ -163,7 +223,10 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
     const int Mp = a.ctl->n_pcore;
 
     double *sp = reinterpret_cast<double *>(smem_raw);
-    double *xT = sp;
+    double *xTb[2];
+    xTb[0] = sp;
+    sp += (size_t)D * XS;
+    xTb[1] = sp;
     sp += (size_t)D * XS;
     double *v_cf1 = sp;
     sp += 32 * D;
@@ -173,8 +236,6 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
     sp += 32 * D;
     double *v_w = sp;
     sp += 32;
-    double *sumscr = sp + warp * CCB_MAX_D;
-    sp += PCORE_WARPS * CCB_MAX_D;
     double *dist = a.dist_gmem;
     if (a.dist_in_smem) {
         dist = sp;
@@ -202,15 +263,13 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
     int *ip = reinterpret_cast<int *>(up);
     int *cand = ip;
     ip += 32;
-    int *cand2 = ip;
-    ip += 32;
     int *distinct = ip;
     ip += 32;
     unsigned *dmask = reinterpret_cast<unsigned *>(ip);
     ip += 32;
     unsigned *amask = reinterpret_cast<unsigned *>(ip);
     ip += 32;
-    int *misc = ip; // [0] n_distinct, [1] m (commit length), [2] stop flag, [3] nrej (running), [4] mismatch pos
+    int *misc = ip; // [0] n_distinct, [1] m (commit length), [2] stop flag, [3] nrej (running), [4] rollback flag
 
     if (a.state_in_smem) {
         for (int i = tid; i < Mp * D; i += PCORE_THREADS) {
@@ -228,60 +287,87 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
         misc[3] = 0;
     }
     const double maxw0 = fmax(a.ctl->max_w_outlier, 0.0);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     int64_t pos = a.start;
     int64_t st_waves = 0, st_roll = 0, st_pairs = 0;
+
+    // prefetch of a wave tile: cells [p0, p0 + 32) clipped to the chunk, transposed into xT[d][i]
+    auto prefetch = [&](int buf, int64_t p0) {
+        const int nb = (int)min((int64_t)a.wave, a.end - p0);
+        for (int i = tid; i < nb * D; i += PCORE_THREADS) {
+            const int r = i / D, d = i - r * D;
+            cp_async8(&xTb[buf][d * XS + r], a.X + (p0 + r) * a.ld + d);
+        }
+    };
+    long long pc_t = clock64();
+    long long pc_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define CCB_PHASE(k)                     \
+    do {                                 \
+        if (tid == 0) {                  \
+            const long long n_ = clock64(); \
+            pc_acc[k] += n_ - pc_t;      \
+            pc_t = n_;                   \
+        }                                \
+    } while (0)
+    int buf = 0;
+    if (pos < a.end) prefetch(0, pos);
+    int64_t pf_pos = pos; // position the tile in xTb[buf] was fetched for
+    cp_async_commit_wait_all();
     __syncthreads();
 
     while (pos < a.end && !misc[2]) {
         const int b = (int)min((int64_t)a.wave, a.end - pos);
-        // ---- A0: wave tile, transposed: xT[d][i]
-        for (int i = tid; i < b * D; i += PCORE_THREADS) {
-            const int r = i / D, d = i - r * D;
-            xT[d * XS + r] = a.X[(pos + r) * a.ld + d];
+        if (pf_pos != pos) { // the previous wave was cut short: the speculative tile is misaligned
+            prefetch(buf, pos);
+            pf_pos = pos;
+            cp_async_commit_wait_all();
+            __syncthreads();
         }
-        __syncthreads();
+        const double *xT = xTb[buf];
+        // speculative prefetch of the next wave (assumes this one commits completely)
+        if (pos + b < a.end) prefetch(buf ^ 1, pos + b);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         // ---- A: speculative distances against the state at the start of the wave
         for (int pidx = tid; pidx < Mp * 32; pidx += PCORE_THREADS) {
             const int i = pidx & 31, j = pidx >> 5;
             if (i < b) {
                 double dv;
                 if (nm.pi_active && !feasible(xT + i, XS, m_cf1 + (size_t)j * D, m_cf2 + (size_t)j * D, m_w[j], nm))
-                    dv = __longlong_as_double(0x7ff8000000000000LL); // infeasible: never a candidate
+                    dv = qnan; // infeasible: never a candidate
                 else
-                    dv = proj_dist(xT + i, XS, m_cen + (size_t)j * D, m_mask[j], nm);
+                    dv = proj_dist_t<DP>(xT + i, m_cen + (size_t)j * D, m_mask[j], nm);
                 dist[(size_t)j * XS + i] = dv;
             }
         }
         __syncthreads();
-        // ---- B: argmin per cell (one warp per cell, lanes over MCs)
-        for (int i = warp; i < b; i += PCORE_WARPS) {
+        CCB_PHASE(0);
+        // ---- B + C0 (warp 0): argmin per cell (lane = cell, ascending MC index, strict <), then the distinct
+        //      candidate MCs with the bitmask of their cells (ascending bit = input order)
+        if (warp == 0) {
             double bd = 0.0;
             int bj = -1;
-            for (int j = lane; j < Mp; j += 32) {
-                const double v = dist[(size_t)j * XS + i];
-                if (!(v != v) && better(v, j, bd, bj)) {
-                    bd = v;
-                    bj = j;
+            if (lane < b) {
+                for (int j = 0; j < Mp; ++j) {
+                    const double v = dist[(size_t)j * XS + lane];
+                    if (!(v != v) && (bj < 0 || v < bd)) {
+                        bd = v;
+                        bj = j;
+                    }
                 }
             }
-            warp_argmin(bd, bj);
-            if (lane == 0) cand[i] = bj;
-        }
-        __syncthreads();
-        // ---- C0: distinct candidate MCs and, per MC, the bitmask of its cells (ascending = input order)
-        if (warp == 0) {
-            const int c = (lane < b) ? cand[lane] : -1;
-            const unsigned grp = __match_any_sync(0xffffffffu, c);
-            const bool leader = (c >= 0) && ((__ffs(grp) - 1) == lane);
+            cand[lane] = bj;
+            const unsigned grp = __match_any_sync(0xffffffffu, bj);
+            const bool leader = (bj >= 0) && ((__ffs(grp) - 1) == lane);
             const unsigned lead = __ballot_sync(0xffffffffu, leader);
             if (leader) {
                 const int r = __popc(lead & ((1u << lane) - 1u));
-                distinct[r] = c;
+                distinct[r] = bj;
                 dmask[r] = grp;
             }
             if (lane == 0) misc[0] = __popc(lead);
         }
         __syncthreads();
+        CCB_PHASE(1);
         const int nd = misc[0];
         // ---- C: one warp per candidate MC replays its cells in order
         for (int e = warp; e < nd; e += PCORE_WARPS) {
@@ -291,8 +377,8 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int d = lane + 32 * h;
-                m.cf1[h] = d < D ? m_cf1[(size_t)j * D + d] : 0.0;
-                m.cf2[h] = d < D ? m_cf2[(size_t)j * D + d] : 0.0;
+                m.cf1[h] = d < D ? m_cf1[(size_t)j * D + d] : 1.0;
+                m.cf2[h] = d < D ? m_cf2[(size_t)j * D + d] : 1.0;
                 m.cen[h] = 0.0;
             }
             double w = m_w[j];
@@ -302,18 +388,18 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
                 pts &= pts - 1;
                 double x[2];
                 x[0] = lane < D ? xT[lane * XS + i] : 0.0;
-                x[1] = lane + 32 < D ? xT[(lane + 32) * XS + i] : 0.0;
+                x[1] = (DP > 32 && lane + 32 < D) ? xT[(lane + 32) * XS + i] : 0.0;
                 LaneMc o;
                 double wn;
                 uint64_t nmask;
-                if (tentative_absorb(m, w, x, nm, sumscr, o, wn, nmask)) {
+                if (tentative_absorb_t<DP>(m, w, x, nm, o, wn, nmask)) {
                     m = o;
                     w = wn;
                     acc |= 1u << i;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int d = lane + 32 * h;
-                        if (d < D) {
+                        if ((h == 0 || DP > 32) && d < D) {
                             v_cf1[i * D + d] = o.cf1[h];
                             v_cf2[i * D + d] = o.cf2[h];
                             v_cen[i * D + d] = o.cen[h];
@@ -328,7 +414,8 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
             if (lane == 0) amask[e] = acc;
         }
         __syncthreads();
-        // ---- D: re-evaluate (cell, MC) pairs whose MC changed earlier in the wave, then argmin again
+        CCB_PHASE(2);
+        // ---- D: re-evaluate (cell, MC) pairs whose MC changed earlier in the wave
         int npatch = 0;
         for (int pidx = tid; pidx < nd * 32; pidx += PCORE_THREADS) {
             const int i = pidx & 31, e = pidx >> 5;
@@ -339,9 +426,9 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
                     const int j = distinct[e];
                     double dv;
                     if (nm.pi_active && !feasible(xT + i, XS, v_cf1 + v * D, v_cf2 + v * D, v_w[v], nm))
-                        dv = __longlong_as_double(0x7ff8000000000000LL);
+                        dv = qnan;
                     else
-                        dv = proj_dist(xT + i, XS, v_cen + v * D, v_mask[v], nm);
+                        dv = proj_dist_t<DP>(xT + i, v_cen + v * D, v_mask[v], nm);
                     dist[(size_t)j * XS + i] = dv;
                     ++npatch;
                 }
@@ -349,23 +436,22 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
         }
         st_pairs += npatch;
         __syncthreads();
-        for (int i = warp; i < b; i += PCORE_WARPS) {
+        CCB_PHASE(3);
+        // ---- D2 + E (warp 0): argmin again, first mismatch, reject budget, per-cell outputs
+        if (warp == 0) {
             double bd = 0.0;
             int bj = -1;
-            for (int j = lane; j < Mp; j += 32) {
-                const double v = dist[(size_t)j * XS + i];
-                if (!(v != v) && better(v, j, bd, bj)) {
-                    bd = v;
-                    bj = j;
+            if (lane < b) {
+                for (int j = 0; j < Mp; ++j) {
+                    const double v = dist[(size_t)j * XS + lane];
+                    if (!(v != v) && (bj < 0 || v < bd)) {
+                        bd = v;
+                        bj = j;
+                    }
                 }
             }
-            warp_argmin(bd, bj);
-            if (lane == 0) cand2[i] = bj;
-        }
-        __syncthreads();
-        // ---- E: commit the verified prefix
-        if (warp == 0) {
-            const bool bad = (lane < b) && (cand2[lane] != cand[lane]);
+            const int mycand = cand[lane];
+            const bool bad = (lane < b) && (bj != mycand);
             const unsigned badm = __ballot_sync(0xffffffffu, bad);
             int m = badm ? (__ffs(badm) - 1) : b; // cell m itself is not committed (its candidate was wrong)
             unsigned accb = 0u;
@@ -398,10 +484,11 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
                     a.assign[r] = -1;
                     a.rej_list[misc[3] + __popc(rej & ((1u << lane) - 1u))] = (int32_t)r;
                 } else {
-                    a.assign[r] = a.P.uid[cand[lane]];
+                    a.assign[r] = a.P.uid[mycand];
                     if (a.stage) a.stage[r] = 0;
                 }
             }
+            __syncwarp();
             if (lane == 0) {
                 misc[1] = m;
                 misc[2] = stop;
@@ -410,6 +497,7 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
             }
         }
         __syncthreads();
+        CCB_PHASE(4);
         const int m = misc[1];
         {
             const unsigned low = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
@@ -431,9 +519,16 @@ __global__ void __launch_bounds__(PCORE_THREADS, 1) k_pcore_stage(PcoreArgs a) {
         st_waves += 1;
         st_roll += misc[4];
         if (tid == 0) st_pairs += (int64_t)b * Mp;
+        pf_pos = pos + b; // what the speculative prefetch targeted
         pos += m;
+        buf ^= 1;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        CCB_PHASE(5);
     }
+#undef CCB_PHASE
+    if (tid == 0)
+        for (int k = 0; k < 8; ++k) a.ctl->phase_cycles[k] += pc_acc[k];
 
     if (a.state_in_smem) {
         for (int i = tid; i < Mp * D; i += PCORE_THREADS) {

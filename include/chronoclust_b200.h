@@ -92,6 +92,8 @@ const char *ccb_last_error(const ccb_handle *h);
 /* cudaStream_t the handle launches on (for CUDA-event timing by the caller). */
 void *ccb_stream(ccb_handle *h);
 int ccb_get_stats(const ccb_handle *h, ccb_stats *out);
+/* Diagnostics: cycles thread 0 of kernel 2a spent in each phase (A, B, C, D, E, commit) since ccb_reset. */
+int ccb_debug_phase_cycles(ccb_handle *h, int64_t out[8]);
 /* Forgets every microcluster and both id counters (a new run on the same device / stream). */
 int ccb_reset(ccb_handle *h);
 

@@ -34,4 +34,9 @@ for t, X in enumerate(Xs):
     print(f"t={t} online {t1-t0:.3f}s offline {t2-t1:.3f}s  {N/(t2-t0):.0f} cells/s  pcore={c[0]} outlier={c[1]} "
           f"clusters={len(h.final_clusters)}")
     print("   ", {k: v for k, v in d.items() if v})
+    import ctypes as C
+    from chronoclust_b200 import _lib
+    pc = (C.c_int64 * 8)()
+    _lib.lib().ccb_debug_phase_cycles(h._h, C.byref(pc))
+    print("    phase cycles/wave (cumulative):", [round(v / max(st["waves"], 1)) for v in pc])
     print("    gpu ms:", {k: (round(v[0], 2), v[1]) for k, v in h.timing(reset=True).items() if v[1]})
