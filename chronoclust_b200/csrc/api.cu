@@ -1149,6 +1149,17 @@ int ccb_off_neighbours(int32_t device, void *stream, const double *cen, int64_t 
                                  border_cap, n_border);
 }
 
+int ccb_off_patch(int32_t device, void *stream, uint32_t *nbr, int32_t *cnt, const int32_t *pairs, const uint8_t *decision,
+                  int32_t n, int64_t r0, int64_t M) {
+    if (n < 0 || M < 0) return fail(nullptr, CCB_EINVAL, "bad arguments");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    if (n == 0) return CCB_OK;
+    k_off_patch<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nbr, cnt, pairs, decision, n, (int)r0, (int)((M + 31) / 32));
+    e = cudaGetLastError();
+    return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "k_off_patch: %s", cudaGetErrorString(e));
+}
+
 int ccb_off_subspace(int32_t device, void *stream, const double *cen, int64_t M, int32_t D, int64_t r0, int64_t r1,
                      const uint32_t *nbr, const int32_t *cnt, double delta, uint64_t *submask) {
     if (D < 1 || D > CCB_MAX_D || M < 0 || r0 < 0 || r1 < r0 || r1 > M) return fail(nullptr, CCB_EINVAL, "bad arguments");

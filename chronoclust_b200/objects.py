@@ -49,8 +49,10 @@ class Microcluster(object):
         self._points = {}
 
     def __getstate__(self):
+        # the per-cell dictionary is only pickled if somebody already materialised it (the reference
+        # pickles every cell of the timepoint; the next timepoint resets it anyway, hddstream.py:208-213)
         st = dict(self.__dict__)
-        st["_points"] = self.points
+        st["_points"] = self._points if self._points is not None else {}
         st["_points_source"] = None
         return st
 

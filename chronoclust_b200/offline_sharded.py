@@ -1,0 +1,133 @@
+"""Row-sharded offline phase over G ranks (one process per GPU, torch.distributed / NCCL over NVLink).
+
+BASELINE.json config 4: M pcore MCs x D dims, the pairwise eps-neighbourhood (predecon.py:161-188) is the
+O(M^2 D) part.  Rank g owns the contiguous rows [g*R, (g+1)*R), R = ceil(M/G):
+
+  stage 1 (local)   N(p) bit rows + |N(p)| for own rows            ccb_off_neighbours  (kernel 4b)
+                    borderline pairs settled on the host via dnrm2, patched back    ccb_off_patch
+  stage 2 (local)   subspace preference masks w_p of own rows       ccb_off_subspace    (kernel 4c)
+  all-gather        w_p masks of every row (M * 8 B)                NCCL all_gather_into_tensor
+  stage 3 (local)   weighted-neighbour bit rows WN(p) of own rows   ccb_off_weighted    (kernel 4d)
+  all-gather        WN rows (M * ceil(M/32) * 4 B)                  NCCL all_gather_into_tensor
+  stage 4 (every rank, redundantly -- deterministic, so no broadcast is needed)
+                    ordered cluster growth                           ccb_off_clusters    (kernel 4e)
+
+The messages are small (<= 1.25 GB at M = 1e5, usually KBs); the collectives are latency-bound.  PyTorch
+is only plumbing here (device buffers, the NCCL communicator); every stage is a kernel of this repo.
+The compute backend is injectable so that the sharding / gather logic is testable on CPU with gloo.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class CudaStages:
+    """The C-ABI stage functions on raw device pointers of torch tensors."""
+
+    def __init__(self, device, dnrm2_ptr=None):
+        import torch
+
+        self.torch = torch
+        self.device = device
+        self.dev = torch.device("cuda", device)
+        self.L = _lib.lib()
+        self.dnrm2_ptr = dnrm2_ptr
+
+    def stream(self):
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def empty(self, shape, dtype):
+        return self.torch.zeros(shape, dtype=dtype, device=self.dev)
+
+    def neighbours(self, cen, M, D, r0, r1, E, E2, nbr, cnt):
+        t = self.torch
+        cap = 1 << 16
+        border = t.zeros(2 * cap, dtype=t.int32, device=self.dev)
+        nb = t.zeros(1, dtype=t.int32, device=self.dev)
+        _lib.check(self.L.ccb_off_neighbours(self.device, self.stream(), cen.data_ptr(), M, D, r0, r1, E2, nbr.data_ptr(),
+                                             cnt.data_ptr(), border.data_ptr(), cap, nb.data_ptr()))
+        n = int(nb.item())
+        if n > cap:
+            raise _lib.CCBError(f"{n} borderline pairs exceed the resolver capacity")
+        if n:
+            pairs = border[:2 * n].cpu().numpy().reshape(n, 2)
+            hc = cen.cpu().numpy()
+            dec = np.zeros(n, np.uint8)
+            fn = None
+            if self.dnrm2_ptr:
+                fn = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int))(self.dnrm2_ptr)
+            for i, (p, q) in enumerate(pairs):
+                x = np.ascontiguousarray(hc[q] - hc[p])
+                if fn is not None:
+                    nn, inc = C.c_int(D), C.c_int(1)
+                    r = fn(C.byref(nn), x.ctypes.data_as(C.POINTER(C.c_double)), C.byref(inc))
+                else:
+                    r = float(np.sqrt(np.sum(x.astype(np.longdouble) ** 2)))
+                dec[i] = r <= E
+            ddec = t.from_numpy(dec).to(self.dev)
+            _lib.check(self.L.ccb_off_patch(self.device, self.stream(), nbr.data_ptr(), cnt.data_ptr(), border.data_ptr(),
+                                            ddec.data_ptr(), n, r0, M))
+        return n
+
+    def subspace(self, cen, M, D, r0, r1, nbr, cnt, delta, submask):
+        _lib.check(self.L.ccb_off_subspace(self.device, self.stream(), cen.data_ptr(), M, D, r0, r1, nbr.data_ptr(),
+                                           cnt.data_ptr(), delta, submask.data_ptr()))
+
+    def weighted(self, cen, M, D, r0, r1, nbr, submask_all, k, E2, wnbr):
+        _lib.check(self.L.ccb_off_weighted(self.device, self.stream(), cen.data_ptr(), M, D, r0, r1, nbr.data_ptr(),
+                                           submask_all.data_ptr(), k, E2, wnbr.data_ptr()))
+
+    def clusters(self, M, wnbr_all, core, submask_all, k, pi):
+        t = self.torch
+        label = t.empty(max(M, 1), dtype=t.int32, device=self.dev)
+        order = t.empty(max(M, 1), dtype=t.int32, device=self.dev)
+        cl_off = t.zeros(M + 2, dtype=t.int32, device=self.dev)
+        ncl = t.zeros(1, dtype=t.int32, device=self.dev)
+        _lib.check(self.L.ccb_off_clusters(self.device, self.stream(), M, wnbr_all.data_ptr(), core.data_ptr(),
+                                           submask_all.data_ptr(), k, pi, label.data_ptr(), order.data_ptr(),
+                                           cl_off.data_ptr(), ncl.data_ptr()))
+        n = int(ncl.item())
+        return label[:M].cpu().numpy(), order.cpu().numpy(), cl_off[:n + 1].cpu().numpy(), n
+
+
+def row_range(M, world, rank):
+    R = (M + world - 1) // world
+    r0 = min(M, rank * R)
+    return R, r0, min(M, r0 + R)
+
+
+def sharded_offline(stages, cen, core, M, D, k, pi, delta, E, E2, group=None, dist=None, timers=None):
+    """Runs the offline phase row-sharded over the ranks of `group`.
+
+    cen: [M, D] fp64 centroids (replicated on every rank), core: [M] uint8 core flags (replicated).
+    Returns (label [M], order, cl_off, n_clusters, info) -- identical on every rank.
+    """
+    world = dist.get_world_size(group) if dist is not None else 1
+    rank = dist.get_rank(group) if dist is not None else 0
+    words = (M + 31) // 32
+    R, r0, r1 = row_range(M, world, rank)
+    torch = stages.torch
+    nbr = stages.empty((R, words), torch.int32)
+    cnt = stages.empty((R,), torch.int32)
+    submask = stages.empty((R,), torch.int64)
+    wn = stages.empty((R, words), torch.int32)
+    n_border = stages.neighbours(cen, M, D, r0, r1, E, E2, nbr, cnt)
+    stages.subspace(cen, M, D, r0, r1, nbr, cnt, delta, submask)
+    if world > 1:
+        sub_all = stages.empty((world * R,), torch.int64)
+        dist.all_gather_into_tensor(sub_all, submask, group=group)
+    else:
+        sub_all = submask
+    stages.weighted(cen, M, D, r0, r1, nbr, sub_all, k, E2, wn)
+    if world > 1:
+        wn_all = stages.empty((world * R, words), torch.int32)
+        dist.all_gather_into_tensor(wn_all, wn, group=group)
+    else:
+        wn_all = wn
+    label, order, cl_off, ncl = stages.clusters(M, wn_all, core, sub_all, k, pi)
+    info = {"rows": (r0, r1), "rows_per_rank": R, "borderline_pairs": n_border,
+            "gather_bytes": int(world * R * 8 + world * R * words * 4) if world > 1 else 0,
+            "neighbour_count": int(cnt[:max(r1 - r0, 0)].sum().item()) if r1 > r0 else 0}
+    return label, order, cl_off, ncl, info

@@ -175,6 +175,10 @@ int ccb_fp64_peak(int32_t device, void *stream, int32_t mode, int32_t iters, int
  * n_border [1] int32, counted even beyond border_cap). */
 int ccb_off_neighbours(int32_t device, void *stream, const double *cen, int64_t M, int32_t D, int64_t r0, int64_t r1,
                        double E2, uint32_t *nbr, int32_t *cnt, int32_t *border, int32_t border_cap, int32_t *n_border);
+/* Settles borderline pairs on the device after the host decided them with dnrm2: pairs [2*n] (row, col) as
+ * reported by ccb_off_neighbours, decision [n] (1 = neighbour). */
+int ccb_off_patch(int32_t device, void *stream, uint32_t *nbr, int32_t *cnt, const int32_t *pairs, const uint8_t *decision,
+                  int32_t n, int64_t r0, int64_t M);
 /* Offline stage 2: subspace preference masks submask [(r1-r0)] from the neighbour rows (delta, not delta^2). */
 int ccb_off_subspace(int32_t device, void *stream, const double *cen, int64_t M, int32_t D, int64_t r0, int64_t r1,
                      const uint32_t *nbr, const int32_t *cnt, double delta, uint64_t *submask);

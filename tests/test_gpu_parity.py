@@ -220,3 +220,118 @@ def test_online_offline_vs_oracle_mid_size(cfgname, N, T):
             assert bits_equal(a1, a2) and bits_equal(b1, b2) and bits_equal(c1, c2) and bits_equal(p1, p2)
     st = h.stats()
     print(cfgname, st)
+
+
+def test_app_run_matches_reference_files(tmp_path):
+    """chronoclust_b200.app.run on the reference's synthetic d0-d4 with the integration test's parameters
+    and gating file: result.csv byte-identical to the reference's golden file, cluster_points labels
+    identical on every row (normal_test.py:78-157)."""
+    import pandas as pd
+
+    from chronoclust_b200 import app
+
+    z = load("c1.npz")
+    files = []
+    for t in range(5):
+        f = tmp_path / f"synthetic_d{t}.csv"
+        pd.DataFrame(z[f"raw{t}"], columns=["x", "y", "z"]).to_csv(f, index=False)
+        files.append(str(f))
+    cfg = config_of(z)
+    out = tmp_path / "out"
+    out.mkdir()
+    app.run(data=files, output_directory=str(out), gating_centroid_file=os.path.join(GOLDEN, "c1_gating_centroids.csv"),
+            param_beta=cfg["beta"], param_delta=cfg["delta"], param_epsilon=cfg["epsilon"], param_lambda=cfg["lambda"],
+            param_k=cfg["k"], param_mu=cfg["mu"], param_pi=cfg["pi"], param_omicron=cfg["omicron"],
+            param_upsilon=cfg["upsilon"])
+    got = open(out / "result.csv", "rb").read()
+    exp = open(os.path.join(GOLDEN, "c1_result.csv"), "rb").read()
+    assert got == exp, "result.csv differs from the reference's golden file"
+    lab = load("c1_labels.npz")
+    for t in range(5):
+        df = pd.read_csv(out / f"cluster_points_D{t}.csv", keep_default_na=False)
+        assert (df["id"].to_numpy() == lab[f"ids{t}"]).all()
+        assert (df["cluster_id"].astype(str).to_numpy() == lab[f"labels{t}"]).all()
+        assert np.abs(df[["x", "y", "z"]].to_numpy() - lab[f"xyz{t}"]).max() < 1e-12
+    assert os.path.exists(out / "parameters.csv") and os.path.exists(out / "program_images" / "hddstream")
+    # degenerate run (no_cluster_test.py:29-43, 70-85): beta = mu = 1 -> no cluster, every cell labelled None
+    out2 = tmp_path / "out2"
+    out2.mkdir()
+    small = []
+    for t in range(5):
+        f = tmp_path / f"small_d{t}.csv"
+        pd.DataFrame(z[f"raw{t}"][:10], columns=["x", "y", "z"]).to_csv(f, index=False)
+        small.append(str(f))
+    app.run(data=small, output_directory=str(out2), param_beta=1, param_delta=0.05, param_epsilon=0.03, param_lambda=2,
+            param_k=4, param_mu=1, param_pi=3, param_omicron=0.000000435, param_upsilon=6.5)
+    assert len(open(out2 / "result.csv").read().splitlines()) == 1
+    for t in range(5):
+        df = pd.read_csv(out2 / f"cluster_points_D{t}.csv", keep_default_na=False)
+        assert len(df) == 10 and (df["cluster_id"] == "None").all()
+
+
+def test_pickle_roundtrip_continues_identically():
+    import pickle
+
+    z = load("stress_churn.npz")
+    Xs = stress_inputs(z)
+    h = make(config_of(z))
+    for t in range(2):
+        h.online_microcluster_maintenance(Xs[t], t)
+    h2 = pickle.loads(pickle.dumps(h))
+    for t in range(2, len(Xs)):
+        h2.online_microcluster_maintenance(Xs[t], t)
+        P = f"t{t}_"
+        assert (h2.last_assignment == z[P + "assign"]).all()
+        for which, name in ((0, "p_"), (1, "o_")):
+            assert_list_equal(h2.export_arrays(which), z, P + name, f"restored t{t} list{which}")
+        assert_clusters_equal(clusters_of(h2), z, P, f"restored t{t}")
+
+
+def test_stateless_offline_stages_match_handle_path():
+    """The row-sharded stage functions (world = 1) against the handle-level offline phase and the golden
+    PreDeCon results: neighbour / weighted-neighbour rows, masks, labels, claim order."""
+    import torch
+
+    from chronoclust_b200.offline_sharded import CudaStages, sharded_offline
+
+    z = load("offline_sets.npz")
+    st = CudaStages(0, dnrm2_ptr=None)
+    for s in range(int(z["nset"])):
+        P = f"s{s}_"
+        D, M, k, pi, delta, E = z[P + "params"]
+        D, M, pi = int(D), int(M), int(pi)
+        cen, core = z[P + "cen"], z[P + "core"]
+        tc = torch.from_numpy(np.ascontiguousarray(cen)).cuda()
+        tcore = torch.from_numpy(core.astype(np.uint8)).cuda()
+        lab, order, cl_off, ncl, info = sharded_offline(st, tc, tcore, M, D, float(k), pi, float(delta), float(E),
+                                                        float(E) ** 2)
+        # membership per emitted cluster equals the reference's id sets (clusters with members only)
+        ids = z[P + "ids"]
+        got = [sorted(int(ids[x]) for x in order[cl_off[c]:cl_off[c + 1]]) for c in range(ncl)
+               if cl_off[c + 1] > cl_off[c]]
+        off = z[P + "cl_off"]
+        exp = [sorted(z[P + "cl_idlist"][off[c]:off[c + 1]].tolist()) for c in range(len(off) - 1)]
+        assert got == exp, f"set {s}"
+        assert info["neighbour_count"] == int(np.unpackbits(z[P + "nbr"])[:M * M].sum())
+
+
+def test_offline_borderline_pairs_resolved_by_dnrm2():
+    """Centroids placed exactly on the eps-boundary (3-4-5 triangles): the device must flag them and the
+    host must settle them with dnrm2 (<= E is inclusive)."""
+    cfg = {"beta": 0.0, "delta": 0.5, "epsilon": 1.0, "lambda": 0, "k": 4.0, "mu": 0.0, "pi": 0, "omicron": 0.0,
+           "upsilon": 5.0}
+    h = make(cfg)
+    D = 2
+    h.dataset_dimensionality = D
+    h._ensure_handle(D)
+    from chronoclust_b200 import _lib
+    _lib.check(_lib.lib().ccb_begin_timepoint(h._h, 0.0, 0.0, D, 0, 1.0), h._h)
+    cen = np.array([[0.0, 0.0], [3.0, 4.0], [6.0, 8.0], [3.0, 4.0000000000000036]])  # |c0-c1| = 5 = E exactly
+    M = len(cen)
+    w = np.full(M, 10.0)
+    h.import_arrays(0, np.arange(M), np.arange(M), w, cen * 10, (cen ** 2 + 0.01) * 10, cen, np.ones((M, D)))
+    h.offline_clustering(0)
+    core, nbr, wn, subw = h.offline_intermediates()
+    assert h.stats()["borderline_pairs"] >= 2
+    assert nbr[0, 1] == 1 and nbr[1, 0] == 1 and nbr[1, 2] == 1  # distance exactly E is a neighbour
+    assert nbr[0, 2] == 0 and nbr[0, 3] == 0  # 10 > 5; 5.000000000000003 > 5

@@ -1,0 +1,148 @@
+"""CPU suite for the host side: the C-ABI library loads and exports every declared symbol, the
+lineage / association trackers behave like the reference's (scenarios of tests/tracking_test/*), the
+parameter derivation matches hddstream.py:89-128 (unittest_hddstream.py:10-41)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from chronoclust_b200 import _lib, build
+
+    build.build()
+    L = C.CDLL(_lib.SO_PATH)
+    header = open(os.path.join(ROOT, "include", "chronoclust_b200.h")).read()
+    declared = set(re.findall(r"\b(ccb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ccb_handle"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device handle creation must fail loudly (this container has no GPU)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import logging
+
+    from chronoclust_b200 import _lib
+    from chronoclust_b200.hddstream import HDDStream
+
+    h = HDDStream({"beta": 0.2, "delta": 0.05, "epsilon": 0.03, "lambda": 2, "k": 4, "mu": 0.01, "pi": 3,
+                   "omicron": 0.0, "upsilon": 6.5}, logging.getLogger("t"))
+    with pytest.raises(_lib.CCBError):
+        h.online_microcluster_maintenance(np.random.rand(10, 3), 0)
+
+
+def test_product_does_not_import_oracle():
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r); import chronoclust_b200.app, chronoclust_b200.hddstream; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'") % ROOT
+    subprocess.check_call([sys.executable, "-c", code])
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "chronoclust_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "libcco" not in src
+
+
+def test_dataset_dependent_parameters():
+    """unittest_hddstream.py:10-41: pi = D when 0, mu = mu*N, omicron from the PREVIOUS N, upsilon = v*eps."""
+    import logging
+
+    from chronoclust_b200.hddstream import HDDStream
+
+    cfg = {"beta": 0.5, "delta": 0.1, "epsilon": 0.2, "lambda": 1, "k": 3, "mu": 0.05, "pi": 0, "omicron": 0.01,
+           "upsilon": 2}
+    h = HDDStream(cfg, logging.getLogger("t"))
+    assert h.upsilon == 2.0 * 0.2 and h.epsilon_squared == 0.2 ** 2 and h.delta_squared == 0.1 ** 2
+    X = np.zeros((200, 7))
+    h._set_dataset_dependent_parameters(X)
+    assert h.pi == 7 and h.mu == 0.05 * 200 and h.omicron == 0.0
+    h._set_dataset_dependent_parameters(np.zeros((50, 7)))
+    assert h.omicron == 0.01 * 200 and h.mu == 0.05 * 50
+    cfg["pi"] = 2.5
+    h2 = HDDStream(cfg, logging.getLogger("t"))
+    h2._set_dataset_dependent_parameters(X)
+    assert h2.pi == round(2.5)
+    with pytest.raises(SystemExit):
+        HDDStream(dict(cfg, delta=1.5), logging.getLogger("t"))
+
+
+def _cl(pcores, w=1.0):
+    from chronoclust_b200.objects import Cluster
+
+    return Cluster(list(pcores), [0.0], w, [1.0])
+
+
+def test_lineage_new_split_merge():
+    from chronoclust_b200.tracking import TrackByLineage
+
+    t = TrackByLineage()
+    a, b = _cl([0, 1], 5), _cl([2], 9)
+    t.add_new_child_cluster(b)
+    t.add_new_child_cluster(a)
+    t.calculate_ids()
+    assert [c.id for c in t.child_clusters] == ["A", "B"]  # sorted by weight, letters in that order
+    t.transfer_child_to_parent()
+    # split: pcores 0 and 1 part ways; the child with more parent pcores keeps the label
+    c1, c2, c3 = _cl([0, 5], 3), _cl([1], 2), _cl([2], 9)
+    for c in (c1, c2, c3):
+        t.add_new_child_cluster(c)
+    t.calculate_ids()
+    ids = {tuple(c.pcore_ids): c.id for c in t.child_clusters}
+    assert ids[(0, 5)] == "A" and ids[(1,)] == "A|1" and ids[(2,)] == "B"
+    t.transfer_child_to_parent()
+    # merge of A|1 and B, and A splits again -> A|2 (split counter remembered)
+    m, s1, s2 = _cl([1, 2], 8), _cl([0], 1), _cl([5], 2)
+    for c in (m, s1, s2):
+        t.add_new_child_cluster(c)
+    t.calculate_ids()
+    ids = {tuple(c.pcore_ids): c.id for c in t.child_clusters}
+    assert ids[(1, 2)] == "(A|1,B)"
+    assert sorted([ids[(0,)], ids[(5,)]]) == ["A", "A|2"]
+
+
+def test_lineage_more_than_26_clusters():
+    from chronoclust_b200.tracking import TrackByLineage
+
+    t = TrackByLineage()
+    for i in range(28):
+        t.add_new_child_cluster(_cl([i], i))
+    t.calculate_ids()
+    ids = [c.id for c in t.child_clusters]
+    assert ids[:26] == list("ABCDEFGHIJKLMNOPQRSTUVWXYZ") and ids[26:] == ["AA", "BB"]
+
+
+def test_historical_association():
+    from chronoclust_b200.objects import Microcluster
+    from chronoclust_b200.tracking import TrackByHistoricalAssociation
+
+    def mc(pid, cen):
+        return Microcluster(cf1=np.zeros(2), cf2=np.zeros(2), id=[pid], cumulative_weight=1,
+                            preferred_dimension_vector=np.ones(2), cluster_centroids=np.array(cen, float))
+
+    t = TrackByHistoricalAssociation()
+    p1, p2 = _cl([0]), _cl([1])
+    p1.id, p2.id = "A", "B"
+    p1.pcore_objects, p2.pcore_objects = [mc(0, [0, 0])], [mc(1, [10, 10])]
+    t.set_current_clusters([p1, p2])
+    t.track_cluster_history()
+    assert p1.get_historical_associates_as_str() == "None"
+    t.transfer_current_to_previous()
+    c = _cl([2, 3])
+    c.id = "C"
+    c.pcore_objects = [mc(2, [1, 1]), mc(3, [9, 9])]
+    t.set_current_clusters([c])
+    t.track_cluster_history()
+    assert c.get_historical_associates_as_str() == "A&B"
