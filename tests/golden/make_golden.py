@@ -138,7 +138,7 @@ def make_c1():
         assert (a["id"].to_numpy() == b["id"].to_numpy()).all()
         assert (a["cluster_id"].astype(str).to_numpy() == b["cluster_id"].astype(str).to_numpy()).all()
         labels[f"ids{t}"] = a["id"].to_numpy().astype(np.int32)
-        labels[f"labels{t}"] = a["cluster_id"].astype(str).to_numpy()
+        labels[f"labels{t}"] = a["cluster_id"].astype(str).to_numpy().astype("U")
         labels[f"xyz{t}"] = a[["x", "y", "z"]].to_numpy()
     np.savez_compressed(f"{HERE}/c1_labels.npz", **labels)
     logging.shutdown()
