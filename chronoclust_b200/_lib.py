@@ -19,13 +19,16 @@ vp = C.c_void_p
 
 class Params(C.Structure):
     _fields_ = [("D", i32), ("device", i32), ("eps2", f64), ("upsilon_eps", f64), ("upsilon_eps2", f64),
-                ("delta", f64), ("delta2", f64), ("beta", f64), ("k", f64), ("wave", i32), ("chunk", i32)]
+                ("delta", f64), ("delta2", f64), ("beta", f64), ("k", f64), ("wave", i32), ("chunk", i32),
+                ("bsv_bmin", i32), ("bsv_iters", i32)]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, i64) for n in (
         "points", "chunks", "waves", "wave_rollbacks", "rejects", "resolver_calls", "resolver_cuts", "nearest_pairs",
-        "pcore_pairs", "upgrades", "created", "downgraded", "deleted", "kernel_launches", "borderline_pairs")]
+        "pcore_pairs", "upgrades", "created", "downgraded", "deleted", "kernel_launches", "borderline_pairs",
+        "bsv_blocks", "bsv_rounds", "bsv_mismatches", "bsv_cuts_unknown", "bsv_cuts_rounds", "bsv_cuts_capacity",
+        "bsv_late_topk", "bsv_outlier_stage_cells")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -64,7 +67,7 @@ SYMBOLS = {
 }
 
 
-CATEGORIES = ["pcore_stage", "nearest", "resolve", "maintenance", "offline", "misc", "copy", "reserved"]
+CATEGORIES = ["chains", "nearest", "verify", "maintenance", "offline", "misc", "copy", "speculate"]
 
 
 class CCBError(RuntimeError):

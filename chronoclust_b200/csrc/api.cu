@@ -14,6 +14,7 @@
 #include "nearest.cuh"
 #include "offline.cuh"
 #include "online.cuh"
+#include "engine.cuh"
 
 using namespace ccb;
 
@@ -80,6 +81,18 @@ struct ccb_handle {
     int32_t *d_pnew = nullptr, *d_pfin = nullptr, *d_onew = nullptr;
     double *d_dist_gmem = nullptr;
     size_t dist_gmem_cap = 0;
+    // block-speculative engine (engine.cuh)
+    int engine = 0;             // 0: block-speculative versioned commit, 1: wave engine (kernels 2a/2b of online.cuh)
+    int bs_bmax = 32768, bs_bmin = 1024, bs_iters = 3;
+    BsCtl *d_bc = nullptr, *h_bc = nullptr;
+    BsWs ws{};
+    std::vector<void *> ws_allocs;
+    void *ws_tiles[2] = {nullptr, nullptr};
+    int32_t *ws_first = nullptr;
+    int ws_first_cap = 0;
+    double *d_bs_tk_dist_slab = nullptr;
+    int32_t *d_bs_tk_idx_slab = nullptr;
+    BsCtl bc_base{}; // counters folded in by ccb_reset
     // offline results (host copies)
     int64_t off_M = 0;
     std::vector<int64_t> cl_off, cl_members;
@@ -270,7 +283,7 @@ template <int K>
 int launch_nearest(ccb_handle *h, cudaStream_t s, int DP, int div_mode, const double *X, const int32_t *rows,
                    const int32_t *nrows_dev, int64_t row_off, int64_t nrows_max, int64_t ld, int D, const double2 *cw,
                    int M, double *slab_dist, int32_t *slab_idx, double *out_dist, int32_t *out_idx, int max_slabs,
-                   int *nslab_out) {
+                   int *nslab_out, const int32_t *range_dev = nullptr, const int32_t *M_dev = nullptr) {
     int launched = 0;
     CCB_DISPATCH_DP(DP, {
         using Cfg = NearestCfg<kDP>;
@@ -287,14 +300,14 @@ int launch_nearest(ccb_handle *h, cudaStream_t s, int DP, int div_mode, const do
         int32_t *oi = nslab == 1 ? out_idx : slab_idx;
         if (div_mode)
             k_nearest<kDP, K, true><<<grid, NEAREST_THREADS, 0, s>>>(X, rows, nrows_dev, row_off, nrows_max, ld, D, cw,
-                                                                     M, slab_mcs, od, oi);
+                                                                     M, slab_mcs, od, oi, range_dev, M_dev);
         else
             k_nearest<kDP, K, false><<<grid, NEAREST_THREADS, 0, s>>>(X, rows, nrows_dev, row_off, nrows_max, ld, D, cw,
-                                                                      M, slab_mcs, od, oi);
+                                                                      M, slab_mcs, od, oi, range_dev, M_dev);
         launched = 1;
         if (nslab > 1) {
             k_topk_merge<K><<<(unsigned)((nrows_max + 255) / 256), 256, 0, s>>>(slab_dist, slab_idx, nrows_dev, row_off,
-                                                                                nrows_max, nslab, out_dist, out_idx);
+                                                                                nrows_max, nslab, out_dist, out_idx, range_dev);
             launched = 2;
         }
         if (nslab_out) *nslab_out = nslab;
@@ -458,6 +471,214 @@ int ingest_core(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t 
     return CCB_OK;
 }
 
+// ---- block-speculative engine: workspace and block enqueue ------------------------------------------
+constexpr int BS_MAX_SLABS = 32;
+
+template <typename T>
+int ws_alloc(ccb_handle *h, T *&p, size_t n) {
+    void *q = nullptr;
+    CK(h, cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    h->ws_allocs.push_back(q);
+    p = (T *)q;
+    return CCB_OK;
+}
+
+int ensure_bs_ws(ccb_handle *h) {
+    int rc;
+    const int B = h->bs_bmax, D = h->D;
+    if (!h->d_bc) {
+        CK(h, cudaMalloc(&h->d_bc, sizeof(BsCtl)));
+        CK(h, cudaMemset(h->d_bc, 0, sizeof(BsCtl)));
+        CK(h, cudaMallocHost(&h->h_bc, sizeof(BsCtl)));
+        memset(h->h_bc, 0, sizeof(BsCtl));
+        BsWs &w = h->ws;
+        w.bmax = B;
+#define WSA(field, n) if ((rc = ws_alloc(h, w.field, (n)))) return rc
+        WSA(pcand, B); WSA(ospec, B); WSA(tkpos, B); WSA(dec, B); WSA(eff, B); WSA(newrank, B); WSA(pend, B);
+        WSA(plist, B); WSA(pflag, B); WSA(prej, B); WSA(upf, B); WSA(want, B);
+        WSA(vcf1, (size_t)B * D + 2); WSA(vcf2, (size_t)B * D + 2); WSA(vcen, (size_t)B * D + 2);
+        WSA(vw, B); WSA(vr2, B); WSA(vmask, B);
+        WSA(nrows, BS_RMAX); WSA(ncell, BS_RMAX);
+        WSA(tk_dist, (size_t)BS_RMAX * BS_TOPK); WSA(tk_idx, (size_t)BS_RMAX * BS_TOPK);
+        WSA(hkey, BS_RMAX + 1); WSA(hoff, BS_RMAX + 2); WSA(omem, BS_RMAX + 1); WSA(hrank, BS_RMAX + 2);
+#undef WSA
+        if ((rc = ws_alloc(h, h->d_bs_tk_dist_slab, (size_t)BS_RMAX * BS_MAX_SLABS * BS_TOPK))) return rc;
+        if ((rc = ws_alloc(h, h->d_bs_tk_idx_slab, (size_t)BS_RMAX * BS_MAX_SLABS * BS_TOPK))) return rc;
+    }
+    // per-(tile, pcore key) tables follow the pcore capacity; the modified-flags follow the outlier capacity
+    const int stride = h->P[h->pcur].cap;
+    if (stride != h->ws.mp_stride) {
+        cudaFree(h->ws_tiles[0]);
+        cudaFree(h->ws_tiles[1]);
+        h->ws_tiles[0] = h->ws_tiles[1] = nullptr;
+        const size_t n = ((size_t)B / 32 + 2) * stride;
+        CK(h, cudaMalloc(&h->ws_tiles[0], n * 4));
+        CK(h, cudaMalloc(&h->ws_tiles[1], n * 4));
+        h->ws.tilecnt = (int32_t *)h->ws_tiles[0];
+        h->ws.tbase = (int32_t *)h->ws_tiles[1];
+        int32_t *poff = nullptr;
+        if ((rc = ws_alloc(h, poff, (size_t)stride + 2))) return rc;
+        h->ws.poff = poff;
+        h->ws.mp_stride = stride;
+    }
+    const int ocap = h->O[h->ocur].cap;
+    if (ocap != h->ws_first_cap) {
+        cudaFree(h->ws_first);
+        h->ws_first = nullptr;
+        CK(h, cudaMalloc(&h->ws_first, (size_t)ocap * 4));
+        CK(h, cudaMemsetAsync(h->ws_first, 0x7f, (size_t)ocap * 4, h->stream)); // 0x7f7f7f7f: "not modified"
+        h->ws_first_cap = ocap;
+        h->ws.firstmember = h->ws_first;
+    }
+    return CCB_OK;
+}
+
+int sync_bc(ccb_handle *h) { // both control blocks -> pinned host mirrors
+    CK(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(h->h_bc, h->d_bc, sizeof(BsCtl), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->timing) drain_timing(h);
+    return CCB_OK;
+}
+
+// One block = prologue + bs_iters refinement rounds + commit.  Every kernel reads its work description from the
+// device-side control block, so a converged (or finished) block turns the remaining launches into no-ops.
+int enqueue_block(ccb_handle *h, const Eng &e, int mp_bound, int mo_bound) {
+    cudaStream_t s = h->stream;
+    const int B = h->bs_bmax;
+    const int g_cells = (B + BS_THREADS - 1) / BS_THREADS;
+    const int g_tiles = (B / 32 + 1 + 3) / 4;
+    int rc, launches = 0;
+    auto nearest = [&]() -> int {
+        Timed tm(h, CCB_CAT_NEAREST);
+        return launch_nearest<BS_TOPK>(h, s, h->DP, h->div_mode, e.X, e.ws.nrows, nullptr, 0, BS_RMAX, e.ld, h->D, e.O.cw,
+                                       mo_bound, h->d_bs_tk_dist_slab, h->d_bs_tk_idx_slab, e.ws.tk_dist, e.ws.tk_idx,
+                                       BS_MAX_SLABS, nullptr, &e.bc->tk_lo, &e.bc->Mo0);
+    };
+    {
+        Timed tm(h, CCB_CAT_SPEC);
+        k_bs_begin<<<1, 1, 0, s>>>(e);
+        CCB_DISPATCH_DP(h->DP, { k_bs_spec<kDP><<<g_cells, BS_THREADS, 0, s>>>(e); })
+        k_bs_need<<<1, BS_CTA1, 0, s>>>(e);
+        launches += 3;
+    }
+    if ((rc = nearest())) return rc;
+    {
+        Timed tm(h, CCB_CAT_SPEC);
+        k_bs_spec_o<<<BS_RMAX / BS_THREADS, BS_THREADS, 0, s>>>(e);
+        launches += 1;
+    }
+    for (int it = 0; it < h->bs_iters; ++it) {
+        if (it > 0 && (rc = nearest())) return rc;
+        {
+            Timed tm(h, CCB_CAT_MISC);
+            k_bs_tilecnt<<<g_tiles, BS_THREADS, 0, s>>>(e);
+            k_bs_pscan<<<1, BS_CTA1, 0, s>>>(e);
+            k_bs_pscatter<<<g_tiles, BS_THREADS, 0, s>>>(e);
+        }
+        {
+            Timed tm(h, CCB_CAT_PCORE);
+            CCB_DISPATCH_DP(h->DP, { k_bs_chain<kDP, 0><<<std::max(mp_bound, 1), BS_THREADS, 0, s>>>(e); })
+        }
+        {
+            Timed tm(h, CCB_CAT_MISC);
+            k_bs_olist<<<1, BS_CTA1, 0, s>>>(e);
+        }
+        {
+            Timed tm(h, CCB_CAT_PCORE);
+            CCB_DISPATCH_DP(h->DP, { k_bs_chain<kDP, 1><<<BS_RMAX, BS_THREADS, 0, s>>>(e); })
+        }
+        {
+            Timed tm(h, CCB_CAT_MISC);
+            k_bs_derive<<<g_cells, BS_THREADS, 0, s>>>(e);
+        }
+        {
+            Timed tm(h, CCB_CAT_RESOLVE);
+            CCB_DISPATCH_DP(h->DP, {
+                k_bs_verify_p<kDP><<<g_tiles, BS_THREADS, 0, s>>>(e);
+                k_bs_verify_o<kDP><<<148 * 2, BS_THREADS, 0, s>>>(e);
+            })
+        }
+        {
+            Timed tm(h, CCB_CAT_MISC);
+            k_bs_decide<<<1, BS_CTA1, 0, s>>>(e);
+        }
+        launches += 10;
+    }
+    {
+        Timed tm(h, CCB_CAT_MISC);
+        k_bs_commit_rows<<<(mp_bound + BS_RMAX + 3) / 4, BS_THREADS, 0, s>>>(e);
+        k_bs_commit_cells<<<g_cells, BS_THREADS, 0, s>>>(e);
+        k_bs_finish<<<1, BS_THREADS, 0, s>>>(e);
+        launches += 3;
+    }
+    CKL(h);
+    h->st.kernel_launches += launches;
+    return CCB_OK;
+}
+
+// the ordered loop over cells [0, N) of a device-resident X, block-speculative engine
+int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t *d_assign, uint8_t *d_stage) {
+    if (!h->have_params) return fail(h, CCB_ESTATE, "ccb_begin_timepoint must precede ccb_ingest");
+    if (N >= ((int64_t)1 << 31)) return fail(h, CCB_ELIMIT, "more than 2^31 - 1 cells in one call");
+    cudaStream_t s = h->stream;
+    int rc;
+    if ((rc = ensure_bs_ws(h))) return rc;
+    const int bmax = h->bs_bmax, bmin = std::min(h->bs_bmin, h->bs_bmax);
+    k_bs_init<<<1, 1, 0, s>>>(h->d_bc, N, h->bs_iters, bmin, bmax);
+    CKL(h);
+    h->st.kernel_launches++;
+    if ((rc = sync_bc(h))) return rc;
+    const double theta = 4.0 * h->prm.eps2; // CONTESTED above 4 eps^2: heuristic only, never affects results
+    int guard = 0;
+    while (!h->h_bc->done) {
+        const Ctl &c = *h->h_ctl;
+        const BsCtl &b = *h->h_bc;
+        // blocks to enqueue before the next look at the control block
+        const int64_t left = N - b.pos;
+        int G = (int)std::min<int64_t>(16, (left + std::max(b.next_B, 1) - 1) / std::max(b.next_B, 1) + 1);
+        if (G < 1) G = 1;
+        // capacity: every block may append BS_RMAX outlier MCs and upgrade one MC
+        const int64_t need_o = (int64_t)c.n_outlier + (int64_t)(G + 1) * BS_RMAX + 1;
+        if (need_o > h->O[h->ocur].cap) {
+            if ((rc = grow_store(h, h->O, h->ocur, c.n_outlier, need_o))) return rc;
+            if ((rc = realloc_aux_for_outlier_cap(h))) return rc;
+        }
+        if (c.n_pcore + G + 1 > h->P[h->pcur].cap) {
+            if ((rc = grow_store(h, h->P, h->pcur, c.n_pcore, c.n_pcore + G + 1))) return rc;
+            if ((rc = realloc_aux_for_pcore_cap(h))) return rc;
+        }
+        if ((rc = ensure_bs_ws(h))) return rc;
+        if (b.need_grow) {
+            h->h_bc->need_grow = 0;
+            CK(h, cudaMemcpyAsync(&h->d_bc->need_grow, &h->h_bc->need_grow, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        }
+        Eng e{};
+        e.X = dX;
+        e.ld = ld;
+        e.P = h->P[h->pcur];
+        e.O = h->O[h->ocur];
+        e.nm = make_num(h);
+        e.ctl = h->d_ctl;
+        e.bc = h->d_bc;
+        e.ws = h->ws;
+        e.assign = d_assign;
+        e.stage = d_stage;
+        e.theta = theta;
+        for (int g = 0; g < G; ++g)
+            if ((rc = enqueue_block(h, e, c.n_pcore + g + 1, (int)std::min<int64_t>(c.n_outlier + (int64_t)(g + 1) * BS_RMAX,
+                                                                                   h->O[h->ocur].cap))))
+                return rc;
+        const int64_t pos0 = b.pos;
+        if ((rc = sync_bc(h))) return rc;
+        if (h->h_bc->pos == pos0 && !h->h_bc->need_grow && !h->h_bc->done && ++guard > 4)
+            return fail(h, CCB_ESTATE, "internal: block-speculative engine made no progress at row %lld", (long long)pos0);
+        if (h->h_bc->pos != pos0) guard = 0;
+    }
+    h->st.points += N;
+    return CCB_OK;
+}
+
 int pcore_ids_host(ccb_handle *h, int n, std::vector<int64_t> &ids) {
     ids.resize(n);
     if (n) CK(h, cudaMemcpy(ids.data(), h->P[h->pcur].id, (size_t)n * 8, cudaMemcpyDeviceToHost));
@@ -518,8 +739,13 @@ int ccb_create(const ccb_params *p, ccb_handle **out) {
     h->prm = *p;
     h->D = p->D;
     h->DP = round_dp(p->D);
+    h->engine = p->wave ? 1 : 0; // wave == 0: block-speculative engine; wave >= 1: wave engine of that width
     h->wave = p->wave ? p->wave : 32;
     h->chunk = p->chunk > 0 ? p->chunk : 65536;
+    if (p->chunk > 0) h->bs_bmax = std::max(32, (p->chunk + 31) / 32 * 32); // block length cap of the BSV engine
+    if (p->bsv_bmin > 0) h->bs_bmin = p->bsv_bmin;
+    if (p->bsv_iters > 0) h->bs_iters = std::min(p->bsv_iters, 16);
+    h->bs_bmax = std::min(h->bs_bmax, 1 << 20);
     const bool p2 = is_pow2(p->k);
     h->div_mode = p2 ? 0 : 1;
     h->wsel = p2 ? 1.0 / p->k : p->k; // exact reciprocal of a power of two, else the divisor itself
@@ -588,6 +814,12 @@ void ccb_destroy(ccb_handle *h) {
     cudaFree(h->d_pfin);
     cudaFree(h->d_onew);
     cudaFree(h->d_dist_gmem);
+    cudaFree(h->d_bc);
+    if (h->h_bc) cudaFreeHost(h->h_bc);
+    for (void *q : h->ws_allocs) cudaFree(q);
+    cudaFree(h->ws_tiles[0]);
+    cudaFree(h->ws_tiles[1]);
+    cudaFree(h->ws_first);
     for (auto &e : h->ev_pending) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
@@ -609,6 +841,17 @@ int ccb_get_stats(const ccb_handle *h, ccb_stats *out) {
     out->created = h->st_base.created + c.created;
     out->downgraded = h->st_base.downgraded + c.downgraded;
     out->deleted = h->st_base.deleted + c.deleted;
+    if (h->h_bc) {
+        const BsCtl &b = *h->h_bc, &bb = h->bc_base;
+        out->bsv_blocks = bb.blocks + b.blocks;
+        out->bsv_rounds = bb.iters + b.iters;
+        out->bsv_mismatches = bb.mismatches + b.mismatches;
+        out->bsv_cuts_unknown = bb.cuts_unknown + b.cuts_unknown;
+        out->bsv_cuts_rounds = bb.cuts_iter + b.cuts_iter;
+        out->bsv_cuts_capacity = bb.cuts_cap + b.cuts_cap;
+        out->bsv_late_topk = bb.tk_late + b.tk_late;
+        out->bsv_outlier_stage_cells = bb.rejects + b.rejects;
+    }
     return CCB_OK;
 }
 
@@ -638,6 +881,18 @@ int ccb_reset(ccb_handle *h) {
     memset(h->h_ctl, 0, sizeof(Ctl));
     rc = push_ctl(h);
     if (rc) return rc;
+    if (h->d_bc) {
+        CK(h, cudaMemcpyAsync(h->h_bc, h->d_bc, sizeof(BsCtl), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        const BsCtl &b = *h->h_bc;
+        BsCtl &bb = h->bc_base;
+        bb.blocks += b.blocks, bb.iters += b.iters, bb.mismatches += b.mismatches, bb.cuts_unknown += b.cuts_unknown;
+        bb.cuts_iter += b.cuts_iter, bb.cuts_cap += b.cuts_cap, bb.tk_late += b.tk_late, bb.rejects += b.rejects;
+        const int32_t keep_B = b.next_B;
+        memset(h->h_bc, 0, sizeof(BsCtl));
+        h->h_bc->next_B = keep_B;
+        CK(h, cudaMemcpyAsync(h->d_bc, h->h_bc, sizeof(BsCtl), cudaMemcpyHostToDevice, h->stream));
+    }
     CK(h, cudaStreamSynchronize(h->stream));
     h->have_params = false;
     h->off_M = 0;
@@ -733,7 +988,8 @@ int ccb_ingest_device(ccb_handle *h, const double *X_dev, int64_t N, int64_t ld,
     if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
     if (N < 0 || ld < h->D || (!X_dev && N > 0) || (!assign_uid_dev && N > 0)) return fail(h, CCB_EINVAL, "bad ingest arguments");
     CK(h, cudaSetDevice(h->prm.device));
-    return ingest_core(h, X_dev, N, ld, assign_uid_dev, stage_dev);
+    return h->engine ? ingest_core(h, X_dev, N, ld, assign_uid_dev, stage_dev)
+                     : ingest_core_bsv(h, X_dev, N, ld, assign_uid_dev, stage_dev);
 }
 
 int ccb_ingest(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *assign_uid, uint8_t *stage) {
@@ -754,7 +1010,8 @@ int ccb_ingest(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *a
         Timed tm(h, CCB_CAT_COPY);
         CK(h, cudaMemcpyAsync(h->d_X, X, need * 8, cudaMemcpyHostToDevice, h->stream));
     }
-    rc = ingest_core(h, h->d_X, N, ld, h->d_assign, h->d_stage);
+    rc = h->engine ? ingest_core(h, h->d_X, N, ld, h->d_assign, h->d_stage)
+                   : ingest_core_bsv(h, h->d_X, N, ld, h->d_assign, h->d_stage);
     if (rc) return rc;
     {
         Timed tm(h, CCB_CAT_COPY);

@@ -1,0 +1,1168 @@
+// engine.cuh -- KERNEL 2, second generation: the BLOCK-SPECULATIVE VERSIONED COMMIT ("BSV").
+//
+// Replaces the ordered per-cell loop of HDDStream.online_microcluster_maintenance
+// (clustering/hddstream.py:220-237: _add_to_pcore :288-343, _add_to_outlier :345-395,
+// _upgrade_outlier_microcluster :397-430, _create_new_outlier_cluster :434-462, with the Microcluster maths
+// of objects/microcluster.py:89-153, 213-233 and utilities/mc_functions.py:14-56) -- bit for bit, but with
+// the work of a block of B consecutive cells spread over the whole GPU.  tests/proto/bsv_proto.c is the
+// CPU model of exactly this scheme (validated against the reference's golden vectors).
+//
+// A cell's decision is a target KEY:  j < Mp                  absorbed by pcore MC j
+//                                     Mp + o  (o < Mo0)       absorbed by outlier MC o of the snapshot
+//                                     KNEW + c (c <= i)       absorbed by the MC that cell c of this block
+//                                                             creates (c == i: the cell itself creates it)
+// with KNEW = Mp + Mo0.  One block runs
+//   S   k_bs_spec      speculate from the snapshot: nearest feasible pcore MC (candidate), SAFE / CONTESTED,
+//       k_bs_need      ordered list of the cells that may reach the outlier stage, k_nearest top-K of the
+//       k_bs_spec_o    snapshot outlier list for them, speculated outlier decision
+//   then up to ITMAX rounds of
+//   L   k_bs_tilecnt / k_bs_pscan / k_bs_pscatter   ordered candidate list of every pcore MC
+//   C   k_bs_chain<P>  per pcore MC, its candidates in input order: CF1 += x, CF2 += x*x, W += 1 as dependent
+//                      fp64 adds (the only inherently serial work: ~1 DADD latency per cell); CONTESTED cells
+//                      take the exact radius test in place; the state after every absorb is kept (VERSION)
+//       k_bs_olist     sort (key, cell) of the pcore-rejected cells -> outlier-side chains
+//       k_bs_chain<O>  the same replay for modified snapshot outlier MCs and MCs created in this block
+//   D   k_bs_derive    centroid, preference mask, radius^2 of every version (cell-parallel)
+//   V   k_bs_verify_p  every cell recomputes its pcore decision against the version every pcore MC had just
+//       k_bs_verify_o  before it; rejected cells recompute the outlier decision (nearest unmodified snapshot
+//                      MC from the top-K list, every modified / created MC at its version)
+//   M   k_bs_decide    first cell whose exact decision differs from the speculation = end of the exact
+//                      prefix (induction: every earlier cell saw exact versions).  The recomputed decisions
+//                      become the next speculation; an upgrade ends the block at that cell.
+//   and finally k_bs_commit_rows / k_bs_commit_cells / k_bs_finish write the exact prefix back.
+// All control flow lives in device memory (BsCtl): the host only enqueues kernels and polls once per batch
+// of blocks.
+#pragma once
+#include <limits.h>
+
+#include "common.cuh"
+#include "online.cuh"
+
+namespace ccb {
+
+constexpr int BS_KEY_NONE = -4;    // no outlier-side decision recorded
+constexpr int BS_KEY_NEED = -3;    // reaches the outlier stage but has no top-K list yet
+constexpr int BS_KEY_PENDING = -5; // rejected by the pcore stage in V, outlier stage not evaluated yet
+constexpr int BS_KEY_UNKNOWN = -1; // every listed snapshot candidate was modified earlier in the block
+constexpr int BS_RMAX = 4096;      // cells per block that may reach the outlier stage
+constexpr int BS_TOPK = 8;
+
+struct BsCtl {
+    int64_t N, pos;
+    int32_t Bcur, Beff, next_B, Bmin, Bmax;
+    int32_t active, phase, it, itmax; // phase 0: iterating, 1: commit pending
+    int32_t Mp, Mo0;
+    int32_t nneed, tk_lo, tk_hi; // need-list length; range of entries whose top-K list is to be computed
+    int32_t nh, hnew0, no;       // hot outlier-side keys, index of the first created-in-block key, members
+    int32_t npend;
+    int32_t m_commit, upgrade;
+    int32_t need_grow, done;
+    int32_t pad0;
+    int64_t blocks, iters, mismatches, cuts_unknown, cuts_iter, cuts_cap, tk_late, rejects, contested;
+};
+
+struct BsWs {
+    int32_t *pcand, *ospec, *tkpos, *dec, *eff, *newrank, *pend, *plist;
+    uint8_t *pflag, *prej, *upf, *want;
+    double *vcf1, *vcf2, *vcen, *vw, *vr2;
+    uint64_t *vmask;
+    int32_t *tilecnt, *tbase, *poff; // [ntiles + 1][mp_stride], [ntiles + 1][mp_stride], [mp_stride + 1]
+    int32_t *nrows, *ncell;          // [BS_RMAX] absolute row / block-relative cell of the need list
+    double *tk_dist;
+    int32_t *tk_idx; // [BS_RMAX][BS_TOPK]
+    int32_t *hkey, *hoff, *omem, *hrank; // hrank[q]: real creations before key hnew0 + q
+    int32_t *firstmember; // [O.cap], INT_MAX = unmodified in this block
+    int32_t mp_stride, bmax;
+};
+
+struct Eng {
+    const double *X;
+    int64_t ld;
+    Store P, O;
+    Num nm;
+    Ctl *ctl;
+    BsCtl *bc;
+    BsWs ws;
+    int32_t *assign;
+    uint8_t *stage;
+    double theta; // contested threshold on the snapshot distance
+};
+
+// ---------------------------------------------------------------------------------------------------
+// thread-sequential arithmetic (one thread, dimensions in index order)
+
+template <int DP>
+__device__ __forceinline__ void load_row(const double *row, int D, double (&x)[DP]) {
+#pragma unroll
+    for (int d = 0; d < DP; ++d) x[d] = d < D ? row[d] : 0.0;
+}
+
+// mc_functions.py:35-43 with the cell in registers
+template <int DP>
+__device__ __forceinline__ double dist_regs(const double (&x)[DP], const double *__restrict__ c, uint64_t mask,
+                                            const Num &nm) {
+    double acc = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+        if (d < nm.D) {
+            double t = dsub(x[d], c[d]);
+            t = dmul(t, t);
+            if ((mask >> d) & 1ull) t = nm.div_mode ? ddiv(t, nm.k) : dmul(t, nm.wsel);
+            acc = dadd(acc, t);
+        }
+    }
+    return acc;
+}
+
+// get_copy_with_new_point + calculate_projected_radius_squared (microcluster.py:213-233, mc_functions.py:45-56)
+// by one thread.  Returns r^2; wn = W + 1, nmask = preference mask of the tentative MC.
+template <int DP>
+__device__ __forceinline__ double tent_regs(const double *__restrict__ cf1, const double *__restrict__ cf2, double w,
+                                            const double (&x)[DP], const Num &nm, double &wn, uint64_t &nmask) {
+    wn = dadd(w, 1.0);
+    double s = 0.0;
+    uint64_t mk = 0ull;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+        if (d < nm.D) {
+            const double c1 = dadd(cf1[d], x[d]);
+            const double c2 = dadd(cf2[d], dmul(x[d], x[d]));
+            const double a = ddiv(c2, wn);
+            const double c = ddiv(c1, wn);
+            const double var = dsub(a, dmul(c, c));
+            const bool bit = var <= nm.delta2;
+            mk |= (uint64_t)bit << d;
+            s = dadd(s, bit ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var);
+        }
+    }
+    nmask = mk;
+    return s;
+}
+
+// feasibility gate of _add_to_pcore (hddstream.py:315-321) with the cell in registers
+template <int DP>
+__device__ __forceinline__ bool feasible_regs(const double *__restrict__ cf1, const double *__restrict__ cf2, double w,
+                                              const double (&x)[DP], const Num &nm) {
+    const double w1 = dadd(w, 1.0);
+    int cnt = 0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+        if (d < nm.D) {
+            const double a = ddiv(dadd(cf2[d], dmul(x[d], x[d])), w1);
+            double b = ddiv(dadd(cf1[d], x[d]), w1);
+            b = dmul(b, b);
+            cnt += (dsub(a, b) <= nm.delta2);
+        }
+    }
+    return (int64_t)cnt <= nm.pi;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+
+// latest element < i of the ascending list l[0..n), or -1
+__device__ __forceinline__ int latest_before(const int32_t *__restrict__ l, int n, int i) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (l[mid] < i) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo ? l[lo - 1] : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_bs_init(BsCtl *bc, int64_t N, int32_t itmax, int32_t bmin, int32_t bmax) {
+    bc->N = N;
+    bc->pos = 0;
+    bc->done = N <= 0;
+    bc->need_grow = 0;
+    bc->active = 0;
+    bc->itmax = itmax;
+    bc->Bmin = bmin;
+    bc->Bmax = bmax;
+    if (bc->next_B < bmin) bc->next_B = bmin;
+    if (bc->next_B > bmax) bc->next_B = bmax;
+}
+
+__global__ void k_bs_begin(Eng e) {
+    BsCtl *bc = e.bc;
+    bc->active = 0;
+    if (bc->done || bc->need_grow) return;
+    if (bc->pos >= bc->N) {
+        bc->done = 1;
+        return;
+    }
+    const int Mp = e.ctl->n_pcore, Mo0 = e.ctl->n_outlier;
+    if ((int64_t)Mo0 + BS_RMAX + 1 > e.O.cap) {
+        bc->need_grow = 1;
+        return;
+    }
+    if (Mp + 1 > e.P.cap || Mp + 1 > e.ws.mp_stride) {
+        bc->need_grow = 2;
+        return;
+    }
+    const int64_t left = bc->N - bc->pos;
+    bc->Bcur = (int32_t)(left < bc->next_B ? left : bc->next_B);
+    bc->Beff = bc->Bcur;
+    bc->Mp = Mp;
+    bc->Mo0 = Mo0;
+    bc->nneed = bc->tk_lo = bc->tk_hi = 0;
+    bc->nh = bc->hnew0 = bc->no = 0;
+    bc->npend = 0;
+    bc->it = 0;
+    bc->phase = 0;
+    bc->m_commit = 0;
+    bc->upgrade = 0;
+    bc->active = 1;
+}
+
+// ---- S ----------------------------------------------------------------------------------------------
+constexpr int BS_THREADS = 128;
+
+template <int DP>
+__global__ void __launch_bounds__(BS_THREADS) k_bs_spec(Eng e) {
+    const BsCtl *bc = e.bc;
+    if (!bc->active) return;
+    const int i = blockIdx.x * BS_THREADS + threadIdx.x;
+    if (i >= bc->Bcur) return;
+    const Num nm = e.nm;
+    const int D = nm.D, Mp = bc->Mp;
+    double x[DP];
+    load_row<DP>(e.X + (bc->pos + i) * e.ld, D, x);
+    int best = -1;
+    double bd = 0.0;
+    for (int j = 0; j < Mp; ++j) {
+        if (nm.pi_active && !feasible_regs<DP>(e.P.cf1 + (size_t)j * D, e.P.cf2 + (size_t)j * D, e.P.w[j], x, nm)) continue;
+        const double dv = dist_regs<DP>(x, e.P.cen + (size_t)j * D, e.P.mask[j], nm);
+        if (!(dv != dv) && (best < 0 || dv < bd)) {
+            best = j;
+            bd = dv;
+        }
+    }
+    int flag = 1;
+    if (best >= 0) {
+        double wn;
+        uint64_t nmask;
+        const double r2s = tent_regs<DP>(e.P.cf1 + (size_t)best * D, e.P.cf2 + (size_t)best * D, e.P.w[best], x, nm, wn, nmask);
+        if (bd <= e.theta && r2s <= nm.eps2) flag = 0;
+    }
+    e.ws.pcand[i] = best;
+    e.ws.pflag[i] = (uint8_t)flag;
+    e.ws.prej[i] = best < 0;
+    e.ws.ospec[i] = BS_KEY_NONE;
+    e.ws.tkpos[i] = -1;
+}
+
+// ordered need list: every cell that is not SAFE gets a top-K slot, in cell order; the block is truncated at
+// the first cell that does not fit (bounds the outlier-stage work of one block)
+constexpr int BS_CTA1 = 1024;
+
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int *s_warp, int &total) {
+    // inclusive scan inside the warp, then across the 32 warp totals
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - w;   // exclusive offset of each warp
+        if (lane == 31) s_warp[32] = winc; // grand total
+    }
+    __syncthreads();
+    total = s_warp[32];
+    const int r = s_warp[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
+    __shared__ int s_warp[33];
+    __shared__ int s_cut;
+    BsCtl *bc = e.bc;
+    if (!bc->active) return;
+    const int B = bc->Bcur, tid = threadIdx.x;
+    const int per = (B + BS_CTA1 - 1) / BS_CTA1;
+    const int lo = min(B, tid * per), hi = min(B, lo + per);
+    if (tid == 0) s_cut = B;
+    int cnt = 0;
+    for (int i = lo; i < hi; ++i) cnt += e.ws.pflag[i];
+    int total;
+    int base = block_exclusive_scan_1024(cnt, s_warp, total);
+    const int32_t row0 = (int32_t)bc->pos;
+    for (int i = lo; i < hi; ++i) {
+        if (!e.ws.pflag[i]) continue;
+        if (base < BS_RMAX) {
+            e.ws.tkpos[i] = base;
+            e.ws.nrows[base] = row0 + i;
+            e.ws.ncell[base] = i;
+        } else if (base == BS_RMAX) {
+            s_cut = i; // exactly one thread sees the first overflowing cell
+        }
+        ++base;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        bc->Beff = s_cut;
+        bc->nneed = min(total, BS_RMAX);
+        bc->tk_lo = 0;
+        bc->tk_hi = bc->nneed;
+        bc->rejects += bc->nneed;
+    }
+}
+
+// speculated outlier-stage decision of the need list: nearest snapshot MC + radius test on the snapshot state
+__global__ void __launch_bounds__(BS_THREADS) k_bs_spec_o(Eng e) {
+    const BsCtl *bc = e.bc;
+    if (!bc->active) return;
+    const int t = blockIdx.x * BS_THREADS + threadIdx.x;
+    if (t >= bc->nneed) return;
+    const int i = e.ws.ncell[t];
+    const Num nm = e.nm;
+    const int D = nm.D;
+    const int KNEW = bc->Mp + bc->Mo0;
+    int key = KNEW + i;
+    const int o = bc->Mo0 > 0 ? e.ws.tk_idx[(size_t)t * BS_TOPK] : -1;
+    if (o >= 0) {
+        const double *x = e.X + (bc->pos + i) * e.ld;
+        const double *cf1 = e.O.cf1 + (size_t)o * D, *cf2 = e.O.cf2 + (size_t)o * D;
+        const double wn = dadd(e.O.w[o], 1.0);
+        double s = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double xv = x[d];
+            const double a = ddiv(dadd(cf2[d], dmul(xv, xv)), wn);
+            const double c = ddiv(dadd(cf1[d], xv), wn);
+            const double var = dsub(a, dmul(c, c));
+            s = dadd(s, (var <= nm.delta2) ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var);
+        }
+        if (s <= nm.eps2) key = bc->Mp + o;
+    }
+    e.ws.ospec[i] = key;
+}
+
+// ---- L ----------------------------------------------------------------------------------------------
+// per (tile of 32 cells, pcore key): number of candidates
+__global__ void __launch_bounds__(BS_THREADS) k_bs_tilecnt(Eng e) {
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
+    const int ntiles = (bc->Beff + 31) >> 5;
+    if (t >= ntiles) return;
+    const int i = t * 32 + lane;
+    const int c = i < bc->Beff ? e.ws.pcand[i] : -1;
+    const int Mp = bc->Mp;
+    int32_t *row = e.ws.tilecnt + (size_t)t * e.ws.mp_stride;
+    for (int j0 = 0; j0 < Mp; j0 += 32) {
+        int my = 0;
+        const int jn = min(32, Mp - j0);
+        for (int jj = 0; jj < jn; ++jj) {
+            const unsigned b = __ballot_sync(0xffffffffu, c == j0 + jj);
+            if (lane == jj) my = __popc(b);
+        }
+        if (lane < jn) row[j0 + lane] = my;
+    }
+}
+
+// per key: exclusive prefix of the tile counts (in place), then the key offsets
+__global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
+    __shared__ int s_warp[33];
+    BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Mp = bc->Mp, stride = e.ws.mp_stride;
+    const int ntiles = (bc->Beff + 31) >> 5;
+    const int per = (ntiles + 31) / 32;
+    for (int j = warp; j < Mp; j += BS_CTA1 / 32) {
+        const int t0 = min(ntiles, lane * per), t1 = min(ntiles, t0 + per);
+        int sum = 0;
+        for (int t = t0; t < t1; ++t) sum += e.ws.tilecnt[(size_t)t * stride + j];
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        int run = inc - sum;
+        for (int t = t0; t < t1; ++t) {
+            const int c = e.ws.tilecnt[(size_t)t * stride + j];
+            e.ws.tilecnt[(size_t)t * stride + j] = run;
+            run += c;
+        }
+        if (lane == 31) e.ws.poff[j + 1] = inc; // total of key j, turned into an offset below
+    }
+    __syncthreads();
+    // exclusive scan of the totals over the keys (Mp is small; chunks of 1024)
+    int carry = 0;
+    for (int j0 = 0; j0 < Mp; j0 += BS_CTA1) {
+        const int j = j0 + threadIdx.x;
+        const int v = j < Mp ? e.ws.poff[j + 1] : 0;
+        int total;
+        const int ex = block_exclusive_scan_1024(v, s_warp, total);
+        if (j < Mp) e.ws.poff[j + 1] = carry + ex + v;
+        carry += total;
+    }
+    if (threadIdx.x == 0) e.ws.poff[0] = 0;
+}
+
+__global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
+    const int ntiles = (bc->Beff + 31) >> 5;
+    if (t >= ntiles) return;
+    const int i = t * 32 + lane;
+    const int c = i < bc->Beff ? e.ws.pcand[i] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    if (c >= 0) {
+        const int rank = __popc(peers & lanemask_lt());
+        e.ws.plist[e.ws.poff[c] + e.ws.tilecnt[(size_t)t * e.ws.mp_stride + c] + rank] = i;
+    }
+}
+
+// ---- C ----------------------------------------------------------------------------------------------
+// One CTA per key.  All four warps stage the cells of the next batch into shared memory with cp.async
+// (index list first, then the rows); warp 0 replays the current batch in order, lane d owning dimensions d
+// and d + 32.  PHASE 0: pcore keys (CONTESTED members take the exact radius test; accepted members also
+// maintain tbase[tile][key] = latest accepted member before that tile).  PHASE 1: outlier-side keys.
+template <int DP>
+struct ChainCfg {
+    static constexpr int NB = DP <= 16 ? 128 : (DP <= 32 ? 64 : 32);
+};
+
+template <int DP, int PHASE>
+__global__ void __launch_bounds__(BS_THREADS) k_bs_chain(Eng e) {
+    constexpr int NB = ChainCfg<DP>::NB;
+    __shared__ __align__(16) double xs[2][NB][DP];
+    __shared__ int mi[2][NB];
+    __shared__ unsigned char fl[2][NB];
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const Num nm = e.nm;
+    const int D = nm.D;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Mp = bc->Mp, KNEW = bc->Mp + bc->Mo0;
+    const int key_idx = blockIdx.x;
+    const int32_t *mem;
+    int n;
+    const double *s1 = nullptr, *s2 = nullptr;
+    double w = 0.0;
+    if (PHASE == 0) {
+        if (key_idx >= Mp) return;
+        mem = e.ws.plist + e.ws.poff[key_idx];
+        n = e.ws.poff[key_idx + 1] - e.ws.poff[key_idx];
+        s1 = e.P.cf1 + (size_t)key_idx * D;
+        s2 = e.P.cf2 + (size_t)key_idx * D;
+        w = e.P.w[key_idx];
+    } else {
+        if (key_idx >= bc->nh) return;
+        mem = e.ws.omem + e.ws.hoff[key_idx];
+        n = e.ws.hoff[key_idx + 1] - e.ws.hoff[key_idx];
+        const int key = e.ws.hkey[key_idx];
+        if (key < KNEW) {
+            const int o = key - Mp;
+            s1 = e.O.cf1 + (size_t)o * D;
+            s2 = e.O.cf2 + (size_t)o * D;
+            w = e.O.w[o];
+        }
+    }
+    const int ntiles = (bc->Beff + 31) >> 5;
+    const double *Xb = e.X + bc->pos * e.ld;
+
+    auto stage_idx = [&](int b) {
+        const int buf = b & 1, cnt = min(NB, n - b * NB);
+        for (int m = tid; m < cnt; m += BS_THREADS) {
+            const int i = mem[b * NB + m];
+            mi[buf][m] = i;
+            fl[buf][m] = PHASE == 0 ? e.ws.pflag[i] : 0;
+        }
+    };
+    auto stage_rows = [&](int b) {
+        const int buf = b & 1, cnt = min(NB, n - b * NB);
+        for (int idx = tid; idx < cnt * D; idx += BS_THREADS) {
+            const int m = idx / D, d = idx - m * D;
+            cp_async8(&xs[buf][m][d], Xb + (int64_t)mi[buf][m] * e.ld + d);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nb = (n + NB - 1) / NB;
+    LaneMc st;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int d = lane + 32 * h;
+        // idle lanes carry 1.0 so that their (discarded) quotients stay on the fast path of the IEEE division
+        st.cf1[h] = d < D ? (s1 ? s1[d] : 0.0) : 1.0;
+        st.cf2[h] = d < D ? (s2 ? s2[d] : 0.0) : 1.0;
+        st.cen[h] = 0.0;
+    }
+    int pv = -1, nextfill = 0;
+    int32_t *tb = e.ws.tbase + key_idx; // [t * mp_stride]
+    if (nb > 0) {
+        stage_idx(0);
+        __syncthreads();
+        stage_rows(0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
+    for (int b = 0; b < nb; ++b) {
+        const int cur = b & 1;
+        if (b + 1 < nb) stage_idx(b + 1);
+        __syncthreads();
+        if (b + 1 < nb) stage_rows(b + 1);
+        if (warp == 0) {
+            const int cnt = min(NB, n - b * NB);
+            for (int m = 0; m < cnt; ++m) {
+                const int i = mi[cur][m];
+                double x[2];
+                x[0] = lane < D ? xs[cur][m][lane] : 0.0;
+                x[1] = (DP > 32 && lane + 32 < D) ? xs[cur][m][lane + 32] : 0.0;
+                LaneMc o;
+                double wn;
+                if (PHASE == 0 && fl[cur][m]) {
+                    uint64_t nmask;
+                    if (!tentative_absorb_t<DP>(st, w, x, nm, o, wn, nmask)) {
+                        if (lane == 0) e.ws.prej[i] = 1;
+                        continue;
+                    }
+                } else {
+                    wn = dadd(w, 1.0);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 0 || DP > 32) {
+                            o.cf1[h] = dadd(st.cf1[h], x[h]);
+                            o.cf2[h] = dadd(st.cf2[h], dmul(x[h], x[h]));
+                        }
+                    }
+                }
+                st = o;
+                w = wn;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int d = lane + 32 * h;
+                    if ((h == 0 || DP > 32) && d < D) {
+                        e.ws.vcf1[(size_t)i * D + d] = o.cf1[h];
+                        e.ws.vcf2[(size_t)i * D + d] = o.cf2[h];
+                    }
+                }
+                if (lane == 0) e.ws.vw[i] = wn;
+                if (PHASE == 0) {
+                    if (lane == 0) e.ws.prej[i] = 0;
+                    const int ti = i >> 5;
+                    for (int t = nextfill + lane; t <= ti; t += 32) tb[(size_t)t * e.ws.mp_stride] = pv;
+                    nextfill = ti + 1;
+                    pv = i;
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
+    if (PHASE == 0 && warp == 0)
+        for (int t = nextfill + lane; t <= ntiles; t += 32) tb[(size_t)t * e.ws.mp_stride] = pv;
+}
+
+// ---- outlier-side member lists: sort (key, cell) of the pcore-rejected cells --------------------------
+__global__ void __launch_bounds__(BS_CTA1, 1) k_bs_olist(Eng e) {
+    __shared__ unsigned long long keys[BS_RMAX];
+    __shared__ int s_warp[33];
+    __shared__ int s_n;
+    BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const int tid = threadIdx.x;
+    const int Mp = bc->Mp, KNEW = bc->Mp + bc->Mo0;
+    // forget the modified-flags of the previous round
+    for (int h = tid; h < bc->nh; h += BS_CTA1) {
+        const int key = e.ws.hkey[h];
+        if (key < KNEW) e.ws.firstmember[key - Mp] = INT_MAX;
+    }
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const int nneed = bc->nneed, Beff = bc->Beff;
+    for (int t = tid; t < nneed; t += BS_CTA1) {
+        const int i = e.ws.ncell[t];
+        if (i < Beff && e.ws.prej[i] && e.ws.ospec[i] >= 0) {
+            const int slot = atomicAdd(&s_n, 1);
+            keys[slot] = ((unsigned long long)(unsigned)e.ws.ospec[i] << 32) | (unsigned)i;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int t = n + tid; t < np2; t += BS_CTA1) keys[t] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < np2; t += BS_CTA1) {
+                const int p = t ^ j;
+                if (p > t) {
+                    const unsigned long long a = keys[t], b = keys[p];
+                    const bool up = (t & k) == 0;
+                    if ((a > b) == up) {
+                        keys[t] = b;
+                        keys[p] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // heads of the key segments, in key order (= list order: snapshot slots, then creations by creator)
+    const int per = (n + BS_CTA1 - 1) / BS_CTA1;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    int cnt = 0;
+    for (int t = lo; t < hi; ++t) cnt += (t == 0) || ((keys[t] >> 32) != (keys[t - 1] >> 32));
+    int total;
+    int h = block_exclusive_scan_1024(cnt, s_warp, total);
+    if (tid == 0) {
+        bc->nh = total;
+        bc->no = n;
+        bc->hnew0 = total; // lowered below by the first created-in-block key
+        e.ws.hoff[total] = n;
+    }
+    __syncthreads();
+    for (int t = lo; t < hi; ++t) {
+        const int key = (int)(keys[t] >> 32), i = (int)(keys[t] & 0xffffffffu);
+        e.ws.omem[t] = i;
+        if ((t == 0) || ((keys[t] >> 32) != (keys[t - 1] >> 32))) {
+            e.ws.hkey[h] = key;
+            e.ws.hoff[h] = t;
+            if (key < KNEW) e.ws.firstmember[key - Mp] = i;
+            else atomicMin(&bc->hnew0, h);
+            ++h;
+        }
+    }
+    __syncthreads();
+    // rank of every created-in-block key among the creations, in key (= creator) order.  A key is REAL when
+    // its first member is its creator; a stale speculation can leave phantom keys (members, but the creator
+    // decided otherwise) -- those lie beyond the first mismatch and get no rank.
+    const int nh = bc->nh, hnew0 = bc->hnew0;
+    const int nk = nh - hnew0, per2 = (nk + BS_CTA1 - 1) / BS_CTA1;
+    const int k0 = min(nk, tid * per2), k1 = min(nk, k0 + per2);
+    int creal = 0;
+    for (int q = k0; q < k1; ++q) creal += e.ws.omem[e.ws.hoff[hnew0 + q]] == e.ws.hkey[hnew0 + q] - KNEW;
+    int rtotal;
+    int rk = block_exclusive_scan_1024(creal, s_warp, rtotal);
+    for (int q = k0; q < k1; ++q) {
+        const int creator = e.ws.hkey[hnew0 + q] - KNEW;
+        e.ws.hrank[q] = rk; // real creations before key hnew0 + q
+        if (e.ws.omem[e.ws.hoff[hnew0 + q]] == creator) e.ws.newrank[creator] = rk++;
+    }
+    if (tid == 0) e.ws.hrank[nk] = rtotal;
+}
+
+// ---- D ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BS_THREADS) k_bs_derive(Eng e) {
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const int i = blockIdx.x * BS_THREADS + threadIdx.x;
+    if (i >= bc->Beff) return;
+    const Num nm = e.nm;
+    const int D = nm.D;
+    const double w = e.ws.vw[i];
+    const double *c1 = e.ws.vcf1 + (size_t)i * D, *c2 = e.ws.vcf2 + (size_t)i * D;
+    double *cen = e.ws.vcen + (size_t)i * D;
+    double s = 0.0;
+    uint64_t mk = 0ull;
+    for (int d = 0; d < D; ++d) {
+        const double a = ddiv(c2[d], w);
+        const double c = ddiv(c1[d], w);
+        cen[d] = c;
+        const double var = dsub(a, dmul(c, c));
+        const bool bit = var <= nm.delta2;
+        mk |= (uint64_t)bit << d;
+        s = dadd(s, bit ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var);
+    }
+    e.ws.vmask[i] = mk;
+    e.ws.vr2[i] = s;
+}
+
+// ---- V ----------------------------------------------------------------------------------------------
+// pcore stage, one warp per tile of 32 cells: for every pcore MC the version it had just before each cell =
+// the latest accepted member of its chain inside the tile (ballot) or before the tile (tbase).
+template <int DP>
+__global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
+    BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
+    const int Beff = bc->Beff;
+    if (t * 32 >= Beff) return;
+    const Num nm = e.nm;
+    const int D = nm.D, Mp = bc->Mp;
+    const int i = t * 32 + lane;
+    const bool live = i < Beff;
+    double x[DP];
+    load_row<DP>(e.X + (bc->pos + (live ? i : t * 32)) * e.ld, D, x);
+    const int myc = live ? e.ws.pcand[i] : -1;
+    const bool myrej = live ? (e.ws.prej[i] != 0) : true;
+    const int acc_key = (myc >= 0 && !myrej) ? myc : -1;
+    const int eff = !live ? BS_KEY_NONE : (myrej ? e.ws.ospec[i] : myc);
+    if (live) e.ws.eff[i] = eff;
+    int best = -1, bprev = -1;
+    double bd = 0.0;
+    const unsigned lt = lanemask_lt();
+    const int32_t *tb = e.ws.tbase + (size_t)t * e.ws.mp_stride;
+    for (int j = 0; j < Mp; ++j) {
+        const unsigned lower = __ballot_sync(0xffffffffu, acc_key == j) & lt;
+        const int prev = lower ? (t * 32 + 31 - __clz(lower)) : tb[j];
+        const double *cen = prev >= 0 ? e.ws.vcen + (size_t)prev * D : e.P.cen + (size_t)j * D;
+        const uint64_t mask = prev >= 0 ? e.ws.vmask[prev] : e.P.mask[j];
+        bool feas = true;
+        if (nm.pi_active) {
+            const double *c1 = prev >= 0 ? e.ws.vcf1 + (size_t)prev * D : e.P.cf1 + (size_t)j * D;
+            const double *c2 = prev >= 0 ? e.ws.vcf2 + (size_t)prev * D : e.P.cf2 + (size_t)j * D;
+            const double w = prev >= 0 ? e.ws.vw[prev] : e.P.w[j];
+            feas = feasible_regs<DP>(c1, c2, w, x, nm);
+        }
+        const double dv = dist_regs<DP>(x, cen, mask, nm);
+        if (feas && !(dv != dv) && (best < 0 || dv < bd)) {
+            best = j;
+            bd = dv;
+            bprev = prev;
+        }
+    }
+    if (!live) return;
+    bool acc = false;
+    if (best >= 0) {
+        if (eff == best) {
+            acc = e.ws.vr2[i] <= nm.eps2; // this very absorb is version i of the chain
+        } else {
+            const double *c1 = bprev >= 0 ? e.ws.vcf1 + (size_t)bprev * D : e.P.cf1 + (size_t)best * D;
+            const double *c2 = bprev >= 0 ? e.ws.vcf2 + (size_t)bprev * D : e.P.cf2 + (size_t)best * D;
+            const double w = bprev >= 0 ? e.ws.vw[bprev] : e.P.w[best];
+            double wn;
+            uint64_t nmask;
+            acc = tent_regs<DP>(c1, c2, w, x, nm, wn, nmask) <= nm.eps2;
+        }
+    }
+    e.ws.upf[i] = 0;
+    if (acc) {
+        e.ws.dec[i] = best;
+    } else {
+        e.ws.dec[i] = BS_KEY_PENDING;
+        e.ws.pend[atomicAdd(&bc->npend, 1)] = i;
+    }
+}
+
+// outlier stage of the cells the pcore stage rejected: one warp per cell
+template <int DP>
+__global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const Num nm = e.nm;
+    const int D = nm.D, Mp = bc->Mp, Mo0 = bc->Mo0, KNEW = Mp + Mo0;
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5), nw = gridDim.x * (BS_THREADS / 32);
+    const int npend = bc->npend, nh = bc->nh;
+    for (int pidx = gw; pidx < npend; pidx += nw) {
+        const int i = e.ws.pend[pidx];
+        double x[DP];
+        load_row<DP>(e.X + (bc->pos + i) * e.ld, D, x);
+        // (1) nearest snapshot MC not modified before cell i, from the top-K list
+        double bd = 0.0;
+        int bkey = INT_MAX, bver = -1, status = 0; // status 1: UNKNOWN, 2: NEED
+        if (lane == 0 && Mo0 > 0) {
+            const int tk = e.ws.tkpos[i];
+            if (tk < 0) {
+                status = 2;
+            } else {
+                int s = 0;
+                for (; s < BS_TOPK; ++s) {
+                    const int o = e.ws.tk_idx[(size_t)tk * BS_TOPK + s];
+                    if (o < 0) break;
+                    if (e.ws.firstmember[o] >= i) {
+                        bd = e.ws.tk_dist[(size_t)tk * BS_TOPK + s];
+                        bkey = Mp + o;
+                        break;
+                    }
+                }
+                if (s == BS_TOPK) status = 1;
+            }
+        }
+        status = __shfl_sync(0xffffffffu, status, 0);
+        if (status) {
+            if (lane == 0) {
+                e.ws.dec[i] = status == 2 ? BS_KEY_NEED : BS_KEY_UNKNOWN;
+                e.ws.upf[i] = 0;
+            }
+            continue;
+        }
+        // (2) every MC modified or created earlier in the block, at its version just before cell i
+        for (int h = lane; h < nh; h += 32) {
+            const int32_t *mem = e.ws.omem + e.ws.hoff[h];
+            if (mem[0] >= i) continue;
+            const int v = latest_before(mem, e.ws.hoff[h + 1] - e.ws.hoff[h], i);
+            const double dv = dist_regs<DP>(x, e.ws.vcen + (size_t)v * D, e.ws.vmask[v], nm);
+            const int key = e.ws.hkey[h];
+            if (!(dv != dv) && (bkey == INT_MAX || dv < bd || (dv == bd && key < bkey))) {
+                bd = dv;
+                bkey = key;
+                bver = v;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bkey, o);
+            const int ov = __shfl_xor_sync(0xffffffffu, bver, o);
+            if (ok != INT_MAX && (bkey == INT_MAX || od < bd || (od == bd && ok < bkey))) {
+                bd = od;
+                bkey = ok;
+                bver = ov;
+            }
+        }
+        int dec = KNEW + i, up = 0;
+        if (bkey != INT_MAX) {
+            const double *c1, *c2;
+            double w;
+            if (bver >= 0) {
+                c1 = e.ws.vcf1 + (size_t)bver * D;
+                c2 = e.ws.vcf2 + (size_t)bver * D;
+                w = e.ws.vw[bver];
+            } else {
+                const int o = bkey - Mp;
+                c1 = e.O.cf1 + (size_t)o * D;
+                c2 = e.O.cf2 + (size_t)o * D;
+                w = e.O.w[o];
+            }
+            LaneMc m, o2;
+            double xl[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int d = lane + 32 * h;
+                m.cf1[h] = d < D ? c1[d] : 1.0;
+                m.cf2[h] = d < D ? c2[d] : 1.0;
+                m.cen[h] = 0.0;
+                xl[h] = d < D ? e.X[(bc->pos + i) * e.ld + d] : 0.0;
+            }
+            double wn;
+            uint64_t nmask;
+            if (tentative_absorb_t<DP>(m, w, xl, nm, o2, wn, nmask)) {
+                dec = bkey;
+                const int pd = nm.cnt_gt1 ? popc64(nmask) : 0;
+                up = (wn >= nm.beta_mu) && ((int64_t)pd <= nm.pi); // hddstream.py:413-418
+            }
+        }
+        if (lane == 0) {
+            e.ws.dec[i] = dec;
+            e.ws.upf[i] = (uint8_t)up;
+        }
+    }
+}
+
+// ---- M ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_min_1024(int v, int *s_warp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    v = s_warp[threadIdx.x & 31];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
+    __shared__ int s_warp[33];
+    __shared__ int s_act, s_cut;
+    BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const int tid = threadIdx.x;
+    const int Beff = bc->Beff, Mp = bc->Mp, KNEW = bc->Mp + bc->Mo0;
+    const int per = (Beff + BS_CTA1 - 1) / BS_CTA1;
+    const int lo = min(Beff, tid * per), hi = min(Beff, lo + per);
+    int m0 = Beff;
+    for (int i = lo; i < hi; ++i)
+        if (e.ws.dec[i] != e.ws.eff[i]) {
+            m0 = i;
+            break;
+        }
+    m0 = block_min_1024(m0, s_warp);
+    int up = INT_MAX;
+    for (int i = lo; i < min(hi, m0); ++i)
+        if (e.ws.upf[i]) {
+            up = i;
+            break;
+        }
+    up = block_min_1024(up, s_warp);
+    if (tid == 0) {
+        int act = 0; // 0 refine, 1 commit
+        bc->iters += 1;
+        if (up != INT_MAX) {
+            bc->m_commit = up + 1;
+            bc->upgrade = 1;
+            act = 1;
+        } else if (m0 == Beff) {
+            bc->m_commit = Beff;
+            act = 1;
+        } else {
+            bc->mismatches += 1;
+            const int d0 = e.ws.dec[m0];
+            if (d0 == BS_KEY_UNKNOWN) {
+                bc->m_commit = m0;
+                bc->cuts_unknown += 1;
+                act = 1;
+            } else if (bc->it + 1 >= bc->itmax) {
+                bc->m_commit = m0;
+                bc->cuts_iter += 1;
+                act = 1;
+            }
+        }
+        s_act = act;
+        s_cut = Beff;
+    }
+    __syncthreads();
+    if (s_act == 1) {
+        if (tid == 0) bc->phase = 1;
+        return;
+    }
+    // ---- refinement: the recomputed decisions of [m0, Beff) become the next speculation
+    int cut = Beff;
+    for (int i = max(lo, m0); i < hi; ++i)
+        if (e.ws.dec[i] == BS_KEY_UNKNOWN) {
+            cut = i;
+            break;
+        }
+    cut = block_min_1024(cut, s_warp);
+    // cells that need a (new) top-K slot, handed out in cell order: cells that reach the outlier stage without
+    // a list, and SAFE cells whose nearest pcore MC changed (they become CONTESTED, which needs a fallback
+    // outlier decision should the chain reject them)
+    const int r_lo = max(lo, m0), r_hi = min(hi, cut);
+    int cnt = 0;
+    for (int i = r_lo; i < r_hi; ++i) {
+        const int dc = e.ws.dec[i];
+        const bool want = dc != e.ws.eff[i] &&
+                          (dc == BS_KEY_NEED || (dc >= 0 && dc < Mp && e.ws.pcand[i] != dc && !e.ws.pflag[i]));
+        e.ws.want[i] = (uint8_t)want;
+        cnt += want;
+    }
+    const int nneed_old = bc->nneed;
+    int total;
+    const int base = nneed_old + block_exclusive_scan_1024(cnt, s_warp, total);
+    {
+        int slot = base;
+        for (int i = r_lo; i < r_hi; ++i) {
+            if (!e.ws.want[i]) continue;
+            if (slot == BS_RMAX) s_cut = i; // first cell that does not fit (seen by exactly one thread)
+            ++slot;
+        }
+    }
+    __syncthreads();
+    const int Bnew = min(cut, s_cut);
+    if (Bnew <= m0) { // the first mismatching cell itself cannot be refined: commit the exact prefix
+        if (tid == 0) {
+            bc->m_commit = m0;
+            bc->cuts_cap += 1;
+            bc->phase = 1;
+        }
+        return;
+    }
+    {
+        int slot = base;
+        const int32_t row0 = (int32_t)bc->pos;
+        for (int i = r_lo; i < min(r_hi, Bnew); ++i) {
+            const int dc = e.ws.dec[i];
+            if (dc == e.ws.eff[i]) continue;
+            const bool want = e.ws.want[i] != 0;
+            if (want) {
+                e.ws.tkpos[i] = slot;
+                e.ws.nrows[slot] = row0 + i;
+                e.ws.ncell[slot] = i;
+                ++slot;
+            }
+            if (dc == BS_KEY_NEED) {
+                e.ws.ospec[i] = KNEW + i; // provisional: create; the next round decides with the top-K list
+                e.ws.pflag[i] = 1;
+            } else if (dc < Mp) {
+                if (want) {
+                    e.ws.ospec[i] = KNEW + i;
+                    e.ws.pflag[i] = 1;
+                }
+                e.ws.pcand[i] = dc;
+            } else {
+                e.ws.ospec[i] = dc;
+                e.ws.pflag[i] = 1;
+            }
+        }
+    }
+    if (tid == 0) {
+        const int nneed_new = min(nneed_old + total, BS_RMAX);
+        bc->tk_lo = nneed_old;
+        bc->tk_hi = nneed_new;
+        bc->nneed = nneed_new;
+        bc->tk_late += nneed_new - nneed_old;
+        bc->Beff = Bnew;
+        bc->it += 1;
+        bc->npend = 0;
+    }
+}
+
+// ---- commit -----------------------------------------------------------------------------------------
+// one warp per key: the last version before m_commit becomes the stored state of the MC
+__global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 1) return;
+    const Num nm = e.nm;
+    const int D = nm.D, DP = nm.DP;
+    const int lane = threadIdx.x & 31;
+    const int kidx = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
+    const int Mp = bc->Mp, Mo0 = bc->Mo0, KNEW = Mp + Mo0, m = bc->m_commit;
+    if (kidx < Mp) {
+        const int j = kidx, tm = m >> 5;
+        const int i = tm * 32 + lane;
+        const bool accd = i < m && e.ws.pcand[i] == j && !e.ws.prej[i];
+        const unsigned mk = __ballot_sync(0xffffffffu, accd);
+        const int v = mk ? (tm * 32 + 31 - __clz(mk)) : e.ws.tbase[(size_t)tm * e.ws.mp_stride + j];
+        if (v < 0) return;
+        for (int d = lane; d < D; d += 32) {
+            e.P.cf1[(size_t)j * D + d] = e.ws.vcf1[(size_t)v * D + d];
+            e.P.cf2[(size_t)j * D + d] = e.ws.vcf2[(size_t)v * D + d];
+            e.P.cen[(size_t)j * D + d] = e.ws.vcen[(size_t)v * D + d];
+        }
+        if (lane == 0) {
+            e.P.w[j] = e.ws.vw[v];
+            e.P.mask[j] = e.ws.vmask[v];
+        }
+        return;
+    }
+    const int h = kidx - Mp;
+    if (h >= bc->nh) return;
+    const int32_t *mem = e.ws.omem + e.ws.hoff[h];
+    if (mem[0] >= m) return;
+    const int v = latest_before(mem, e.ws.hoff[h + 1] - e.ws.hoff[h], m);
+    const int key = e.ws.hkey[h];
+    const bool created = key >= KNEW;
+    if (created && mem[0] != key - KNEW) return; // phantom key (cannot reach into the exact prefix)
+    const int rank = created ? e.ws.newrank[key - KNEW] : 0;
+    const int slot = created ? Mo0 + rank : key - Mp;
+    const uint64_t mask = e.ws.vmask[v];
+    for (int d = lane; d < DP; d += 32) {
+        double2 cv;
+        cv.x = 0.0;
+        cv.y = 1.0;
+        if (d < D) {
+            const double c = e.ws.vcen[(size_t)v * D + d];
+            e.O.cf1[(size_t)slot * D + d] = e.ws.vcf1[(size_t)v * D + d];
+            e.O.cf2[(size_t)slot * D + d] = e.ws.vcf2[(size_t)v * D + d];
+            e.O.cen[(size_t)slot * D + d] = c;
+            cv.x = c;
+            cv.y = ((mask >> d) & 1ull) ? nm.wsel : 1.0;
+        }
+        e.O.cw[(size_t)slot * DP + d] = cv;
+    }
+    if (lane == 0) {
+        e.O.w[slot] = e.ws.vw[v];
+        e.O.mask[slot] = mask;
+        if (created) {
+            const int64_t id = e.ctl->outlier_last_id + rank;
+            e.O.id[slot] = id;
+            e.O.uid[slot] = (int32_t)id;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BS_THREADS) k_bs_commit_cells(Eng e) {
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 1) return;
+    const int i = blockIdx.x * BS_THREADS + threadIdx.x;
+    const int m = bc->m_commit;
+    if (i >= m) return;
+    const int Mp = bc->Mp, KNEW = bc->Mp + bc->Mo0;
+    const int key = e.ws.eff[i];
+    int32_t uid;
+    uint8_t st;
+    if (key < Mp) {
+        uid = e.P.uid[key];
+        st = 0;
+    } else if (key < KNEW) {
+        uid = e.O.uid[key - Mp];
+        st = 1;
+    } else {
+        const int c = key - KNEW;
+        uid = (int32_t)(e.ctl->outlier_last_id + e.ws.newrank[c]);
+        st = c == i ? 3 : 1;
+    }
+    if (bc->upgrade && i == m - 1) st = 2;
+    e.assign[bc->pos + i] = uid;
+    if (e.stage) e.stage[bc->pos + i] = st;
+}
+
+// upgrade (hddstream.py:397-430), list lengths, id counters, next block length
+__global__ void __launch_bounds__(BS_THREADS) k_bs_finish(Eng e) {
+    __shared__ int s_ncreated;
+    BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 1) return;
+    Ctl *ctl = e.ctl;
+    const Num nm = e.nm;
+    const int D = nm.D, DP = nm.DP, tid = threadIdx.x;
+    const int Mp = bc->Mp, Mo0 = bc->Mo0, KNEW = Mp + Mo0, m = bc->m_commit;
+    const int nh = bc->nh, hnew0 = bc->hnew0;
+    if (tid == 0) { // creations committed = created-in-block keys whose creator is < m (keys ascend with the creator)
+        int lo = hnew0, hi = nh;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (e.ws.hkey[mid] - KNEW < m) lo = mid + 1;
+            else hi = mid;
+        }
+        s_ncreated = e.ws.hrank[lo - hnew0];
+    }
+    for (int h = tid; h < nh; h += BS_THREADS) { // forget the modified-flags of this block
+        const int key = e.ws.hkey[h];
+        if (key < KNEW) e.ws.firstmember[key - Mp] = INT_MAX;
+    }
+    __syncthreads();
+    const int ncreated = s_ncreated;
+    int slot = -1;
+    if (bc->upgrade) {
+        const int key = e.ws.eff[m - 1];
+        slot = key < KNEW ? key - Mp : Mo0 + e.ws.newrank[key - KNEW];
+        const int pj = Mp;
+        for (int d = tid; d < D; d += BS_THREADS) {
+            e.P.cf1[(size_t)pj * D + d] = e.O.cf1[(size_t)slot * D + d];
+            e.P.cf2[(size_t)pj * D + d] = e.O.cf2[(size_t)slot * D + d];
+            e.P.cen[(size_t)pj * D + d] = e.O.cen[(size_t)slot * D + d];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (slot >= 0) {
+            const int pj = Mp;
+            e.P.w[pj] = e.O.w[slot];
+            e.P.mask[pj] = e.O.mask[slot];
+            e.P.uid[pj] = e.O.uid[slot];
+            e.P.id[pj] = ctl->pcore_last_id;
+            ctl->pcore_last_id += 1;
+            ctl->n_pcore = pj + 1;
+            e.O.w[slot] = -1.0; // tombstone (a live weight is never negative); NaN keeps it out of kernel 1
+            e.O.cw[(size_t)slot * DP].x = __longlong_as_double(0x7ff8000000000000LL);
+            ctl->n_outlier_alive -= 1;
+            ctl->upgrades += 1;
+        }
+        ctl->n_outlier = Mo0 + ncreated;
+        ctl->n_outlier_alive += ncreated;
+        ctl->outlier_last_id += ncreated;
+        ctl->created += ncreated;
+        bc->pos += m;
+        bc->blocks += 1;
+        if (m == bc->Bcur) bc->next_B = min(bc->next_B * 2, bc->Bmax);
+        else if (!bc->upgrade) bc->next_B = max(bc->next_B / 2, bc->Bmin);
+        bc->nh = 0;
+        bc->active = 0;
+        if (bc->pos >= bc->N) bc->done = 1;
+    }
+}
+
+} // namespace ccb

@@ -61,13 +61,23 @@ template <int DP, int K, bool DIV>
 __global__ void __launch_bounds__(NEAREST_THREADS)
     k_nearest(const double *__restrict__ X, const int32_t *__restrict__ rows, const int32_t *__restrict__ nrows_dev,
               int64_t row_off, int64_t nrows, int64_t ld, int D, const double2 *__restrict__ cw, int M, int slab_mcs,
-              double *__restrict__ out_dist, int32_t *__restrict__ out_idx) {
+              double *__restrict__ out_dist, int32_t *__restrict__ out_idx, const int32_t *__restrict__ range_dev,
+              const int32_t *__restrict__ M_dev) {
     using Cfg = NearestCfg<DP>;
     constexpr int PPT = Cfg::PPT, TM = Cfg::TM, JU = NEAREST_JU;
     __shared__ __align__(128) double2 tile[2][TM * DP];
     __shared__ __align__(8) uint64_t bar[2];
 
     if (nrows_dev) nrows = (int64_t)(*nrows_dev) - row_off;
+    // device-side work description (block-speculative engine): rows[range_dev[0] .. range_dev[1]) against the
+    // first *M_dev microclusters, results written at the absolute list positions
+    int64_t out_off = 0;
+    if (range_dev) {
+        row_off = range_dev[0];
+        nrows = (int64_t)range_dev[1] - row_off;
+        out_off = row_off;
+    }
+    if (M_dev) M = min(M, *M_dev);
     const int64_t cell0 = (int64_t)blockIdx.x * Cfg::CELLS;
     if (cell0 >= nrows) return;
     const int nslab = gridDim.y;
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS)
 #pragma unroll
     for (int u = 0; u < PPT; ++u) {
         if (cell[u] < nrows) {
-            const size_t o = ((size_t)cell[u] * nslab + blockIdx.y) * K;
+            const size_t o = ((size_t)(out_off + cell[u]) * nslab + blockIdx.y) * K;
 #pragma unroll
             for (int s = 0; s < K; ++s) {
                 out_dist[o + s] = bd[u][s];
@@ -183,10 +193,17 @@ __global__ void __launch_bounds__(NEAREST_THREADS)
 template <int K>
 __global__ void k_topk_merge(const double *__restrict__ in_dist, const int32_t *__restrict__ in_idx,
                              const int32_t *__restrict__ nrows_dev, int64_t row_off, int64_t nrows, int nslab,
-                             double *__restrict__ out_dist, int32_t *__restrict__ out_idx) {
+                             double *__restrict__ out_dist, int32_t *__restrict__ out_idx,
+                             const int32_t *__restrict__ range_dev) {
     if (nrows_dev) nrows = (int64_t)(*nrows_dev) - row_off;
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nrows) return;
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (range_dev) {
+        nrows = (int64_t)range_dev[1] - range_dev[0];
+        if (c >= nrows) return;
+        c += range_dev[0];
+    } else if (c >= nrows) {
+        return;
+    }
     double bd[K];
     int bi[K];
 #pragma unroll

@@ -65,8 +65,12 @@ typedef struct {
     double delta2;       /* delta ** 2                            hddstream.py:49 */
     double beta;         /*                                       hddstream.py:50 */
     double k;            /*                                       hddstream.py:51 */
-    int32_t wave;        /* ordered-commit micro-batch width 1..32; 0 = default (32); 1 = fully serial */
-    int32_t chunk;       /* max points per ordered-commit launch; 0 = default */
+    int32_t wave;        /* 0 = block-speculative versioned commit (default engine, csrc/engine.cuh);
+                            1..32 = single-CTA wave engine of that micro-batch width (1 = fully serial) */
+    int32_t chunk;       /* wave engine: max cells per ordered-commit launch; block-speculative engine: max cells
+                            per block; 0 = default */
+    int32_t bsv_bmin;    /* block-speculative engine: smallest block length; 0 = default (1024) */
+    int32_t bsv_iters;   /* block-speculative engine: refinement rounds enqueued per block; 0 = default (3) */
 } ccb_params;
 
 /* Counters since ccb_create (monotonic); all int64. */
@@ -83,6 +87,15 @@ typedef struct {
     int64_t upgrades, created, downgraded, deleted;
     int64_t kernel_launches; /* every kernel this library launched */
     int64_t borderline_pairs; /* offline pairs resolved on the host through dnrm2 */
+    /* block-speculative engine */
+    int64_t bsv_blocks;        /* blocks committed */
+    int64_t bsv_rounds;        /* speculate / verify rounds executed */
+    int64_t bsv_mismatches;    /* rounds whose verification found a cell decided differently than speculated */
+    int64_t bsv_cuts_unknown;  /* blocks cut because every listed snapshot candidate of a cell was stale */
+    int64_t bsv_cuts_rounds;   /* blocks cut because the enqueued rounds ran out */
+    int64_t bsv_cuts_capacity; /* blocks cut because the outlier-stage list of the block was full */
+    int64_t bsv_late_topk;     /* cells whose top-K list had to be fetched in a refinement round */
+    int64_t bsv_outlier_stage_cells; /* cells given a top-K list up front (not SAFE) */
 } ccb_stats;
 
 int ccb_create(const ccb_params *params, ccb_handle **out);
@@ -99,13 +112,14 @@ int ccb_reset(ccb_handle *h);
 
 /* Optional GPU timing per kernel category, taken with CUDA events on the handle's stream (this is
  * what bench.py reads for the live roofline).  ms / launches: arrays of CCB_NCAT. */
-#define CCB_CAT_PCORE 0   /* kernel 2a  k_pcore_stage */
-#define CCB_CAT_NEAREST 1 /* kernel 1   k_nearest (+ k_topk_merge) on the rejected cells */
-#define CCB_CAT_RESOLVE 2 /* kernel 2b  k_resolve */
+#define CCB_CAT_PCORE 0   /* kernel 2   ordered chains (k_bs_chain; wave engine: k_pcore_stage) */
+#define CCB_CAT_NEAREST 1 /* kernel 1   k_nearest (+ k_topk_merge) on the cells that may reach the outlier stage */
+#define CCB_CAT_RESOLVE 2 /* kernel 2   exact verification (k_bs_verify_p/o; wave engine: k_resolve) */
 #define CCB_CAT_MAINT 3   /* kernel 3   k_maint_plan + k_maint_gather */
 #define CCB_CAT_OFFLINE 4 /* kernel 4   offline pipeline (device part) */
 #define CCB_CAT_MISC 5    /* small helpers */
 #define CCB_CAT_COPY 6    /* host<->device copies of ccb_ingest */
+#define CCB_CAT_SPEC 7    /* kernel 2   speculation from the snapshot (k_bs_spec, k_bs_need, k_bs_spec_o) */
 #define CCB_NCAT 8
 int ccb_enable_timing(ccb_handle *h, int32_t on);
 int ccb_get_timing(ccb_handle *h, double ms[CCB_NCAT], int64_t launches[CCB_NCAT], int32_t reset);

@@ -50,6 +50,20 @@ def test_stress_matches_reference(name, wave):
     run_against_golden(z, stress_inputs(z), f"{name}/wave{wave}", wave=wave)
 
 
+# block-speculative engine (wave == 0): block length cap / smallest block / refinement rounds never change results
+BSV_KNOBS = [dict(), dict(chunk=96, bsv_bmin=32, bsv_iters=1), dict(chunk=2048, bsv_bmin=64, bsv_iters=2),
+             dict(chunk=512, bsv_bmin=512, bsv_iters=6)]
+
+
+@pytest.mark.parametrize("knobs", BSV_KNOBS, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()) or "default")
+@pytest.mark.parametrize("name", STRESS_NAMES)
+def test_stress_matches_reference_bsv(name, knobs):
+    z = load(f"stress_{name}.npz")
+    h = run_against_golden(z, stress_inputs(z), f"{name}/bsv{knobs}", **knobs)
+    st = h.stats()
+    assert st["bsv_blocks"] > 0 and st["kernel_launches"] > 0
+
+
 @pytest.mark.parametrize("chunk", [0, 97])
 def test_c1_matches_reference(chunk):
     z = load("c1.npz")

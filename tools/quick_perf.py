@@ -17,7 +17,9 @@ N = int(N * scale)
 t0 = time.time()
 Xs = gen(N, D, T, Cn, seed)
 print(f"gen {time.time()-t0:.1f}s  N={N} D={D} T={T}")
-h = HDDStream(config_params(name), logging.getLogger("q"), wave=wave)
+chunk = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+iters = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+h = HDDStream(config_params(name), logging.getLogger("q"), wave=wave, chunk=chunk, bsv_iters=iters)
 prev = None
 h._ensure_handle(D)
 h.enable_timing()
@@ -34,9 +36,10 @@ for t, X in enumerate(Xs):
     print(f"t={t} online {t1-t0:.3f}s offline {t2-t1:.3f}s  {N/(t2-t0):.0f} cells/s  pcore={c[0]} outlier={c[1]} "
           f"clusters={len(h.final_clusters)}")
     print("   ", {k: v for k, v in d.items() if v})
-    import ctypes as C
-    from chronoclust_b200 import _lib
-    pc = (C.c_int64 * 8)()
-    _lib.lib().ccb_debug_phase_cycles(h._h, C.byref(pc))
-    print("    phase cycles/wave (cumulative):", [round(v / max(st["waves"], 1)) for v in pc])
+    if wave:
+        import ctypes as C
+        from chronoclust_b200 import _lib
+        pc = (C.c_int64 * 8)()
+        _lib.lib().ccb_debug_phase_cycles(h._h, C.byref(pc))
+        print("    phase cycles/wave (cumulative):", [round(v / max(st["waves"], 1)) for v in pc])
     print("    gpu ms:", {k: (round(v[0], 2), v[1]) for k, v in h.timing(reset=True).items() if v[1]})
