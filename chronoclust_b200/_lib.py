@@ -28,7 +28,7 @@ class Stats(C.Structure):
         "points", "chunks", "waves", "wave_rollbacks", "rejects", "resolver_calls", "resolver_cuts", "nearest_pairs",
         "pcore_pairs", "upgrades", "created", "downgraded", "deleted", "kernel_launches", "borderline_pairs",
         "bsv_blocks", "bsv_rounds", "bsv_mismatches", "bsv_cuts_unknown", "bsv_cuts_rounds", "bsv_cuts_capacity",
-        "bsv_late_topk", "bsv_outlier_stage_cells")]
+        "bsv_late_topk", "bsv_outlier_stage_cells", "bsv_replayed_cells")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -45,7 +45,7 @@ SYMBOLS = {
     "ccb_debug_phase_cycles": (C.c_int, [vp, C.POINTER(i64 * 8)]),
     "ccb_fp64_peak": (C.c_int, [i32, vp, i32, i32, i32, vp, C.POINTER(f64)]),
     "ccb_enable_timing": (C.c_int, [vp, i32]),
-    "ccb_get_timing": (C.c_int, [vp, C.POINTER(f64 * 8), C.POINTER(i64 * 8), i32]),
+    "ccb_get_timing": (C.c_int, [vp, C.POINTER(f64 * 16), C.POINTER(i64 * 16), i32]),
     "ccb_set_dnrm2": (C.c_int, [vp, vp]),
     "ccb_begin_timepoint": (C.c_int, [vp, f64, f64, i64, i32, f64]),
     "ccb_ingest": (C.c_int, [vp, vp, i64, i64, vp, vp]),
@@ -67,7 +67,8 @@ SYMBOLS = {
 }
 
 
-CATEGORIES = ["chains", "nearest", "verify", "maintenance", "offline", "misc", "copy", "speculate"]
+CATEGORIES = ["chain_p", "nearest", "verify", "maintenance", "offline", "misc", "copy", "speculate", "lists", "chain_o",
+              "olist", "derive", "decide", "commit", "reserved14", "reserved15"]
 
 
 class CCBError(RuntimeError):

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "api.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "common.cuh", "nearest.cuh", "online.cuh", "offline.cuh")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "common.cuh", "nearest.cuh", "online.cuh", "offline.cuh", "engine.cuh")]
 DEPS.append(os.path.join(os.path.dirname(HERE), "include", "chronoclust_b200.h"))
 SO = os.path.join(HERE, "libchronoclust_b200.so")
 
@@ -14,6 +14,7 @@ NVCC_FLAGS = [
     "-fmad=false",            # parity: the reference never contracts mul+add
     "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if os.environ.get("CCB_PTXAS_V") else "-O3",
+    "--split-compile", "0",   # optimise the kernels of this one translation unit on all host cores
 ]
 
 

@@ -87,7 +87,7 @@ struct ccb_handle {
     BsCtl *d_bc = nullptr, *h_bc = nullptr;
     BsWs ws{};
     std::vector<void *> ws_allocs;
-    void *ws_tiles[2] = {nullptr, nullptr};
+    void *ws_tiles[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int32_t *ws_first = nullptr;
     int ws_first_cap = 0;
     double *d_bs_tk_dist_slab = nullptr;
@@ -300,10 +300,10 @@ int launch_nearest(ccb_handle *h, cudaStream_t s, int DP, int div_mode, const do
         int32_t *oi = nslab == 1 ? out_idx : slab_idx;
         if (div_mode)
             k_nearest<kDP, K, true><<<grid, NEAREST_THREADS, 0, s>>>(X, rows, nrows_dev, row_off, nrows_max, ld, D, cw,
-                                                                     M, slab_mcs, od, oi, range_dev, M_dev);
+                                                                     M, slab_mcs, od, oi, range_dev, M_dev, 0);
         else
             k_nearest<kDP, K, false><<<grid, NEAREST_THREADS, 0, s>>>(X, rows, nrows_dev, row_off, nrows_max, ld, D, cw,
-                                                                      M, slab_mcs, od, oi, range_dev, M_dev);
+                                                                      M, slab_mcs, od, oi, range_dev, M_dev, 0);
         launched = 1;
         if (nslab > 1) {
             k_topk_merge<K><<<(unsigned)((nrows_max + 255) / 256), 256, 0, s>>>(slab_dist, slab_idx, nrows_dev, row_off,
@@ -311,6 +311,33 @@ int launch_nearest(ccb_handle *h, cudaStream_t s, int DP, int div_mode, const do
             launched = 2;
         }
         if (nslab_out) *nslab_out = nslab;
+    })
+    if (!launched) return fail(h, CCB_ELIMIT, "unsupported padded dimensionality %d", DP);
+    if (h) h->st.kernel_launches += launched;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, CCB_ECUDA, "k_nearest launch: %s", cudaGetErrorString(e));
+    return CCB_OK;
+}
+
+// kernel 1 with the device-side work split (block-speculative engine): rows[range_dev[0] .. range_dev[1]) of the
+// row list against the first min(M_bound, *M_dev) entries of cw; slab lists at [list position][max_slabs][K]
+constexpr int NEAREST_DYN_GRID = 148 * 4;
+template <int K>
+int launch_nearest_dyn(ccb_handle *h, cudaStream_t s, int DP, int div_mode, const double *X, const int32_t *rows, int64_t ld,
+                       int D, const double2 *cw, int M_bound, double *slab_dist, int32_t *slab_idx, double *out_dist,
+                       int32_t *out_idx, int max_slabs, int rows_max, const int32_t *range_dev, const int32_t *M_dev) {
+    int launched = 0;
+    CCB_DISPATCH_DP(DP, {
+        using Cfg = NearestCfg<kDP>;
+        if (div_mode)
+            k_nearest<kDP, K, true><<<NEAREST_DYN_GRID, NEAREST_THREADS, 0, s>>>(X, rows, nullptr, 0, 0, ld, D, cw, M_bound, 0,
+                                                                                 slab_dist, slab_idx, range_dev, M_dev, max_slabs);
+        else
+            k_nearest<kDP, K, false><<<NEAREST_DYN_GRID, NEAREST_THREADS, 0, s>>>(X, rows, nullptr, 0, 0, ld, D, cw, M_bound, 0,
+                                                                                  slab_dist, slab_idx, range_dev, M_dev, max_slabs);
+        k_topk_merge_dyn<K><<<std::min(NEAREST_DYN_GRID, (rows_max + 3) / 4), 128, 0, s>>>(
+            slab_dist, slab_idx, range_dev, M_dev, M_bound, NEAREST_DYN_GRID, max_slabs, Cfg::TM, Cfg::CELLS, out_dist, out_idx);
+        launched = 2;
     })
     if (!launched) return fail(h, CCB_ELIMIT, "unsupported padded dimensionality %d", DP);
     if (h) h->st.kernel_launches += launched;
@@ -472,7 +499,7 @@ int ingest_core(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t 
 }
 
 // ---- block-speculative engine: workspace and block enqueue ------------------------------------------
-constexpr int BS_MAX_SLABS = 32;
+constexpr int BS_MAX_SLABS = 128;
 
 template <typename T>
 int ws_alloc(ccb_handle *h, T *&p, size_t n) {
@@ -487,6 +514,10 @@ int ensure_bs_ws(ccb_handle *h) {
     int rc;
     const int B = h->bs_bmax, D = h->D;
     if (!h->d_bc) {
+        CCB_DISPATCH_DP(h->DP, {
+            CK(h, cudaFuncSetAttribute(k_bs_chain_p<kDP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)ChainPCfg<kDP>::SMEM));
+        })
         CK(h, cudaMalloc(&h->d_bc, sizeof(BsCtl)));
         CK(h, cudaMemset(h->d_bc, 0, sizeof(BsCtl)));
         CK(h, cudaMallocHost(&h->h_bc, sizeof(BsCtl)));
@@ -495,9 +526,11 @@ int ensure_bs_ws(ccb_handle *h) {
         w.bmax = B;
 #define WSA(field, n) if ((rc = ws_alloc(h, w.field, (n)))) return rc
         WSA(pcand, B); WSA(ospec, B); WSA(tkpos, B); WSA(dec, B); WSA(eff, B); WSA(newrank, B); WSA(pend, B);
-        WSA(plist, B); WSA(pflag, B); WSA(prej, B); WSA(upf, B); WSA(want, B);
-        WSA(vcf1, (size_t)B * D + 2); WSA(vcf2, (size_t)B * D + 2); WSA(vcen, (size_t)B * D + 2);
-        WSA(vw, B); WSA(vr2, B); WSA(vmask, B);
+        WSA(pflag, B); WSA(prej, B); WSA(upf, B); WSA(want, B);
+        w.dp = h->DP;
+        w.lsp = 2 * h->DP + 2;
+        WSA(ver, (size_t)B * w.lsp); WSA(vcen, (size_t)B * D + 2);
+        WSA(vr2, B); WSA(vmask, B);
         WSA(nrows, BS_RMAX); WSA(ncell, BS_RMAX);
         WSA(tk_dist, (size_t)BS_RMAX * BS_TOPK); WSA(tk_idx, (size_t)BS_RMAX * BS_TOPK);
         WSA(hkey, BS_RMAX + 1); WSA(hoff, BS_RMAX + 2); WSA(omem, BS_RMAX + 1); WSA(hrank, BS_RMAX + 2);
@@ -508,17 +541,25 @@ int ensure_bs_ws(ccb_handle *h) {
     // per-(tile, pcore key) tables follow the pcore capacity; the modified-flags follow the outlier capacity
     const int stride = h->P[h->pcur].cap;
     if (stride != h->ws.mp_stride) {
-        cudaFree(h->ws_tiles[0]);
-        cudaFree(h->ws_tiles[1]);
-        h->ws_tiles[0] = h->ws_tiles[1] = nullptr;
+        for (void *&q : h->ws_tiles) {
+            cudaFree(q);
+            q = nullptr;
+        }
         const size_t n = ((size_t)B / 32 + 2) * stride;
+        const size_t npl = (size_t)B + 4 * (size_t)stride + 8; // every key's segment is padded to a multiple of 4
+        const size_t ds = (size_t)h->ws.lsp;
         CK(h, cudaMalloc(&h->ws_tiles[0], n * 4));
         CK(h, cudaMalloc(&h->ws_tiles[1], n * 4));
+        CK(h, cudaMalloc(&h->ws_tiles[2], ((size_t)stride + 2) * 4));
+        CK(h, cudaMalloc(&h->ws_tiles[3], ((size_t)stride + 2) * 4));
+        CK(h, cudaMalloc(&h->ws_tiles[4], npl * 4));
+        CK(h, cudaMalloc(&h->ws_tiles[5], npl * ds * 8));
         h->ws.tilecnt = (int32_t *)h->ws_tiles[0];
         h->ws.tbase = (int32_t *)h->ws_tiles[1];
-        int32_t *poff = nullptr;
-        if ((rc = ws_alloc(h, poff, (size_t)stride + 2))) return rc;
-        h->ws.poff = poff;
+        h->ws.poff = (int32_t *)h->ws_tiles[2];
+        h->ws.pcnt = (int32_t *)h->ws_tiles[3];
+        h->ws.plist = (int32_t *)h->ws_tiles[4];
+        h->ws.xg = (double *)h->ws_tiles[5];
         h->ws.mp_stride = stride;
     }
     const int ocap = h->O[h->ocur].cap;
@@ -551,9 +592,9 @@ int enqueue_block(ccb_handle *h, const Eng &e, int mp_bound, int mo_bound) {
     int rc, launches = 0;
     auto nearest = [&]() -> int {
         Timed tm(h, CCB_CAT_NEAREST);
-        return launch_nearest<BS_TOPK>(h, s, h->DP, h->div_mode, e.X, e.ws.nrows, nullptr, 0, BS_RMAX, e.ld, h->D, e.O.cw,
-                                       mo_bound, h->d_bs_tk_dist_slab, h->d_bs_tk_idx_slab, e.ws.tk_dist, e.ws.tk_idx,
-                                       BS_MAX_SLABS, nullptr, &e.bc->tk_lo, &e.bc->Mo0);
+        return launch_nearest_dyn<BS_TOPK>(h, s, h->DP, h->div_mode, e.X, e.ws.nrows, e.ld, h->D, e.O.cw, mo_bound,
+                                           h->d_bs_tk_dist_slab, h->d_bs_tk_idx_slab, e.ws.tk_dist, e.ws.tk_idx, BS_MAX_SLABS,
+                                           BS_RMAX, &e.bc->tk_lo, &e.bc->Mo0);
     };
     {
         Timed tm(h, CCB_CAT_SPEC);
@@ -571,25 +612,25 @@ int enqueue_block(ccb_handle *h, const Eng &e, int mp_bound, int mo_bound) {
     for (int it = 0; it < h->bs_iters; ++it) {
         if (it > 0 && (rc = nearest())) return rc;
         {
-            Timed tm(h, CCB_CAT_MISC);
+            Timed tm(h, CCB_CAT_LISTS);
             k_bs_tilecnt<<<g_tiles, BS_THREADS, 0, s>>>(e);
             k_bs_pscan<<<1, BS_CTA1, 0, s>>>(e);
             k_bs_pscatter<<<g_tiles, BS_THREADS, 0, s>>>(e);
         }
         {
             Timed tm(h, CCB_CAT_PCORE);
-            CCB_DISPATCH_DP(h->DP, { k_bs_chain<kDP, 0><<<std::max(mp_bound, 1), BS_THREADS, 0, s>>>(e); })
+            CCB_DISPATCH_DP(h->DP, { k_bs_chain_p<kDP><<<std::max(mp_bound, 1), BS_CHAINP_THREADS, ChainPCfg<kDP>::SMEM, s>>>(e); })
         }
         {
-            Timed tm(h, CCB_CAT_MISC);
+            Timed tm(h, CCB_CAT_OLIST);
             k_bs_olist<<<1, BS_CTA1, 0, s>>>(e);
         }
         {
-            Timed tm(h, CCB_CAT_PCORE);
-            CCB_DISPATCH_DP(h->DP, { k_bs_chain<kDP, 1><<<BS_RMAX, BS_THREADS, 0, s>>>(e); })
+            Timed tm(h, CCB_CAT_CHAIN_O);
+            CCB_DISPATCH_DP(h->DP, { k_bs_chain_o<kDP><<<BS_RMAX, BS_THREADS, 0, s>>>(e); })
         }
         {
-            Timed tm(h, CCB_CAT_MISC);
+            Timed tm(h, CCB_CAT_DERIVE);
             k_bs_derive<<<g_cells, BS_THREADS, 0, s>>>(e);
         }
         {
@@ -600,13 +641,13 @@ int enqueue_block(ccb_handle *h, const Eng &e, int mp_bound, int mo_bound) {
             })
         }
         {
-            Timed tm(h, CCB_CAT_MISC);
+            Timed tm(h, CCB_CAT_DECIDE);
             k_bs_decide<<<1, BS_CTA1, 0, s>>>(e);
         }
         launches += 10;
     }
     {
-        Timed tm(h, CCB_CAT_MISC);
+        Timed tm(h, CCB_CAT_COMMIT);
         k_bs_commit_rows<<<(mp_bound + BS_RMAX + 3) / 4, BS_THREADS, 0, s>>>(e);
         k_bs_commit_cells<<<g_cells, BS_THREADS, 0, s>>>(e);
         k_bs_finish<<<1, BS_THREADS, 0, s>>>(e);
@@ -817,8 +858,7 @@ void ccb_destroy(ccb_handle *h) {
     cudaFree(h->d_bc);
     if (h->h_bc) cudaFreeHost(h->h_bc);
     for (void *q : h->ws_allocs) cudaFree(q);
-    cudaFree(h->ws_tiles[0]);
-    cudaFree(h->ws_tiles[1]);
+    for (void *q : h->ws_tiles) cudaFree(q);
     cudaFree(h->ws_first);
     for (auto &e : h->ev_pending) {
         cudaEventDestroy(e.a);
@@ -851,6 +891,8 @@ int ccb_get_stats(const ccb_handle *h, ccb_stats *out) {
         out->bsv_cuts_capacity = bb.cuts_cap + b.cuts_cap;
         out->bsv_late_topk = bb.tk_late + b.tk_late;
         out->bsv_outlier_stage_cells = bb.rejects + b.rejects;
+        out->bsv_replayed_cells = bb.replayed + b.replayed;
+        out->nearest_pairs += bb.pairs + b.pairs;
     }
     return CCB_OK;
 }
@@ -888,6 +930,7 @@ int ccb_reset(ccb_handle *h) {
         BsCtl &bb = h->bc_base;
         bb.blocks += b.blocks, bb.iters += b.iters, bb.mismatches += b.mismatches, bb.cuts_unknown += b.cuts_unknown;
         bb.cuts_iter += b.cuts_iter, bb.cuts_cap += b.cuts_cap, bb.tk_late += b.tk_late, bb.rejects += b.rejects;
+        bb.replayed += b.replayed, bb.pairs += b.pairs;
         const int32_t keep_B = b.next_B;
         memset(h->h_bc, 0, sizeof(BsCtl));
         h->h_bc->next_B = keep_B;

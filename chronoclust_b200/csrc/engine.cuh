@@ -58,22 +58,28 @@ struct BsCtl {
     int32_t m_commit, upgrade;
     int32_t need_grow, done;
     int32_t pad0;
-    int64_t blocks, iters, mismatches, cuts_unknown, cuts_iter, cuts_cap, tk_late, rejects, contested;
+    int64_t blocks, iters, mismatches, cuts_unknown, cuts_iter, cuts_cap, tk_late, rejects, contested, replayed, pairs;
 };
 
 struct BsWs {
     int32_t *pcand, *ospec, *tkpos, *dec, *eff, *newrank, *pend, *plist;
     uint8_t *pflag, *prej, *upf, *want;
-    double *vcf1, *vcf2, *vcen, *vw, *vr2;
+    double *ver;  // [bmax][lsp] VERSION records: CF1 at [0, D), CF2 at [dp, dp + D), W at [2 dp]; lsp = 2 dp + 2
+    double *vcen, *vr2;
     uint64_t *vmask;
     int32_t *tilecnt, *tbase, *poff; // [ntiles + 1][mp_stride], [ntiles + 1][mp_stride], [mp_stride + 1]
+    int32_t *pcnt;                   // [mp_stride + 1] candidates of every pcore key (poff is padded to multiples of 4)
+    double *xg;                      // [bmax + 4 * mp_stride][lsp] ADDEND records in plist order: x, x*x, 1.0 (layout of ver)
     int32_t *nrows, *ncell;          // [BS_RMAX] absolute row / block-relative cell of the need list
     double *tk_dist;
     int32_t *tk_idx; // [BS_RMAX][BS_TOPK]
     int32_t *hkey, *hoff, *omem, *hrank; // hrank[q]: real creations before key hnew0 + q
     int32_t *firstmember; // [O.cap], INT_MAX = unmodified in this block
-    int32_t mp_stride, bmax;
+    int32_t mp_stride, bmax, dp, lsp;
 };
+__device__ __forceinline__ double *ver_cf1(const BsWs &w, int i) { return w.ver + (size_t)i * w.lsp; }
+__device__ __forceinline__ double *ver_cf2(const BsWs &w, int i) { return w.ver + (size_t)i * w.lsp + w.dp; }
+__device__ __forceinline__ double &ver_w(const BsWs &w, int i) { return w.ver[(size_t)i * w.lsp + 2 * w.dp]; }
 
 struct Eng {
     const double *X;
@@ -187,6 +193,7 @@ __global__ void k_bs_init(BsCtl *bc, int64_t N, int32_t itmax, int32_t bmin, int
 __global__ void k_bs_begin(Eng e) {
     BsCtl *bc = e.bc;
     bc->active = 0;
+    bc->tk_lo = bc->tk_hi = 0; // an idle block must not leave kernel 1 any work
     if (bc->done || bc->need_grow) return;
     if (bc->pos >= bc->N) {
         bc->done = 1;
@@ -318,6 +325,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
         bc->tk_lo = 0;
         bc->tk_hi = bc->nneed;
         bc->rejects += bc->nneed;
+        bc->pairs += (int64_t)bc->nneed * bc->Mo0;
     }
 }
 
@@ -399,22 +407,24 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
             e.ws.tilecnt[(size_t)t * stride + j] = run;
             run += c;
         }
-        if (lane == 31) e.ws.poff[j + 1] = inc; // total of key j, turned into an offset below
+        if (lane == 31) e.ws.pcnt[j] = inc; // total of key j
     }
     __syncthreads();
-    // exclusive scan of the totals over the keys (Mp is small; chunks of 1024)
+    // exclusive scan of the totals, each rounded up to a multiple of 4 entries so that every key's segment of
+    // plist / xg starts 16-byte aligned (bulk-copy requirement of the chain kernel); Mp is small: chunks of 1024
     int carry = 0;
     for (int j0 = 0; j0 < Mp; j0 += BS_CTA1) {
         const int j = j0 + threadIdx.x;
-        const int v = j < Mp ? e.ws.poff[j + 1] : 0;
+        const int v = j < Mp ? ((e.ws.pcnt[j] + 3) & ~3) : 0;
         int total;
         const int ex = block_exclusive_scan_1024(v, s_warp, total);
-        if (j < Mp) e.ws.poff[j + 1] = carry + ex + v;
+        if (j < Mp) e.ws.poff[j] = carry + ex;
         carry += total;
     }
-    if (threadIdx.x == 0) e.ws.poff[0] = 0;
+    if (threadIdx.x == 0) e.ws.poff[Mp] = carry;
 }
 
+// plist[pos] = cell | CONTESTED << 31 and xg[pos] = the cell's ADDEND record (x, x*x, 1.0), pos in (key, cell) order
 __global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
@@ -425,28 +435,54 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
     const int i = t * 32 + lane;
     const int c = i < bc->Beff ? e.ws.pcand[i] : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, c);
+    int pos = -1;
     if (c >= 0) {
         const int rank = __popc(peers & lanemask_lt());
-        e.ws.plist[e.ws.poff[c] + e.ws.tilecnt[(size_t)t * e.ws.mp_stride + c] + rank] = i;
+        pos = e.ws.poff[c] + e.ws.tilecnt[(size_t)t * e.ws.mp_stride + c] + rank;
+        e.ws.plist[pos] = i | (e.ws.pflag[i] ? (int)0x80000000 : 0);
+    }
+    // the warp writes the 32 records together, lane = element of the record (coalesced rows)
+    const int D = e.nm.D, dp = e.ws.dp, lsp = e.ws.lsp;
+    const double *Xt = e.X + (bc->pos + (int64_t)t * 32) * e.ld;
+    for (int q = 0; q < 32; ++q) {
+        const int pq = __shfl_sync(0xffffffffu, pos, q);
+        if (pq < 0) continue;
+        const double *src = Xt + (int64_t)q * e.ld;
+        double *dst = e.ws.xg + (size_t)pq * lsp;
+        for (int el = lane; el < lsp; el += 32) {
+            double v = 0.0;
+            if (el < D) v = src[el];
+            else if (el >= dp && el < dp + D) {
+                const double x = src[el - dp];
+                v = dmul(x, x);
+            } else if (el == 2 * dp) v = 1.0;
+            dst[el] = v;
+        }
     }
 }
 
 // ---- C ----------------------------------------------------------------------------------------------
-// One CTA per key.  All four warps stage the cells of the next batch into shared memory with cp.async
-// (index list first, then the rows); warp 0 replays the current batch in order, lane d owning dimensions d
-// and d + 32.  PHASE 0: pcore keys (CONTESTED members take the exact radius test; accepted members also
-// maintain tbase[tile][key] = latest accepted member before that tile).  PHASE 1: outlier-side keys.
+// The replay of a key's members in input order is the only inherently serial work of the whole engine -- one
+// dependent DADD per cell and dimension -- so both chain kernels are written for latency: cells are taken eight
+// at a time, their coordinates and indices are fetched from shared memory up front, only the CF adds are chained.
+// Lane d of the replaying warp owns dimensions d and d + 32.
+//
+// k_bs_chain_o: OUTLIER-SIDE keys (modified snapshot outlier MCs and MCs created in this block), one CTA per key;
+// members are few and scattered, so warps 1-3 gather the next batch with cp.async (index list first, then the
+// rows) while warp 0 replays the current one.
 template <int DP>
 struct ChainCfg {
     static constexpr int NB = DP <= 16 ? 128 : (DP <= 32 ? 64 : 32);
 };
+constexpr int BS_CHAIN_PRODUCERS = BS_THREADS - 32;
 
-template <int DP, int PHASE>
-__global__ void __launch_bounds__(BS_THREADS) k_bs_chain(Eng e) {
+template <int DP>
+__global__ void __launch_bounds__(BS_THREADS) k_bs_chain_o(Eng e) {
     constexpr int NB = ChainCfg<DP>::NB;
+    constexpr int GS = 8;
+    constexpr int NH = DP > 32 ? 2 : 1;
     __shared__ __align__(16) double xs[2][NB][DP];
     __shared__ int mi[2][NB];
-    __shared__ unsigned char fl[2][NB];
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const Num nm = e.nm;
@@ -458,17 +494,10 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_chain(Eng e) {
     int n;
     const double *s1 = nullptr, *s2 = nullptr;
     double w = 0.0;
-    if (PHASE == 0) {
-        if (key_idx >= Mp) return;
-        mem = e.ws.plist + e.ws.poff[key_idx];
-        n = e.ws.poff[key_idx + 1] - e.ws.poff[key_idx];
-        s1 = e.P.cf1 + (size_t)key_idx * D;
-        s2 = e.P.cf2 + (size_t)key_idx * D;
-        w = e.P.w[key_idx];
-    } else {
-        if (key_idx >= bc->nh) return;
-        mem = e.ws.omem + e.ws.hoff[key_idx];
-        n = e.ws.hoff[key_idx + 1] - e.ws.hoff[key_idx];
+    if (key_idx >= bc->nh) return;
+    mem = e.ws.omem + e.ws.hoff[key_idx];
+    n = e.ws.hoff[key_idx + 1] - e.ws.hoff[key_idx];
+    {
         const int key = e.ws.hkey[key_idx];
         if (key < KNEW) {
             const int o = key - Mp;
@@ -477,99 +506,302 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_chain(Eng e) {
             w = e.O.w[o];
         }
     }
-    const int ntiles = (bc->Beff + 31) >> 5;
+    if (n <= 0) return;
     const double *Xb = e.X + bc->pos * e.ld;
+    const bool vec16 = ((D & 1) == 0) && ((e.ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(e.X) & 15) == 0);
+    const int nb = (n + NB - 1) / NB;
 
-    auto stage_idx = [&](int b) {
+    // ---- producers: batch b -> buffer b & 1
+    auto produce = [&](int b) {
         const int buf = b & 1, cnt = min(NB, n - b * NB);
-        for (int m = tid; m < cnt; m += BS_THREADS) {
+        const int pt = tid - 32;
+        for (int m = pt; m < cnt; m += BS_CHAIN_PRODUCERS) {
             const int i = mem[b * NB + m];
             mi[buf][m] = i;
-            fl[buf][m] = PHASE == 0 ? e.ws.pflag[i] : 0;
         }
-    };
-    auto stage_rows = [&](int b) {
-        const int buf = b & 1, cnt = min(NB, n - b * NB);
-        for (int idx = tid; idx < cnt * D; idx += BS_THREADS) {
-            const int m = idx / D, d = idx - m * D;
-            cp_async8(&xs[buf][m][d], Xb + (int64_t)mi[buf][m] * e.ld + d);
+        asm volatile("bar.sync 1, %0;" ::"n"(BS_CHAIN_PRODUCERS) : "memory");
+        if (vec16) {
+            const int hd = D >> 1;
+            for (int idx = pt; idx < cnt * hd; idx += BS_CHAIN_PRODUCERS) {
+                const int m = idx / hd, d2 = (idx - m * hd) * 2;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&xs[buf][m][d2])),
+                             "l"(Xb + (int64_t)mi[buf][m] * e.ld + d2)
+                             : "memory");
+            }
+        } else {
+            for (int idx = pt; idx < cnt * D; idx += BS_CHAIN_PRODUCERS) {
+                const int m = idx / D, d = idx - m * D;
+                cp_async8(&xs[buf][m][d], Xb + (int64_t)mi[buf][m] * e.ld + d);
+            }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     };
-    const int nb = (n + NB - 1) / NB;
-    LaneMc st;
+
+    if (warp != 0) {
+        produce(0);
+        __syncthreads();
+        for (int b = 0; b < nb; ++b) {
+            if (b + 1 < nb) produce(b + 1);
+            __syncthreads();
+        }
+        return;
+    }
+
+    // ---- consumer (warp 0)
+    double cf1[NH], cf2[NH];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NH; ++h) {
         const int d = lane + 32 * h;
         // idle lanes carry 1.0 so that their (discarded) quotients stay on the fast path of the IEEE division
-        st.cf1[h] = d < D ? (s1 ? s1[d] : 0.0) : 1.0;
-        st.cf2[h] = d < D ? (s2 ? s2[d] : 0.0) : 1.0;
-        st.cen[h] = 0.0;
+        cf1[h] = d < D ? (s1 ? s1[d] : 0.0) : 1.0;
+        cf2[h] = d < D ? (s2 ? s2[d] : 0.0) : 1.0;
     }
-    int pv = -1, nextfill = 0;
-    int32_t *tb = e.ws.tbase + key_idx; // [t * mp_stride]
-    if (nb > 0) {
-        stage_idx(0);
-        __syncthreads();
-        stage_rows(0);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-    }
+    __syncthreads(); // batch 0 staged
     for (int b = 0; b < nb; ++b) {
         const int cur = b & 1;
-        if (b + 1 < nb) stage_idx(b + 1);
-        __syncthreads();
-        if (b + 1 < nb) stage_rows(b + 1);
-        if (warp == 0) {
-            const int cnt = min(NB, n - b * NB);
-            for (int m = 0; m < cnt; ++m) {
+        const int cnt = min(NB, n - b * NB);
+        for (int m0 = 0; m0 < cnt; m0 += GS) {
+            const int g = min(GS, cnt - m0);
+            if (g == GS) {
+                int ii[GS];
+                double xv[GS][NH];
+#pragma unroll
+                for (int s = 0; s < GS; ++s) {
+                    ii[s] = mi[cur][m0 + s];
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) {
+                        const int d = lane + 32 * h;
+                        xv[s][h] = d < D ? xs[cur][m0 + s][d < DP ? d : 0] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < GS; ++s) {
+                    w = dadd(w, 1.0);
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) {
+                        const int d = lane + 32 * h;
+                        cf1[h] = dadd(cf1[h], xv[s][h]);
+                        cf2[h] = dadd(cf2[h], dmul(xv[s][h], xv[s][h]));
+                        if (d < D) {
+                            ver_cf1(e.ws, ii[s])[d] = cf1[h];
+                            ver_cf2(e.ws, ii[s])[d] = cf2[h];
+                        }
+                    }
+                    if (lane == 0) ver_w(e.ws, ii[s]) = w;
+                }
+                continue;
+            }
+            for (int m = m0; m < m0 + g; ++m) {
                 const int i = mi[cur][m];
                 double x[2];
-                x[0] = lane < D ? xs[cur][m][lane] : 0.0;
-                x[1] = (DP > 32 && lane + 32 < D) ? xs[cur][m][lane + 32] : 0.0;
-                LaneMc o;
-                double wn;
-                if (PHASE == 0 && fl[cur][m]) {
-                    uint64_t nmask;
-                    if (!tentative_absorb_t<DP>(st, w, x, nm, o, wn, nmask)) {
-                        if (lane == 0) e.ws.prej[i] = 1;
-                        continue;
+                x[0] = lane < D ? xs[cur][m][lane < DP ? lane : 0] : 0.0;
+                x[1] = (DP > 32 && lane + 32 < D) ? xs[cur][m][lane + 32 < DP ? lane + 32 : 0] : 0.0;
+                w = dadd(w, 1.0);
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    cf1[h] = dadd(cf1[h], x[h]);
+                    cf2[h] = dadd(cf2[h], dmul(x[h], x[h]));
+                }
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const int d = lane + 32 * h;
+                    if (d < D) {
+                        ver_cf1(e.ws, i)[d] = cf1[h];
+                        ver_cf2(e.ws, i)[d] = cf2[h];
                     }
-                } else {
-                    wn = dadd(w, 1.0);
+                }
+                if (lane == 0) ver_w(e.ws, i) = w;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// k_bs_chain_p: PCORE keys (CONTESTED members take the exact radius test in place).  The candidates of a key lie
+// CONTIGUOUSLY in plist / xg (k_bs_pscatter) as ADDEND records a = (x, x*x, 1.0), and an MC is the record
+// v = (CF1, CF2, W): absorbing a cell is v += a, element-wise -- ONE dependent DADD per cell for the lane that
+// owns the element.  Three warps, specialised:
+//   producer  one thread streams the records through a ring of shared-memory stages with 1-D bulk TMA copies
+//             (cp.async.bulk + mbarrier complete_tx);
+//   replay    warp 0, lane = record element: a <- LDS, v += a, v -> STS over the addend it just consumed (the stage
+//             now holds the VERSION after every cell);
+//   storer    one warp sends every version record to ver[cell] with a bulk TMA store (shared -> global) and
+//             releases the stage.
+// A single warp cannot hide instruction latency, so everything that is not the dependent add lives in the other two.
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+template <int DP>
+struct ChainPCfg {
+    static constexpr int LSP = 2 * DP + 2;
+    static constexpr int NH = (LSP + 31) / 32;
+    static constexpr int NB = DP <= 16 ? 64 : 32;
+    static constexpr int S = DP <= 48 ? 8 : 6;
+    static constexpr size_t SMEM = (size_t)S * NB * (LSP * 8 + 4) + 3 * S * 8 + 128;
+};
+constexpr int BS_CHAINP_THREADS = 96;
+
+template <int DP>
+__global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
+    using Cfg = ChainPCfg<DP>;
+    constexpr int NB = Cfg::NB, S = Cfg::S, GS = 8, NH = Cfg::NH, LSP = Cfg::LSP;
+    extern __shared__ __align__(128) unsigned char bs_smem[];
+    double *xs = reinterpret_cast<double *>(bs_smem);              // [S][NB][LSP]
+    int *ms = reinterpret_cast<int *>(xs + (size_t)S * NB * LSP);  // [S][NB]
+    uint64_t *full = reinterpret_cast<uint64_t *>(ms + S * NB);    // [S] producer -> replay
+    uint64_t *done = full + S;                                     // [S] replay -> storer
+    uint64_t *empty = done + S;                                    // [S] storer -> producer
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const Num nm = e.nm;
+    const int D = nm.D;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j = blockIdx.x;
+    if (j >= bc->Mp) return;
+    const int n = e.ws.pcnt[j];
+    if (n <= 0) return;
+    const int p0 = e.ws.poff[j];
+    const double *xg = e.ws.xg + (size_t)p0 * LSP;
+    const int32_t *pl = e.ws.plist + p0;
+    const int nb = (n + NB - 1) / NB;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&done[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == 1) { // ---- producer
+        if (lane == 0) {
+            for (int b = 0; b < nb; ++b) {
+                const int s = b % S;
+                if (b >= S) mbar_wait(&empty[s], ((b / S) - 1) & 1);
+                const int cnt = min(NB, n - b * NB);
+                const uint32_t bx = (uint32_t)cnt * LSP * 8u, bi = (uint32_t)((cnt + 3) & ~3) * 4u;
+                mbar_expect_tx(&full[s], bx + bi);
+                tma_load_1d(xs + (size_t)s * NB * LSP, xg + (size_t)b * NB * LSP, bx, &full[s]);
+                tma_load_1d(ms + s * NB, pl + b * NB, bi, &full[s]);
+            }
+        }
+        return;
+    }
+    if (warp == 2) { // ---- storer: bulk stores run LAG stages behind before their stage is handed back
+        constexpr int LAG = 2;
+        for (int b = 0; b < nb; ++b) {
+            const int s = b % S;
+            mbar_wait(&done[s], (b / S) & 1);
+            const int cnt = min(NB, n - b * NB);
+            for (int m = lane; m < cnt; m += 32) {
+                const int i = ms[s * NB + m] & 0x7fffffff;
+                tma_store_1d(e.ws.ver + (size_t)i * LSP, xs + ((size_t)s * NB + m) * LSP, LSP * 8u);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (b >= LAG) {
+                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(LAG) : "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[(b - LAG) % S]);
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        return;
+    }
+    // ---- replay (warp 0): lane owns elements lane + 32 h of the record
+    double v[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+        const int el = lane + 32 * h;
+        double x = 0.0;
+        if (el < D) x = e.P.cf1[(size_t)j * D + el];
+        else if (el >= DP && el < DP + D) x = e.P.cf2[(size_t)j * D + el - DP];
+        else if (el == 2 * DP) x = e.P.w[j];
+        v[h] = x;
+    }
+    for (int b = 0; b < nb; ++b) {
+        const int s = b % S;
+        mbar_wait(&full[s], (b / S) & 1);
+        double *xb = xs + (size_t)s * NB * LSP;
+        const int *mb = ms + s * NB;
+        const int cnt = min(NB, n - b * NB);
+        for (int m0 = 0; m0 < cnt; m0 += GS) {
+            const int g = min(GS, cnt - m0);
+            bool fast = g == GS;
+            if (fast) {
+                const int4 a = *reinterpret_cast<const int4 *>(mb + m0), c = *reinterpret_cast<const int4 *>(mb + m0 + 4);
+                fast = (a.x | a.y | a.z | a.w | c.x | c.y | c.z | c.w) >= 0;
+            }
+            if (fast) {
+                double av[GS][NH];
+#pragma unroll
+                for (int q = 0; q < GS; ++q)
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) {
+                        const int el = lane + 32 * h;
+                        av[q][h] = (NH * 32 == LSP || el < LSP) ? xb[(m0 + q) * LSP + el] : 0.0;
+                    }
+#pragma unroll
+                for (int q = 0; q < GS; ++q)
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) {
+                        const int el = lane + 32 * h;
+                        v[h] = dadd(v[h], av[q][h]);
+                        if (NH * 32 == LSP || el < LSP) xb[(m0 + q) * LSP + el] = v[h];
+                    }
+                continue;
+            }
+            for (int m = m0; m < m0 + g; ++m) {
+                const int raw = mb[m];
+                double nv[NH];
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const int el = lane + 32 * h;
+                    const double a = el < LSP ? xb[m * LSP + el] : 0.0;
+                    nv[h] = dadd(v[h], a);
+                    if (el < LSP) xb[m * LSP + el] = nv[h];
+                }
+                if (raw < 0) { // CONTESTED: exact radius test of the tentative MC (mc_functions.py:45-56)
+                    __syncwarp();
+                    const double wn = xb[m * LSP + 2 * DP];
+                    double term[2] = {0.0, 0.0};
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         if (h == 0 || DP > 32) {
-                            o.cf1[h] = dadd(st.cf1[h], x[h]);
-                            o.cf2[h] = dadd(st.cf2[h], dmul(x[h], x[h]));
+                            const int d = lane + 32 * h;
+                            const bool act = d < D;
+                            // idle lanes carry 1.0: their (discarded) quotients stay on the fast path of the division
+                            const double c1 = act ? xb[m * LSP + d] : 1.0;
+                            const double c2 = act ? xb[m * LSP + DP + d] : 1.0;
+                            const double a = ddiv(c2, wn);
+                            const double c = ddiv(c1, wn);
+                            const double var = dsub(a, dmul(c, c));
+                            const bool bit = act && (var <= nm.delta2);
+                            term[h] = bit ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var;
                         }
                     }
-                }
-                st = o;
-                w = wn;
+                    double r2 = 0.0;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int d = lane + 32 * h;
-                    if ((h == 0 || DP > 32) && d < D) {
-                        e.ws.vcf1[(size_t)i * D + d] = o.cf1[h];
-                        e.ws.vcf2[(size_t)i * D + d] = o.cf2[h];
+                    for (int d = 0; d < DP; ++d) {
+                        if (d < D) r2 = dadd(r2, __shfl_sync(0xffffffffu, term[d >> 5], d & 31));
                     }
+                    const bool ok = r2 <= nm.eps2;
+                    if (lane == 0) e.ws.prej[raw & 0x7fffffff] = ok ? 0 : 1;
+                    if (!ok) continue; // the record of a rejected cell is never read as a version
                 }
-                if (lane == 0) e.ws.vw[i] = wn;
-                if (PHASE == 0) {
-                    if (lane == 0) e.ws.prej[i] = 0;
-                    const int ti = i >> 5;
-                    for (int t = nextfill + lane; t <= ti; t += 32) tb[(size_t)t * e.ws.mp_stride] = pv;
-                    nextfill = ti + 1;
-                    pv = i;
-                }
+#pragma unroll
+                for (int h = 0; h < NH; ++h) v[h] = nv[h];
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[s]);
     }
-    if (PHASE == 0 && warp == 0)
-        for (int t = nextfill + lane; t <= ntiles; t += 32) tb[(size_t)t * e.ws.mp_stride] = pv;
 }
 
 // ---- outlier-side member lists: sort (key, cell) of the pcore-rejected cells --------------------------
@@ -667,11 +899,23 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive(Eng e) {
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const int i = blockIdx.x * BS_THREADS + threadIdx.x;
+    {
+        // tbase[t][j] = latest ACCEPTED member of pcore chain j before tile t (t == ntiles: of the whole block)
+        const int Mp = bc->Mp, stride = e.ws.mp_stride, ntiles = (bc->Beff + 31) >> 5;
+        const int total = (ntiles + 1) * Mp;
+        for (int idx = i; idx < total; idx += gridDim.x * BS_THREADS) {
+            const int t = idx / Mp, j = idx - t * Mp;
+            const int lo = e.ws.poff[j];
+            int pos = lo + (t < ntiles ? e.ws.tilecnt[(size_t)t * stride + j] : e.ws.pcnt[j]);
+            while (pos > lo && e.ws.prej[e.ws.plist[pos - 1] & 0x7fffffff]) --pos;
+            e.ws.tbase[(size_t)t * stride + j] = pos > lo ? (e.ws.plist[pos - 1] & 0x7fffffff) : -1;
+        }
+    }
     if (i >= bc->Beff) return;
     const Num nm = e.nm;
     const int D = nm.D;
-    const double w = e.ws.vw[i];
-    const double *c1 = e.ws.vcf1 + (size_t)i * D, *c2 = e.ws.vcf2 + (size_t)i * D;
+    const double w = ver_w(e.ws, i);
+    const double *c1 = ver_cf1(e.ws, i), *c2 = ver_cf2(e.ws, i);
     double *cen = e.ws.vcen + (size_t)i * D;
     double s = 0.0;
     uint64_t mk = 0ull;
@@ -721,9 +965,9 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
         const uint64_t mask = prev >= 0 ? e.ws.vmask[prev] : e.P.mask[j];
         bool feas = true;
         if (nm.pi_active) {
-            const double *c1 = prev >= 0 ? e.ws.vcf1 + (size_t)prev * D : e.P.cf1 + (size_t)j * D;
-            const double *c2 = prev >= 0 ? e.ws.vcf2 + (size_t)prev * D : e.P.cf2 + (size_t)j * D;
-            const double w = prev >= 0 ? e.ws.vw[prev] : e.P.w[j];
+            const double *c1 = prev >= 0 ? ver_cf1(e.ws, prev) : e.P.cf1 + (size_t)j * D;
+            const double *c2 = prev >= 0 ? ver_cf2(e.ws, prev) : e.P.cf2 + (size_t)j * D;
+            const double w = prev >= 0 ? ver_w(e.ws, prev) : e.P.w[j];
             feas = feasible_regs<DP>(c1, c2, w, x, nm);
         }
         const double dv = dist_regs<DP>(x, cen, mask, nm);
@@ -739,9 +983,9 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
         if (eff == best) {
             acc = e.ws.vr2[i] <= nm.eps2; // this very absorb is version i of the chain
         } else {
-            const double *c1 = bprev >= 0 ? e.ws.vcf1 + (size_t)bprev * D : e.P.cf1 + (size_t)best * D;
-            const double *c2 = bprev >= 0 ? e.ws.vcf2 + (size_t)bprev * D : e.P.cf2 + (size_t)best * D;
-            const double w = bprev >= 0 ? e.ws.vw[bprev] : e.P.w[best];
+            const double *c1 = bprev >= 0 ? ver_cf1(e.ws, bprev) : e.P.cf1 + (size_t)best * D;
+            const double *c2 = bprev >= 0 ? ver_cf2(e.ws, bprev) : e.P.cf2 + (size_t)best * D;
+            const double w = bprev >= 0 ? ver_w(e.ws, bprev) : e.P.w[best];
             double wn;
             uint64_t nmask;
             acc = tent_regs<DP>(c1, c2, w, x, nm, wn, nmask) <= nm.eps2;
@@ -828,9 +1072,9 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
             const double *c1, *c2;
             double w;
             if (bver >= 0) {
-                c1 = e.ws.vcf1 + (size_t)bver * D;
-                c2 = e.ws.vcf2 + (size_t)bver * D;
-                w = e.ws.vw[bver];
+                c1 = ver_cf1(e.ws, bver);
+                c2 = ver_cf2(e.ws, bver);
+                w = ver_w(e.ws, bver);
             } else {
                 const int o = bkey - Mp;
                 c1 = e.O.cf1 + (size_t)o * D;
@@ -901,6 +1145,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
     if (tid == 0) {
         int act = 0; // 0 refine, 1 commit
         bc->iters += 1;
+        bc->replayed += Beff;
         if (up != INT_MAX) {
             bc->m_commit = up + 1;
             bc->upgrade = 1;
@@ -926,7 +1171,10 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
     }
     __syncthreads();
     if (s_act == 1) {
-        if (tid == 0) bc->phase = 1;
+        if (tid == 0) {
+            bc->phase = 1;
+            bc->tk_lo = bc->tk_hi = 0;
+        }
         return;
     }
     // ---- refinement: the recomputed decisions of [m0, Beff) become the next speculation
@@ -967,6 +1215,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
             bc->m_commit = m0;
             bc->cuts_cap += 1;
             bc->phase = 1;
+            bc->tk_lo = bc->tk_hi = 0;
         }
         return;
     }
@@ -1004,6 +1253,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
         bc->tk_hi = nneed_new;
         bc->nneed = nneed_new;
         bc->tk_late += nneed_new - nneed_old;
+        bc->pairs += (int64_t)(nneed_new - nneed_old) * bc->Mo0;
         bc->Beff = Bnew;
         bc->it += 1;
         bc->npend = 0;
@@ -1028,12 +1278,12 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
         const int v = mk ? (tm * 32 + 31 - __clz(mk)) : e.ws.tbase[(size_t)tm * e.ws.mp_stride + j];
         if (v < 0) return;
         for (int d = lane; d < D; d += 32) {
-            e.P.cf1[(size_t)j * D + d] = e.ws.vcf1[(size_t)v * D + d];
-            e.P.cf2[(size_t)j * D + d] = e.ws.vcf2[(size_t)v * D + d];
+            e.P.cf1[(size_t)j * D + d] = ver_cf1(e.ws, v)[d];
+            e.P.cf2[(size_t)j * D + d] = ver_cf2(e.ws, v)[d];
             e.P.cen[(size_t)j * D + d] = e.ws.vcen[(size_t)v * D + d];
         }
         if (lane == 0) {
-            e.P.w[j] = e.ws.vw[v];
+            e.P.w[j] = ver_w(e.ws, v);
             e.P.mask[j] = e.ws.vmask[v];
         }
         return;
@@ -1055,8 +1305,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
         cv.y = 1.0;
         if (d < D) {
             const double c = e.ws.vcen[(size_t)v * D + d];
-            e.O.cf1[(size_t)slot * D + d] = e.ws.vcf1[(size_t)v * D + d];
-            e.O.cf2[(size_t)slot * D + d] = e.ws.vcf2[(size_t)v * D + d];
+            e.O.cf1[(size_t)slot * D + d] = ver_cf1(e.ws, v)[d];
+            e.O.cf2[(size_t)slot * D + d] = ver_cf2(e.ws, v)[d];
             e.O.cen[(size_t)slot * D + d] = c;
             cv.x = c;
             cv.y = ((mask >> d) & 1ull) ? nm.wsel : 1.0;
@@ -1064,7 +1314,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
         e.O.cw[(size_t)slot * DP + d] = cv;
     }
     if (lane == 0) {
-        e.O.w[slot] = e.ws.vw[v];
+        e.O.w[slot] = ver_w(e.ws, v);
         e.O.mask[slot] = mask;
         if (created) {
             const int64_t id = e.ctl->outlier_last_id + rank;

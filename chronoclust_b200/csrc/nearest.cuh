@@ -55,35 +55,30 @@ __device__ __forceinline__ void topk_insert(double (&bd)[K], int (&bi)[K], doubl
     }
 }
 
-// rows == nullptr: cell r is row r of X.  nrows_dev (optional) overrides nrows with a device-side count.
-// out_dist/out_idx: [nrows][nslab][K]; unused entries hold (+inf, -1).
+// Device-side work split of the block-speculative engine's calls: R rows x M microclusters are cut into
+// row groups of `cells` rows and nslab slabs of slab_mcs microclusters so that about `target` CTAs have work,
+// whatever R and M turn out to be on the device (the host only knows upper bounds).
+__device__ __forceinline__ void dyn_split(int R, int M, int target, int max_slabs, int tm, int cells, int &groups,
+                                          int &slab_mcs, int &nslab) {
+    groups = (R + cells - 1) / cells;
+    const int tiles = (M + tm - 1) / tm;
+    int want = groups > 0 ? (target + groups - 1) / groups : 1;
+    want = min(want, min(max_slabs, tiles));
+    want = max(want, 1);
+    slab_mcs = max(1, (tiles + want - 1) / want) * tm;
+    nslab = M > 0 ? (M + slab_mcs - 1) / slab_mcs : 0;
+}
+
+// One (row group, slab) work item: cells [cell0, cell0 + CELLS) of the row list against MCs [j0, j1).
+// seq counts the tiles this CTA has streamed so far (mbarrier buffer / parity bookkeeping across items).
 template <int DP, int K, bool DIV>
-__global__ void __launch_bounds__(NEAREST_THREADS)
-    k_nearest(const double *__restrict__ X, const int32_t *__restrict__ rows, const int32_t *__restrict__ nrows_dev,
-              int64_t row_off, int64_t nrows, int64_t ld, int D, const double2 *__restrict__ cw, int M, int slab_mcs,
-              double *__restrict__ out_dist, int32_t *__restrict__ out_idx, const int32_t *__restrict__ range_dev,
-              const int32_t *__restrict__ M_dev) {
+__device__ __forceinline__ void nearest_item(const double *__restrict__ X, const int32_t *__restrict__ rows, int64_t row_off,
+                                             int64_t nrows, int64_t ld, int D, const double2 *__restrict__ cw, int64_t cell0,
+                                             int j0, int j1, double *__restrict__ out_dist, int32_t *__restrict__ out_idx,
+                                             int64_t out_off, int out_stride, int out_slab, double2 (*tile)[NearestCfg<DP>::TM * DP],
+                                             uint64_t *bar, uint32_t &seq) {
     using Cfg = NearestCfg<DP>;
     constexpr int PPT = Cfg::PPT, TM = Cfg::TM, JU = NEAREST_JU;
-    __shared__ __align__(128) double2 tile[2][TM * DP];
-    __shared__ __align__(8) uint64_t bar[2];
-
-    if (nrows_dev) nrows = (int64_t)(*nrows_dev) - row_off;
-    // device-side work description (block-speculative engine): rows[range_dev[0] .. range_dev[1]) against the
-    // first *M_dev microclusters, results written at the absolute list positions
-    int64_t out_off = 0;
-    if (range_dev) {
-        row_off = range_dev[0];
-        nrows = (int64_t)range_dev[1] - row_off;
-        out_off = row_off;
-    }
-    if (M_dev) M = min(M, *M_dev);
-    const int64_t cell0 = (int64_t)blockIdx.x * Cfg::CELLS;
-    if (cell0 >= nrows) return;
-    const int nslab = gridDim.y;
-    const int j0 = blockIdx.y * slab_mcs;
-    const int j1 = min(M, j0 + slab_mcs);
-
     // ---- this thread's cells -> registers (row-contiguous 16-byte loads; every fetched sector is used)
     double p[PPT][DP];
     int64_t cell[PPT];
@@ -120,27 +115,22 @@ __global__ void __launch_bounds__(NEAREST_THREADS)
             bi[u][s] = -1;
         }
 
-    if (threadIdx.x == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
     const int ntiles = (j1 - j0 + TM - 1) / TM;
     auto issue = [&](int t) {
         const int jt = j0 + t * TM;
         const int n = min(TM, j1 - jt);
         const uint32_t bytes = (uint32_t)n * DP * (uint32_t)sizeof(double2);
-        mbar_expect_tx(&bar[t & 1], bytes);
-        tma_load_1d(&tile[t & 1][0], cw + (size_t)jt * DP, bytes, &bar[t & 1]);
+        const uint32_t q = seq + (uint32_t)t;
+        mbar_expect_tx(&bar[q & 1], bytes);
+        tma_load_1d(&tile[q & 1][0], cw + (size_t)jt * DP, bytes, &bar[q & 1]);
     };
     if (threadIdx.x == 0 && ntiles > 0) issue(0);
 
     for (int t = 0; t < ntiles; ++t) {
-        if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1); // buffer (t+1)&1 was released by the barrier below
-        mbar_wait(&bar[t & 1], (t >> 1) & 1);
-        const double2 *tl = tile[t & 1];
+        if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1); // that buffer was released by the barrier below
+        const uint32_t q = seq + (uint32_t)t;
+        mbar_wait(&bar[q & 1], (q >> 1) & 1);
+        const double2 *tl = tile[q & 1];
         const int jt = j0 + t * TM;
         const int n = min(TM, j1 - jt);
         for (int jj = 0; jj < n; jj += JU) {
@@ -173,15 +163,118 @@ __global__ void __launch_bounds__(NEAREST_THREADS)
         }
         __syncthreads();
     }
+    seq += (uint32_t)ntiles;
 
 #pragma unroll
     for (int u = 0; u < PPT; ++u) {
         if (cell[u] < nrows) {
-            const size_t o = ((size_t)(out_off + cell[u]) * nslab + blockIdx.y) * K;
+            const size_t o = ((size_t)(out_off + cell[u]) * out_stride + out_slab) * K;
 #pragma unroll
             for (int s = 0; s < K; ++s) {
                 out_dist[o + s] = bd[u][s];
                 out_idx[o + s] = bi[u][s];
+            }
+        }
+    }
+}
+
+// rows == nullptr: cell r is row r of X.  nrows_dev (optional) overrides nrows with a device-side count.
+// out_dist/out_idx: [nrows][nslab][K]; unused entries hold (+inf, -1).
+// STATIC split (range_dev == nullptr): grid = (row groups, slabs) chosen by the host.
+// DYNAMIC split (range_dev != nullptr, block-speculative engine): 1-D grid; rows[range_dev[0] .. range_dev[1])
+// against the first min(M, *M_dev) microclusters; every CTA derives the split with dyn_split and loops over its
+// work items; results land at [absolute list position][dyn_max_slabs][K].
+template <int DP, int K, bool DIV>
+__global__ void __launch_bounds__(NEAREST_THREADS)
+    k_nearest(const double *__restrict__ X, const int32_t *__restrict__ rows, const int32_t *__restrict__ nrows_dev,
+              int64_t row_off, int64_t nrows, int64_t ld, int D, const double2 *__restrict__ cw, int M, int slab_mcs,
+              double *__restrict__ out_dist, int32_t *__restrict__ out_idx, const int32_t *__restrict__ range_dev,
+              const int32_t *__restrict__ M_dev, int dyn_max_slabs) {
+    using Cfg = NearestCfg<DP>;
+    __shared__ __align__(128) double2 tile[2][Cfg::TM * DP];
+    __shared__ __align__(8) uint64_t bar[2];
+
+    if (nrows_dev) nrows = (int64_t)(*nrows_dev) - row_off;
+    if (M_dev) M = min(M, *M_dev);
+    if (range_dev) {
+        row_off = range_dev[0];
+        nrows = (int64_t)range_dev[1] - row_off;
+        if (nrows <= 0) return;
+    } else if ((int64_t)blockIdx.x * Cfg::CELLS >= nrows) {
+        return;
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t seq = 0;
+    if (range_dev) {
+        int groups, smcs, nslab;
+        dyn_split((int)nrows, M, gridDim.x, dyn_max_slabs, Cfg::TM, Cfg::CELLS, groups, smcs, nslab);
+        const int items = groups * nslab;
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            const int g = it / nslab, sl = it - g * nslab;
+            const int j0 = sl * smcs;
+            nearest_item<DP, K, DIV>(X, rows, row_off, nrows, ld, D, cw, (int64_t)g * Cfg::CELLS, j0, min(M, j0 + smcs),
+                                     out_dist, out_idx, row_off, dyn_max_slabs, sl, tile, bar, seq);
+        }
+    } else {
+        const int j0 = blockIdx.y * slab_mcs;
+        nearest_item<DP, K, DIV>(X, rows, row_off, nrows, ld, D, cw, (int64_t)blockIdx.x * Cfg::CELLS, j0,
+                                 min(M, j0 + slab_mcs), out_dist, out_idx, 0, gridDim.y, blockIdx.y, tile, bar, seq);
+    }
+}
+
+// Merge for the DYNAMIC split: one warp per row; lane l walks the (already ascending) lists of slabs l, l + 32, ...
+// and the warp extracts the K lexicographically smallest (dist, idx) entries -- ties go to the smaller list
+// position, exactly like a scan in list order with strict <.
+template <int K>
+__global__ void __launch_bounds__(128) k_topk_merge_dyn(const double *__restrict__ in_dist, const int32_t *__restrict__ in_idx,
+                                                        const int32_t *__restrict__ range_dev, const int32_t *__restrict__ M_dev,
+                                                        int M, int target, int max_slabs, int tm, int cells,
+                                                        double *__restrict__ out_dist, int32_t *__restrict__ out_idx) {
+    constexpr int QMAX = 4; // max_slabs <= 128
+    const int lane = threadIdx.x & 31;
+    const int R = range_dev[1] - range_dev[0];
+    if (M_dev) M = min(M, *M_dev);
+    int groups, smcs, nslab;
+    dyn_split(R, M, target, max_slabs, tm, cells, groups, smcs, nslab);
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < R; r += nw) {
+        const size_t row = (size_t)range_dev[0] + r;
+        int hd[QMAX];
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q) hd[q] = 0;
+        for (int s = 0; s < K; ++s) {
+            double bdv = 0.0;
+            int biv = -1, bq = 0;
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q) {
+                const int sl = lane + 32 * q;
+                if (sl < nslab && hd[q] < K) {
+                    const size_t o = (row * max_slabs + sl) * K + hd[q];
+                    const int j = in_idx[o];
+                    const double dv = in_dist[o];
+                    if (better(dv, j, bdv, biv)) {
+                        bdv = dv;
+                        biv = j;
+                        bq = q;
+                    }
+                }
+            }
+            double wd = bdv;
+            int wi = biv;
+            warp_argmin(wd, wi);
+            if (wi >= 0 && wi == biv) {
+#pragma unroll
+                for (int q = 0; q < QMAX; ++q)
+                    if (q == bq) hd[q] += 1;
+            }
+            if (lane == 0) {
+                out_dist[row * K + s] = wi >= 0 ? wd : __longlong_as_double(0x7ff0000000000000LL);
+                out_idx[row * K + s] = wi;
             }
         }
     }

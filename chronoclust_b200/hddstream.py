@@ -288,7 +288,7 @@ class HDDStream(object):
 
     def timing(self, reset=False):
         """{category: (gpu milliseconds, bracketed launch groups)} measured with CUDA events."""
-        ms, n = (C.c_double * 8)(), (C.c_int64 * 8)()
+        ms, n = (C.c_double * 16)(), (C.c_int64 * 16)()
         _lib.check(_lib.lib().ccb_get_timing(self._h, C.byref(ms), C.byref(n), int(reset)), self._h)
         return {c: (float(ms[i]), int(n[i])) for i, c in enumerate(_lib.CATEGORIES)}
 

@@ -96,6 +96,7 @@ typedef struct {
     int64_t bsv_cuts_capacity; /* blocks cut because the outlier-stage list of the block was full */
     int64_t bsv_late_topk;     /* cells whose top-K list had to be fetched in a refinement round */
     int64_t bsv_outlier_stage_cells; /* cells given a top-K list up front (not SAFE) */
+    int64_t bsv_replayed_cells;      /* cells replayed by the chain kernels, summed over rounds */
 } ccb_stats;
 
 int ccb_create(const ccb_params *params, ccb_handle **out);
@@ -112,15 +113,21 @@ int ccb_reset(ccb_handle *h);
 
 /* Optional GPU timing per kernel category, taken with CUDA events on the handle's stream (this is
  * what bench.py reads for the live roofline).  ms / launches: arrays of CCB_NCAT. */
-#define CCB_CAT_PCORE 0   /* kernel 2   ordered chains (k_bs_chain; wave engine: k_pcore_stage) */
-#define CCB_CAT_NEAREST 1 /* kernel 1   k_nearest (+ k_topk_merge) on the cells that may reach the outlier stage */
+#define CCB_CAT_PCORE 0   /* kernel 2   ordered replay of the pcore keys (k_bs_chain_p; wave engine: k_pcore_stage) */
+#define CCB_CAT_NEAREST 1 /* kernel 1   k_nearest (+ merge) on the cells that may reach the outlier stage */
 #define CCB_CAT_RESOLVE 2 /* kernel 2   exact verification (k_bs_verify_p/o; wave engine: k_resolve) */
 #define CCB_CAT_MAINT 3   /* kernel 3   k_maint_plan + k_maint_gather */
 #define CCB_CAT_OFFLINE 4 /* kernel 4   offline pipeline (device part) */
 #define CCB_CAT_MISC 5    /* small helpers */
 #define CCB_CAT_COPY 6    /* host<->device copies of ccb_ingest */
-#define CCB_CAT_SPEC 7    /* kernel 2   speculation from the snapshot (k_bs_spec, k_bs_need, k_bs_spec_o) */
-#define CCB_NCAT 8
+#define CCB_CAT_SPEC 7    /* kernel 2   speculation from the snapshot (k_bs_begin/spec/need/spec_o) */
+#define CCB_CAT_LISTS 8   /* kernel 2   candidate lists + addend records (k_bs_tilecnt/pscan/pscatter) */
+#define CCB_CAT_CHAIN_O 9 /* kernel 2   ordered replay of the outlier-side keys (k_bs_chain_o) */
+#define CCB_CAT_OLIST 10  /* kernel 2   outlier-side member lists (k_bs_olist) */
+#define CCB_CAT_DERIVE 11 /* kernel 2   centroid / preference mask / radius of every version (k_bs_derive) */
+#define CCB_CAT_DECIDE 12 /* kernel 2   exact-prefix decision / refinement (k_bs_decide) */
+#define CCB_CAT_COMMIT 13 /* kernel 2   write-back of the exact prefix (k_bs_commit_rows/cells, k_bs_finish) */
+#define CCB_NCAT 16
 int ccb_enable_timing(ccb_handle *h, int32_t on);
 int ccb_get_timing(ccb_handle *h, double ms[CCB_NCAT], int64_t launches[CCB_NCAT], int32_t reset);
 
