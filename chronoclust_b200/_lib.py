@@ -20,7 +20,7 @@ vp = C.c_void_p
 class Params(C.Structure):
     _fields_ = [("D", i32), ("device", i32), ("eps2", f64), ("upsilon_eps", f64), ("upsilon_eps2", f64),
                 ("delta", f64), ("delta2", f64), ("beta", f64), ("k", f64), ("wave", i32), ("chunk", i32),
-                ("bsv_bmin", i32), ("bsv_iters", i32)]
+                ("bsv_bmin", i32), ("bsv_iters", i32), ("bsv_stream", i32), ("reserved0", i32)]
 
 
 class Stats(C.Structure):
@@ -43,6 +43,8 @@ SYMBOLS = {
     "ccb_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
     "ccb_reset": (C.c_int, [vp]),
     "ccb_debug_phase_cycles": (C.c_int, [vp, C.POINTER(i64 * 8)]),
+    "ccb_debug_chain": (C.c_int, [vp, vp, i32]),
+    "ccb_debug_set": (C.c_int, [vp, i32]),
     "ccb_fp64_peak": (C.c_int, [i32, vp, i32, i32, i32, vp, C.POINTER(f64)]),
     "ccb_enable_timing": (C.c_int, [vp, i32]),
     "ccb_get_timing": (C.c_int, [vp, C.POINTER(f64 * 16), C.POINTER(i64 * 16), i32]),

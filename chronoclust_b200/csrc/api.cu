@@ -93,6 +93,12 @@ struct ccb_handle {
     double *d_bs_tk_dist_slab = nullptr;
     int32_t *d_bs_tk_idx_slab = nullptr;
     BsCtl bc_base{}; // counters folded in by ccb_reset
+    bool bs_use_graph = true;   // CUDA graph with device-driven WHILE nodes (stream launches when per-kernel timing is on)
+    cudaGraph_t bs_graph = nullptr;
+    cudaGraphExec_t bs_exec = nullptr;
+    cudaStream_t cap1 = nullptr, cap2 = nullptr;
+    Eng bs_graph_eng{};         // the pointers / capacities the graph was captured with
+    EngIo *d_io = nullptr, *h_io = nullptr;
     // offline results (host copies)
     int64_t off_M = 0;
     std::vector<int64_t> cl_off, cl_members;
@@ -300,10 +306,10 @@ int launch_nearest(ccb_handle *h, cudaStream_t s, int DP, int div_mode, const do
         int32_t *oi = nslab == 1 ? out_idx : slab_idx;
         if (div_mode)
             k_nearest<kDP, K, true><<<grid, NEAREST_THREADS, 0, s>>>(X, rows, nrows_dev, row_off, nrows_max, ld, D, cw,
-                                                                     M, slab_mcs, od, oi, range_dev, M_dev, 0);
+                                                                     M, slab_mcs, od, oi, range_dev, M_dev, 0, nullptr);
         else
             k_nearest<kDP, K, false><<<grid, NEAREST_THREADS, 0, s>>>(X, rows, nrows_dev, row_off, nrows_max, ld, D, cw,
-                                                                      M, slab_mcs, od, oi, range_dev, M_dev, 0);
+                                                                      M, slab_mcs, od, oi, range_dev, M_dev, 0, nullptr);
         launched = 1;
         if (nslab > 1) {
             k_topk_merge<K><<<(unsigned)((nrows_max + 255) / 256), 256, 0, s>>>(slab_dist, slab_idx, nrows_dev, row_off,
@@ -325,16 +331,17 @@ constexpr int NEAREST_DYN_GRID = 148 * 4;
 template <int K>
 int launch_nearest_dyn(ccb_handle *h, cudaStream_t s, int DP, int div_mode, const double *X, const int32_t *rows, int64_t ld,
                        int D, const double2 *cw, int M_bound, double *slab_dist, int32_t *slab_idx, double *out_dist,
-                       int32_t *out_idx, int max_slabs, int rows_max, const int32_t *range_dev, const int32_t *M_dev) {
+                       int32_t *out_idx, int max_slabs, int rows_max, const int32_t *range_dev, const int32_t *M_dev,
+                       const XRef *xref) {
     int launched = 0;
     CCB_DISPATCH_DP(DP, {
         using Cfg = NearestCfg<kDP>;
         if (div_mode)
             k_nearest<kDP, K, true><<<NEAREST_DYN_GRID, NEAREST_THREADS, 0, s>>>(X, rows, nullptr, 0, 0, ld, D, cw, M_bound, 0,
-                                                                                 slab_dist, slab_idx, range_dev, M_dev, max_slabs);
+                                                                                 slab_dist, slab_idx, range_dev, M_dev, max_slabs, xref);
         else
             k_nearest<kDP, K, false><<<NEAREST_DYN_GRID, NEAREST_THREADS, 0, s>>>(X, rows, nullptr, 0, 0, ld, D, cw, M_bound, 0,
-                                                                                  slab_dist, slab_idx, range_dev, M_dev, max_slabs);
+                                                                                  slab_dist, slab_idx, range_dev, M_dev, max_slabs, xref);
         k_topk_merge_dyn<K><<<std::min(NEAREST_DYN_GRID, (rows_max + 3) / 4), 128, 0, s>>>(
             slab_dist, slab_idx, range_dev, M_dev, M_bound, NEAREST_DYN_GRID, max_slabs, Cfg::TM, Cfg::CELLS, out_dist, out_idx);
         launched = 2;
@@ -522,6 +529,8 @@ int ensure_bs_ws(ccb_handle *h) {
         CK(h, cudaMemset(h->d_bc, 0, sizeof(BsCtl)));
         CK(h, cudaMallocHost(&h->h_bc, sizeof(BsCtl)));
         memset(h->h_bc, 0, sizeof(BsCtl));
+        CK(h, cudaMalloc(&h->d_io, sizeof(EngIo)));
+        CK(h, cudaMallocHost(&h->h_io, sizeof(EngIo)));
         BsWs &w = h->ws;
         w.bmax = B;
 #define WSA(field, n) if ((rc = ws_alloc(h, w.field, (n)))) return rc
@@ -561,6 +570,12 @@ int ensure_bs_ws(ccb_handle *h) {
         h->ws.plist = (int32_t *)h->ws_tiles[4];
         h->ws.xg = (double *)h->ws_tiles[5];
         h->ws.mp_stride = stride;
+        if (h->ws.dbg) {
+            cudaFree(h->ws.dbg);
+            h->ws.dbg = nullptr;
+            CK(h, cudaMalloc(&h->ws.dbg, (size_t)stride * 8 * sizeof(int64_t)));
+            CK(h, cudaMemset(h->ws.dbg, 0, (size_t)stride * 8 * sizeof(int64_t)));
+        }
     }
     const int ocap = h->O[h->ocur].cap;
     if (ocap != h->ws_first_cap) {
@@ -582,80 +597,169 @@ int sync_bc(ccb_handle *h) { // both control blocks -> pinned host mirrors
     return CCB_OK;
 }
 
-// One block = prologue + bs_iters refinement rounds + commit.  Every kernel reads its work description from the
-// device-side control block, so a converged (or finished) block turns the remaining launches into no-ops.
-int enqueue_block(ccb_handle *h, const Eng &e, int mp_bound, int mo_bound) {
-    cudaStream_t s = h->stream;
+// One block = prologue + refinement rounds + commit.  Every kernel reads its work description from the device-side
+// control block, so a converged (or finished) block turns the remaining launches into no-ops.  The three pieces are
+// launched either on the handle's stream (bs_iters rounds enqueued per block; used when per-kernel timing is on) or
+// captured once into a CUDA graph whose block loop and round loop are WHILE conditional nodes driven from the
+// device (k_bs_begin / k_bs_decide / k_bs_finish call cudaGraphSetConditional): no idle launches, no host round trip.
+int launch_prologue(ccb_handle *h, const Eng &e, cudaStream_t s) {
+    const int g_cells = (h->bs_bmax + BS_THREADS - 1) / BS_THREADS;
+    Timed tm(h, CCB_CAT_SPEC);
+    k_bs_begin<<<1, 1, 0, s>>>(e);
+    CCB_DISPATCH_DP(h->DP, { k_bs_spec<kDP><<<g_cells, BS_THREADS, 0, s>>>(e); })
+    k_bs_need<<<1, BS_CTA1, 0, s>>>(e);
+    CKL(h);
+    return CCB_OK;
+}
+
+int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int mo_bound) {
     const int B = h->bs_bmax;
     const int g_cells = (B + BS_THREADS - 1) / BS_THREADS;
     const int g_tiles = (B / 32 + 1 + 3) / 4;
-    int rc, launches = 0;
-    auto nearest = [&]() -> int {
-        Timed tm(h, CCB_CAT_NEAREST);
-        return launch_nearest_dyn<BS_TOPK>(h, s, h->DP, h->div_mode, e.X, e.ws.nrows, e.ld, h->D, e.O.cw, mo_bound,
-                                           h->d_bs_tk_dist_slab, h->d_bs_tk_idx_slab, e.ws.tk_dist, e.ws.tk_idx, BS_MAX_SLABS,
-                                           BS_RMAX, &e.bc->tk_lo, &e.bc->Mo0);
-    };
+    int rc;
     {
-        Timed tm(h, CCB_CAT_SPEC);
-        k_bs_begin<<<1, 1, 0, s>>>(e);
-        CCB_DISPATCH_DP(h->DP, { k_bs_spec<kDP><<<g_cells, BS_THREADS, 0, s>>>(e); })
-        k_bs_need<<<1, BS_CTA1, 0, s>>>(e);
-        launches += 3;
+        Timed tm(h, CCB_CAT_NEAREST);
+        if ((rc = launch_nearest_dyn<BS_TOPK>(nullptr, s, h->DP, h->div_mode, e.X, e.ws.nrows, e.ld, h->D, e.O.cw, mo_bound,
+                                              h->d_bs_tk_dist_slab, h->d_bs_tk_idx_slab, e.ws.tk_dist, e.ws.tk_idx,
+                                              BS_MAX_SLABS, BS_RMAX, &e.bc->tk_lo, &e.bc->Mo0,
+                                              reinterpret_cast<const XRef *>(e.io))))
+            return fail(h, rc, "%s", ccb_last_error(nullptr));
     }
-    if ((rc = nearest())) return rc;
     {
         Timed tm(h, CCB_CAT_SPEC);
         k_bs_spec_o<<<BS_RMAX / BS_THREADS, BS_THREADS, 0, s>>>(e);
-        launches += 1;
-    }
-    for (int it = 0; it < h->bs_iters; ++it) {
-        if (it > 0 && (rc = nearest())) return rc;
-        {
-            Timed tm(h, CCB_CAT_LISTS);
-            k_bs_tilecnt<<<g_tiles, BS_THREADS, 0, s>>>(e);
-            k_bs_pscan<<<1, BS_CTA1, 0, s>>>(e);
-            k_bs_pscatter<<<g_tiles, BS_THREADS, 0, s>>>(e);
-        }
-        {
-            Timed tm(h, CCB_CAT_PCORE);
-            CCB_DISPATCH_DP(h->DP, { k_bs_chain_p<kDP><<<std::max(mp_bound, 1), BS_CHAINP_THREADS, ChainPCfg<kDP>::SMEM, s>>>(e); })
-        }
-        {
-            Timed tm(h, CCB_CAT_OLIST);
-            k_bs_olist<<<1, BS_CTA1, 0, s>>>(e);
-        }
-        {
-            Timed tm(h, CCB_CAT_CHAIN_O);
-            CCB_DISPATCH_DP(h->DP, { k_bs_chain_o<kDP><<<BS_RMAX, BS_THREADS, 0, s>>>(e); })
-        }
-        {
-            Timed tm(h, CCB_CAT_DERIVE);
-            k_bs_derive<<<g_cells, BS_THREADS, 0, s>>>(e);
-        }
-        {
-            Timed tm(h, CCB_CAT_RESOLVE);
-            CCB_DISPATCH_DP(h->DP, {
-                k_bs_verify_p<kDP><<<g_tiles, BS_THREADS, 0, s>>>(e);
-                k_bs_verify_o<kDP><<<148 * 2, BS_THREADS, 0, s>>>(e);
-            })
-        }
-        {
-            Timed tm(h, CCB_CAT_DECIDE);
-            k_bs_decide<<<1, BS_CTA1, 0, s>>>(e);
-        }
-        launches += 10;
     }
     {
-        Timed tm(h, CCB_CAT_COMMIT);
-        k_bs_commit_rows<<<(mp_bound + BS_RMAX + 3) / 4, BS_THREADS, 0, s>>>(e);
-        k_bs_commit_cells<<<g_cells, BS_THREADS, 0, s>>>(e);
-        k_bs_finish<<<1, BS_THREADS, 0, s>>>(e);
-        launches += 3;
+        Timed tm(h, CCB_CAT_LISTS);
+        k_bs_tilecnt<<<g_tiles, BS_THREADS, 0, s>>>(e);
+        k_bs_pscan<<<std::max(mp_grid, 1), BS_CTA1, 0, s>>>(e);
+        k_bs_pscatter<<<g_tiles, BS_THREADS, 0, s>>>(e);
+    }
+    {
+        Timed tm(h, CCB_CAT_PCORE);
+        CCB_DISPATCH_DP(h->DP, { k_bs_chain_p<kDP><<<std::max(mp_grid, 1), BS_CHAINP_THREADS, ChainPCfg<kDP>::SMEM, s>>>(e); })
+    }
+    {
+        Timed tm(h, CCB_CAT_OLIST);
+        k_bs_olist<<<1, BS_CTA1, 0, s>>>(e);
+    }
+    {
+        Timed tm(h, CCB_CAT_CHAIN_O);
+        CCB_DISPATCH_DP(h->DP, { k_bs_chain_o<kDP><<<BS_RMAX, BS_THREADS, 0, s>>>(e); })
+    }
+    {
+        Timed tm(h, CCB_CAT_DERIVE);
+        k_bs_derive<<<g_cells, BS_THREADS, 0, s>>>(e);
+    }
+    {
+        Timed tm(h, CCB_CAT_RESOLVE);
+        CCB_DISPATCH_DP(h->DP, {
+            k_bs_verify_p<kDP><<<g_tiles, BS_THREADS, 0, s>>>(e);
+            k_bs_verify_o<kDP><<<148 * 2, BS_THREADS, 0, s>>>(e);
+        })
+    }
+    {
+        Timed tm(h, CCB_CAT_DECIDE);
+        k_bs_decide<<<1, BS_CTA1, 0, s>>>(e);
     }
     CKL(h);
-    h->st.kernel_launches += launches;
     return CCB_OK;
+}
+constexpr int BS_LAUNCHES_PROLOGUE = 3, BS_LAUNCHES_ROUND = 13, BS_LAUNCHES_COMMIT = 3;
+
+int launch_commit(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid) {
+    const int g_cells = (h->bs_bmax + BS_THREADS - 1) / BS_THREADS;
+    Timed tm(h, CCB_CAT_COMMIT);
+    k_bs_commit_rows<<<(mp_grid + BS_RMAX + 3) / 4, BS_THREADS, 0, s>>>(e);
+    k_bs_commit_cells<<<g_cells, BS_THREADS, 0, s>>>(e);
+    k_bs_finish<<<1, BS_THREADS, 0, s>>>(e);
+    CKL(h);
+    return CCB_OK;
+}
+
+Eng make_eng(ccb_handle *h) {
+    Eng e{};
+    e.P = h->P[h->pcur];
+    e.O = h->O[h->ocur];
+    e.ctl = h->d_ctl;
+    e.bc = h->d_bc;
+    e.ws = h->ws;
+    return e;
+}
+
+// ---- CUDA graph of the whole ordered loop: WHILE(block) { prologue; WHILE(round) { round }; commit } ----------
+void drop_graph(ccb_handle *h) {
+    if (h->bs_exec) cudaGraphExecDestroy(h->bs_exec);
+    if (h->bs_graph) cudaGraphDestroy(h->bs_graph);
+    h->bs_exec = nullptr;
+    h->bs_graph = nullptr;
+}
+
+int build_graph(ccb_handle *h, const Eng &base) {
+    drop_graph(h);
+    if (!h->cap1) {
+        CK(h, cudaStreamCreateWithFlags(&h->cap1, cudaStreamNonBlocking));
+        CK(h, cudaStreamCreateWithFlags(&h->cap2, cudaStreamNonBlocking));
+    }
+    Eng e = base;
+    e.io = h->d_io;
+    CK(h, cudaGraphCreate(&h->bs_graph, 0));
+    cudaGraphConditionalHandle ho, hi;
+    CK(h, cudaGraphConditionalHandleCreate(&ho, h->bs_graph, 1, cudaGraphCondAssignDefault));
+    CK(h, cudaGraphConditionalHandleCreate(&hi, h->bs_graph, 0, cudaGraphCondAssignDefault));
+    e.h_outer = ho;
+    e.h_inner = hi;
+    cudaGraphNodeParams po = {};
+    po.type = cudaGraphNodeTypeConditional;
+    po.conditional.handle = ho;
+    po.conditional.type = cudaGraphCondTypeWhile;
+    po.conditional.size = 1;
+    cudaGraphNode_t outer;
+    CK(h, cudaGraphAddNode(&outer, h->bs_graph, nullptr, 0, &po));
+    cudaGraph_t body_o = po.conditional.phGraph_out[0];
+    const int mp_grid = e.P.cap, mo_bound = e.O.cap;
+    int rc;
+    CK(h, cudaStreamBeginCaptureToGraph(h->cap1, body_o, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    if ((rc = launch_prologue(h, e, h->cap1))) return rc;
+    {
+        cudaStreamCaptureStatus st;
+        cudaGraph_t cg = nullptr;
+        const cudaGraphNode_t *deps = nullptr;
+        size_t ndeps = 0;
+        CK(h, cudaStreamGetCaptureInfo(h->cap1, &st, nullptr, &cg, &deps, &ndeps));
+        cudaGraphNodeParams pi = {};
+        pi.type = cudaGraphNodeTypeConditional;
+        pi.conditional.handle = hi;
+        pi.conditional.type = cudaGraphCondTypeWhile;
+        pi.conditional.size = 1;
+        cudaGraphNode_t inner;
+        CK(h, cudaGraphAddNode(&inner, cg, deps, ndeps, &pi));
+        CK(h, cudaStreamUpdateCaptureDependencies(h->cap1, &inner, 1, cudaStreamSetCaptureDependencies));
+        cudaGraph_t body_i = pi.conditional.phGraph_out[0];
+        CK(h, cudaStreamBeginCaptureToGraph(h->cap2, body_i, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+        if ((rc = launch_round(h, e, h->cap2, mp_grid, mo_bound))) return rc;
+        CK(h, cudaStreamEndCapture(h->cap2, nullptr));
+    }
+    if ((rc = launch_commit(h, e, h->cap1, mp_grid))) return rc;
+    CK(h, cudaStreamEndCapture(h->cap1, nullptr));
+    CK(h, cudaGraphInstantiate(&h->bs_exec, h->bs_graph, 0));
+    h->bs_graph_eng = base;
+    return CCB_OK;
+}
+
+int ensure_bsv_capacity(ccb_handle *h, int blocks_ahead) {
+    int rc;
+    const Ctl &c = *h->h_ctl;
+    const int64_t need_o = (int64_t)c.n_outlier + (int64_t)(blocks_ahead + 1) * BS_RMAX + 1;
+    if (need_o > h->O[h->ocur].cap) {
+        if ((rc = grow_store(h, h->O, h->ocur, c.n_outlier, need_o))) return rc;
+        if ((rc = realloc_aux_for_outlier_cap(h))) return rc;
+    }
+    if (c.n_pcore + blocks_ahead + 1 > h->P[h->pcur].cap) {
+        if ((rc = grow_store(h, h->P, h->pcur, c.n_pcore, c.n_pcore + blocks_ahead + 1))) return rc;
+        if ((rc = realloc_aux_for_pcore_cap(h))) return rc;
+    }
+    return ensure_bs_ws(h);
 }
 
 // the ordered loop over cells [0, N) of a device-resident X, block-speculative engine
@@ -665,53 +769,61 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
     cudaStream_t s = h->stream;
     int rc;
     if ((rc = ensure_bs_ws(h))) return rc;
+    const bool graph = h->bs_use_graph && !h->timing;
     const int bmax = h->bs_bmax, bmin = std::min(h->bs_bmin, h->bs_bmax);
-    k_bs_init<<<1, 1, 0, s>>>(h->d_bc, N, h->bs_iters, bmin, bmax);
+    const int itmax = graph ? (h->prm.bsv_iters > 0 ? h->bs_iters : 8) : h->bs_iters;
+    k_bs_init<<<1, 1, 0, s>>>(h->d_bc, N, itmax, bmin, bmax);
     CKL(h);
     h->st.kernel_launches++;
     if ((rc = sync_bc(h))) return rc;
-    const double theta = 4.0 * h->prm.eps2; // CONTESTED above 4 eps^2: heuristic only, never affects results
+    EngIo io{};
+    io.X = dX;
+    io.ld = ld;
+    io.assign = d_assign;
+    io.stage = d_stage;
+    io.theta = 4.0 * h->prm.eps2; // CONTESTED above 4 eps^2: heuristic only, never affects results
+    io.nm = make_num(h);
+    if (graph) {
+        *h->h_io = io;
+        CK(h, cudaMemcpyAsync(h->d_io, h->h_io, sizeof(EngIo), cudaMemcpyHostToDevice, s));
+    }
     int guard = 0;
     while (!h->h_bc->done) {
-        const Ctl &c = *h->h_ctl;
         const BsCtl &b = *h->h_bc;
-        // blocks to enqueue before the next look at the control block
         const int64_t left = N - b.pos;
+        // blocks to enqueue before the next look at the control block (stream launches); the graph runs until the
+        // input is consumed or a store is full, so give it room for a good stretch of blocks
         int G = (int)std::min<int64_t>(16, (left + std::max(b.next_B, 1) - 1) / std::max(b.next_B, 1) + 1);
         if (G < 1) G = 1;
-        // capacity: every block may append BS_RMAX outlier MCs and upgrade one MC
-        const int64_t need_o = (int64_t)c.n_outlier + (int64_t)(G + 1) * BS_RMAX + 1;
-        if (need_o > h->O[h->ocur].cap) {
-            if ((rc = grow_store(h, h->O, h->ocur, c.n_outlier, need_o))) return rc;
-            if ((rc = realloc_aux_for_outlier_cap(h))) return rc;
-        }
-        if (c.n_pcore + G + 1 > h->P[h->pcur].cap) {
-            if ((rc = grow_store(h, h->P, h->pcur, c.n_pcore, c.n_pcore + G + 1))) return rc;
-            if ((rc = realloc_aux_for_pcore_cap(h))) return rc;
-        }
-        if ((rc = ensure_bs_ws(h))) return rc;
+        if ((rc = ensure_bsv_capacity(h, graph ? 32 : G))) return rc;
         if (b.need_grow) {
             h->h_bc->need_grow = 0;
             CK(h, cudaMemcpyAsync(&h->d_bc->need_grow, &h->h_bc->need_grow, sizeof(int32_t), cudaMemcpyHostToDevice, s));
         }
-        Eng e{};
-        e.X = dX;
-        e.ld = ld;
-        e.P = h->P[h->pcur];
-        e.O = h->O[h->ocur];
-        e.nm = make_num(h);
-        e.ctl = h->d_ctl;
-        e.bc = h->d_bc;
-        e.ws = h->ws;
-        e.assign = d_assign;
-        e.stage = d_stage;
-        e.theta = theta;
-        for (int g = 0; g < G; ++g)
-            if ((rc = enqueue_block(h, e, c.n_pcore + g + 1, (int)std::min<int64_t>(c.n_outlier + (int64_t)(g + 1) * BS_RMAX,
-                                                                                   h->O[h->ocur].cap))))
-                return rc;
+        Eng e = make_eng(h);
         const int64_t pos0 = b.pos;
+        const int64_t blocks0 = b.blocks, iters0 = b.iters;
+        if (graph) {
+            if (!h->bs_exec || memcmp(&h->bs_graph_eng, &e, sizeof(Eng)) != 0)
+                if ((rc = build_graph(h, e))) return rc;
+            CK(h, cudaGraphLaunch(h->bs_exec, s));
+        } else {
+            const Ctl &c = *h->h_ctl;
+            e.X = io.X, e.ld = io.ld, e.assign = io.assign, e.stage = io.stage, e.theta = io.theta, e.nm = io.nm;
+            for (int g = 0; g < G; ++g) {
+                const int mp_grid = c.n_pcore + g + 1;
+                const int mo_bound = (int)std::min<int64_t>(c.n_outlier + (int64_t)(g + 1) * BS_RMAX, h->O[h->ocur].cap);
+                if ((rc = launch_prologue(h, e, s))) return rc;
+                for (int it = 0; it < h->bs_iters; ++it)
+                    if ((rc = launch_round(h, e, s, mp_grid, mo_bound))) return rc;
+                if ((rc = launch_commit(h, e, s, mp_grid))) return rc;
+                h->st.kernel_launches += BS_LAUNCHES_PROLOGUE + h->bs_iters * BS_LAUNCHES_ROUND + BS_LAUNCHES_COMMIT;
+            }
+        }
         if ((rc = sync_bc(h))) return rc;
+        if (graph) // kernels the graph executed: per block prologue + commit, per round the round's kernels
+            h->st.kernel_launches += (h->h_bc->blocks - blocks0) * (BS_LAUNCHES_PROLOGUE + BS_LAUNCHES_COMMIT) +
+                                     (h->h_bc->iters - iters0) * BS_LAUNCHES_ROUND + BS_LAUNCHES_PROLOGUE;
         if (h->h_bc->pos == pos0 && !h->h_bc->need_grow && !h->h_bc->done && ++guard > 4)
             return fail(h, CCB_ESTATE, "internal: block-speculative engine made no progress at row %lld", (long long)pos0);
         if (h->h_bc->pos != pos0) guard = 0;
@@ -786,6 +898,7 @@ int ccb_create(const ccb_params *p, ccb_handle **out) {
     if (p->chunk > 0) h->bs_bmax = std::max(32, (p->chunk + 31) / 32 * 32); // block length cap of the BSV engine
     if (p->bsv_bmin > 0) h->bs_bmin = p->bsv_bmin;
     if (p->bsv_iters > 0) h->bs_iters = std::min(p->bsv_iters, 16);
+    h->bs_use_graph = p->bsv_stream == 0;
     h->bs_bmax = std::min(h->bs_bmax, 1 << 20);
     const bool p2 = is_pow2(p->k);
     h->div_mode = p2 ? 0 : 1;
@@ -855,10 +968,16 @@ void ccb_destroy(ccb_handle *h) {
     cudaFree(h->d_pfin);
     cudaFree(h->d_onew);
     cudaFree(h->d_dist_gmem);
+    drop_graph(h);
+    if (h->cap1) cudaStreamDestroy(h->cap1);
+    if (h->cap2) cudaStreamDestroy(h->cap2);
+    cudaFree(h->d_io);
+    if (h->h_io) cudaFreeHost(h->h_io);
     cudaFree(h->d_bc);
     if (h->h_bc) cudaFreeHost(h->h_bc);
     for (void *q : h->ws_allocs) cudaFree(q);
     for (void *q : h->ws_tiles) cudaFree(q);
+    cudaFree(h->ws.dbg);
     cudaFree(h->ws_first);
     for (auto &e : h->ev_pending) {
         cudaEventDestroy(e.a);
@@ -902,6 +1021,29 @@ int ccb_debug_phase_cycles(ccb_handle *h, int64_t out[8]) {
     int rc = sync_ctl(h);
     if (rc) return rc;
     for (int i = 0; i < 8; ++i) out[i] = h->h_ctl->phase_cycles[i];
+    return CCB_OK;
+}
+
+int ccb_debug_set(ccb_handle *h, int32_t mode) {
+    if (!h) return fail(h, CCB_EINVAL, "null argument");
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaMemcpyToSymbol(g_bs_dbg_mode, &mode, sizeof(int)));
+    return CCB_OK;
+}
+
+int ccb_debug_chain(ccb_handle *h, int64_t *out, int32_t max_keys) {
+    if (!h || !out) return fail(h, CCB_EINVAL, "null argument");
+    if (!h->ws.dbg) { // first call switches the counters on
+        if (h->ws.mp_stride <= 0) return fail(h, CCB_ESTATE, "no block-speculative workspace yet");
+        CK(h, cudaStreamSynchronize(h->stream));
+        CK(h, cudaMalloc(&h->ws.dbg, (size_t)h->ws.mp_stride * 8 * sizeof(int64_t)));
+        CK(h, cudaMemset(h->ws.dbg, 0, (size_t)h->ws.mp_stride * 8 * sizeof(int64_t)));
+        memset(out, 0, (size_t)max_keys * 8 * sizeof(int64_t));
+        return CCB_OK;
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    const int n = std::min<int>(max_keys, h->ws.mp_stride);
+    CK(h, cudaMemcpy(out, h->ws.dbg, (size_t)n * 8 * sizeof(int64_t), cudaMemcpyDeviceToHost));
     return CCB_OK;
 }
 
@@ -1396,10 +1538,71 @@ __global__ void k_fp64_peak(int mode, int iters, double *sink) {
     if (r == 123.456) sink[0] = r;
 }
 
+// single-warp latency probes (cycles per dependent step), results in sink[1..]
+__global__ void k_fp64_latency(double *sink) {
+    __shared__ double sm[64 * 26];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 64 * 26; i += 32) sm[i] = 1e-9 * i;
+    __syncwarp();
+    double a = lane * 1e-9 + 1.0;
+    const double c = 1e-12, m = 1.0000000001;
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < 1024; ++i) a = __dadd_rn(a, c);
+    long long t1 = clock64();
+    const double r_add = (double)(t1 - t0) / 1024.0;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < 1024; ++i) a = __dmul_rn(a, m);
+    t1 = clock64();
+    const double r_mul = (double)(t1 - t0) / 1024.0;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < 1024; ++i) a = __fma_rn(a, m, c);
+    t1 = clock64();
+    const double r_fma = (double)(t1 - t0) / 1024.0;
+    // the replay pattern: 8 loads, 8 chained adds, 8 stores in place
+    t0 = clock64();
+    for (int g = 0; g < 128; ++g) {
+        double av[8];
+        const int base = (g & 7) * 8 * 26 + (lane < 26 ? lane : 0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) av[q] = sm[base + q * 26];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            a = __dadd_rn(a, av[q]);
+            if (lane < 26) sm[base + q * 26] = a;
+        }
+    }
+    t1 = clock64();
+    const double r_rep = (double)(t1 - t0) / 1024.0;
+    float f = (float)a;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < 1024; ++i) f = __fadd_rn(f, 1e-6f);
+    t1 = clock64();
+    const double r_fadd = (double)(t1 - t0) / 1024.0;
+    if (lane == 0) {
+        sink[1] = r_add;
+        sink[2] = r_mul;
+        sink[3] = r_fma;
+        sink[4] = r_rep;
+        sink[5] = r_fadd;
+        sink[6] = a + f;
+    }
+}
+
 int ccb_fp64_peak(int32_t device, void *stream, int32_t mode, int32_t iters, int32_t blocks, double *sink,
                   double *flops_out) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    if (mode == 2) { // latency probes: sink[1..5] = cycles per dependent DADD, DMUL, DFMA, replay step, FADD
+        k_fp64_latency<<<1, 32, 0, (cudaStream_t)stream>>>(sink);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "k_fp64_latency: %s", cudaGetErrorString(e));
+        if (flops_out) *flops_out = 0.0;
+        return CCB_OK;
+    }
     k_fp64_peak<<<blocks, 256, 0, (cudaStream_t)stream>>>(mode, iters, sink);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "k_fp64_peak: %s", cudaGetErrorString(e));

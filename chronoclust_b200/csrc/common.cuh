@@ -13,6 +13,13 @@
 
 namespace ccb {
 
+// Per-call input reference read from device memory (CUDA-graph launches bake kernel arguments in; what changes
+// from call to call is reached through this indirection instead).
+struct XRef {
+    const double *X;
+    int64_t ld;
+};
+
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }

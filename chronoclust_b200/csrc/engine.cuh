@@ -57,7 +57,7 @@ struct BsCtl {
     int32_t npend;
     int32_t m_commit, upgrade;
     int32_t need_grow, done;
-    int32_t pad0;
+    int32_t ticket; // k_bs_pscan: CTAs finished (last one computes the key offsets)
     int64_t blocks, iters, mismatches, cuts_unknown, cuts_iter, cuts_cap, tk_late, rejects, contested, replayed, pairs;
 };
 
@@ -75,11 +75,23 @@ struct BsWs {
     int32_t *tk_idx; // [BS_RMAX][BS_TOPK]
     int32_t *hkey, *hoff, *omem, *hrank; // hrank[q]: real creations before key hnew0 + q
     int32_t *firstmember; // [O.cap], INT_MAX = unmodified in this block
+    int64_t *dbg; // optional [mp_stride][8] per-key cycle counters of k_bs_chain_p (diagnostics), or nullptr
     int32_t mp_stride, bmax, dp, lsp;
 };
 __device__ __forceinline__ double *ver_cf1(const BsWs &w, int i) { return w.ver + (size_t)i * w.lsp; }
 __device__ __forceinline__ double *ver_cf2(const BsWs &w, int i) { return w.ver + (size_t)i * w.lsp + w.dp; }
 __device__ __forceinline__ double &ver_w(const BsWs &w, int i) { return w.ver[(size_t)i * w.lsp + 2 * w.dp]; }
+
+// What changes from one ccb_ingest call to the next.  Stream launches pass it inside Eng; CUDA-graph launches (whose
+// kernel arguments are baked in) read it from device memory through Eng::io.
+struct EngIo {
+    const double *X; // first two fields = XRef (kernel 1 reads them through the same pointer)
+    int64_t ld;
+    int32_t *assign;
+    uint8_t *stage;
+    double theta; // contested threshold on the snapshot distance
+    Num nm;
+};
 
 struct Eng {
     const double *X;
@@ -91,7 +103,19 @@ struct Eng {
     BsWs ws;
     int32_t *assign;
     uint8_t *stage;
-    double theta; // contested threshold on the snapshot distance
+    double theta;
+    const EngIo *io;                 // nullptr: the fields above are current
+    unsigned long long h_outer, h_inner; // cudaGraphConditionalHandle of the block loop / round loop, 0 = stream launches
+    __device__ __forceinline__ void fetch() {
+        if (io) {
+            X = io->X;
+            ld = io->ld;
+            assign = io->assign;
+            stage = io->stage;
+            theta = io->theta;
+            nm = io->nm;
+        }
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -191,36 +215,42 @@ __global__ void k_bs_init(BsCtl *bc, int64_t N, int32_t itmax, int32_t bmin, int
 }
 
 __global__ void k_bs_begin(Eng e) {
+    e.fetch();
     BsCtl *bc = e.bc;
     bc->active = 0;
     bc->tk_lo = bc->tk_hi = 0; // an idle block must not leave kernel 1 any work
-    if (bc->done || bc->need_grow) return;
-    if (bc->pos >= bc->N) {
-        bc->done = 1;
-        return;
-    }
-    const int Mp = e.ctl->n_pcore, Mo0 = e.ctl->n_outlier;
-    if ((int64_t)Mo0 + BS_RMAX + 1 > e.O.cap) {
-        bc->need_grow = 1;
-        return;
-    }
-    if (Mp + 1 > e.P.cap || Mp + 1 > e.ws.mp_stride) {
-        bc->need_grow = 2;
-        return;
-    }
-    const int64_t left = bc->N - bc->pos;
-    bc->Bcur = (int32_t)(left < bc->next_B ? left : bc->next_B);
-    bc->Beff = bc->Bcur;
-    bc->Mp = Mp;
-    bc->Mo0 = Mo0;
-    bc->nneed = bc->tk_lo = bc->tk_hi = 0;
-    bc->nh = bc->hnew0 = bc->no = 0;
-    bc->npend = 0;
-    bc->it = 0;
-    bc->phase = 0;
-    bc->m_commit = 0;
-    bc->upgrade = 0;
-    bc->active = 1;
+    do {
+        if (bc->done || bc->need_grow) break;
+        if (bc->pos >= bc->N) {
+            bc->done = 1;
+            break;
+        }
+        const int Mp = e.ctl->n_pcore, Mo0 = e.ctl->n_outlier;
+        if ((int64_t)Mo0 + BS_RMAX + 1 > e.O.cap) {
+            bc->need_grow = 1;
+            break;
+        }
+        if (Mp + 1 > e.P.cap || Mp + 1 > e.ws.mp_stride) {
+            bc->need_grow = 2;
+            break;
+        }
+        const int64_t left = bc->N - bc->pos;
+        bc->Bcur = (int32_t)(left < bc->next_B ? left : bc->next_B);
+        bc->Beff = bc->Bcur;
+        bc->Mp = Mp;
+        bc->Mo0 = Mo0;
+        bc->nneed = 0;
+        bc->nh = bc->hnew0 = bc->no = 0;
+        bc->npend = 0;
+        bc->it = 0;
+        bc->phase = 0;
+        bc->m_commit = 0;
+        bc->upgrade = 0;
+        bc->active = 1;
+    } while (0);
+    // graph launches: the round loop runs iff the block is active; an idle block also ends the block loop
+    if (e.h_inner) cudaGraphSetConditional(e.h_inner, bc->active ? 1u : 0u);
+    if (e.h_outer && !bc->active) cudaGraphSetConditional(e.h_outer, 0u);
 }
 
 // ---- S ----------------------------------------------------------------------------------------------
@@ -228,6 +258,7 @@ constexpr int BS_THREADS = 128;
 
 template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_spec(Eng e) {
+    e.fetch();
     const BsCtl *bc = e.bc;
     if (!bc->active) return;
     const int i = blockIdx.x * BS_THREADS + threadIdx.x;
@@ -294,6 +325,7 @@ __device__ __forceinline__ int block_exclusive_scan_1024(int v, int *s_warp, int
 }
 
 __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
+    e.fetch();
     __shared__ int s_warp[33];
     __shared__ int s_cut;
     BsCtl *bc = e.bc;
@@ -331,8 +363,9 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
 
 // speculated outlier-stage decision of the need list: nearest snapshot MC + radius test on the snapshot state
 __global__ void __launch_bounds__(BS_THREADS) k_bs_spec_o(Eng e) {
+    e.fetch();
     const BsCtl *bc = e.bc;
-    if (!bc->active) return;
+    if (!bc->active || bc->phase != 0 || bc->it != 0) return; // first round of a block only
     const int t = blockIdx.x * BS_THREADS + threadIdx.x;
     if (t >= bc->nneed) return;
     const int i = e.ws.ncell[t];
@@ -361,6 +394,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_spec_o(Eng e) {
 // ---- L ----------------------------------------------------------------------------------------------
 // per (tile of 32 cells, pcore key): number of candidates
 __global__ void __launch_bounds__(BS_THREADS) k_bs_tilecnt(Eng e) {
+    e.fetch();
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const int lane = threadIdx.x & 31;
@@ -382,50 +416,55 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_tilecnt(Eng e) {
     }
 }
 
-// per key: exclusive prefix of the tile counts (in place), then the key offsets
+// per key (one CTA each): exclusive prefix of the tile counts (in place) and the key's total; the last CTA to
+// finish turns the totals into the (padded) key offsets
 __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
+    e.fetch();
     __shared__ int s_warp[33];
+    __shared__ int s_last;
     BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Mp = bc->Mp, stride = e.ws.mp_stride;
+    const int j = blockIdx.x;
+    if (j >= Mp) return;
     const int ntiles = (bc->Beff + 31) >> 5;
-    const int per = (ntiles + 31) / 32;
-    for (int j = warp; j < Mp; j += BS_CTA1 / 32) {
-        const int t0 = min(ntiles, lane * per), t1 = min(ntiles, t0 + per);
-        int sum = 0;
-        for (int t = t0; t < t1; ++t) sum += e.ws.tilecnt[(size_t)t * stride + j];
-        int inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        int run = inc - sum;
-        for (int t = t0; t < t1; ++t) {
-            const int c = e.ws.tilecnt[(size_t)t * stride + j];
-            e.ws.tilecnt[(size_t)t * stride + j] = run;
-            run += c;
-        }
-        if (lane == 31) e.ws.pcnt[j] = inc; // total of key j
-    }
-    __syncthreads();
-    // exclusive scan of the totals, each rounded up to a multiple of 4 entries so that every key's segment of
-    // plist / xg starts 16-byte aligned (bulk-copy requirement of the chain kernel); Mp is small: chunks of 1024
     int carry = 0;
-    for (int j0 = 0; j0 < Mp; j0 += BS_CTA1) {
-        const int j = j0 + threadIdx.x;
-        const int v = j < Mp ? ((e.ws.pcnt[j] + 3) & ~3) : 0;
+    for (int t0 = 0; t0 < ntiles; t0 += BS_CTA1) {
+        const int t = t0 + threadIdx.x;
+        const int v = t < ntiles ? e.ws.tilecnt[(size_t)t * stride + j] : 0;
         int total;
         const int ex = block_exclusive_scan_1024(v, s_warp, total);
-        if (j < Mp) e.ws.poff[j] = carry + ex;
+        if (t < ntiles) e.ws.tilecnt[(size_t)t * stride + j] = carry + ex;
         carry += total;
     }
-    if (threadIdx.x == 0) e.ws.poff[Mp] = carry;
+    if (threadIdx.x == 0) {
+        e.ws.pcnt[j] = carry;
+        __threadfence();
+        s_last = atomicAdd(&bc->ticket, 1) == Mp - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // exclusive scan of the totals, each rounded up to a multiple of 4 entries so that every key's segment of
+    // plist / xg starts 16-byte aligned (bulk-copy requirement of the chain kernel)
+    carry = 0;
+    for (int j0 = 0; j0 < Mp; j0 += BS_CTA1) {
+        const int jj = j0 + threadIdx.x;
+        const int v = jj < Mp ? ((((volatile int32_t *)e.ws.pcnt)[jj] + 3) & ~3) : 0;
+        int total;
+        const int ex = block_exclusive_scan_1024(v, s_warp, total);
+        if (jj < Mp) e.ws.poff[jj] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        e.ws.poff[Mp] = carry;
+        bc->ticket = 0;
+    }
 }
 
 // plist[pos] = cell | CONTESTED << 31 and xg[pos] = the cell's ADDEND record (x, x*x, 1.0), pos in (key, cell) order
 __global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
+    e.fetch();
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const int lane = threadIdx.x & 31;
@@ -478,6 +517,7 @@ constexpr int BS_CHAIN_PRODUCERS = BS_THREADS - 32;
 
 template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_chain_o(Eng e) {
+    e.fetch();
     constexpr int NB = ChainCfg<DP>::NB;
     constexpr int GS = 8;
     constexpr int NH = DP > 32 ? 2 : 1;
@@ -625,8 +665,9 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_chain_o(Eng e) {
 //             (cp.async.bulk + mbarrier complete_tx);
 //   replay    warp 0, lane = record element: a <- LDS, v += a, v -> STS over the addend it just consumed (the stage
 //             now holds the VERSION after every cell);
-//   storer    one warp sends every version record to ver[cell] with a bulk TMA store (shared -> global) and
-//             releases the stage.
+//   storers   two warps copy every version record to ver[cell] (scattered 16 D + 16 byte rows: plain coalesced
+//             stores -- one bulk TMA store per record caps the kernel at the TMA unit's per-operation rate) and
+//             release the stage.
 // A single warp cannot hide instruction latency, so everything that is not the dependent add lives in the other two.
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -637,18 +678,35 @@ __device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_sme
                  : "memory");
 }
 
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ int4 lds_v4(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+
 template <int DP>
 struct ChainPCfg {
     static constexpr int LSP = 2 * DP + 2;
     static constexpr int NH = (LSP + 31) / 32;
     static constexpr int NB = DP <= 16 ? 64 : 32;
     static constexpr int S = DP <= 48 ? 8 : 6;
-    static constexpr size_t SMEM = (size_t)S * NB * (LSP * 8 + 4) + 3 * S * 8 + 128;
+    static constexpr size_t SMEM = (size_t)S * NB * (LSP * 8 + 4) + 3 * S * 8 + DP * 8 + 128;
 };
-constexpr int BS_CHAINP_THREADS = 96;
+constexpr int BS_CHAINP_THREADS = 128;
+
+__device__ int g_bs_dbg_mode = 0; // diagnostics only (ccb_debug_set): 1 = storers skip the global stores, 2 = skip the copies
 
 template <int DP>
 __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
+    e.fetch();
     using Cfg = ChainPCfg<DP>;
     constexpr int NB = Cfg::NB, S = Cfg::S, GS = 8, NH = Cfg::NH, LSP = Cfg::LSP;
     extern __shared__ __align__(128) unsigned char bs_smem[];
@@ -657,6 +715,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
     uint64_t *full = reinterpret_cast<uint64_t *>(ms + S * NB);    // [S] producer -> replay
     uint64_t *done = full + S;                                     // [S] replay -> storer
     uint64_t *empty = done + S;                                    // [S] storer -> producer
+    double *scr = reinterpret_cast<double *>(empty + S);           // [DP] radius terms of a CONTESTED cell
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const Num nm = e.nm;
@@ -674,43 +733,79 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&done[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], 2);
         }
         mbar_fence_init();
     }
     __syncthreads();
     if (warp == 1) { // ---- producer
         if (lane == 0) {
+            long long tw = 0;
             for (int b = 0; b < nb; ++b) {
                 const int s = b % S;
-                if (b >= S) mbar_wait(&empty[s], ((b / S) - 1) & 1);
+                if (b >= S) {
+                    const long long t0 = clock64();
+                    mbar_wait(&empty[s], ((b / S) - 1) & 1);
+                    tw += clock64() - t0;
+                }
                 const int cnt = min(NB, n - b * NB);
                 const uint32_t bx = (uint32_t)cnt * LSP * 8u, bi = (uint32_t)((cnt + 3) & ~3) * 4u;
                 mbar_expect_tx(&full[s], bx + bi);
                 tma_load_1d(xs + (size_t)s * NB * LSP, xg + (size_t)b * NB * LSP, bx, &full[s]);
                 tma_load_1d(ms + s * NB, pl + b * NB, bi, &full[s]);
             }
+            if (e.ws.dbg) e.ws.dbg[j * 8 + 7] = tw;
         }
         return;
     }
-    if (warp == 2) { // ---- storer: bulk stores run LAG stages behind before their stage is handed back
-        constexpr int LAG = 2;
+    if (warp >= 2) { // ---- storers: two warps; ver[cell] <- the version left in the stage
+        // the stage is one flat array of cnt * LSP doubles: lane = element, eight elements in flight per lane
+        // (index and value loads first, then the stores) so that the shared-memory latency is paid once per eight
+        constexpr int U = 4, L2 = LSP / 2; // records are L2 double2 wide
+        const int st = (warp - 2) * 32 + lane;
+        long long tw = 0;
+        const long long tbeg = clock64();
         for (int b = 0; b < nb; ++b) {
             const int s = b % S;
-            mbar_wait(&done[s], (b / S) & 1);
-            const int cnt = min(NB, n - b * NB);
-            for (int m = lane; m < cnt; m += 32) {
-                const int i = ms[s * NB + m] & 0x7fffffff;
-                tma_store_1d(e.ws.ver + (size_t)i * LSP, xs + ((size_t)s * NB + m) * LSP, LSP * 8u);
+            {
+                const long long t0 = clock64();
+                mbar_wait(&done[s], (b / S) & 1);
+                tw += clock64() - t0;
             }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            if (b >= LAG) {
-                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(LAG) : "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[(b - LAG) % S]);
+            const int dbgm = g_bs_dbg_mode;
+            const int tot = dbgm == 2 ? 0 : min(NB, n - b * NB) * L2;
+            const double2 *xb = reinterpret_cast<const double2 *>(xs + (size_t)s * NB * LSP);
+            const int *mb = ms + s * NB;
+            double2 *ver2 = reinterpret_cast<double2 *>(e.ws.ver);
+            for (int e0 = st; e0 < tot; e0 += 64 * U) {
+                double2 val[U];
+                size_t off[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int el = e0 + 64 * u;
+                    if (el < tot) {
+                        const int row = el / L2;
+                        off[u] = (size_t)(mb[row] & 0x7fffffff) * L2 + (el - row * L2);
+                        val[u] = xb[el];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (e0 + 64 * u < tot) {
+                        if (dbgm == 1) {
+                            if (val[u].x == 1.2345e300) ver2[off[u]] = val[u];
+                        } else {
+                            ver2[off[u]] = val[u];
+                        }
+                    }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
         }
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (e.ws.dbg && warp == 2 && lane == 0) {
+            e.ws.dbg[j * 8 + 5] = clock64() - tbeg;
+            e.ws.dbg[j * 8 + 6] = tw;
+        }
         return;
     }
     // ---- replay (warp 0): lane owns elements lane + 32 h of the record
@@ -724,88 +819,172 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         else if (el == 2 * DP) x = e.P.w[j];
         v[h] = x;
     }
-    for (int b = 0; b < nb; ++b) {
-        const int s = b % S;
-        mbar_wait(&full[s], (b / S) & 1);
-        double *xb = xs + (size_t)s * NB * LSP;
-        const int *mb = ms + s * NB;
-        const int cnt = min(NB, n - b * NB);
-        for (int m0 = 0; m0 < cnt; m0 += GS) {
-            const int g = min(GS, cnt - m0);
-            bool fast = g == GS;
-            if (fast) {
-                const int4 a = *reinterpret_cast<const int4 *>(mb + m0), c = *reinterpret_cast<const int4 *>(mb + m0 + 4);
-                fast = (a.x | a.y | a.z | a.w | c.x | c.y | c.z | c.w) >= 0;
-            }
-            if (fast) {
-                double av[GS][NH];
+    long long t_wait = 0, t_slow = 0, n_cont = 0;
+    const long long t_beg = clock64();
+    // shared-window addresses as opaque registers: otherwise the compiler re-derives them from special registers
+    // (S2UR / S2R, tens of cycles each) inside the loop, which a lone warp cannot hide
+    uint32_t xs_lane = smem_u32(xs) + lane * 8, ms_base = smem_u32(ms);
+    asm volatile("" : "+r"(xs_lane), "+r"(ms_base));
+    bool st_ok[NH];
 #pragma unroll
-                for (int q = 0; q < GS; ++q)
+    for (int h = 0; h < NH; ++h) st_ok[h] = lane + 32 * h < LSP;
+
+    // One cell at a time (a group with a CONTESTED cell, or the ragged tail of a stage): the next cell's index and
+    // addend are fetched while the current one is processed.
+    auto slow = [&](double *xb, const int *mb, int m0, int g) {
+        const long long t_s0 = clock64();
+        int raw = mb[m0];
+        double a[NH];
 #pragma unroll
-                    for (int h = 0; h < NH; ++h) {
-                        const int el = lane + 32 * h;
-                        av[q][h] = (NH * 32 == LSP || el < LSP) ? xb[(m0 + q) * LSP + el] : 0.0;
-                    }
+        for (int h = 0; h < NH; ++h) {
+            const int el = lane + 32 * h;
+            a[h] = el < LSP ? xb[m0 * LSP + el] : 0.0;
+        }
+        for (int m = m0; m < m0 + g; ++m) {
+            const int raw_c = raw;
+            double nv[NH];
 #pragma unroll
-                for (int q = 0; q < GS; ++q)
-#pragma unroll
-                    for (int h = 0; h < NH; ++h) {
-                        const int el = lane + 32 * h;
-                        v[h] = dadd(v[h], av[q][h]);
-                        if (NH * 32 == LSP || el < LSP) xb[(m0 + q) * LSP + el] = v[h];
-                    }
-                continue;
-            }
-            for (int m = m0; m < m0 + g; ++m) {
-                const int raw = mb[m];
-                double nv[NH];
+            for (int h = 0; h < NH; ++h) nv[h] = dadd(v[h], a[h]);
+            if (m + 1 < m0 + g) {
+                raw = mb[m + 1];
 #pragma unroll
                 for (int h = 0; h < NH; ++h) {
                     const int el = lane + 32 * h;
-                    const double a = el < LSP ? xb[m * LSP + el] : 0.0;
-                    nv[h] = dadd(v[h], a);
-                    if (el < LSP) xb[m * LSP + el] = nv[h];
+                    a[h] = el < LSP ? xb[(m + 1) * LSP + el] : 0.0;
                 }
-                if (raw < 0) { // CONTESTED: exact radius test of the tentative MC (mc_functions.py:45-56)
+            }
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                const int el = lane + 32 * h;
+                if (el < LSP) xb[m * LSP + el] = nv[h];
+            }
+            if (raw_c < 0) { // CONTESTED: exact radius test of the tentative MC (mc_functions.py:45-56)
+                ++n_cont;
+                double wn, c1[2], c2[2];
+                if (NH == 1) { // the whole record lives in one register per lane: fetch CF2', W' by shuffle
+                    wn = __shfl_sync(0xffffffffu, nv[0], 2 * DP);
+                    c1[0] = nv[0];
+                    c2[0] = __shfl_sync(0xffffffffu, nv[0], (lane + DP) & 31);
+                    c1[1] = c2[1] = 1.0;
+                } else {
                     __syncwarp();
-                    const double wn = xb[m * LSP + 2 * DP];
-                    double term[2] = {0.0, 0.0};
+                    wn = xb[m * LSP + 2 * DP];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        if (h == 0 || DP > 32) {
-                            const int d = lane + 32 * h;
-                            const bool act = d < D;
-                            // idle lanes carry 1.0: their (discarded) quotients stay on the fast path of the division
-                            const double c1 = act ? xb[m * LSP + d] : 1.0;
-                            const double c2 = act ? xb[m * LSP + DP + d] : 1.0;
-                            const double a = ddiv(c2, wn);
-                            const double c = ddiv(c1, wn);
-                            const double var = dsub(a, dmul(c, c));
-                            const bool bit = act && (var <= nm.delta2);
-                            term[h] = bit ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var;
-                        }
+                        const int d = lane + 32 * h;
+                        const bool rd = (h == 0 || DP > 32) && d < D;
+                        c1[h] = rd ? xb[m * LSP + d] : 1.0;
+                        c2[h] = rd ? xb[m * LSP + DP + d] : 1.0;
                     }
-                    double r2 = 0.0;
-#pragma unroll
-                    for (int d = 0; d < DP; ++d) {
-                        if (d < D) r2 = dadd(r2, __shfl_sync(0xffffffffu, term[d >> 5], d & 31));
-                    }
-                    const bool ok = r2 <= nm.eps2;
-                    if (lane == 0) e.ws.prej[raw & 0x7fffffff] = ok ? 0 : 1;
-                    if (!ok) continue; // the record of a rejected cell is never read as a version
                 }
+                double term[2] = {0.0, 0.0};
 #pragma unroll
-                for (int h = 0; h < NH; ++h) v[h] = nv[h];
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 0 || DP > 32) {
+                        const int d = lane + 32 * h;
+                        const bool act = d < D;
+                        // idle lanes carry 1.0: their (discarded) quotients stay on the fast path of the division
+                        const double q2 = ddiv(act ? c2[h] : 1.0, wn);
+                        const double c = ddiv(act ? c1[h] : 1.0, wn);
+                        const double var = dsub(q2, dmul(c, c));
+                        const bool bit = act && (var <= nm.delta2);
+                        term[h] = bit ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var;
+                    }
+                }
+                // the D terms are summed in index order by every lane from shared memory (broadcast LDS.128)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if ((h == 0 || DP > 32) && lane + 32 * h < DP) scr[lane + 32 * h] = term[h];
+                __syncwarp();
+                double r2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < DP; d += 2) {
+                    const double2 t2 = *reinterpret_cast<const double2 *>(scr + d);
+                    if (d < D) r2 = dadd(r2, t2.x);
+                    if (d + 1 < D) r2 = dadd(r2, t2.y);
+                }
+                __syncwarp();
+                const bool ok = r2 <= nm.eps2;
+                if (lane == 0) e.ws.prej[raw_c & 0x7fffffff] = ok ? 0 : 1;
+                if (!ok) continue; // the record of a rejected cell is never read as a version
+            }
+#pragma unroll
+            for (int h = 0; h < NH; ++h) v[h] = nv[h];
+        }
+        t_slow += clock64() - t_s0;
+    };
+
+    for (int b = 0; b < nb; ++b) {
+        const int s = b % S;
+        {
+            const long long t0 = clock64();
+            mbar_wait(&full[s], (b / S) & 1);
+            t_wait += clock64() - t0;
+        }
+        double *xb = xs + (size_t)s * NB * LSP;
+        const int *mb = ms + s * NB;
+        const int cnt = __shfl_sync(0xffffffffu, min(NB, n - b * NB), 0); // warp-uniform for the compiler, too
+        const uint32_t xa = xs_lane + s * (NB * LSP * 8), ma = ms_base + s * (NB * 4);
+        // CONTESTED flags of the whole stage in one pass: lane l looks at cells 2 l and 2 l + 1; nibble g of cm is
+        // non-zero iff group g (cells 8 g .. 8 g + 7) holds a CONTESTED cell
+        unsigned cm;
+        {
+            int fx = 0, fy = 0;
+            if (2 * lane < NB) {
+                asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(fx), "=r"(fy) : "r"(ma + lane * 8));
+            }
+            cm = __ballot_sync(0xffffffffu, (fx < 0 && 2 * lane < cnt) || (fy < 0 && 2 * lane + 1 < cnt));
+        }
+        const int nfull = cnt / GS;
+        // software pipeline over the full groups of eight, two register sets (A / B): the addends of group g + 1 are
+        // fetched from shared memory before the dependent adds of group g.  Explicit shared-space accesses with
+        // immediate offsets; loads are unguarded (a lane past the end of a record reads its neighbour, always inside
+        // the ring), only the stores are predicated.
+        double A[GS][NH], B[GS][NH];
+        auto fetch = [&](double (&R)[GS][NH], int g) {
+            const uint32_t ga = xa + g * (GS * LSP * 8);
+#pragma unroll
+            for (int q = 0; q < GS; ++q)
+#pragma unroll
+                for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8);
+        };
+        auto chain = [&](double (&R)[GS][NH], int g) {
+            const uint32_t ga = xa + g * (GS * LSP * 8);
+#pragma unroll
+            for (int q = 0; q < GS; ++q)
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    v[h] = dadd(v[h], R[q][h]);
+                    if (st_ok[h]) sts_f64(ga + (q * LSP + 32 * h) * 8, v[h]);
+                }
+        };
+        if (nfull > 0) fetch(A, 0);
+        for (int g = 0; g < nfull; g += 2) {
+            if (g + 1 < nfull) fetch(B, g + 1);
+            if (((cm >> (4 * g)) & 0xfu) == 0) chain(A, g);
+            else slow(xb, mb, g * GS, GS);
+            if (g + 1 < nfull) {
+                if (g + 2 < nfull) fetch(A, g + 2);
+                if (((cm >> (4 * (g + 1))) & 0xfu) == 0) chain(B, g + 1);
+                else slow(xb, mb, (g + 1) * GS, GS);
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (cnt > nfull * GS) slow(xb, mb, nfull * GS, cnt - nfull * GS);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&done[s]);
+        if (lane == 0) mbar_arrive(&done[s]); // release: the versions written above are visible to the storers
+    }
+    if (e.ws.dbg && lane == 0) {
+        e.ws.dbg[j * 8 + 0] = n;
+        e.ws.dbg[j * 8 + 1] = clock64() - t_beg;
+        e.ws.dbg[j * 8 + 2] = t_wait;
+        e.ws.dbg[j * 8 + 3] = t_slow;
+        e.ws.dbg[j * 8 + 4] = n_cont;
     }
 }
 
 // ---- outlier-side member lists: sort (key, cell) of the pcore-rejected cells --------------------------
 __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_olist(Eng e) {
+    e.fetch();
     __shared__ unsigned long long keys[BS_RMAX];
     __shared__ int s_warp[33];
     __shared__ int s_n;
@@ -896,6 +1075,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_olist(Eng e) {
 
 // ---- D ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BS_THREADS) k_bs_derive(Eng e) {
+    e.fetch();
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const int i = blockIdx.x * BS_THREADS + threadIdx.x;
@@ -937,6 +1117,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive(Eng e) {
 // the latest accepted member of its chain inside the tile (ballot) or before the tile (tbase).
 template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
+    e.fetch();
     BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const int lane = threadIdx.x & 31;
@@ -1003,6 +1184,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
 // outlier stage of the cells the pcore stage rejected: one warp per cell
 template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
+    e.fetch();
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const Num nm = e.nm;
@@ -1120,23 +1302,23 @@ __device__ __forceinline__ int block_min_1024(int v, int *s_warp) {
 }
 
 __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
+    e.fetch();
     __shared__ int s_warp[33];
     __shared__ int s_act, s_cut;
     BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const int tid = threadIdx.x;
     const int Beff = bc->Beff, Mp = bc->Mp, KNEW = bc->Mp + bc->Mo0;
-    const int per = (Beff + BS_CTA1 - 1) / BS_CTA1;
-    const int lo = min(Beff, tid * per), hi = min(Beff, lo + per);
+    // first cell whose exact decision differs from the speculation (threads stride the cells: coalesced)
     int m0 = Beff;
-    for (int i = lo; i < hi; ++i)
+    for (int i = tid; i < Beff; i += BS_CTA1)
         if (e.ws.dec[i] != e.ws.eff[i]) {
             m0 = i;
             break;
         }
     m0 = block_min_1024(m0, s_warp);
     int up = INT_MAX;
-    for (int i = lo; i < min(hi, m0); ++i)
+    for (int i = tid; i < m0; i += BS_CTA1)
         if (e.ws.upf[i]) {
             up = i;
             break;
@@ -1174,63 +1356,49 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
         if (tid == 0) {
             bc->phase = 1;
             bc->tk_lo = bc->tk_hi = 0;
+            if (e.h_inner) cudaGraphSetConditional(e.h_inner, 0u);
         }
         return;
     }
     // ---- refinement: the recomputed decisions of [m0, Beff) become the next speculation
     int cut = Beff;
-    for (int i = max(lo, m0); i < hi; ++i)
+    for (int i = m0 + tid; i < Beff; i += BS_CTA1)
         if (e.ws.dec[i] == BS_KEY_UNKNOWN) {
             cut = i;
             break;
         }
     cut = block_min_1024(cut, s_warp);
-    // cells that need a (new) top-K slot, handed out in cell order: cells that reach the outlier stage without
-    // a list, and SAFE cells whose nearest pcore MC changed (they become CONTESTED, which needs a fallback
-    // outlier decision should the chain reject them)
-    const int r_lo = max(lo, m0), r_hi = min(hi, cut);
-    int cnt = 0;
-    for (int i = r_lo; i < r_hi; ++i) {
-        const int dc = e.ws.dec[i];
-        const bool want = dc != e.ws.eff[i] &&
-                          (dc == BS_KEY_NEED || (dc >= 0 && dc < Mp && e.ws.pcand[i] != dc && !e.ws.pflag[i]));
-        e.ws.want[i] = (uint8_t)want;
-        cnt += want;
-    }
+    // One ordered pass over [m0, cut), 1024 cells at a time.  Cells that need a (new) top-K slot get one in cell
+    // order: cells that reach the outlier stage without a list, and SAFE cells whose nearest pcore MC changed
+    // (they become CONTESTED, which needs a fallback outlier decision should the chain reject them).  The block
+    // is truncated at the first cell that finds the list full (cells behind it may already have been rewritten;
+    // they are outside the block from now on and every block starts from a fresh speculation).
     const int nneed_old = bc->nneed;
-    int total;
-    const int base = nneed_old + block_exclusive_scan_1024(cnt, s_warp, total);
-    {
-        int slot = base;
-        for (int i = r_lo; i < r_hi; ++i) {
-            if (!e.ws.want[i]) continue;
-            if (slot == BS_RMAX) s_cut = i; // first cell that does not fit (seen by exactly one thread)
-            ++slot;
+    const int32_t row0 = (int32_t)bc->pos;
+    int base = nneed_old;
+    for (int c0 = m0; c0 < cut; c0 += BS_CTA1) {
+        const int i = c0 + tid;
+        int dc = 0;
+        bool diff = false, want = false;
+        if (i < cut) {
+            dc = e.ws.dec[i];
+            diff = dc != e.ws.eff[i];
+            want = diff && (dc == BS_KEY_NEED || (dc >= 0 && dc < Mp && e.ws.pcand[i] != dc && !e.ws.pflag[i]));
         }
-    }
-    __syncthreads();
-    const int Bnew = min(cut, s_cut);
-    if (Bnew <= m0) { // the first mismatching cell itself cannot be refined: commit the exact prefix
-        if (tid == 0) {
-            bc->m_commit = m0;
-            bc->cuts_cap += 1;
-            bc->phase = 1;
-            bc->tk_lo = bc->tk_hi = 0;
-        }
-        return;
-    }
-    {
+        const int nwant = __syncthreads_count(want);
         int slot = base;
-        const int32_t row0 = (int32_t)bc->pos;
-        for (int i = r_lo; i < min(r_hi, Bnew); ++i) {
-            const int dc = e.ws.dec[i];
-            if (dc == e.ws.eff[i]) continue;
-            const bool want = e.ws.want[i] != 0;
+        if (nwant) {
+            int total;
+            slot = base + block_exclusive_scan_1024(want ? 1 : 0, s_warp, total);
+        }
+        if (want && slot >= BS_RMAX) atomicMin(&s_cut, i);
+        __syncthreads();
+        const bool fits = i < s_cut;
+        if (diff && fits) {
             if (want) {
                 e.ws.tkpos[i] = slot;
                 e.ws.nrows[slot] = row0 + i;
                 e.ws.ncell[slot] = i;
-                ++slot;
             }
             if (dc == BS_KEY_NEED) {
                 e.ws.ospec[i] = KNEW + i; // provisional: create; the next round decides with the top-K list
@@ -1246,23 +1414,36 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
                 e.ws.pflag[i] = 1;
             }
         }
+        base += nwant;
+        if (s_cut < Beff) break; // uniform: s_cut was read after the barrier
     }
+    __syncthreads();
+    const int Bnew = min(cut, s_cut);
     if (tid == 0) {
-        const int nneed_new = min(nneed_old + total, BS_RMAX);
-        bc->tk_lo = nneed_old;
-        bc->tk_hi = nneed_new;
-        bc->nneed = nneed_new;
-        bc->tk_late += nneed_new - nneed_old;
-        bc->pairs += (int64_t)(nneed_new - nneed_old) * bc->Mo0;
-        bc->Beff = Bnew;
-        bc->it += 1;
-        bc->npend = 0;
+        if (Bnew <= m0) { // the first mismatching cell itself cannot be refined: commit the exact prefix
+            bc->m_commit = m0;
+            bc->cuts_cap += 1;
+            bc->phase = 1;
+            bc->tk_lo = bc->tk_hi = 0;
+        } else {
+            const int nneed_new = min(base, BS_RMAX);
+            bc->tk_lo = nneed_old;
+            bc->tk_hi = nneed_new;
+            bc->nneed = nneed_new;
+            bc->tk_late += nneed_new - nneed_old;
+            bc->pairs += (int64_t)(nneed_new - nneed_old) * bc->Mo0;
+            bc->Beff = Bnew;
+            bc->it += 1;
+            bc->npend = 0;
+        }
+        if (e.h_inner) cudaGraphSetConditional(e.h_inner, bc->phase == 0 ? 1u : 0u);
     }
 }
 
 // ---- commit -----------------------------------------------------------------------------------------
 // one warp per key: the last version before m_commit becomes the stored state of the MC
 __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
+    e.fetch();
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 1) return;
     const Num nm = e.nm;
@@ -1325,6 +1506,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
 }
 
 __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_cells(Eng e) {
+    e.fetch();
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 1) return;
     const int i = blockIdx.x * BS_THREADS + threadIdx.x;
@@ -1352,6 +1534,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_cells(Eng e) {
 
 // upgrade (hddstream.py:397-430), list lengths, id counters, next block length
 __global__ void __launch_bounds__(BS_THREADS) k_bs_finish(Eng e) {
+    e.fetch();
     __shared__ int s_ncreated;
     BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 1) return;
@@ -1412,6 +1595,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_finish(Eng e) {
         bc->nh = 0;
         bc->active = 0;
         if (bc->pos >= bc->N) bc->done = 1;
+        if (e.h_outer) cudaGraphSetConditional(e.h_outer, bc->done ? 0u : 1u);
     }
 }
 

@@ -189,11 +189,15 @@ __global__ void __launch_bounds__(NEAREST_THREADS)
     k_nearest(const double *__restrict__ X, const int32_t *__restrict__ rows, const int32_t *__restrict__ nrows_dev,
               int64_t row_off, int64_t nrows, int64_t ld, int D, const double2 *__restrict__ cw, int M, int slab_mcs,
               double *__restrict__ out_dist, int32_t *__restrict__ out_idx, const int32_t *__restrict__ range_dev,
-              const int32_t *__restrict__ M_dev, int dyn_max_slabs) {
+              const int32_t *__restrict__ M_dev, int dyn_max_slabs, const XRef *__restrict__ xref) {
     using Cfg = NearestCfg<DP>;
     __shared__ __align__(128) double2 tile[2][Cfg::TM * DP];
     __shared__ __align__(8) uint64_t bar[2];
 
+    if (xref) { // graph launches: the input array of this call
+        X = xref->X;
+        ld = xref->ld;
+    }
     if (nrows_dev) nrows = (int64_t)(*nrows_dev) - row_off;
     if (M_dev) M = min(M, *M_dev);
     if (range_dev) {

@@ -62,7 +62,7 @@ class _PointsView(object):
 
 
 class HDDStream(object):
-    def __init__(self, config, logger, device=0, wave=0, chunk=0, bsv_bmin=0, bsv_iters=0):
+    def __init__(self, config, logger, device=0, wave=0, chunk=0, bsv_bmin=0, bsv_iters=0, bsv_stream=0):
         """config: dict with beta, delta, epsilon, lambda, k, mu, pi, omicron, upsilon (hddstream.py:30-67)."""
         self.config = config
         self.pi = None
@@ -86,7 +86,7 @@ class HDDStream(object):
         # engine knobs (never affect results): wave == 0 selects the block-speculative versioned commit, wave >= 1
         # the single-CTA wave engine; chunk caps the block (or launch) length
         self._device, self._wave, self._chunk = device, wave, chunk
-        self._bsv = (bsv_bmin, bsv_iters)
+        self._bsv = (bsv_bmin, bsv_iters, bsv_stream)
         self._h = None
         self._views = _PointsView()
         self._lists = [None, None]  # cached Microcluster lists (pcore, outlier)
@@ -119,7 +119,7 @@ class HDDStream(object):
         self.final_clusters = []
         self.logger = logging.getLogger("chronoclust_b200")
         self._device, self._wave, self._chunk = 0, 0, 0
-        self._bsv = (0, 0)
+        self._bsv = (0, 0, 0)
         self._h = None
         self._views = _PointsView()
         self._lists = [None, None]
@@ -165,7 +165,8 @@ class HDDStream(object):
         L = _lib.lib()
         prm = _lib.Params(D=D, device=self._device, eps2=self.epsilon_squared, upsilon_eps=self.upsilon,
                           upsilon_eps2=self.upsilon ** 2, delta=self.delta, delta2=self.delta_squared, beta=self.beta,
-                          k=self.k, wave=self._wave, chunk=self._chunk, bsv_bmin=self._bsv[0], bsv_iters=self._bsv[1])
+                          k=self.k, wave=self._wave, chunk=self._chunk, bsv_bmin=self._bsv[0], bsv_iters=self._bsv[1],
+                          bsv_stream=self._bsv[2])
         h = C.c_void_p()
         rc = L.ccb_create(C.byref(prm), C.byref(h))
         if rc != 0:

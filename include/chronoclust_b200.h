@@ -70,7 +70,11 @@ typedef struct {
     int32_t chunk;       /* wave engine: max cells per ordered-commit launch; block-speculative engine: max cells
                             per block; 0 = default */
     int32_t bsv_bmin;    /* block-speculative engine: smallest block length; 0 = default (1024) */
-    int32_t bsv_iters;   /* block-speculative engine: refinement rounds enqueued per block; 0 = default (3) */
+    int32_t bsv_iters;   /* block-speculative engine: refinement rounds per block before the exact prefix is committed;
+                            0 = default (3 with stream launches, 8 inside the CUDA graph) */
+    int32_t bsv_stream;  /* block-speculative engine: 1 = plain stream launches instead of the CUDA graph with device-driven
+                            WHILE nodes (the graph is also bypassed while ccb_enable_timing is on) */
+    int32_t reserved0;
 } ccb_params;
 
 /* Counters since ccb_create (monotonic); all int64. */
@@ -108,6 +112,13 @@ void *ccb_stream(ccb_handle *h);
 int ccb_get_stats(const ccb_handle *h, ccb_stats *out);
 /* Diagnostics: cycles thread 0 of kernel 2a spent in each phase (A, B, C, D, E, commit) since ccb_reset. */
 int ccb_debug_phase_cycles(ccb_handle *h, int64_t out[8]);
+/* Diagnostics of the block-speculative engine's pcore replay kernel (k_bs_chain_p), last launch, per pcore key:
+ * out[key][8] = {members, replay cycles, replay waiting for data, replay in groups with a CONTESTED cell,
+ * CONTESTED cells, storer cycles, storer waiting, producer waiting}.  The first call switches the counters on. */
+int ccb_debug_chain(ccb_handle *h, int64_t *out, int32_t max_keys);
+/* Diagnostics only, results become WRONG: 1 = the storer warps of k_bs_chain_p skip their global stores, 2 = skip the
+ * copies altogether (isolates the replay warp's own speed).  0 restores normal operation. */
+int ccb_debug_set(ccb_handle *h, int32_t mode);
 /* Forgets every microcluster and both id counters (a new run on the same device / stream). */
 int ccb_reset(ccb_handle *h);
 

@@ -52,7 +52,7 @@ def test_stress_matches_reference(name, wave):
 
 # block-speculative engine (wave == 0): block length cap / smallest block / refinement rounds never change results
 BSV_KNOBS = [dict(), dict(chunk=96, bsv_bmin=32, bsv_iters=1), dict(chunk=2048, bsv_bmin=64, bsv_iters=2),
-             dict(chunk=512, bsv_bmin=512, bsv_iters=6)]
+             dict(chunk=512, bsv_bmin=512, bsv_iters=6), dict(bsv_stream=1), dict(chunk=300, bsv_bmin=16, bsv_stream=1)]
 
 
 @pytest.mark.parametrize("knobs", BSV_KNOBS, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()) or "default")

@@ -23,7 +23,11 @@ h = HDDStream(config_params(name), logging.getLogger("q"), wave=wave, chunk=chun
 prev = None
 h._ensure_handle(D)
 h.enable_timing()
+dbg_mode = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--dbg=")]
 for t, X in enumerate(Xs):
+    if dbg_mode and t == 2:
+        from chronoclust_b200 import _lib as _l
+        _l.check(_l.lib().ccb_debug_set(h._h, dbg_mode[0]), h._h)
     t0 = time.time()
     h.online_microcluster_maintenance(X, t, run_offline=False)
     t1 = time.time()
@@ -43,3 +47,11 @@ for t, X in enumerate(Xs):
         _lib.lib().ccb_debug_phase_cycles(h._h, C.byref(pc))
         print("    phase cycles/wave (cumulative):", [round(v / max(st["waves"], 1)) for v in pc])
     print("    gpu ms:", {k: (round(v[0], 2), v[1]) for k, v in h.timing(reset=True).items() if v[1]})
+    if not wave and "--chain" in sys.argv:
+        import ctypes as C
+        from chronoclust_b200 import _lib
+        buf = np.zeros((64, 8), dtype=np.int64)
+        _lib.check(_lib.lib().ccb_debug_chain(h._h, buf.ctypes.data_as(C.c_void_p), 64), h._h)
+        print("    chain_p last launch [members, replay cyc, wait, slow cyc, contested, storer cyc, storer wait, producer wait]:")
+        for j in np.argsort(-buf[:, 0])[:6]:
+            print("      key", j, buf[j].tolist())

@@ -1,0 +1,37 @@
+"""Per-timepoint wall time of the device-resident path without event timing (what bench.py's `value` sees)."""
+import logging
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from chronoclust_b200.hddstream import HDDStream
+from chronoclust_b200.synth import CONFIGS, config_params, gen
+
+name = sys.argv[1] if len(sys.argv) > 1 else "C2"
+scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+N, D, T, Cn, seed, eps, pi = CONFIGS[name]
+N = int(N * scale)
+Xs = gen(N, D, T, Cn, seed)
+h = HDDStream(config_params(name), logging.getLogger("q"))
+h.dataset_dimensionality = D
+h._ensure_handle(D)
+Xd = [torch.from_numpy(x).cuda() for x in Xs]
+a = torch.empty(N, dtype=torch.int32, device="cuda")
+s = torch.empty(N, dtype=torch.uint8, device="cuda")
+for rep in range(3):
+    h.reset()
+    prev = h.stats()
+    line = []
+    for t in range(T):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h.ingest_device(Xd[t].data_ptr(), N, D, t, a.data_ptr(), s.data_ptr())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        st = h.stats()
+        line.append(f"t{t} {dt*1e3:.1f}ms blocks={st['bsv_blocks']-prev['bsv_blocks']} rounds={st['bsv_rounds']-prev['bsv_rounds']} "
+                    f"launches={st['kernel_launches']-prev['kernel_launches']}")
+        prev = st
+    print(f"rep {rep}: " + " | ".join(line))
