@@ -36,6 +36,17 @@ struct NearestCfg {
     static constexpr int CELLS = NEAREST_THREADS * PPT;
 };
 
+// guards of the fused weight step (nearest_item): a non-zero magnitude below 2^-400, or a weight below 2^-64 / not a
+// power of two (never produced by k_pack_cw / the commit kernels, checked anyway), forces the unfused sequence
+__device__ __forceinline__ bool tiny_nonzero(double v) {
+    const uint64_t b = (uint64_t)__double_as_longlong(v) & 0x7fffffffffffffffull;
+    return b != 0ull && b < 0x26f0000000000000ull; // biased exponent 623 = 2^-400
+}
+__device__ __forceinline__ bool small_weight(double w) {
+    const uint64_t b = (uint64_t)__double_as_longlong(w);
+    return (b & 0x000fffffffffffffull) != 0ull || b < 0x3bf0000000000000ull || b > 0x3ff0000000000000ull; // [2^-64, 1]
+}
+
 template <int K>
 __device__ __forceinline__ void topk_insert(double (&bd)[K], int (&bi)[K], double d, int j) {
     // strict <: an equal distance never displaces an earlier (smaller-index) entry
@@ -126,6 +137,22 @@ __device__ __forceinline__ void nearest_item(const double *__restrict__ X, const
     };
     if (threadIdx.x == 0 && ntiles > 0) issue(0);
 
+    // FUSED weight step (power-of-two weights only): acc = fma(t^2, w, acc) instead of acc + (t^2 * w).  The product
+    // of a double and 2^-m is exact unless it lands in the subnormal range, so the two are the same IEEE result
+    // whenever every non-zero (p - c)^2 is far above 2^-1022 / w.  That holds when every coordinate involved is 0 or
+    // at least 2^-400 in magnitude: p and c are then multiples of 2^-452, a non-zero difference is >= 2^-452, its
+    // square >= 2^-904.  The kernel checks that itself -- this warp's cells here, every tile below (each warp scans
+    // the whole tile: ~DP * TM / 32 integer compares per lane against ~3 * DP * TM * PPT fp64 instructions) -- and
+    // falls back to the unfused sequence for a tile that fails, so the result is bit-exact unconditionally.
+    bool tiny_p = false;
+    if (!DIV) {
+#pragma unroll
+        for (int u = 0; u < PPT; ++u)
+#pragma unroll
+            for (int d = 0; d < DP; ++d) tiny_p |= tiny_nonzero(p[u][d]);
+        tiny_p = __any_sync(0xffffffffu, tiny_p);
+    }
+
     for (int t = 0; t < ntiles; ++t) {
         if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1); // that buffer was released by the barrier below
         const uint32_t q = seq + (uint32_t)t;
@@ -133,23 +160,49 @@ __device__ __forceinline__ void nearest_item(const double *__restrict__ X, const
         const double2 *tl = tile[q & 1];
         const int jt = j0 + t * TM;
         const int n = min(TM, j1 - jt);
+        bool fuse = false;
+        if (!DIV) {
+            bool tiny_c = tiny_p;
+            if (!tiny_c) {
+                const int lane = threadIdx.x & 31;
+                for (int e = lane; e < n * DP; e += 32) tiny_c |= tiny_nonzero(tl[e].x) | small_weight(tl[e].y);
+                tiny_c = __any_sync(0xffffffffu, tiny_c);
+            }
+            fuse = !tiny_c;
+        }
         for (int jj = 0; jj < n; jj += JU) {
             double acc[PPT][JU];
 #pragma unroll
             for (int u = 0; u < PPT; ++u)
 #pragma unroll
                 for (int v = 0; v < JU; ++v) acc[u][v] = 0.0;
+            if (fuse) {
 #pragma unroll
-            for (int d = 0; d < DP; ++d) {
+                for (int d = 0; d < DP; ++d) {
 #pragma unroll
-                for (int v = 0; v < JU; ++v) {
-                    const double2 c = tl[(jj + v) * DP + d]; // broadcast LDS.128 (garbage past n is masked below)
+                    for (int v = 0; v < JU; ++v) {
+                        const double2 c = tl[(jj + v) * DP + d]; // broadcast LDS.128 (garbage past n is masked below)
 #pragma unroll
-                    for (int u = 0; u < PPT; ++u) {
-                        double tt = dsub(p[u][d], c.x);
-                        tt = dmul(tt, tt);
-                        tt = DIV ? ddiv(tt, c.y) : dmul(tt, c.y);
-                        acc[u][v] = dadd(acc[u][v], tt);
+                        for (int u = 0; u < PPT; ++u) {
+                            double tt = dsub(p[u][d], c.x);
+                            tt = dmul(tt, tt);
+                            acc[u][v] = __fma_rn(tt, c.y, acc[u][v]); // exact product (see above): == acc + tt * w
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < DP; ++d) {
+#pragma unroll
+                    for (int v = 0; v < JU; ++v) {
+                        const double2 c = tl[(jj + v) * DP + d];
+#pragma unroll
+                        for (int u = 0; u < PPT; ++u) {
+                            double tt = dsub(p[u][d], c.x);
+                            tt = dmul(tt, tt);
+                            tt = DIV ? ddiv(tt, c.y) : dmul(tt, c.y);
+                            acc[u][v] = dadd(acc[u][v], tt);
+                        }
                     }
                 }
             }

@@ -204,6 +204,48 @@ def test_kernel1_nearest_bit_exact(D, M, k):
         assert slot[i].item() == best and dist[i].item() == bd, (i, slot[i].item(), best, dist[i].item(), bd)
 
 
+@pytest.mark.parametrize("D,M,k,tiny", [(12, 500, 4.0, 0.0), (12, 500, 4.0, 1e-160), (40, 200, 16.0, 1e-158),
+                                        (12, 260, 4.0, 1e-200), (5, 90, 2.0, 3e-162)])
+def test_kernel1_fused_weight_step_bit_exact(D, M, k, tiny):
+    """Kernel 1 folds the power-of-two preference weight into the accumulate (fma(t*t, 1/k, acc)); that is the
+    reference's acc + (t*t)/k (mc_functions.py:35-43) only while (t*t)/k stays normal.  Inputs whose squared
+    differences fall into the subnormal range must take the unfused sequence: every row is compared with numpy's
+    elementwise IEEE arithmetic (no contraction), summed over d in index order, first minimum wins."""
+    import torch
+    from chronoclust_b200 import _lib
+
+    rng = np.random.default_rng(D * 77 + M)
+    N = 2048
+    X = rng.random((N, D))
+    cen = rng.random((M, D))
+    if tiny:
+        # a band of cells and microclusters living at magnitude `tiny`: (x - c)^2 ~ 1e-320 (subnormal), / k loses bits
+        X[::3] *= tiny
+        cen[::2] *= tiny
+        X[5::7, ::2] = 0.0
+    maskbits = rng.random((M, D)) < 0.6
+    pref = np.where(maskbits, k, 1.0)
+    masks = np.array([sum(1 << d for d in range(D) if maskbits[j, d]) for j in range(M)], np.uint64).astype(np.int64)
+    tX, tc, tm = torch.from_numpy(X).cuda(), torch.from_numpy(cen).cuda(), torch.from_numpy(masks).cuda()
+    slot = torch.empty(N, dtype=torch.int32, device="cuda")
+    dist = torch.empty(N, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().ccb_nearest(0, None, tX.data_ptr(), N, D, D, tc.data_ptr(), tm.data_ptr(), M, k,
+                                      slot.data_ptr(), dist.data_ptr()))
+    torch.cuda.synchronize()
+    acc = np.zeros((N, M))
+    for d in range(D):
+        t = X[:, d, None] - cen[None, :, d]
+        t = t * t
+        t = t / pref[None, :, d]
+        acc = acc + t
+    exp_slot = acc.argmin(axis=1)
+    exp_dist = acc[np.arange(N), exp_slot]
+    assert (slot.cpu().numpy() == exp_slot).all()
+    assert bits_equal(dist.cpu().numpy(), exp_dist)
+    if tiny > 1e-165:  # (1e-200 squares underflow to exact zeros: a tie-break case, first minimum wins)
+        assert ((acc > 0) & (acc < 2.3e-308)).any(), "the fixture must reach the subnormal range"
+
+
 @pytest.mark.parametrize("cfgname,N,T", [("C2", 60000, 3), ("C3", 20000, 2)])
 def test_online_offline_vs_oracle_mid_size(cfgname, N, T):
     """CUDA vs the (reference-pinned) oracle at sizes the reference itself cannot reach in test time."""

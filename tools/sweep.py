@@ -1,0 +1,92 @@
+#!/usr/bin/env python3
+"""Config C5 (BASELINE.json configs[4]): epsilon x upsilon x beta parameter sweep, 64 independent runs of the C2
+workload, partitioned over the ranks (run i goes to rank i mod G; no data-path collective -- every run is its own
+ordered stream).  The dataset is replicated on every device once; each run is a fresh handle fed device-resident
+timepoints through ccb_ingest_device.  Prints one JSON line on rank 0.
+
+    python tools/sweep.py [--scale 1.0]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/sweep.py
+"""
+import argparse
+import itertools
+import json
+import logging
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from chronoclust_b200.hddstream import HDDStream  # noqa: E402
+from chronoclust_b200.synth import CONFIGS, config_params, gen  # noqa: E402
+
+GRID = list(itertools.product((0.04, 0.045, 0.05, 0.055), (4.0, 5.5, 6.5, 8.0), (0.1, 0.2, 0.4, 0.8)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--configs", type=int, default=len(GRID))
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    N, D, T, Cn, seed, _, _ = CONFIGS["C2"]
+    N = max(1000, int(N * a.scale))
+    Xd = [torch.from_numpy(x).cuda(local) for x in gen(N, D, T, Cn, seed)]
+    assign = torch.empty(N, dtype=torch.int32, device=f"cuda:{local}")
+    stage = torch.empty(N, dtype=torch.uint8, device=f"cuda:{local}")
+    grid = GRID[:a.configs]
+    mine = [i for i in range(len(grid)) if i % world == rank]
+
+    def run(i):
+        eps, ups, beta = grid[i]
+        cfg = dict(config_params("C2"), epsilon=eps, upsilon=ups, beta=beta)
+        h = HDDStream(cfg, logging.getLogger("sweep"), device=local)
+        h.dataset_dimensionality = D
+        h._ensure_handle(D)
+        for t in range(T):
+            h.ingest_device(Xd[t].data_ptr(), N, D, t, assign.data_ptr(), stage.data_ptr())
+        c = h.counts()
+        return {"epsilon": eps, "upsilon": ups, "beta": beta, "pcore": int(c[0]), "outlier": int(c[1]),
+                "clusters": len(h.final_clusters)}
+
+    run(mine[0] if mine else 0)  # warm-up (module load, workspace growth)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    res = [run(i) for i in mine]
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    wall = time.perf_counter() - w0
+    if dist is not None:
+        tt = torch.tensor([sec, wall], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec, wall = float(tt[0]), float(tt[1])
+        allres = [None] * world
+        dist.all_gather_object(allres, res)
+        res = [r for rr in allres for r in rr]
+    if rank == 0:
+        cells = len(grid) * N * T
+        print(json.dumps({"metric": "cells/sec over the whole parameter sweep", "value": cells / sec, "unit": "cells/s",
+                          "n_gpus": world, "configs": len(grid), "cells_per_config": N * T, "seconds": sec,
+                          "wall_s": wall, "scaling": "strong", "partition": "config i -> rank i mod G, no collective",
+                          "clusters_min_max": [min(r["clusters"] for r in res), max(r["clusters"] for r in res)],
+                          "runs": res}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
