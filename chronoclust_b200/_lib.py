@@ -28,7 +28,7 @@ class Stats(C.Structure):
         "points", "chunks", "waves", "wave_rollbacks", "rejects", "resolver_calls", "resolver_cuts", "nearest_pairs",
         "pcore_pairs", "upgrades", "created", "downgraded", "deleted", "kernel_launches", "borderline_pairs",
         "bsv_blocks", "bsv_rounds", "bsv_mismatches", "bsv_cuts_unknown", "bsv_cuts_rounds", "bsv_cuts_capacity",
-        "bsv_late_topk", "bsv_outlier_stage_cells", "bsv_replayed_cells")]
+        "bsv_late_topk", "bsv_outlier_stage_cells", "bsv_replayed_cells", "bsv_light_rounds")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -96,7 +96,8 @@ struct ccb_handle {
     bool bs_use_graph = true;   // CUDA graph with device-driven WHILE nodes (stream launches when per-kernel timing is on)
     cudaGraph_t bs_graph = nullptr;
     cudaGraphExec_t bs_exec = nullptr;
-    cudaStream_t cap1 = nullptr, cap2 = nullptr;
+    cudaStream_t cap1 = nullptr, cap2 = nullptr, cap3 = nullptr; // capture streams: block loop, round loop, side branch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Eng bs_graph_eng{};         // the pointers / capacities the graph was captured with
     EngIo *d_io = nullptr, *h_io = nullptr;
     // offline results (host copies)
@@ -299,6 +300,22 @@ int launch_nearest(ccb_handle *h, cudaStream_t s, int DP, int div_mode, const do
         const int tiles = (M + Cfg::TM - 1) / Cfg::TM;
         if (want > tiles) want = tiles;
         if (want < 1) want = 1;
+        if (gx > 148) {
+            // wave quantisation: gx CTAs in ceil(gx / resident) waves waste the tail of the last one (13 % for the dense
+            // 1e6 x 4096 benchmark at one slab); cutting the MC axis into a few slabs makes the waves finer
+            int occ = 1;
+            if (div_mode) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nearest<kDP, K, true>, NEAREST_THREADS, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nearest<kDP, K, false>, NEAREST_THREADS, 0);
+            const double resident = 148.0 * std::max(occ, 1);
+            auto loss = [&](int sl) {
+                const double w = (double)gx * sl / resident;
+                return w <= 1.0 ? 0.0 : std::ceil(w) / w - 1.0;
+            };
+            int best = want;
+            for (int sl = want + 1; sl <= std::min(std::min(max_slabs, tiles), want + 7) && loss(best) > 0.03; ++sl)
+                if (loss(sl) < loss(best)) best = sl;
+            want = best;
+        }
         int slab_mcs = ((tiles + want - 1) / want) * Cfg::TM;
         const int nslab = (M + slab_mcs - 1) / slab_mcs;
         dim3 grid(gx, nslab);
@@ -612,14 +629,22 @@ int launch_prologue(ccb_handle *h, const Eng &e, cudaStream_t s) {
     return CCB_OK;
 }
 
-int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int mo_bound) {
+// side != nullptr (graph capture): kernel 1 + the speculated outlier decisions run on a side branch next to the
+// candidate lists + pcore replay (they touch disjoint data; see the dependency notes in DESIGN.md) and join before
+// k_bs_olist.
+int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int mo_bound, cudaStream_t side = nullptr) {
     const int B = h->bs_bmax;
     const int g_cells = (B + BS_THREADS - 1) / BS_THREADS;
     const int g_tiles = (B / 32 + 1 + 3) / 4;
     int rc;
+    cudaStream_t sa = side ? side : s;
+    if (side) {
+        CK(h, cudaEventRecord(h->ev_fork, s));
+        CK(h, cudaStreamWaitEvent(side, h->ev_fork, 0));
+    }
     {
         Timed tm(h, CCB_CAT_NEAREST);
-        if ((rc = launch_nearest_dyn<BS_TOPK>(nullptr, s, h->DP, h->div_mode, e.X, e.ws.nrows, e.ld, h->D, e.O.cw, mo_bound,
+        if ((rc = launch_nearest_dyn<BS_TOPK>(nullptr, sa, h->DP, h->div_mode, e.X, e.ws.nrows, e.ld, h->D, e.O.cw, mo_bound,
                                               h->d_bs_tk_dist_slab, h->d_bs_tk_idx_slab, e.ws.tk_dist, e.ws.tk_idx,
                                               BS_MAX_SLABS, BS_RMAX, &e.bc->tk_lo, &e.bc->Mo0,
                                               reinterpret_cast<const XRef *>(e.io))))
@@ -627,7 +652,7 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     }
     {
         Timed tm(h, CCB_CAT_SPEC);
-        k_bs_spec_o<<<BS_RMAX / BS_THREADS, BS_THREADS, 0, s>>>(e);
+        k_bs_spec_o<<<BS_RMAX / BS_THREADS, BS_THREADS, 0, sa>>>(e);
     }
     {
         Timed tm(h, CCB_CAT_LISTS);
@@ -638,6 +663,10 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     {
         Timed tm(h, CCB_CAT_PCORE);
         CCB_DISPATCH_DP(h->DP, { k_bs_chain_p<kDP><<<std::max(mp_grid, 1), BS_CHAINP_THREADS, ChainPCfg<kDP>::SMEM, s>>>(e); })
+    }
+    if (side) {
+        CK(h, cudaEventRecord(h->ev_join, side));
+        CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     }
     {
         Timed tm(h, CCB_CAT_OLIST);
@@ -667,11 +696,19 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
 }
 constexpr int BS_LAUNCHES_PROLOGUE = 3, BS_LAUNCHES_ROUND = 13, BS_LAUNCHES_COMMIT = 3;
 
-int launch_commit(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid) {
+int launch_commit(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, cudaStream_t side = nullptr) {
     const int g_cells = (h->bs_bmax + BS_THREADS - 1) / BS_THREADS;
     Timed tm(h, CCB_CAT_COMMIT);
+    if (side) { // rows and cells write disjoint data (stores vs. per-cell results)
+        CK(h, cudaEventRecord(h->ev_fork, s));
+        CK(h, cudaStreamWaitEvent(side, h->ev_fork, 0));
+    }
     k_bs_commit_rows<<<(mp_grid + BS_RMAX + 3) / 4, BS_THREADS, 0, s>>>(e);
-    k_bs_commit_cells<<<g_cells, BS_THREADS, 0, s>>>(e);
+    k_bs_commit_cells<<<g_cells, BS_THREADS, 0, side ? side : s>>>(e);
+    if (side) {
+        CK(h, cudaEventRecord(h->ev_join, side));
+        CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+    }
     k_bs_finish<<<1, BS_THREADS, 0, s>>>(e);
     CKL(h);
     return CCB_OK;
@@ -700,6 +737,9 @@ int build_graph(ccb_handle *h, const Eng &base) {
     if (!h->cap1) {
         CK(h, cudaStreamCreateWithFlags(&h->cap1, cudaStreamNonBlocking));
         CK(h, cudaStreamCreateWithFlags(&h->cap2, cudaStreamNonBlocking));
+        CK(h, cudaStreamCreateWithFlags(&h->cap3, cudaStreamNonBlocking));
+        CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     }
     Eng e = base;
     e.io = h->d_io;
@@ -737,10 +777,10 @@ int build_graph(ccb_handle *h, const Eng &base) {
         CK(h, cudaStreamUpdateCaptureDependencies(h->cap1, &inner, 1, cudaStreamSetCaptureDependencies));
         cudaGraph_t body_i = pi.conditional.phGraph_out[0];
         CK(h, cudaStreamBeginCaptureToGraph(h->cap2, body_i, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-        if ((rc = launch_round(h, e, h->cap2, mp_grid, mo_bound))) return rc;
+        if ((rc = launch_round(h, e, h->cap2, mp_grid, mo_bound, h->cap3))) return rc;
         CK(h, cudaStreamEndCapture(h->cap2, nullptr));
     }
-    if ((rc = launch_commit(h, e, h->cap1, mp_grid))) return rc;
+    if ((rc = launch_commit(h, e, h->cap1, mp_grid, h->cap3))) return rc;
     CK(h, cudaStreamEndCapture(h->cap1, nullptr));
     CK(h, cudaGraphInstantiate(&h->bs_exec, h->bs_graph, 0));
     h->bs_graph_eng = base;
@@ -856,10 +896,16 @@ int launch_off_neighbours(ccb_handle *h, cudaStream_t s, const double *cen, int 
                           uint32_t *nbr, int32_t *cnt, int32_t *border, int border_cap, int32_t *n_border) {
     const int DP = round_dp(D);
     int ok = 0;
+    if (r1 > r0 && cudaMemsetAsync(cnt, 0, (size_t)(r1 - r0) * sizeof(int32_t), s) != cudaSuccess)
+        return fail(h, CCB_ECUDA, "k_off_neighbours: clearing the row counts failed");
     CCB_DISPATCH_DP(DP, {
-        const int gx = (r1 - r0 + OFFN_THREADS - 1) / OFFN_THREADS;
+        // rows x column slabs: at least ~4 waves of CTAs on 148 SMs so that the tail does not dominate
+        const int gx = (r1 - r0 + OffCfg<kDP>::ROWS - 1) / OffCfg<kDP>::ROWS;
+        const int ntiles = (M + OffCfg<kDP>::TM - 1) / OffCfg<kDP>::TM;
+        const int gy = gx > 0 ? std::max(1, std::min(ntiles, (148 * 2 * 4 + gx - 1) / gx)) : 1;
         if (gx > 0)
-            k_off_neighbours<kDP><<<gx, OFFN_THREADS, 0, s>>>(cen, M, D, r0, r1, E2, nbr, cnt, border, border_cap, n_border);
+            k_off_neighbours<kDP><<<dim3(gx, gy), OFFN_THREADS, 0, s>>>(cen, M, D, r0, r1, E2, nbr, cnt, border, border_cap,
+                                                                          n_border);
         ok = 1;
     })
     if (!ok) return fail(h, CCB_ELIMIT, "unsupported dimensionality %d", D);
@@ -971,6 +1017,9 @@ void ccb_destroy(ccb_handle *h) {
     drop_graph(h);
     if (h->cap1) cudaStreamDestroy(h->cap1);
     if (h->cap2) cudaStreamDestroy(h->cap2);
+    if (h->cap3) cudaStreamDestroy(h->cap3);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     cudaFree(h->d_io);
     if (h->h_io) cudaFreeHost(h->h_io);
     cudaFree(h->d_bc);
@@ -1011,6 +1060,7 @@ int ccb_get_stats(const ccb_handle *h, ccb_stats *out) {
         out->bsv_late_topk = bb.tk_late + b.tk_late;
         out->bsv_outlier_stage_cells = bb.rejects + b.rejects;
         out->bsv_replayed_cells = bb.replayed + b.replayed;
+        out->bsv_light_rounds = bb.rounds_light + b.rounds_light;
         out->nearest_pairs += bb.pairs + b.pairs;
     }
     return CCB_OK;
@@ -1072,7 +1122,7 @@ int ccb_reset(ccb_handle *h) {
         BsCtl &bb = h->bc_base;
         bb.blocks += b.blocks, bb.iters += b.iters, bb.mismatches += b.mismatches, bb.cuts_unknown += b.cuts_unknown;
         bb.cuts_iter += b.cuts_iter, bb.cuts_cap += b.cuts_cap, bb.tk_late += b.tk_late, bb.rejects += b.rejects;
-        bb.replayed += b.replayed, bb.pairs += b.pairs;
+        bb.replayed += b.replayed, bb.pairs += b.pairs, bb.rounds_light += b.rounds_light;
         const int32_t keep_B = b.next_B;
         memset(h->h_bc, 0, sizeof(BsCtl));
         h->h_bc->next_B = keep_B;
@@ -1629,7 +1679,7 @@ int ccb_nearest(int32_t device, void *stream, const double *X, int64_t N, int64_
     double *sd = nullptr;
     int32_t *si = nullptr;
     // scratch: packed rows + per-slab candidates (slabs only matter when N is small)
-    const int max_slabs = N >= (int64_t)148 * 2 * NEAREST_THREADS * 2 ? 1 : MAX_SLABS; // slabs only matter when N is small
+    const int max_slabs = N >= (int64_t)148 * 2 * NEAREST_THREADS * 2 ? 8 : MAX_SLABS; // many cells: a few slabs for wave balance only
     if ((e = cudaMallocAsync(&cw, (size_t)M * DP * sizeof(double2), s)) != cudaSuccess ||
         (e = cudaMallocAsync(&sd, (size_t)N * max_slabs * 8, s)) != cudaSuccess ||
         (e = cudaMallocAsync(&si, (size_t)N * max_slabs * 4, s)) != cudaSuccess)

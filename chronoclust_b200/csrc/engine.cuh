@@ -58,7 +58,9 @@ struct BsCtl {
     int32_t m_commit, upgrade;
     int32_t need_grow, done;
     int32_t ticket; // k_bs_pscan: CTAs finished (last one computes the key offsets)
+    int32_t pclean; // refinement round whose pcore side (candidates, CONTESTED flags, accepts) is that of the round before
     int64_t blocks, iters, mismatches, cuts_unknown, cuts_iter, cuts_cap, tk_late, rejects, contested, replayed, pairs;
+    int64_t rounds_light; // refinement rounds that re-ran the outlier side only
 };
 
 struct BsWs {
@@ -246,6 +248,7 @@ __global__ void k_bs_begin(Eng e) {
         bc->phase = 0;
         bc->m_commit = 0;
         bc->upgrade = 0;
+        bc->pclean = 0;
         bc->active = 1;
     } while (0);
     // graph launches: the round loop runs iff the block is active; an idle block also ends the block loop
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_spec_o(Eng e) {
 __global__ void __launch_bounds__(BS_THREADS) k_bs_tilecnt(Eng e) {
     e.fetch();
     const BsCtl *bc = e.bc;
-    if (!bc->active || bc->phase != 0) return;
+    if (!bc->active || bc->phase != 0 || bc->pclean) return;
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
     const int ntiles = (bc->Beff + 31) >> 5;
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
     __shared__ int s_warp[33];
     __shared__ int s_last;
     BsCtl *bc = e.bc;
-    if (!bc->active || bc->phase != 0) return;
+    if (!bc->active || bc->phase != 0 || bc->pclean) return;
     const int Mp = bc->Mp, stride = e.ws.mp_stride;
     const int j = blockIdx.x;
     if (j >= Mp) return;
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
 __global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
     e.fetch();
     const BsCtl *bc = e.bc;
-    if (!bc->active || bc->phase != 0) return;
+    if (!bc->active || bc->phase != 0 || bc->pclean) return;
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
     const int ntiles = (bc->Beff + 31) >> 5;
@@ -717,7 +720,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
     uint64_t *empty = done + S;                                    // [S] storer -> producer
     double *scr = reinterpret_cast<double *>(empty + S);           // [DP] radius terms of a CONTESTED cell
     const BsCtl *bc = e.bc;
-    if (!bc->active || bc->phase != 0) return;
+    if (!bc->active || bc->phase != 0 || bc->pclean) return;
     const Num nm = e.nm;
     const int D = nm.D;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -829,91 +832,57 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
 #pragma unroll
     for (int h = 0; h < NH; ++h) st_ok[h] = lane + 32 * h < LSP;
 
-    // One cell at a time (a group with a CONTESTED cell, or the ragged tail of a stage): the next cell's index and
-    // addend are fetched while the current one is processed.
-    auto slow = [&](double *xb, const int *mb, int m0, int g) {
-        const long long t_s0 = clock64();
-        int raw = mb[m0];
-        double a[NH];
+    // exact radius test of the tentative MC nv = v + a (mc_functions.py:45-56) for a CONTESTED cell, by the whole warp
+    auto radius_ok = [&](const double (&nv)[NH], uint32_t rec_addr) -> bool {
+        ++n_cont;
+        double wn, c1[2], c2[2];
+        if (NH == 1) { // the whole record lives in one register per lane: fetch CF2', W' by shuffle
+            wn = __shfl_sync(0xffffffffu, nv[0], 2 * DP);
+            c1[0] = nv[0];
+            c2[0] = __shfl_sync(0xffffffffu, nv[0], (lane + DP) & 31);
+            c1[1] = c2[1] = 1.0;
+        } else { // the record was just written to the stage: read CF1', CF2', W' back
+            __syncwarp();
+            wn = lds_f64(rec_addr - lane * 8 + 2 * DP * 8);
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            const int el = lane + 32 * h;
-            a[h] = el < LSP ? xb[m0 * LSP + el] : 0.0;
+            for (int h = 0; h < 2; ++h) {
+                const int d = lane + 32 * h;
+                const bool rd = (h == 0 || DP > 32) && d < D;
+                c1[h] = rd ? lds_f64(rec_addr + 32 * h * 8) : 1.0;
+                c2[h] = rd ? lds_f64(rec_addr + (DP + 32 * h) * 8) : 1.0;
+            }
         }
-        for (int m = m0; m < m0 + g; ++m) {
-            const int raw_c = raw;
-            double nv[NH];
+        double term[2] = {0.0, 0.0};
 #pragma unroll
-            for (int h = 0; h < NH; ++h) nv[h] = dadd(v[h], a[h]);
-            if (m + 1 < m0 + g) {
-                raw = mb[m + 1];
-#pragma unroll
-                for (int h = 0; h < NH; ++h) {
-                    const int el = lane + 32 * h;
-                    a[h] = el < LSP ? xb[(m + 1) * LSP + el] : 0.0;
-                }
+        for (int h = 0; h < 2; ++h) {
+            if (h == 0 || DP > 32) {
+                const int d = lane + 32 * h;
+                const bool act = d < D;
+                // idle lanes carry 1.0: their (discarded) quotients stay on the fast path of the division
+                const double q2 = ddiv(act ? c2[h] : 1.0, wn);
+                const double c = ddiv(act ? c1[h] : 1.0, wn);
+                const double var = dsub(q2, dmul(c, c));
+                const bool bit = act && (var <= nm.delta2);
+                term[h] = bit ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var;
             }
-#pragma unroll
-            for (int h = 0; h < NH; ++h) {
-                const int el = lane + 32 * h;
-                if (el < LSP) xb[m * LSP + el] = nv[h];
-            }
-            if (raw_c < 0) { // CONTESTED: exact radius test of the tentative MC (mc_functions.py:45-56)
-                ++n_cont;
-                double wn, c1[2], c2[2];
-                if (NH == 1) { // the whole record lives in one register per lane: fetch CF2', W' by shuffle
-                    wn = __shfl_sync(0xffffffffu, nv[0], 2 * DP);
-                    c1[0] = nv[0];
-                    c2[0] = __shfl_sync(0xffffffffu, nv[0], (lane + DP) & 31);
-                    c1[1] = c2[1] = 1.0;
-                } else {
-                    __syncwarp();
-                    wn = xb[m * LSP + 2 * DP];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int d = lane + 32 * h;
-                        const bool rd = (h == 0 || DP > 32) && d < D;
-                        c1[h] = rd ? xb[m * LSP + d] : 1.0;
-                        c2[h] = rd ? xb[m * LSP + DP + d] : 1.0;
-                    }
-                }
-                double term[2] = {0.0, 0.0};
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h == 0 || DP > 32) {
-                        const int d = lane + 32 * h;
-                        const bool act = d < D;
-                        // idle lanes carry 1.0: their (discarded) quotients stay on the fast path of the division
-                        const double q2 = ddiv(act ? c2[h] : 1.0, wn);
-                        const double c = ddiv(act ? c1[h] : 1.0, wn);
-                        const double var = dsub(q2, dmul(c, c));
-                        const bool bit = act && (var <= nm.delta2);
-                        term[h] = bit ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var;
-                    }
-                }
-                // the D terms are summed in index order by every lane from shared memory (broadcast LDS.128)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    if ((h == 0 || DP > 32) && lane + 32 * h < DP) scr[lane + 32 * h] = term[h];
-                __syncwarp();
-                double r2 = 0.0;
-#pragma unroll
-                for (int d = 0; d < DP; d += 2) {
-                    const double2 t2 = *reinterpret_cast<const double2 *>(scr + d);
-                    if (d < D) r2 = dadd(r2, t2.x);
-                    if (d + 1 < D) r2 = dadd(r2, t2.y);
-                }
-                __syncwarp();
-                const bool ok = r2 <= nm.eps2;
-                if (lane == 0) e.ws.prej[raw_c & 0x7fffffff] = ok ? 0 : 1;
-                if (!ok) continue; // the record of a rejected cell is never read as a version
-            }
-#pragma unroll
-            for (int h = 0; h < NH; ++h) v[h] = nv[h];
         }
-        t_slow += clock64() - t_s0;
+        // the D terms are summed in index order by every lane from shared memory (broadcast LDS.128)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if ((h == 0 || DP > 32) && lane + 32 * h < DP) scr[lane + 32 * h] = term[h];
+        __syncwarp();
+        double r2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < DP; d += 2) {
+            const double2 t2 = *reinterpret_cast<const double2 *>(scr + d);
+            if (d < D) r2 = dadd(r2, t2.x);
+            if (d + 1 < D) r2 = dadd(r2, t2.y);
+        }
+        __syncwarp();
+        return r2 <= nm.eps2;
     };
 
+    constexpr int GF = NH == 1 ? 16 : 8; // cells per register batch of the clean-stage path
     for (int b = 0; b < nb; ++b) {
         const int s = b % S;
         {
@@ -921,55 +890,90 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
             mbar_wait(&full[s], (b / S) & 1);
             t_wait += clock64() - t0;
         }
-        double *xb = xs + (size_t)s * NB * LSP;
-        const int *mb = ms + s * NB;
         const int cnt = __shfl_sync(0xffffffffu, min(NB, n - b * NB), 0); // warp-uniform for the compiler, too
         const uint32_t xa = xs_lane + s * (NB * LSP * 8), ma = ms_base + s * (NB * 4);
-        // CONTESTED flags of the whole stage in one pass: lane l looks at cells 2 l and 2 l + 1; nibble g of cm is
-        // non-zero iff group g (cells 8 g .. 8 g + 7) holds a CONTESTED cell
-        unsigned cm;
+        // CONTESTED flags of the whole stage in one pass: lane l looks at cells 2 l and 2 l + 1
+        unsigned m_even, m_odd;
         {
             int fx = 0, fy = 0;
             if (2 * lane < NB) {
                 asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(fx), "=r"(fy) : "r"(ma + lane * 8));
             }
-            cm = __ballot_sync(0xffffffffu, (fx < 0 && 2 * lane < cnt) || (fy < 0 && 2 * lane + 1 < cnt));
+            m_even = __ballot_sync(0xffffffffu, fx < 0 && 2 * lane < cnt);
+            m_odd = __ballot_sync(0xffffffffu, fy < 0 && 2 * lane + 1 < cnt);
         }
-        const int nfull = cnt / GS;
-        // software pipeline over the full groups of eight, two register sets (A / B): the addends of group g + 1 are
-        // fetched from shared memory before the dependent adds of group g.  Explicit shared-space accesses with
-        // immediate offsets; loads are unguarded (a lane past the end of a record reads its neighbour, always inside
-        // the ring), only the stores are predicated.
-        double A[GS][NH], B[GS][NH];
-        auto fetch = [&](double (&R)[GS][NH], int g) {
-            const uint32_t ga = xa + g * (GS * LSP * 8);
+        if (cnt == NB && (m_even | m_odd) == 0u) {
+            // ---- CLEAN FULL STAGE: straight-line code, no branches.  Two register sets: the addends of batch k + 1
+            // are fetched from shared memory before the dependent adds of batch k.  Explicit shared-space accesses
+            // with immediate offsets; loads are unguarded (a lane past the end of a record reads its neighbour, always
+            // inside the ring), only the stores are predicated.
+            double A[GF][NH], B[GF][NH];
+            auto fetch = [&](double (&R)[GF][NH], int k) {
 #pragma unroll
-            for (int q = 0; q < GS; ++q)
+                for (int q = 0; q < GF; ++q)
 #pragma unroll
-                for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8);
-        };
-        auto chain = [&](double (&R)[GS][NH], int g) {
-            const uint32_t ga = xa + g * (GS * LSP * 8);
+                    for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(xa + ((k * GF + q) * LSP + 32 * h) * 8);
+            };
+            auto chain = [&](double (&R)[GF][NH], int k) {
 #pragma unroll
-            for (int q = 0; q < GS; ++q)
+                for (int q = 0; q < GF; ++q)
 #pragma unroll
-                for (int h = 0; h < NH; ++h) {
-                    v[h] = dadd(v[h], R[q][h]);
-                    if (st_ok[h]) sts_f64(ga + (q * LSP + 32 * h) * 8, v[h]);
+                    for (int h = 0; h < NH; ++h) {
+                        v[h] = dadd(v[h], R[q][h]);
+                        if (st_ok[h]) sts_f64(xa + ((k * GF + q) * LSP + 32 * h) * 8, v[h]);
+                    }
+            };
+            fetch(A, 0);
+#pragma unroll
+            for (int k = 0; k < NB / GF; k += 2) {
+                if (k + 1 < NB / GF) fetch(B, k + 1);
+                chain(A, k);
+                if (k + 1 < NB / GF) {
+                    if (k + 2 < NB / GF) fetch(A, k + 2);
+                    chain(B, k + 1);
                 }
-        };
-        if (nfull > 0) fetch(A, 0);
-        for (int g = 0; g < nfull; g += 2) {
-            if (g + 1 < nfull) fetch(B, g + 1);
-            if (((cm >> (4 * g)) & 0xfu) == 0) chain(A, g);
-            else slow(xb, mb, g * GS, GS);
-            if (g + 1 < nfull) {
-                if (g + 2 < nfull) fetch(A, g + 2);
-                if (((cm >> (4 * (g + 1))) & 0xfu) == 0) chain(B, g + 1);
-                else slow(xb, mb, (g + 1) * GS, GS);
             }
+        } else {
+            // ---- stage with CONTESTED cells or a ragged tail: groups of eight through registers; every cell adds
+            // and stores like above, a CONTESTED cell then takes the exact radius test on its tentative record
+            const long long t_s0 = clock64();
+            const int ng = (cnt + GS - 1) / GS;
+            for (int g = 0; g < ng; ++g) {
+                const uint32_t ga = xa + g * (GS * LSP * 8);
+                const unsigned ge = (m_even >> (4 * g)) & 0xfu, go = (m_odd >> (4 * g)) & 0xfu;
+                const int ncell = min(GS, cnt - g * GS);
+                double R[GS][NH];
+#pragma unroll
+                for (int q = 0; q < GS; ++q)
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8);
+#pragma unroll
+                for (int q = 0; q < GS; ++q) {
+                    if (q < ncell) {
+                        double nv[NH];
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) {
+                            nv[h] = dadd(v[h], R[q][h]);
+                            if (st_ok[h]) sts_f64(ga + (q * LSP + 32 * h) * 8, nv[h]);
+                        }
+                        bool keep = true;
+                        if ((((q & 1) ? go : ge) >> (q >> 1)) & 1u) {
+                            keep = radius_ok(nv, ga + q * LSP * 8);
+                            if (lane == 0) {
+                                int raw;
+                                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma + (g * GS + q) * 4));
+                                e.ws.prej[raw & 0x7fffffff] = keep ? 0 : 1;
+                            }
+                        }
+                        if (keep) { // the record of a rejected cell is never read as a version
+#pragma unroll
+                            for (int h = 0; h < NH; ++h) v[h] = nv[h];
+                        }
+                    }
+                }
+            }
+            t_slow += clock64() - t_s0;
         }
-        if (cnt > nfull * GS) slow(xb, mb, nfull * GS, cnt - nfull * GS);
         __syncwarp();
         if (lane == 0) mbar_arrive(&done[s]); // release: the versions written above are visible to the storers
     }
@@ -1079,7 +1083,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive(Eng e) {
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const int i = blockIdx.x * BS_THREADS + threadIdx.x;
-    {
+    if (!bc->pclean) {
         // tbase[t][j] = latest ACCEPTED member of pcore chain j before tile t (t == ntiles: of the whole block)
         const int Mp = bc->Mp, stride = e.ws.mp_stride, ntiles = (bc->Beff + 31) >> 5;
         const int total = (ntiles + 1) * Mp;
@@ -1119,7 +1123,7 @@ template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
     e.fetch();
     BsCtl *bc = e.bc;
-    if (!bc->active || bc->phase != 0) return;
+    if (!bc->active || bc->phase != 0 || bc->pclean) return; // light round: eff / dec / pend of the pcore side stand
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
     const int Beff = bc->Beff;
@@ -1196,9 +1200,11 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
         const int i = e.ws.pend[pidx];
         double x[DP];
         load_row<DP>(e.X + (bc->pos + i) * e.ld, D, x);
-        // (1) nearest snapshot MC not modified before cell i, from the top-K list
-        double bd = 0.0;
-        int bkey = INT_MAX, bver = -1, status = 0; // status 1: UNKNOWN, 2: NEED
+        // (1) nearest snapshot MC not modified before cell i, from the top-K list.  If every listed candidate is
+        // stale the nearest clean MC is unknown, but no clean MC is nearer than the last list entry (BOUND): the
+        // decision still stands when a modified / created MC, at its exact version, beats that bound.
+        double bd = 0.0, bound = 0.0;
+        int bkey = INT_MAX, bver = -1, status = 0, bounded = 0; // status 2: NEED
         if (lane == 0 && Mo0 > 0) {
             const int tk = e.ws.tkpos[i];
             if (tk < 0) {
@@ -1214,17 +1220,22 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
                         break;
                     }
                 }
-                if (s == BS_TOPK) status = 1;
+                if (s == BS_TOPK) {
+                    bounded = 1;
+                    bound = e.ws.tk_dist[(size_t)tk * BS_TOPK + BS_TOPK - 1];
+                }
             }
         }
         status = __shfl_sync(0xffffffffu, status, 0);
         if (status) {
             if (lane == 0) {
-                e.ws.dec[i] = status == 2 ? BS_KEY_NEED : BS_KEY_UNKNOWN;
+                e.ws.dec[i] = BS_KEY_NEED;
                 e.ws.upf[i] = 0;
             }
             continue;
         }
+        bounded = __shfl_sync(0xffffffffu, bounded, 0);
+        bound = __shfl_sync(0xffffffffu, bound, 0);
         // (2) every MC modified or created earlier in the block, at its version just before cell i
         for (int h = lane; h < nh; h += 32) {
             const int32_t *mem = e.ws.omem + e.ws.hoff[h];
@@ -1248,6 +1259,13 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
                 bkey = ok;
                 bver = ov;
             }
+        }
+        if (bounded && !(bkey != INT_MAX && bd < bound)) { // warp-uniform after the reduction
+            if (lane == 0) {
+                e.ws.dec[i] = BS_KEY_UNKNOWN;
+                e.ws.upf[i] = 0;
+            }
+            continue;
         }
         int dec = KNEW + i, up = 0;
         if (bkey != INT_MAX) {
@@ -1327,7 +1345,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
     if (tid == 0) {
         int act = 0; // 0 refine, 1 commit
         bc->iters += 1;
-        bc->replayed += Beff;
+        bc->replayed += bc->pclean ? bc->npend : Beff;
         if (up != INT_MAX) {
             bc->m_commit = up + 1;
             bc->upgrade = 1;
@@ -1376,13 +1394,18 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
     const int nneed_old = bc->nneed;
     const int32_t row0 = (int32_t)bc->pos;
     int base = nneed_old;
+    // A refinement that only moves cells between OUTLIER-SIDE keys leaves the pcore side of the next round exactly
+    // as it is now (same candidates, flags, accepts, hence the same pcore versions, eff / dec of the accepted cells
+    // and the same list of pcore-rejected cells): that round re-runs the outlier side only (bc->pclean).
+    int dirty = 0;
     for (int c0 = m0; c0 < cut; c0 += BS_CTA1) {
         const int i = c0 + tid;
-        int dc = 0;
+        int dc = 0, ef = 0;
         bool diff = false, want = false;
         if (i < cut) {
             dc = e.ws.dec[i];
-            diff = dc != e.ws.eff[i];
+            ef = e.ws.eff[i];
+            diff = dc != ef;
             want = diff && (dc == BS_KEY_NEED || (dc >= 0 && dc < Mp && e.ws.pcand[i] != dc && !e.ws.pflag[i]));
         }
         const int nwant = __syncthreads_count(want);
@@ -1413,11 +1436,13 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
                 e.ws.ospec[i] = dc;
                 e.ws.pflag[i] = 1;
             }
+            if (ef >= Mp && dc >= Mp) e.ws.eff[i] = dc; // what k_bs_verify_p would record for this (rejected) cell
+            else dirty = 1;
         }
         base += nwant;
         if (s_cut < Beff) break; // uniform: s_cut was read after the barrier
     }
-    __syncthreads();
+    dirty = __syncthreads_or(dirty);
     const int Bnew = min(cut, s_cut);
     if (tid == 0) {
         if (Bnew <= m0) { // the first mismatching cell itself cannot be refined: commit the exact prefix
@@ -1434,7 +1459,9 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
             bc->pairs += (int64_t)(nneed_new - nneed_old) * bc->Mo0;
             bc->Beff = Bnew;
             bc->it += 1;
-            bc->npend = 0;
+            bc->pclean = dirty ? 0 : 1;
+            if (dirty) bc->npend = 0; // a light round keeps the list of pcore-rejected cells
+            else bc->rounds_light += 1;
         }
         if (e.h_inner) cudaGraphSetConditional(e.h_inner, bc->phase == 0 ? 1u : 0u);
     }

@@ -15,10 +15,10 @@
 // subspace masks (before 4d) and the weighted-neighbour rows (before 4e) over NCCL.
 //
 // The Euclidean test of 4b is `dnrm2(c_q - c_p) <= E` in the reference (OpenBLAS, third party).  The
-// device evaluates s = sum_d (c_q[d] - c_p[d])^2 sequentially in fp64 and decides every pair whose s is
-// outside a relative guard band of 2^-40 around E^2 -- far wider than any dnrm2 implementation's
-// rounding difference -- and reports the (astronomically rare) pairs inside the band to the host, which
-// settles them with the very dnrm2 the reference calls.
+// device evaluates s = sum_d (c_q[d] - c_p[d])^2 in fp64 (index order, fused multiply-add) and decides every pair
+// whose s is outside a relative guard band of 2^-40 around E^2 -- far wider than the rounding difference between any
+// two summation schemes, dnrm2's included -- and reports the (astronomically rare) pairs inside the band to the
+// host, which settles them with the very dnrm2 the reference calls.
 #pragma once
 #include "common.cuh"
 
@@ -47,85 +47,146 @@ __global__ void k_off_core(const double *cf1, const double *cf2, const double *w
 }
 
 // ---- 4b ------------------------------------------------------------------------------------------
+// FP64-pipe kernel (3 D flops per ORDERED pair).  One thread owns PPT rows with their coordinates in
+// registers; the columns stream through shared memory in double-buffered tiles (1-D bulk TMA) and every lane reads
+// the same coordinates (broadcast LDS.128); JU columns x PPT rows advance together for ILP.  The test only has to be
+// right OUTSIDE the guard band (pairs inside it go to the host's dnrm2), so the sum of squares may be contracted:
+// x = c - p; s = fma(x, x, s) -- 2 instructions for the 3 credited flops; |s_fma - s_seq| <= D 2^-52 s << 2^-40 s.
 constexpr int OFFN_THREADS = 128;
+constexpr int OFFN_JU = 4;
 template <int DP>
 struct OffCfg {
+    static constexpr int PPT = DP <= 40 ? 2 : 1;
     static constexpr int TM = ((2048 / DP) < 32 ? 32 : (2048 / DP)) / 32 * 32; // MCs per tile, multiple of 32
+    static constexpr int ROWS = OFFN_THREADS * PPT;
 };
 
 template <int DP>
 __global__ void __launch_bounds__(OFFN_THREADS)
     k_off_neighbours(const double *__restrict__ cen, int M, int D, int r0, int r1, double E2, uint32_t *__restrict__ nbr,
                      int32_t *__restrict__ cnt, int32_t *__restrict__ border, int border_cap, int32_t *n_border) {
-    constexpr int TM = OffCfg<DP>::TM;
+    constexpr int TM = OffCfg<DP>::TM, PPT = OffCfg<DP>::PPT, JU = OFFN_JU;
     __shared__ __align__(128) double tile[2][TM * DP];
     __shared__ __align__(8) uint64_t bar[2];
     const int words = (M + 31) / 32;
-    const int row = r0 + blockIdx.x * OFFN_THREADS + threadIdx.x;
-    const bool live = row < r1;
-    double p[DP];
+    int row[PPT];
+    bool live[PPT];
+    double p[PPT][DP];
 #pragma unroll
-    for (int d = 0; d < DP; ++d) p[d] = (live && d < D) ? cen[(size_t)row * D + d] : 0.0;
+    for (int u = 0; u < PPT; ++u) {
+        row[u] = r0 + blockIdx.x * OffCfg<DP>::ROWS + u * OFFN_THREADS + threadIdx.x;
+        live[u] = row[u] < r1;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) p[u][d] = (live[u] && d < D) ? cen[(size_t)row[u] * D + d] : 0.0;
+    }
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         mbar_fence_init();
     }
     __syncthreads();
-    const int ntiles = (M + TM - 1) / TM;
+    // column slab of this CTA (blockIdx.y): tiles [t_lo, t_hi); the row counts are accumulated with atomicAdd
+    const int ntiles_all = (M + TM - 1) / TM;
+    const int tps = (ntiles_all + gridDim.y - 1) / gridDim.y;
+    const int t_lo = blockIdx.y * tps, t_hi = min(ntiles_all, t_lo + tps);
     auto issue = [&](int t) {
+        const int q = t - t_lo;
         const int jt = t * TM;
         const int n = min(TM, M - jt);
         uint32_t bytes = (uint32_t)((size_t)n * D * sizeof(double));
         if (bytes & 15u) { // odd element count: the last double travels by a plain store (ordered by the arrive)
             bytes -= 8u;
-            tile[t & 1][(size_t)n * D - 1] = cen[(size_t)jt * D + (size_t)n * D - 1];
+            tile[q & 1][(size_t)n * D - 1] = cen[(size_t)jt * D + (size_t)n * D - 1];
         }
-        mbar_expect_tx(&bar[t & 1], bytes);
-        if (bytes) tma_load_1d(&tile[t & 1][0], cen + (size_t)jt * D, bytes, &bar[t & 1]);
+        mbar_expect_tx(&bar[q & 1], bytes);
+        if (bytes) tma_load_1d(&tile[q & 1][0], cen + (size_t)jt * D, bytes, &bar[q & 1]);
     };
-    if (threadIdx.x == 0) issue(0);
+    if (threadIdx.x == 0 && t_lo < t_hi) issue(t_lo);
     const double guard = dmul(E2, OFF_GUARD);
-    int count = 0;
-    for (int t = 0; t < ntiles; ++t) {
-        if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1);
-        mbar_wait(&bar[t & 1], (t >> 1) & 1);
-        const double *tl = tile[t & 1];
+    const bool full = D == DP; // compile-time offsets and 16-byte loads (DP is a multiple of 4)
+    int count[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) count[u] = 0;
+    for (int t = t_lo; t < t_hi; ++t) {
+        const int q = t - t_lo;
+        if (threadIdx.x == 0 && t + 1 < t_hi) issue(t + 1);
+        mbar_wait(&bar[q & 1], (q >> 1) & 1);
+        const double *tl = tile[q & 1];
         const int jt = t * TM;
         const int n = min(TM, M - jt);
         for (int wq = 0; wq < n; wq += 32) {
-            uint32_t bits = 0u;
-            const int nn = min(32, n - wq);
-            for (int b = 0; b < nn; ++b) {
-                const double *c = tl + (size_t)(wq + b) * D;
-                double s = 0.0;
+            uint32_t bits[PPT];
 #pragma unroll
-                for (int d = 0; d < DP; ++d) {
-                    if (d < D) {
-                        const double x = dsub(c[d], p[d]); // predeconmc_functions.py:16 (a - b, a = the other MC)
-                        s = dadd(s, dmul(x, x));
-                    }
-                }
-                if (live) {
-                    if (fabs(dsub(s, E2)) <= guard) {
-                        const int slot = atomicAdd(n_border, 1);
-                        if (slot < border_cap) {
-                            border[2 * slot] = row;
-                            border[2 * slot + 1] = jt + wq + b;
+            for (int u = 0; u < PPT; ++u) bits[u] = 0u;
+            for (int b0 = 0; b0 < 32 && wq + b0 < n; b0 += JU) {
+                double s[PPT][JU];
+#pragma unroll
+                for (int u = 0; u < PPT; ++u)
+#pragma unroll
+                    for (int v = 0; v < JU; ++v) s[u][v] = 0.0;
+                if (full) {
+#pragma unroll
+                    for (int d = 0; d < DP; d += 2) {
+#pragma unroll
+                        for (int v = 0; v < JU; ++v) { // columns past n read stale shared memory; masked below
+                            const double2 c = *reinterpret_cast<const double2 *>(tl + (size_t)(wq + b0 + v) * DP + d);
+#pragma unroll
+                            for (int u = 0; u < PPT; ++u) {
+                                const double x0 = dsub(c.x, p[u][d]); // predeconmc_functions.py:16 (a - b, a = the other MC)
+                                s[u][v] = __fma_rn(x0, x0, s[u][v]);
+                                const double x1 = dsub(c.y, p[u][d + 1]);
+                                s[u][v] = __fma_rn(x1, x1, s[u][v]);
+                            }
                         }
-                    } else if (s < E2) {
-                        bits |= 1u << b;
+                    }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < DP; ++d) {
+                        if (d < D) {
+#pragma unroll
+                            for (int v = 0; v < JU; ++v) {
+                                const double c = tl[(size_t)(wq + b0 + v) * D + d];
+#pragma unroll
+                                for (int u = 0; u < PPT; ++u) {
+                                    const double x = dsub(c, p[u][d]);
+                                    s[u][v] = __fma_rn(x, x, s[u][v]);
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < JU; ++v) {
+                    const int b = b0 + v;
+                    if (wq + b < n) {
+#pragma unroll
+                        for (int u = 0; u < PPT; ++u) {
+                            if (!live[u]) continue;
+                            if (fabs(dsub(s[u][v], E2)) <= guard) {
+                                const int slot = atomicAdd(n_border, 1);
+                                if (slot < border_cap) {
+                                    border[2 * slot] = row[u];
+                                    border[2 * slot + 1] = jt + wq + b;
+                                }
+                            } else if (s[u][v] < E2) {
+                                bits[u] |= 1u << b;
+                            }
+                        }
                     }
                 }
             }
-            if (live) {
-                nbr[(size_t)(row - r0) * words + ((jt + wq) >> 5)] = bits;
-                count += __popc(bits);
-            }
+#pragma unroll
+            for (int u = 0; u < PPT; ++u)
+                if (live[u]) {
+                    nbr[(size_t)(row[u] - r0) * words + ((jt + wq) >> 5)] = bits[u];
+                    count[u] += __popc(bits[u]);
+                }
         }
         __syncthreads();
     }
-    if (live) cnt[row - r0] = count;
+#pragma unroll
+    for (int u = 0; u < PPT; ++u)
+        if (live[u] && count[u]) atomicAdd(&cnt[row[u] - r0], count[u]); // cnt is zeroed by the launcher
 }
 
 // settles borderline pairs decided on the host: sets the bit and bumps the row count

@@ -113,20 +113,39 @@ def sharded_offline(stages, cen, core, M, D, k, pi, delta, E, E2, group=None, di
     cnt = stages.empty((R,), torch.int32)
     submask = stages.empty((R,), torch.int64)
     wn = stages.empty((R, words), torch.int32)
+    import time
+
+    def lap(name, t0):
+        """optional per-stage wall time (device-synchronised); timers = {} collects seconds per stage"""
+        if timers is None:
+            return t0
+        if hasattr(stages, "torch") and hasattr(stages.torch, "cuda") and stages.torch.cuda.is_available():
+            stages.torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        timers[name] = timers.get(name, 0.0) + (t1 - t0)
+        return t1
+
+    tq = lap("alloc", time.perf_counter()) if timers is not None else 0.0
     n_border = stages.neighbours(cen, M, D, r0, r1, E, E2, nbr, cnt)
+    tq = lap("neighbours", tq)
     stages.subspace(cen, M, D, r0, r1, nbr, cnt, delta, submask)
+    tq = lap("subspace", tq)
     if world > 1:
         sub_all = stages.empty((world * R,), torch.int64)
         dist.all_gather_into_tensor(sub_all, submask, group=group)
     else:
         sub_all = submask
+    tq = lap("allgather_submask", tq)
     stages.weighted(cen, M, D, r0, r1, nbr, sub_all, k, E2, wn)
+    tq = lap("weighted", tq)
     if world > 1:
         wn_all = stages.empty((world * R, words), torch.int32)
         dist.all_gather_into_tensor(wn_all, wn, group=group)
     else:
         wn_all = wn
+    tq = lap("allgather_wn", tq)
     label, order, cl_off, ncl = stages.clusters(M, wn_all, core, sub_all, k, pi)
+    tq = lap("clusters", tq)
     info = {"rows": (r0, r1), "rows_per_rank": R, "borderline_pairs": n_border,
             "gather_bytes": int(world * R * 8 + world * R * words * 4) if world > 1 else 0,
             "neighbour_count": int(cnt[:max(r1 - r0, 0)].sum().item()) if r1 > r0 else 0}

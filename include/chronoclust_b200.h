@@ -101,6 +101,7 @@ typedef struct {
     int64_t bsv_late_topk;     /* cells whose top-K list had to be fetched in a refinement round */
     int64_t bsv_outlier_stage_cells; /* cells given a top-K list up front (not SAFE) */
     int64_t bsv_replayed_cells;      /* cells replayed by the chain kernels, summed over rounds */
+    int64_t bsv_light_rounds;        /* refinement rounds that re-ran the outlier side only (pcore side unchanged) */
 } ccb_stats;
 
 int ccb_create(const ccb_params *params, ccb_handle **out);

@@ -283,7 +283,8 @@ static int64_t bsv_block(cco_state *s, const double *X, int64_t ld, int64_t p0, 
             int64_t obest = -1; /* key */
             double obd = 0.0;
             bsv_view ov = {0, 0, 0, 0, 0};
-            int unknown = 0;
+            int unknown = 0, bounded = 0;
+            double bound = 0.0; /* every snapshot MC outside a full, all-stale list is at least this far away */
             if (Mo0 > 0) {
                 if (tkpos[i] < 0) {
                     unknown = 2;
@@ -298,11 +299,11 @@ static int64_t bsv_block(cco_state *s, const double *X, int64_t ld, int64_t p0, 
                             break;
                         }
                     }
-                    if (e == K) unknown = 1;
+                    if (e == K) bounded = 1, bound = td[K - 1];
                 }
             }
             if (unknown) {
-                dec[i] = unknown == 2 ? KEY_NEED : KEY_UNKNOWN;
+                dec[i] = KEY_NEED;
                 continue;
             }
             /* (2) every MC modified or created earlier in the block, at its version just before i */
@@ -312,6 +313,12 @@ static int64_t bsv_block(cco_state *s, const double *X, int64_t ld, int64_t p0, 
                 bsv_view v = {vcf1 + lat * D, vcf2 + lat * D, vcen + lat * D, vpref + lat * D, vw[lat]};
                 double d = dist_view(&v, p, D);
                 if (obest < 0 || d < obd || (d == obd && hkey[h] < obest)) obest = hkey[h], obd = d, ov = v;
+            }
+            /* all listed snapshot candidates were stale: the nearest clean MC is unknown, but it cannot be nearer
+             * than the last list entry -- the decision stands iff a modified / created MC beats that bound */
+            if (bounded && !(obest >= 0 && obd < bound)) {
+                dec[i] = KEY_UNKNOWN;
+                continue;
             }
             dec[i] = KNEW + i;
             if (obest >= 0 && tent_view(&ov, p, D, s->delta2, s->k, t1, t2, &tw, tp) <= s->eps2) {

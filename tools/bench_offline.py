@@ -53,13 +53,16 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rep:
             times.append(float(t[0]))
+    stage_s = {}
+    sharded_offline(st, tc, tcore, a.M, a.D, 4.0, a.D, 0.05, a.E, a.E ** 2, dist=dist, timers=stage_s)  # one extra pass, per-stage times
     if rank == 0:
         ms = float(np.mean(times))
         pairs = float(a.M) ** 2
         print(json.dumps({"metric": "offline ordered MC pairs/s (eps-neighbourhood + subspace + weighted + clusters)",
                           "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "ms": ms, "M": a.M, "D": a.D,
                           "euclid_gflops": 3.0 * a.D * pairs / (ms * 1e-3) / 1e9, "clusters": int(ncl),
-                          "clustered_mcs": int((lab >= 0).sum()), "info": info, "scaling": "strong"}))
+                          "clustered_mcs": int((lab >= 0).sum()), "info": info, "scaling": "strong",
+                          "stage_ms_rank0": {k: round(v * 1e3, 2) for k, v in stage_s.items()}}))
     if dist is not None:
         dist.destroy_process_group()
 

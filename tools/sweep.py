@@ -43,20 +43,25 @@ def main():
     Xd = [torch.from_numpy(x).cuda(local) for x in gen(N, D, T, Cn, seed)]
     assign = torch.empty(N, dtype=torch.int32, device=f"cuda:{local}")
     stage = torch.empty(N, dtype=torch.uint8, device=f"cuda:{local}")
-    grid = GRID[:a.configs]
+    grid = GRID[::max(1, len(GRID) // a.configs)][:a.configs] if a.configs < len(GRID) else GRID
     mine = [i for i in range(len(grid)) if i % world == rank]
 
     def run(i):
         eps, ups, beta = grid[i]
         cfg = dict(config_params("C2"), epsilon=eps, upsilon=ups, beta=beta)
+        t0 = time.perf_counter()
         h = HDDStream(cfg, logging.getLogger("sweep"), device=local)
         h.dataset_dimensionality = D
         h._ensure_handle(D)
         for t in range(T):
             h.ingest_device(Xd[t].data_ptr(), N, D, t, assign.data_ptr(), stage.data_ptr())
         c = h.counts()
+        torch.cuda.synchronize()
+        st = h.stats()
         return {"epsilon": eps, "upsilon": ups, "beta": beta, "pcore": int(c[0]), "outlier": int(c[1]),
-                "clusters": len(h.final_clusters)}
+                "clusters": len(h.final_clusters), "seconds": round(time.perf_counter() - t0, 3),
+                "blocks": st["bsv_blocks"], "rounds": st["bsv_rounds"], "outlier_stage_cells": st["bsv_outlier_stage_cells"],
+                "cuts": [st["bsv_cuts_unknown"], st["bsv_cuts_rounds"], st["bsv_cuts_capacity"]]}
 
     run(mine[0] if mine else 0)  # warm-up (module load, workspace growth)
     if dist is not None:

@@ -14,7 +14,8 @@ scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 N, D, T, Cn, seed, eps, pi = CONFIGS[name]
 N = int(N * scale)
 Xs = gen(N, D, T, Cn, seed)
-h = HDDStream(config_params(name), logging.getLogger("q"))
+chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+h = HDDStream(config_params(name), logging.getLogger("q"), chunk=chunk)
 h.dataset_dimensionality = D
 h._ensure_handle(D)
 Xd = [torch.from_numpy(x).cuda() for x in Xs]
@@ -32,6 +33,8 @@ for rep in range(3):
         dt = time.perf_counter() - t0
         st = h.stats()
         line.append(f"t{t} {dt*1e3:.1f}ms blocks={st['bsv_blocks']-prev['bsv_blocks']} rounds={st['bsv_rounds']-prev['bsv_rounds']} "
-                    f"launches={st['kernel_launches']-prev['kernel_launches']}")
+                    f"light={st['bsv_light_rounds']-prev['bsv_light_rounds']} "
+                    f"cuts={st['bsv_cuts_unknown']-prev['bsv_cuts_unknown']}/{st['bsv_cuts_rounds']-prev['bsv_cuts_rounds']}/"
+                    f"{st['bsv_cuts_capacity']-prev['bsv_cuts_capacity']} launches={st['kernel_launches']-prev['kernel_launches']}")
         prev = st
     print(f"rep {rep}: " + " | ".join(line))
