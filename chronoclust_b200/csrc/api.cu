@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -98,6 +99,8 @@ struct ccb_handle {
     cudaGraphExec_t bs_exec = nullptr;
     cudaStream_t cap1 = nullptr, cap2 = nullptr, cap3 = nullptr; // capture streams: block loop, round loop, side branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t copy_stream = nullptr; // host -> device segments of ccb_ingest, ahead of the engine
+    cudaEvent_t ev_seg[8] = {nullptr};
     Eng bs_graph_eng{};         // the pointers / capacities the graph was captured with
     EngIo *d_io = nullptr, *h_io = nullptr;
     // offline results (host copies)
@@ -285,6 +288,36 @@ Num make_num(const ccb_handle *h) {
     return nm;
 }
 
+// Static split of kernel 1: (row groups) x (slabs of the MC axis).  Few cells: enough slabs to fill the GPU twice.
+// Many cells: the slab count that balances the waves -- gx CTAs in ceil(gx / resident) waves waste the tail of the last
+// one (13 % for the dense 1e6 x 4096 benchmark at one slab); a few slabs make the waves finer.
+template <int kDP, int K>
+void nearest_static_split(int div_mode, int64_t nrows_max, int M, int max_slabs, int &gx, int &slab_mcs, int &nslab) {
+    using Cfg = NearestCfg<kDP>;
+    gx = (int)((nrows_max + Cfg::CELLS - 1) / Cfg::CELLS);
+    int want = gx > 0 ? (2 * 148 + gx - 1) / gx : 1;
+    if (want > max_slabs) want = max_slabs;
+    const int tiles = (M + Cfg::TM - 1) / Cfg::TM;
+    if (want > tiles) want = tiles;
+    if (want < 1) want = 1;
+    if (gx > 148) {
+        int occ = 1;
+        if (div_mode) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nearest<kDP, K, true>, NEAREST_THREADS, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nearest<kDP, K, false>, NEAREST_THREADS, 0);
+        const double resident = 148.0 * std::max(occ, 1);
+        auto loss = [&](int sl) {
+            const double w = (double)gx * sl / resident;
+            return w <= 1.0 ? 0.0 : std::ceil(w) / w - 1.0;
+        };
+        int best = want;
+        for (int sl = want + 1; sl <= std::min(std::min(max_slabs, tiles), want + 7) && loss(best) > 0.03; ++sl)
+            if (loss(sl) < loss(best)) best = sl;
+        want = best;
+    }
+    slab_mcs = ((tiles + want - 1) / want) * Cfg::TM;
+    nslab = (M + slab_mcs - 1) / slab_mcs;
+}
+
 // kernel 1 launch over an explicit cw array
 template <int K>
 int launch_nearest(ccb_handle *h, cudaStream_t s, int DP, int div_mode, const double *X, const int32_t *rows,
@@ -293,31 +326,8 @@ int launch_nearest(ccb_handle *h, cudaStream_t s, int DP, int div_mode, const do
                    int *nslab_out, const int32_t *range_dev = nullptr, const int32_t *M_dev = nullptr) {
     int launched = 0;
     CCB_DISPATCH_DP(DP, {
-        using Cfg = NearestCfg<kDP>;
-        const int gx = (int)((nrows_max + Cfg::CELLS - 1) / Cfg::CELLS);
-        int want = (2 * 148 + gx - 1) / gx;
-        if (want > max_slabs) want = max_slabs;
-        const int tiles = (M + Cfg::TM - 1) / Cfg::TM;
-        if (want > tiles) want = tiles;
-        if (want < 1) want = 1;
-        if (gx > 148) {
-            // wave quantisation: gx CTAs in ceil(gx / resident) waves waste the tail of the last one (13 % for the dense
-            // 1e6 x 4096 benchmark at one slab); cutting the MC axis into a few slabs makes the waves finer
-            int occ = 1;
-            if (div_mode) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nearest<kDP, K, true>, NEAREST_THREADS, 0);
-            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nearest<kDP, K, false>, NEAREST_THREADS, 0);
-            const double resident = 148.0 * std::max(occ, 1);
-            auto loss = [&](int sl) {
-                const double w = (double)gx * sl / resident;
-                return w <= 1.0 ? 0.0 : std::ceil(w) / w - 1.0;
-            };
-            int best = want;
-            for (int sl = want + 1; sl <= std::min(std::min(max_slabs, tiles), want + 7) && loss(best) > 0.03; ++sl)
-                if (loss(sl) < loss(best)) best = sl;
-            want = best;
-        }
-        int slab_mcs = ((tiles + want - 1) / want) * Cfg::TM;
-        const int nslab = (M + slab_mcs - 1) / slab_mcs;
+        int gx, slab_mcs, nslab;
+        nearest_static_split<kDP, K>(div_mode, nrows_max, M, max_slabs, gx, slab_mcs, nslab);
         dim3 grid(gx, nslab);
         double *od = nslab == 1 ? out_dist : slab_dist;
         int32_t *oi = nslab == 1 ? out_idx : slab_idx;
@@ -803,7 +813,8 @@ int ensure_bsv_capacity(ccb_handle *h, int blocks_ahead) {
 }
 
 // the ordered loop over cells [0, N) of a device-resident X, block-speculative engine
-int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t *d_assign, uint8_t *d_stage) {
+int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t *d_assign, uint8_t *d_stage,
+                    const std::function<int()> *after_first_launch = nullptr) {
     if (!h->have_params) return fail(h, CCB_ESTATE, "ccb_begin_timepoint must precede ccb_ingest");
     if (N >= ((int64_t)1 << 31)) return fail(h, CCB_ELIMIT, "more than 2^31 - 1 cells in one call");
     cudaStream_t s = h->stream;
@@ -860,6 +871,11 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
                 h->st.kernel_launches += BS_LAUNCHES_PROLOGUE + h->bs_iters * BS_LAUNCHES_ROUND + BS_LAUNCHES_COMMIT;
             }
         }
+        if (after_first_launch) { // the engine is running: the caller queues the next input segment behind it
+            const std::function<int()> *f = after_first_launch;
+            after_first_launch = nullptr;
+            if ((rc = (*f)())) return rc;
+        }
         if ((rc = sync_bc(h))) return rc;
         if (graph) // kernels the graph executed: per block prologue + commit, per round the round's kernels
             h->st.kernel_launches += (h->h_bc->blocks - blocks0) * (BS_LAUNCHES_PROLOGUE + BS_LAUNCHES_COMMIT) +
@@ -868,6 +884,7 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
             return fail(h, CCB_ESTATE, "internal: block-speculative engine made no progress at row %lld", (long long)pos0);
         if (h->h_bc->pos != pos0) guard = 0;
     }
+    if (after_first_launch && (rc = (*after_first_launch)())) return rc;
     h->st.points += N;
     return CCB_OK;
 }
@@ -912,6 +929,80 @@ int launch_off_neighbours(ccb_handle *h, cudaStream_t s, const double *cen, int 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, CCB_ECUDA, "k_off_neighbours launch: %s", cudaGetErrorString(e));
     return CCB_OK;
+}
+
+// kernel 4e: ordered cluster growth.  Small M (the online hot path: tens of pcore MCs): the single-launch bit-row
+// kernel.  Large M (config C4): isolated MCs in parallel, CSR lists for the rest, clusters merged by seed rank
+// (offline.cuh).  Both produce identical label / order / cl_off / n_cl.  cls [M] and queue [2M + 2] are scratch.
+int g_off_csr_min_m = 2048; // ccb_debug_set(h, 1000 + m) moves the switch-over (the tests force either path)
+int off_csr_min_m() { return g_off_csr_min_m; }
+
+int launch_off_clusters(ccb_handle *h, cudaStream_t s, int M, const uint32_t *wnbr, const uint8_t *core,
+                        const uint64_t *submask, int cnt_gt1, int64_t pi, uint8_t *cls, int32_t *queue, int32_t *label,
+                        int32_t *order, int32_t *cl_off, int32_t *n_cl, int *launches) {
+    const int words = (M + 31) / 32;
+    *launches = 0;
+    cudaMemsetAsync(cls, 0, (size_t)std::max(M, 1), s);
+    auto old_path = [&]() {
+        k_off_clusters<<<1, OFFC_THREADS, 0, s>>>(M, wnbr, core, submask, cnt_gt1, pi, cls, queue, label, order, cl_off, n_cl);
+        *launches += 1;
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? CCB_OK : fail(h, CCB_ECUDA, "k_off_clusters: %s", cudaGetErrorString(e));
+    };
+    if (M < off_csr_min_m() || M == 0) return old_path();
+    uint8_t *iso = nullptr;
+    int32_t *i32 = nullptr, *col = nullptr;
+    int64_t *off = nullptr;
+    // int32 scratch: nnz | order_s | cl_off_s (M + 1) | seed_of (M + 1) | n_cl_s (1) | seedflag | size_by_node |
+    //                rank (M + 1) | size_by_cluster
+    const size_t m = (size_t)M;
+    const size_t n32 = 8 * m + 16;
+    cudaError_t e;
+    if ((e = cudaMallocAsync(&iso, m, s)) != cudaSuccess || (e = cudaMallocAsync(&i32, n32 * 4, s)) != cudaSuccess ||
+        (e = cudaMallocAsync(&off, (m + 1) * 8, s)) != cudaSuccess)
+        return fail(h, CCB_ENOMEM, "offline scratch: %s", cudaGetErrorString(e));
+    int32_t *nnz = i32, *order_s = nnz + m, *cl_off_s = order_s + m, *seed_of = cl_off_s + m + 1, *n_cl_s = seed_of + m + 1,
+            *seedflag = n_cl_s + 1, *size_by_node = seedflag + m, *rank = size_by_node + m, *size_by_cluster = rank + m + 1;
+    auto release = [&]() {
+        cudaFreeAsync(iso, s);
+        cudaFreeAsync(i32, s);
+        cudaFreeAsync(off, s);
+        if (col) cudaFreeAsync(col, s);
+    };
+    const int wgrid = (M + 3) / 4, tgrid = (M + 255) / 256;
+    k_offc_rowinfo<<<wgrid, 128, 0, s>>>(wnbr, M, words, iso, nnz);
+    k_offc_scan<int64_t><<<1, OFFG_THREADS, 0, s>>>(nnz, M, off);
+    *launches += 2;
+    int64_t total = 0;
+    if ((e = cudaMemcpyAsync(&total, off + M, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(s)) != cudaSuccess) {
+        release();
+        return fail(h, CCB_ECUDA, "offline CSR sizes: %s", cudaGetErrorString(e));
+    }
+    if (total > (int64_t)INT32_MAX - 1) { // a CSR that large buys nothing over the bit rows
+        release();
+        return old_path();
+    }
+    if ((e = cudaMallocAsync(&col, (size_t)std::max<int64_t>(total, 1) * 4, s)) != cudaSuccess) {
+        release();
+        return fail(h, CCB_ENOMEM, "offline CSR (%lld entries): %s", (long long)total, cudaGetErrorString(e));
+    }
+    k_offc_fill<<<wgrid, 128, 0, s>>>(wnbr, M, words, iso, off, col);
+    k_offc_grow<<<1, OFFG_THREADS, 0, s>>>(M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, order_s, cl_off_s, seed_of,
+                                           n_cl_s);
+    k_offc_seeds<<<tgrid, 256, 0, s>>>(M, iso, core, submask, cnt_gt1, pi, seed_of, cl_off_s, n_cl_s, seedflag, size_by_node,
+                                       label);
+    k_offc_seeds_serial<<<tgrid, 256, 0, s>>>(seed_of, cl_off_s, n_cl_s, seedflag, size_by_node);
+    k_offc_scan<int32_t><<<1, OFFG_THREADS, 0, s>>>(seedflag, M, rank);
+    cudaMemsetAsync(size_by_cluster, 0, m * 4, s);
+    k_offc_sizes<<<tgrid, 256, 0, s>>>(M, seedflag, rank, size_by_node, size_by_cluster, n_cl);
+    k_offc_scan<int32_t><<<1, OFFG_THREADS, 0, s>>>(size_by_cluster, M, cl_off);
+    k_offc_scatter_iso<<<tgrid, 256, 0, s>>>(M, iso, seedflag, rank, size_by_node, cl_off, order, label);
+    k_offc_scatter_serial<<<148, 256, 0, s>>>(seed_of, cl_off_s, n_cl_s, order_s, rank, cl_off, order, label);
+    *launches += 9;
+    e = cudaGetLastError();
+    release();
+    return e == cudaSuccess ? CCB_OK : fail(h, CCB_ECUDA, "offline cluster growth: %s", cudaGetErrorString(e));
 }
 
 } // namespace
@@ -1018,6 +1109,9 @@ void ccb_destroy(ccb_handle *h) {
     if (h->cap1) cudaStreamDestroy(h->cap1);
     if (h->cap2) cudaStreamDestroy(h->cap2);
     if (h->cap3) cudaStreamDestroy(h->cap3);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto &ev : h->ev_seg)
+        if (ev) cudaEventDestroy(ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     cudaFree(h->d_io);
@@ -1076,6 +1170,10 @@ int ccb_debug_phase_cycles(ccb_handle *h, int64_t out[8]) {
 
 int ccb_debug_set(ccb_handle *h, int32_t mode) {
     if (!h) return fail(h, CCB_EINVAL, "null argument");
+    if (mode >= 1000) { // not a diagnostic: which of the two (equivalent) cluster-growth paths serves M microclusters
+        g_off_csr_min_m = mode - 1000;
+        return CCB_OK;
+    }
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaMemcpyToSymbol(g_bs_dbg_mode, &mode, sizeof(int)));
     return CCB_OK;
@@ -1241,13 +1339,47 @@ int ccb_ingest(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *a
     }
     int rc = ensure_point_buffers(h, N);
     if (rc) return rc;
-    {
-        Timed tm(h, CCB_CAT_COPY);
-        CK(h, cudaMemcpyAsync(h->d_X, X, need * 8, cudaMemcpyHostToDevice, h->stream));
+    const int nseg = (h->engine || h->timing) ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(8, N / 131072));
+    if (nseg == 1) {
+        {
+            Timed tm(h, CCB_CAT_COPY);
+            CK(h, cudaMemcpyAsync(h->d_X, X, need * 8, cudaMemcpyHostToDevice, h->stream));
+        }
+        rc = h->engine ? ingest_core(h, h->d_X, N, ld, h->d_assign, h->d_stage)
+                       : ingest_core_bsv(h, h->d_X, N, ld, h->d_assign, h->d_stage);
+        if (rc) return rc;
+    } else {
+        // The ordered engine consumes cells front to back, so the input travels in segments on a copy stream and the
+        // engine starts as soon as the first one has landed: segment k + 1 is queued right after the engine has been
+        // launched on segment k (with pageable host memory the staging copy then overlaps the engine, too).
+        if (!h->copy_stream) {
+            CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (auto &ev : h->ev_seg) CK(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        }
+        CK(h, cudaEventRecord(h->ev_seg[0], h->stream)); // earlier work on the handle's stream (previous readers of d_X)
+        CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_seg[0], 0));
+        const int64_t per = (N + nseg - 1) / nseg;
+        auto seg_rows = [&](int k, int64_t &r0, int64_t &n) {
+            r0 = std::min<int64_t>(N, (int64_t)k * per);
+            n = std::min<int64_t>(N, r0 + per) - r0;
+        };
+        auto copy_seg = [&](int k) -> int {
+            int64_t r0, n;
+            seg_rows(k, r0, n);
+            if (n > 0)
+                CK(h, cudaMemcpyAsync(h->d_X + r0 * ld, X + r0 * ld, (size_t)n * ld * 8, cudaMemcpyHostToDevice, h->copy_stream));
+            CK(h, cudaEventRecord(h->ev_seg[k], h->copy_stream));
+            return CCB_OK;
+        };
+        if ((rc = copy_seg(0))) return rc;
+        for (int k = 0; k < nseg; ++k) {
+            int64_t r0, n;
+            seg_rows(k, r0, n);
+            CK(h, cudaStreamWaitEvent(h->stream, h->ev_seg[k], 0));
+            const std::function<int()> next = [&]() -> int { return k + 1 < nseg ? copy_seg(k + 1) : CCB_OK; };
+            if ((rc = ingest_core_bsv(h, h->d_X + r0 * ld, n, ld, h->d_assign + r0, h->d_stage + r0, &next))) return rc;
+        }
     }
-    rc = h->engine ? ingest_core(h, h->d_X, N, ld, h->d_assign, h->d_stage)
-                   : ingest_core_bsv(h, h->d_X, N, ld, h->d_assign, h->d_stage);
-    if (rc) return rc;
     {
         Timed tm(h, CCB_CAT_COPY);
         CK(h, cudaMemcpyAsync(assign_uid, h->d_assign, (size_t)N * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1464,10 +1596,11 @@ int ccb_offline(ccb_handle *h, int64_t *n_clusters) {
         const int64_t t2 = (int64_t)M * words;
         k_off_weighted<<<(unsigned)((t2 + 127) / 128), 128, 0, s>>>(P.cen, M, D, 0, M, nbr.p, submask.p, h->prm.k, E2, wnbr.p);
         CKL(h);
-        k_off_clusters<<<1, OFFC_THREADS, 0, s>>>(M, wnbr.p, core.p, submask.p, h->cnt_gt1, h->pi, cls.p, queue.p, label.p,
-                                                  order.p, cloff.p, ncl.p);
-        CKL(h);
-        h->st.kernel_launches += 3;
+        int nl = 0, rc2;
+        if ((rc2 = launch_off_clusters(h, s, M, wnbr.p, core.p, submask.p, h->cnt_gt1, h->pi, cls.p, queue.p, label.p, order.p,
+                                       cloff.p, ncl.p, &nl)))
+            return rc2;
+        h->st.kernel_launches += 2 + nl;
     }
     int32_t nc_raw = 0;
     CK(h, cudaMemcpyAsync(&nc_raw, ncl.p, 4, cudaMemcpyDeviceToHost, s));
@@ -1678,8 +1811,27 @@ int ccb_nearest(int32_t device, void *stream, const double *X, int64_t N, int64_
     double2 *cw = nullptr;
     double *sd = nullptr;
     int32_t *si = nullptr;
-    // scratch: packed rows + per-slab candidates (slabs only matter when N is small)
-    const int max_slabs = N >= (int64_t)148 * 2 * NEAREST_THREADS * 2 ? 8 : MAX_SLABS; // many cells: a few slabs for wave balance only
+    // scratch: packed rows + per-slab candidates, sized by the split the launch will use; the stream-ordered pool keeps
+    // what it has (release threshold raised once per device) so repeated calls do not go back to the driver
+    static bool pool_tuned[64] = {false};
+    if (device >= 0 && device < 64 && !pool_tuned[device]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_tuned[device] = true;
+    }
+    int max_slabs = 1;
+    {
+        int ok = 0;
+        CCB_DISPATCH_DP(DP, {
+            int gx, slab_mcs;
+            nearest_static_split<kDP, 1>(p2 ? 0 : 1, N, (int)M, MAX_SLABS, gx, slab_mcs, max_slabs);
+            ok = 1;
+        })
+        if (!ok) return fail(nullptr, CCB_ELIMIT, "unsupported dimensionality %d", D);
+    }
     if ((e = cudaMallocAsync(&cw, (size_t)M * DP * sizeof(double2), s)) != cudaSuccess ||
         (e = cudaMallocAsync(&sd, (size_t)N * max_slabs * 8, s)) != cudaSuccess ||
         (e = cudaMallocAsync(&si, (size_t)N * max_slabs * 4, s)) != cudaSuccess)
@@ -1753,13 +1905,12 @@ int ccb_off_clusters(int32_t device, void *stream, int64_t M, const uint32_t *wn
     if ((e = cudaMallocAsync(&cls, (size_t)std::max<int64_t>(M, 1), s)) != cudaSuccess ||
         (e = cudaMallocAsync(&queue, (2 * (size_t)M + 2) * 4, s)) != cudaSuccess)
         return fail(nullptr, CCB_ENOMEM, "scratch allocation: %s", cudaGetErrorString(e));
-    cudaMemsetAsync(cls, 0, (size_t)std::max<int64_t>(M, 1), s);
-    k_off_clusters<<<1, OFFC_THREADS, 0, s>>>((int)M, wnbr, core, submask_all, k > 1.0, pi, cls, queue, label, order, cl_off,
-                                              n_cl);
-    e = cudaGetLastError();
+    int nl = 0;
+    const int rc = launch_off_clusters(nullptr, s, (int)M, wnbr, core, submask_all, k > 1.0, pi, cls, queue, label, order, cl_off,
+                                       n_cl, &nl);
     cudaFreeAsync(cls, s);
     cudaFreeAsync(queue, s);
-    return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "k_off_clusters: %s", cudaGetErrorString(e));
+    return rc;
 }
 
 } // extern "C"

@@ -703,9 +703,65 @@ struct ChainPCfg {
     static constexpr int S = DP <= 48 ? 8 : 6;
     static constexpr size_t SMEM = (size_t)S * NB * (LSP * 8 + 4) + 3 * S * 8 + DP * 8 + 128;
 };
-constexpr int BS_CHAINP_THREADS = 128;
+constexpr int BS_CHAINP_THREADS = 256;
+constexpr int BS_CHAINP_STORERS = 5; // warps 2, 3, 5, 6, 7; warp 4 would share the replay warp's scheduler and exits
 
 __device__ int g_bs_dbg_mode = 0; // diagnostics only (ccb_debug_set): 1 = storers skip the global stores, 2 = skip the copies
+
+// Exact radius test of the tentative MC nv = v + a (mc_functions.py:45-56) for a CONTESTED cell, by the whole replay
+// warp (lane = record element).  Deliberately NOT inlined: the replay warp runs alone on its scheduler, so every cold
+// instruction-cache line it touches is a full miss it cannot hide; one small shared copy keeps the footprint of the
+// rare path at a few hundred instructions.  NH == 1: the record is one register per lane (nv0); otherwise it is read
+// back from the stage at rec_addr (this lane's element 0 of the record, shared-window address).
+template <int DP, int NH>
+__device__ __noinline__ bool bs_radius_test(double nv0, uint32_t rec_addr, int lane, int D, double delta2, double eps2,
+                                            int div_mode, double k, double wsel, double *scr) {
+    double wn, c1[2], c2[2];
+    if (NH == 1) { // fetch CF2', W' by shuffle
+        wn = __shfl_sync(0xffffffffu, nv0, 2 * DP);
+        c1[0] = nv0;
+        c2[0] = __shfl_sync(0xffffffffu, nv0, (lane + DP) & 31);
+        c1[1] = c2[1] = 1.0;
+    } else {
+        __syncwarp();
+        wn = lds_f64(rec_addr - lane * 8 + 2 * DP * 8);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int d = lane + 32 * h;
+            const bool rd = (h == 0 || DP > 32) && d < D;
+            c1[h] = rd ? lds_f64(rec_addr + 32 * h * 8) : 1.0;
+            c2[h] = rd ? lds_f64(rec_addr + (DP + 32 * h) * 8) : 1.0;
+        }
+    }
+    double term[2] = {0.0, 0.0};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (h == 0 || DP > 32) {
+            const int d = lane + 32 * h;
+            const bool act = d < D;
+            // idle lanes carry 1.0: their (discarded) quotients stay on the fast path of the division
+            const double q2 = ddiv(act ? c2[h] : 1.0, wn);
+            const double c = ddiv(act ? c1[h] : 1.0, wn);
+            const double var = dsub(q2, dmul(c, c));
+            const bool bit = act && (var <= delta2);
+            term[h] = bit ? (div_mode ? ddiv(var, k) : dmul(var, wsel)) : var;
+        }
+    }
+    // the D terms are summed in index order by every lane from shared memory (broadcast LDS.128)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        if ((h == 0 || DP > 32) && lane + 32 * h < DP) scr[lane + 32 * h] = term[h];
+    __syncwarp();
+    double r2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; d += 2) {
+        const double2 t2 = *reinterpret_cast<const double2 *>(scr + d);
+        if (d < D) r2 = dadd(r2, t2.x);
+        if (d + 1 < D) r2 = dadd(r2, t2.y);
+    }
+    __syncwarp();
+    return r2 <= eps2;
+}
 
 template <int DP>
 __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
@@ -736,7 +792,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&done[s], 1);
-            mbar_init(&empty[s], 2);
+            mbar_init(&empty[s], BS_CHAINP_STORERS);
         }
         mbar_fence_init();
     }
@@ -761,11 +817,13 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         }
         return;
     }
-    if (warp >= 2) { // ---- storers: two warps; ver[cell] <- the version left in the stage
-        // the stage is one flat array of cnt * LSP doubles: lane = element, eight elements in flight per lane
-        // (index and value loads first, then the stores) so that the shared-memory latency is paid once per eight
-        constexpr int U = 4, L2 = LSP / 2; // records are L2 double2 wide
-        const int st = (warp - 2) * 32 + lane;
+    if (warp == 4) return; // same scheduler as the replay warp: leave its issue slots alone
+    if (warp >= 2) { // ---- storers: ver[cell] <- the version left in the stage
+        // the stage is one flat array of cnt * LSP doubles: lane = element, four elements in flight per lane
+        // (index and value loads first, then the stores) so that the shared-memory latency is paid once per four.
+        // The copy is instruction-bound (index arithmetic per element), hence five warps on the three other schedulers.
+        constexpr int U = 4, L2 = LSP / 2, NST = BS_CHAINP_STORERS * 32; // records are L2 double2 wide
+        const int st = (warp < 4 ? warp - 2 : warp - 3) * 32 + lane;
         long long tw = 0;
         const long long tbeg = clock64();
         for (int b = 0; b < nb; ++b) {
@@ -780,12 +838,12 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
             const double2 *xb = reinterpret_cast<const double2 *>(xs + (size_t)s * NB * LSP);
             const int *mb = ms + s * NB;
             double2 *ver2 = reinterpret_cast<double2 *>(e.ws.ver);
-            for (int e0 = st; e0 < tot; e0 += 64 * U) {
+            for (int e0 = st; e0 < tot; e0 += NST * U) {
                 double2 val[U];
                 size_t off[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int el = e0 + 64 * u;
+                    const int el = e0 + NST * u;
                     if (el < tot) {
                         const int row = el / L2;
                         off[u] = (size_t)(mb[row] & 0x7fffffff) * L2 + (el - row * L2);
@@ -794,7 +852,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u)
-                    if (e0 + 64 * u < tot) {
+                    if (e0 + NST * u < tot) {
                         if (dbgm == 1) {
                             if (val[u].x == 1.2345e300) ver2[off[u]] = val[u];
                         } else {
@@ -831,56 +889,6 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
     bool st_ok[NH];
 #pragma unroll
     for (int h = 0; h < NH; ++h) st_ok[h] = lane + 32 * h < LSP;
-
-    // exact radius test of the tentative MC nv = v + a (mc_functions.py:45-56) for a CONTESTED cell, by the whole warp
-    auto radius_ok = [&](const double (&nv)[NH], uint32_t rec_addr) -> bool {
-        ++n_cont;
-        double wn, c1[2], c2[2];
-        if (NH == 1) { // the whole record lives in one register per lane: fetch CF2', W' by shuffle
-            wn = __shfl_sync(0xffffffffu, nv[0], 2 * DP);
-            c1[0] = nv[0];
-            c2[0] = __shfl_sync(0xffffffffu, nv[0], (lane + DP) & 31);
-            c1[1] = c2[1] = 1.0;
-        } else { // the record was just written to the stage: read CF1', CF2', W' back
-            __syncwarp();
-            wn = lds_f64(rec_addr - lane * 8 + 2 * DP * 8);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int d = lane + 32 * h;
-                const bool rd = (h == 0 || DP > 32) && d < D;
-                c1[h] = rd ? lds_f64(rec_addr + 32 * h * 8) : 1.0;
-                c2[h] = rd ? lds_f64(rec_addr + (DP + 32 * h) * 8) : 1.0;
-            }
-        }
-        double term[2] = {0.0, 0.0};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (h == 0 || DP > 32) {
-                const int d = lane + 32 * h;
-                const bool act = d < D;
-                // idle lanes carry 1.0: their (discarded) quotients stay on the fast path of the division
-                const double q2 = ddiv(act ? c2[h] : 1.0, wn);
-                const double c = ddiv(act ? c1[h] : 1.0, wn);
-                const double var = dsub(q2, dmul(c, c));
-                const bool bit = act && (var <= nm.delta2);
-                term[h] = bit ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var;
-            }
-        }
-        // the D terms are summed in index order by every lane from shared memory (broadcast LDS.128)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-            if ((h == 0 || DP > 32) && lane + 32 * h < DP) scr[lane + 32 * h] = term[h];
-        __syncwarp();
-        double r2 = 0.0;
-#pragma unroll
-        for (int d = 0; d < DP; d += 2) {
-            const double2 t2 = *reinterpret_cast<const double2 *>(scr + d);
-            if (d < D) r2 = dadd(r2, t2.x);
-            if (d + 1 < D) r2 = dadd(r2, t2.y);
-        }
-        __syncwarp();
-        return r2 <= nm.eps2;
-    };
 
     constexpr int GF = NH == 1 ? 16 : 8; // cells per register batch of the clean-stage path
     for (int b = 0; b < nb; ++b) {
@@ -934,41 +942,53 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
                 }
             }
         } else {
-            // ---- stage with CONTESTED cells or a ragged tail: groups of eight through registers; every cell adds
-            // and stores like above, a CONTESTED cell then takes the exact radius test on its tentative record
+            // ---- stage with CONTESTED cells or a ragged tail, kept SMALL (one copy of each piece of code, see
+            // bs_radius_test): a clean full group of eight is a short chain through registers; any other group goes one
+            // cell at a time, and a CONTESTED cell takes the exact radius test on its tentative record
             const long long t_s0 = clock64();
             const int ng = (cnt + GS - 1) / GS;
+#pragma unroll 1
             for (int g = 0; g < ng; ++g) {
                 const uint32_t ga = xa + g * (GS * LSP * 8);
                 const unsigned ge = (m_even >> (4 * g)) & 0xfu, go = (m_odd >> (4 * g)) & 0xfu;
                 const int ncell = min(GS, cnt - g * GS);
-                double R[GS][NH];
+                if ((ge | go) == 0u && ncell == GS) {
+                    double R[GS][NH];
 #pragma unroll
-                for (int q = 0; q < GS; ++q)
+                    for (int q = 0; q < GS; ++q)
 #pragma unroll
-                    for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8);
+                        for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8);
 #pragma unroll
-                for (int q = 0; q < GS; ++q) {
-                    if (q < ncell) {
-                        double nv[NH];
+                    for (int q = 0; q < GS; ++q)
 #pragma unroll
                         for (int h = 0; h < NH; ++h) {
-                            nv[h] = dadd(v[h], R[q][h]);
-                            if (st_ok[h]) sts_f64(ga + (q * LSP + 32 * h) * 8, nv[h]);
+                            v[h] = dadd(v[h], R[q][h]);
+                            if (st_ok[h]) sts_f64(ga + (q * LSP + 32 * h) * 8, v[h]);
                         }
-                        bool keep = true;
-                        if ((((q & 1) ? go : ge) >> (q >> 1)) & 1u) {
-                            keep = radius_ok(nv, ga + q * LSP * 8);
-                            if (lane == 0) {
-                                int raw;
-                                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma + (g * GS + q) * 4));
-                                e.ws.prej[raw & 0x7fffffff] = keep ? 0 : 1;
-                            }
-                        }
-                        if (keep) { // the record of a rejected cell is never read as a version
+                    continue;
+                }
+#pragma unroll 1
+                for (int q = 0; q < ncell; ++q) {
+                    const uint32_t ra = ga + q * (LSP * 8);
+                    double nv[NH];
 #pragma unroll
-                            for (int h = 0; h < NH; ++h) v[h] = nv[h];
+                    for (int h = 0; h < NH; ++h) {
+                        nv[h] = dadd(v[h], lds_f64(ra + 32 * h * 8));
+                        if (st_ok[h]) sts_f64(ra + 32 * h * 8, nv[h]);
+                    }
+                    bool keep = true;
+                    if ((((q & 1) ? go : ge) >> (q >> 1)) & 1u) {
+                        ++n_cont;
+                        keep = bs_radius_test<DP, NH>(nv[0], ra, lane, D, nm.delta2, nm.eps2, nm.div_mode, nm.k, nm.wsel, scr);
+                        if (lane == 0) {
+                            int raw;
+                            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma + (g * GS + q) * 4));
+                            e.ws.prej[raw & 0x7fffffff] = keep ? 0 : 1;
                         }
+                    }
+                    if (keep) { // the record of a rejected cell is never read as a version
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) v[h] = nv[h];
                     }
                 }
             }

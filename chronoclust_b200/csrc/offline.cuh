@@ -387,6 +387,250 @@ __global__ void __launch_bounds__(OFFC_THREADS, 1)
     if (tid == 0) *n_cl = ncl;
 }
 
+// ---- 4e, large M: the same ordered growth on a CSR of the weighted neighbourhoods -----------------------------------
+// k_off_clusters costs one scan of a whole bit row (M / 32 words) per seed and per popped core MC: 2 M row scans,
+// 1.4 s at M = 1e5 (config C4), 95 % of the offline phase.  Three observations remove almost all of it without touching
+// the literal rule of PreDeCon.run / _expand:
+//  (1) an ISOLATED MC (WN(p) = {p}) can neither reach nor be reached by anything (WN is symmetric): core -> it opens
+//      its own cluster {p} (empty if pdim(p) > pi), not core -> noise.  Decided in parallel.
+//  (2) seeds are visited in increasing index order and every seed emits exactly one cluster, so the index of a cluster
+//      is the RANK of its seed among all seeds: clusters grown serially and clusters of isolated MCs are merged by a
+//      prefix sum over seed flags afterwards.
+//  (3) the remaining MCs are walked by ONE CTA exactly like k_off_clusters, but over CSR lists (cost = entries of the
+//      popped lists, not M / 32 words per pop), skipping classified / isolated seeds 1024 at a time.
+constexpr int OFFG_THREADS = 1024;
+
+__device__ __forceinline__ int offc_block_min(int v, int *s_warp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    v = s_warp[threadIdx.x & 31];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    return v;
+}
+
+// warp per row: |WN(row)|, isolated flag, CSR entries the row will need (0 for isolated rows)
+__global__ void k_offc_rowinfo(const uint32_t *__restrict__ wnbr, int M, int words, uint8_t *iso, int32_t *nnz) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const uint32_t *r = wnbr + (size_t)row * words;
+    int c = 0;
+    for (int w = lane; w < words; w += 32) c += __popc(r[w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) {
+        const bool self = (r[row >> 5] >> (row & 31)) & 1u;
+        const bool is = (c == 1 && self);
+        iso[row] = is;
+        nnz[row] = is ? 0 : c;
+    }
+}
+
+// single-CTA exclusive scan of n int32 values into n + 1 outputs (T = int64_t offsets or int32_t ranks)
+template <typename T>
+__global__ void __launch_bounds__(OFFG_THREADS, 1) k_offc_scan(const int32_t *__restrict__ in, int n, T *__restrict__ out) {
+    __shared__ int s_warp[32];
+    __shared__ int s_tot;
+    T carry = 0;
+    for (int b = 0; b < n; b += OFFG_THREADS) {
+        const int i = b + threadIdx.x;
+        const int v = i < n ? in[i] : 0;
+        const int ex = block_excl_scan(v, s_warp, &s_tot);
+        if (i < n) out[i] = carry + (T)ex;
+        carry += (T)s_tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+
+// warp per non-isolated row: column indices of its set bits, ascending
+__global__ void k_offc_fill(const uint32_t *__restrict__ wnbr, int M, int words, const uint8_t *__restrict__ iso,
+                            const int64_t *__restrict__ off, int32_t *__restrict__ col) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M || iso[row]) return;
+    const uint32_t *r = wnbr + (size_t)row * words;
+    int64_t o = off[row];
+    for (int w0 = 0; w0 < words; w0 += 32) {
+        const int w = w0 + lane;
+        uint32_t bits = w < words ? r[w] : 0u;
+        const int c = __popc(bits);
+        int inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        int64_t my = o + inc - c;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            col[my++] = (w << 5) + b;
+        }
+        o += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+// the ordered growth over the non-isolated MCs (PreDeCon.run / _expand, predecon.py:62-120, 242-267)
+__global__ void __launch_bounds__(OFFG_THREADS, 1)
+    k_offc_grow(int M, const int64_t *__restrict__ off, const int32_t *__restrict__ col, const uint8_t *__restrict__ core,
+                const uint8_t *__restrict__ iso, const uint64_t *__restrict__ submask, int cnt_gt1, int64_t pi,
+                uint8_t *cls /*[M] zeroed*/, int32_t *queue /*[2M+2]*/, int32_t *order_s, int32_t *cl_off_s, int32_t *seed_of,
+                int32_t *n_cl_s) {
+    __shared__ int s_warp[32];
+    __shared__ int s_tot[2][2];
+    __shared__ int s_scan[2];
+    const int tid = threadIdx.x;
+    const unsigned lt = (1u << (tid & 31)) - 1u;
+    int ncl = 0, nmem = 0, par = 0;
+    if (tid == 0) cl_off_s[0] = 0;
+    int base = 0;
+    while (base < M) {
+        const int i = base + tid;
+        int c = 1;
+        bool isc = false;
+        if (i < M && !iso[i]) {
+            c = cls[i];
+            isc = core[i] != 0;
+        }
+        const int fc = offc_block_min((c == 0 && isc) ? i : INT_MAX, s_warp);
+        if (c == 0 && !isc && i < fc) cls[i] = 2; // an unclassified non-core MC reached by the seed loop becomes noise
+        __syncthreads();
+        if (fc == INT_MAX) {
+            base += OFFG_THREADS;
+            continue;
+        }
+        // ---- expand(fc): the queue starts as a copy of WN(seed), unfiltered (predecon.py:103)
+        const int64_t o0 = off[fc];
+        const int len0 = (int)(off[fc + 1] - o0);
+        for (int t = tid; t < len0; t += OFFG_THREADS) queue[t] = col[o0 + t];
+        int qt = len0, qh = 0;
+        __syncthreads();
+        while (qh < qt) {
+            const int q = queue[qh++];
+            if (!core[q]) continue; // _find_directly_reachable_points: point_is_core
+            const int64_t o = off[q];
+            const int len = (int)(off[q + 1] - o);
+            for (int c0 = 0; c0 < len; c0 += OFFG_THREADS) {
+                const int t = c0 + tid;
+                int x = -1;
+                bool enq = false, claim = false;
+                if (t < len) {
+                    x = col[o + t];
+                    const int pd = cnt_gt1 ? popc64(submask[x]) : 0;
+                    if ((int64_t)pd <= pi) {
+                        const int cx = cls[x];
+                        enq = cx == 0;
+                        claim = cx == 0 || cx == 2;
+                    }
+                }
+                par ^= 1;
+                if (len - c0 <= 32) { // short list: warp 0 compacts with ballots, in index order
+                    if (tid < 32) {
+                        const unsigned be = __ballot_sync(0xffffffffu, enq), bc = __ballot_sync(0xffffffffu, claim);
+                        if (enq) queue[qt + __popc(be & lt)] = x;
+                        if (claim) {
+                            order_s[nmem + __popc(bc & lt)] = x;
+                            cls[x] = 1;
+                        }
+                        if (tid == 0) {
+                            s_tot[par][0] = __popc(be);
+                            s_tot[par][1] = __popc(bc);
+                        }
+                    }
+                    __syncthreads();
+                } else {
+                    const int qoff = block_excl_scan(enq ? 1 : 0, s_warp, &s_scan[0]);
+                    const int qtot = s_scan[0];
+                    __syncthreads();
+                    const int moff = block_excl_scan(claim ? 1 : 0, s_warp, &s_scan[1]);
+                    const int mtot = s_scan[1];
+                    if (enq) queue[qt + qoff] = x;
+                    if (claim) {
+                        order_s[nmem + moff] = x;
+                        cls[x] = 1;
+                    }
+                    if (tid == 0) {
+                        s_tot[par][0] = qtot;
+                        s_tot[par][1] = mtot;
+                    }
+                    __syncthreads();
+                }
+                qt += s_tot[par][0];
+                nmem += s_tot[par][1];
+            }
+        }
+        if (tid == 0) {
+            seed_of[ncl] = fc;
+            cl_off_s[ncl + 1] = nmem;
+        }
+        ncl += 1; // emitted even if empty; the host drops clusters whose weight is not > 0 (predecon.py:83)
+        base = fc + 1;
+        __syncthreads();
+    }
+    if (tid == 0) *n_cl_s = ncl;
+}
+
+// seeds of both kinds and the size of the cluster each one emits
+__global__ void k_offc_seeds(int M, const uint8_t *__restrict__ iso, const uint8_t *__restrict__ core,
+                             const uint64_t *__restrict__ submask, int cnt_gt1, int64_t pi, const int32_t *__restrict__ seed_of,
+                             const int32_t *__restrict__ cl_off_s, const int32_t *__restrict__ n_cl_s, int32_t *seedflag,
+                             int32_t *size_by_node, int32_t *label) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) {
+        label[i] = -1;
+        const bool sd = iso[i] && core[i];
+        seedflag[i] = sd;
+        const int pd = cnt_gt1 ? popc64(submask[i]) : 0;
+        size_by_node[i] = (sd && (int64_t)pd <= pi) ? 1 : 0;
+    }
+}
+__global__ void k_offc_seeds_serial(const int32_t *__restrict__ seed_of, const int32_t *__restrict__ cl_off_s,
+                                    const int32_t *__restrict__ n_cl_s, int32_t *seedflag, int32_t *size_by_node) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= *n_cl_s) return;
+    const int sd = seed_of[c];
+    seedflag[sd] = 1;
+    size_by_node[sd] = cl_off_s[c + 1] - cl_off_s[c];
+}
+// size of cluster rank[i] for every seed i
+__global__ void k_offc_sizes(int M, const int32_t *__restrict__ seedflag, const int32_t *__restrict__ rank,
+                             const int32_t *__restrict__ size_by_node, int32_t *size_by_cluster, int32_t *n_cl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *n_cl = rank[M];
+    if (i < M && seedflag[i]) size_by_cluster[rank[i]] = size_by_node[i];
+}
+// members of every cluster in claim order, cluster label of every claimed MC
+__global__ void k_offc_scatter_iso(int M, const uint8_t *__restrict__ iso, const int32_t *__restrict__ seedflag,
+                                   const int32_t *__restrict__ rank, const int32_t *__restrict__ size_by_node,
+                                   const int32_t *__restrict__ cl_off, int32_t *order, int32_t *label) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M || !iso[i] || !seedflag[i] || !size_by_node[i]) return;
+    const int r = rank[i];
+    order[cl_off[r]] = i;
+    label[i] = r;
+}
+__global__ void k_offc_scatter_serial(const int32_t *__restrict__ seed_of, const int32_t *__restrict__ cl_off_s,
+                                      const int32_t *__restrict__ n_cl_s, const int32_t *__restrict__ order_s,
+                                      const int32_t *__restrict__ rank, const int32_t *__restrict__ cl_off, int32_t *order,
+                                      int32_t *label) {
+    const int lane = threadIdx.x & 31;
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < *n_cl_s; c += nw) {
+        const int r = rank[seed_of[c]];
+        const int b = cl_off_s[c], n = cl_off_s[c + 1] - b, dst = cl_off[r];
+        for (int t = lane; t < n; t += 32) {
+            const int x = order_s[b + t];
+            order[dst + t] = x;
+            label[x] = r;
+        }
+    }
+}
+
 // ---- 4f: merged cluster statistics: one CTA per cluster, thread per dim, members in claim order ----------
 __global__ void k_off_cluster_cf(const double *cf1, const double *cf2, const double *w, int D, const int32_t *order,
                                  const int32_t *cl_off, double delta2, double *o_cf1, double *o_cf2, double *o_cen,

@@ -118,7 +118,10 @@ int ccb_debug_phase_cycles(ccb_handle *h, int64_t out[8]);
  * CONTESTED cells, storer cycles, storer waiting, producer waiting}.  The first call switches the counters on. */
 int ccb_debug_chain(ccb_handle *h, int64_t *out, int32_t max_keys);
 /* Diagnostics only, results become WRONG: 1 = the storer warps of k_bs_chain_p skip their global stores, 2 = skip the
- * copies altogether (isolates the replay warp's own speed).  0 restores normal operation. */
+ * copies altogether (isolates the replay warp's own speed).  0 restores normal operation.
+ * mode >= 1000 is not a diagnostic: the offline cluster growth uses its CSR formulation (isolated microclusters in
+ * parallel, lists instead of bit rows) for M >= mode - 1000 potential microclusters (default 2048; process-wide).
+ * Both formulations give identical results; the tests run the reference's offline goldens through each. */
 int ccb_debug_set(ccb_handle *h, int32_t mode);
 /* Forgets every microcluster and both id counters (a new run on the same device / stream). */
 int ccb_reset(ccb_handle *h);

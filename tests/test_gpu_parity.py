@@ -87,8 +87,25 @@ def test_points_view_matches_assignment():
     assert seen == X.shape[0]
 
 
-def test_offline_sets_match_predecon():
+@pytest.mark.parametrize("csr_min_m", [2048, 0], ids=["bitrows", "csr"])
+def test_offline_sets_match_predecon(csr_min_m):
+    """24 randomised pcore sets pushed through the reference's PreDeCon.run (predecon.py:49-120): neighbourhoods,
+    subspace vectors, weighted neighbourhoods and the ordered cluster growth -- the latter through both of its
+    device formulations (bit-row scan for small M, isolated-MC pre-pass + CSR lists for large M)."""
+    from chronoclust_b200 import _lib as _l
+
     z = load("offline_sets.npz")
+    try:
+        _run_offline_sets(z, csr_min_m)
+    finally:
+        hh = make({"beta": 0.0, "delta": 0.5, "epsilon": 1.0, "lambda": 0, "k": 4.0, "mu": 0.0, "pi": 0, "omicron": 0.0,
+                   "upsilon": 1.0})
+        hh.dataset_dimensionality = 3
+        hh._ensure_handle(3)
+        _l.check(_l.lib().ccb_debug_set(hh._h, 1000 + 2048), hh._h)
+
+
+def _run_offline_sets(z, csr_min_m):
     for s in range(int(z["nset"])):
         P = f"s{s}_"
         D, M, k, pi, delta, E = z[P + "params"]
@@ -107,6 +124,7 @@ def test_offline_sets_match_predecon():
         h._ensure_handle(D)
         h.pi, h.mu, h.omicron = pi, mu, 0.0
         from chronoclust_b200 import _lib
+        _lib.check(_lib.lib().ccb_debug_set(h._h, 1000 + csr_min_m), h._h)
         _lib.check(_lib.lib().ccb_begin_timepoint(h._h, mu, 0.0, pi, 0, 1.0), h._h)
         h.import_arrays(0, ids, ids, w, cf1, cf2, cen, np.ones((M, D)))
         h.offline_clustering(0)
@@ -391,3 +409,54 @@ def test_offline_borderline_pairs_resolved_by_dnrm2():
     assert h.stats()["borderline_pairs"] >= 2
     assert nbr[0, 1] == 1 and nbr[1, 0] == 1 and nbr[1, 2] == 1  # distance exactly E is a neighbour
     assert nbr[0, 2] == 0 and nbr[0, 3] == 0  # 10 > 5; 5.000000000000003 > 5
+
+
+def test_cluster_growth_formulations_agree():
+    """Kernel 4e has two formulations (bit-row scan; isolated pre-pass + CSR + merge by seed rank).  On a random
+    symmetric weighted-neighbourhood graph with isolated MCs, noise, border MCs shared between clusters and core MCs
+    whose pdim exceeds pi (relay but are never claimed), both must give the same labels, claim order and offsets."""
+    import torch
+    from chronoclust_b200 import _lib
+    from chronoclust_b200.offline_sharded import CudaStages
+
+    rng = np.random.default_rng(11)
+    M, D = 3000, 12
+    words = (M + 31) // 32
+    grp = rng.integers(0, 60, size=M)
+    grp[rng.random(M) < 0.3] = -1  # isolated
+    A = np.zeros((M, M), bool)
+    for g in range(60):
+        idx = np.flatnonzero(grp == g)
+        sub = rng.random((len(idx), len(idx))) < 0.08
+        A[np.ix_(idx, idx)] = sub | sub.T
+    bridges = rng.integers(0, M, size=(40, 2))  # a few edges between groups (border MCs reachable from two clusters)
+    bridges = bridges[(grp[bridges[:, 0]] >= 0) & (grp[bridges[:, 1]] >= 0)]
+    A[bridges[:, 0], bridges[:, 1]] = A[bridges[:, 1], bridges[:, 0]] = True
+    np.fill_diagonal(A, True)
+    bits = np.zeros((M, words * 32), np.uint8)
+    bits[:, :M] = A
+    wn = np.packbits(bits.reshape(M, words, 32), axis=2, bitorder="little").view(np.uint32).reshape(M, words)
+    core = (rng.random(M) < 0.6).astype(np.uint8)
+    pd = rng.integers(0, D + 1, size=M)
+    sub = np.array([sum(1 << int(d) for d in rng.choice(D, size=int(k), replace=False)) for k in pd], np.int64)
+    pi = 8
+    st = CudaStages(0)
+    twn = torch.from_numpy(wn.view(np.int32)).cuda()
+    tcore, tsub = torch.from_numpy(core).cuda(), torch.from_numpy(sub).cuda()
+    h = make({"beta": 0.0, "delta": 0.5, "epsilon": 1.0, "lambda": 0, "k": 4.0, "mu": 0.0, "pi": 0, "omicron": 0.0,
+              "upsilon": 1.0})
+    h.dataset_dimensionality = 3
+    h._ensure_handle(3)
+    res = []
+    try:
+        for min_m in (10 ** 8, 0):
+            _lib.check(_lib.lib().ccb_debug_set(h._h, 1000 + min_m), h._h)
+            lab, order, cl_off, ncl = st.clusters(M, twn, tcore, tsub, 4.0, pi)
+            res.append((lab.copy(), order[:cl_off[-1]].copy(), cl_off.copy(), ncl))
+    finally:
+        _lib.check(_lib.lib().ccb_debug_set(h._h, 1000 + 2048), h._h)
+    (l0, o0, c0, n0), (l1, o1, c1, n1) = res
+    assert n0 == n1 and n0 > 100
+    assert (c0 == c1).all() and (o0 == o1).all() and (l0 == l1).all()
+    sizes = np.diff(c0)
+    assert (sizes > 1).sum() > 20 and (sizes == 0).sum() > 0 and (l0 < 0).sum() > 0  # the fixture exercises every case
