@@ -931,6 +931,19 @@ int launch_off_neighbours(ccb_handle *h, cudaStream_t s, const double *cen, int 
     return CCB_OK;
 }
 
+// The stateless entry points take their scratch from the device's stream-ordered pool; raise its release threshold once
+// so that it keeps what it has instead of handing the memory back to the driver at every synchronisation.
+void tune_pool(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[device] = true;
+}
+
 // kernel 4e: ordered cluster growth.  Small M (the online hot path: tens of pcore MCs): the single-launch bit-row
 // kernel.  Large M (config C4): isolated MCs in parallel, CSR lists for the rest, clusters merged by seed rank
 // (offline.cuh).  Both produce identical label / order / cl_off / n_cl.  cls [M] and queue [2M + 2] are scratch.
@@ -1051,6 +1064,7 @@ int ccb_create(const ccb_params *p, ccb_handle **out) {
         }                                                                                    \
     } while (0)
     CKC(cudaSetDevice(p->device));
+    tune_pool(p->device);
     CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CKC(cudaMalloc(&h->d_ctl, sizeof(Ctl)));
     CKC(cudaMemset(h->d_ctl, 0, sizeof(Ctl)));
@@ -1811,17 +1825,8 @@ int ccb_nearest(int32_t device, void *stream, const double *X, int64_t N, int64_
     double2 *cw = nullptr;
     double *sd = nullptr;
     int32_t *si = nullptr;
-    // scratch: packed rows + per-slab candidates, sized by the split the launch will use; the stream-ordered pool keeps
-    // what it has (release threshold raised once per device) so repeated calls do not go back to the driver
-    static bool pool_tuned[64] = {false};
-    if (device >= 0 && device < 64 && !pool_tuned[device]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        pool_tuned[device] = true;
-    }
+    // scratch: packed rows + per-slab candidates, sized by the split the launch will use
+    tune_pool(device);
     int max_slabs = 1;
     {
         int ok = 0;
@@ -1843,6 +1848,32 @@ int ccb_nearest(int32_t device, void *stream, const double *X, int64_t N, int64_
     cudaFreeAsync(sd, s);
     cudaFreeAsync(si, s);
     return rc;
+}
+
+int ccb_assoc_nearest(int32_t device, void *stream, const double *cur_cen, const uint64_t *cur_prefmask, int64_t Q,
+                      const double *prev_cen, int64_t P, int32_t D, double k, int32_t *best, double *dist) {
+    if (D < 1 || D > CCB_MAX_D || Q < 0 || P < 0 || Q >= ((int64_t)1 << 31) || P >= ((int64_t)1 << 31))
+        return fail(nullptr, CCB_EINVAL, "bad ccb_assoc_nearest arguments");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (Q == 0) return CCB_OK;
+    if (P == 0) {
+        cudaMemsetAsync(best, 0xff, (size_t)Q * 4, s);
+        return CCB_OK;
+    }
+    const int DP = round_dp(D);
+    const bool p2 = is_pow2(k);
+    int ok = 0;
+    CCB_DISPATCH_DP(DP, {
+        const int gx = (int)((Q + ASSOC_THREADS - 1) / ASSOC_THREADS);
+        if (p2) k_assoc<kDP, false><<<gx, ASSOC_THREADS, 0, s>>>(cur_cen, cur_prefmask, (int)Q, prev_cen, (int)P, D, k, 1.0 / k, best, dist);
+        else k_assoc<kDP, true><<<gx, ASSOC_THREADS, 0, s>>>(cur_cen, cur_prefmask, (int)Q, prev_cen, (int)P, D, k, k, best, dist);
+        ok = 1;
+    })
+    if (!ok) return fail(nullptr, CCB_ELIMIT, "unsupported dimensionality %d", D);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "k_assoc launch: %s", cudaGetErrorString(e));
 }
 
 int ccb_off_neighbours(int32_t device, void *stream, const double *cen, int64_t M, int32_t D, int64_t r0, int64_t r1,
@@ -1900,6 +1931,7 @@ int ccb_off_clusters(int32_t device, void *stream, int64_t M, const uint32_t *wn
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     cudaStream_t s = (cudaStream_t)stream;
+    tune_pool(device);
     uint8_t *cls = nullptr;
     int32_t *queue = nullptr;
     if ((e = cudaMallocAsync(&cls, (size_t)std::max<int64_t>(M, 1), s)) != cudaSuccess ||

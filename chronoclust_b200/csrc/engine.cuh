@@ -701,10 +701,11 @@ struct ChainPCfg {
     static constexpr int NH = (LSP + 31) / 32;
     static constexpr int NB = DP <= 16 ? 64 : 32;
     static constexpr int S = DP <= 48 ? 8 : 6;
-    static constexpr size_t SMEM = (size_t)S * NB * (LSP * 8 + 4) + 3 * S * 8 + DP * 8 + 128;
+    static constexpr size_t SMEM = (size_t)S * NB * (LSP * 8 + 4) + 3 * S * 8 + 2 * DP * 8 + 128;
 };
 constexpr int BS_CHAINP_THREADS = 256;
-constexpr int BS_CHAINP_STORERS = 5; // warps 2, 3, 5, 6, 7; warp 4 would share the replay warp's scheduler and exits
+constexpr int BS_CHAINP_STORERS = 4; // warps 2, 3, 6, 7 (schedulers 2 and 3); warps 4 and 5 would share the replay
+                                     // warp's / the producer's scheduler and exit at once
 
 __device__ int g_bs_dbg_mode = 0; // diagnostics only (ccb_debug_set): 1 = storers skip the global stores, 2 = skip the copies
 
@@ -817,13 +818,22 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         }
         return;
     }
-    if (warp == 4) return; // same scheduler as the replay warp: leave its issue slots alone
+    if (warp == 4 || warp == 5) { // same schedulers as the replay warp / the producer: leave their issue slots alone
+        if (warp == 4) { // (the replay warp's scheduler: it is still waiting for its first stage)
+            // ... after one pass through the rare-path code on dummy data: its instruction-cache lines are then on this
+            // SM before the replay warp (which cannot hide a miss) meets its first CONTESTED cell
+            const bool r = bs_radius_test<DP, NH>(1.0, smem_u32(xs) + lane * 8, lane, D, nm.delta2, nm.eps2, nm.div_mode, nm.k,
+                                                  nm.wsel, scr + DP);
+            if (r && D < 0) e.ws.prej[0] = 1; // never taken; keeps the call alive
+        }
+        return;
+    }
     if (warp >= 2) { // ---- storers: ver[cell] <- the version left in the stage
         // the stage is one flat array of cnt * LSP doubles: lane = element, four elements in flight per lane
         // (index and value loads first, then the stores) so that the shared-memory latency is paid once per four.
-        // The copy is instruction-bound (index arithmetic per element), hence five warps on the three other schedulers.
+        // The copy is instruction-bound (index arithmetic per element), hence four warps on the two other schedulers.
         constexpr int U = 4, L2 = LSP / 2, NST = BS_CHAINP_STORERS * 32; // records are L2 double2 wide
-        const int st = (warp < 4 ? warp - 2 : warp - 3) * 32 + lane;
+        const int st = (warp < 4 ? warp - 2 : warp - 4) * 32 + lane;
         long long tw = 0;
         const long long tbeg = clock64();
         for (int b = 0; b < nb; ++b) {

@@ -372,6 +372,110 @@ __global__ void k_topk_merge(const double *__restrict__ in_dist, const int32_t *
     }
 }
 
+// ---- association scan ----------------------------------------------------------------------------------
+// TrackByHistoricalAssociation.track_cluster_history (tracking/cluster_tracker.py:127-144): for every CURRENT pcore MC q
+// the previous-timepoint pcore MC whose centroid p_j minimises q.get_projected_dist_to_point(p_j)
+// (microcluster.py:167-181 -> mc_functions.py:35-43: sum_d ((p_jd - c_qd)^2) / pref_qd, the QUERY's centroid and
+// preference vector), scanning j in list order, first strictly smaller wins.  Same arithmetic as kernel 1 with the roles
+// swapped: here the thread-resident side carries the weights.  One thread owns one query (c_q, w_q in registers), the
+// scanned centroids stream through shared memory in double-buffered tiles (1-D bulk TMA), every lane reads the same
+// coordinates (broadcast LDS), 4 scanned MCs advance together; the fused weight step is guarded exactly like kernel 1's.
+constexpr int ASSOC_THREADS = 128;
+constexpr int ASSOC_JU = 4;
+template <int DP>
+struct AssocCfg {
+    static constexpr int TM = ((2048 / DP) < 32 ? 32 : (2048 / DP)) / ASSOC_JU * ASSOC_JU;
+};
+
+template <int DP, bool DIV>
+__global__ void __launch_bounds__(ASSOC_THREADS)
+    k_assoc(const double *__restrict__ qcen, const uint64_t *__restrict__ qmask, int Q, const double *__restrict__ pcen, int P,
+            int D, double k, double wsel, int32_t *__restrict__ best, double *__restrict__ bdist) {
+    constexpr int TM = AssocCfg<DP>::TM, JU = ASSOC_JU;
+    __shared__ __align__(128) double tile[2][TM * DP];
+    __shared__ __align__(8) uint64_t bar[2];
+    const int q = blockIdx.x * ASSOC_THREADS + threadIdx.x;
+    const bool live = q < Q;
+    double c[DP], w[DP];
+    bool tiny_q = false;
+    {
+        const uint64_t m = live ? qmask[q] : 0ull;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+            c[d] = (live && d < D) ? qcen[(size_t)q * D + d] : 0.0;
+            w[d] = (d < D && ((m >> d) & 1ull)) ? (DIV ? k : wsel) : 1.0;
+            tiny_q |= tiny_nonzero(c[d]) | (!DIV && small_weight(w[d]));
+        }
+    }
+    tiny_q = __any_sync(0xffffffffu, tiny_q);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int ntiles = (P + TM - 1) / TM;
+    auto issue = [&](int t) {
+        const int jt = t * TM;
+        const int n = min(TM, P - jt);
+        uint32_t bytes = (uint32_t)((size_t)n * D * sizeof(double));
+        if (bytes & 15u) { // odd element count: the last double travels by a plain store (ordered by the arrive)
+            bytes -= 8u;
+            tile[t & 1][(size_t)n * D - 1] = pcen[(size_t)jt * D + (size_t)n * D - 1];
+        }
+        mbar_expect_tx(&bar[t & 1], bytes);
+        if (bytes) tma_load_1d(&tile[t & 1][0], pcen + (size_t)jt * D, bytes, &bar[t & 1]);
+    };
+    if (threadIdx.x == 0 && ntiles > 0) issue(0);
+    int bi = -1;
+    double bd = 0.0;
+    for (int t = 0; t < ntiles; ++t) {
+        if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1);
+        mbar_wait(&bar[t & 1], (t >> 1) & 1);
+        const double *tl = tile[t & 1];
+        const int jt = t * TM;
+        const int n = min(TM, P - jt);
+        bool fuse = false;
+        if (!DIV) {
+            bool tiny = tiny_q;
+            if (!tiny) {
+                for (int e = threadIdx.x & 31; e < n * D; e += 32) tiny |= tiny_nonzero(tl[e]);
+                tiny = __any_sync(0xffffffffu, tiny);
+            }
+            fuse = !tiny;
+        }
+        for (int j0 = 0; j0 < n; j0 += JU) {
+            double acc[JU];
+#pragma unroll
+            for (int v = 0; v < JU; ++v) acc[v] = 0.0;
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+                if (d < D) {
+#pragma unroll
+                    for (int v = 0; v < JU; ++v) {
+                        const double pv = tl[(size_t)(j0 + v) * D + d]; // rows past n: stale shared memory, masked below
+                        double tt = dsub(pv, c[d]);
+                        tt = dmul(tt, tt);
+                        if (fuse) acc[v] = __fma_rn(tt, w[d], acc[v]); // exact product (see nearest_item)
+                        else acc[v] = dadd(acc[v], DIV ? ddiv(tt, w[d]) : dmul(tt, w[d]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < JU; ++v)
+                if (j0 + v < n && (bi < 0 || acc[v] < bd)) { // strict <: the first scanned MC keeps a tie
+                    bi = jt + j0 + v;
+                    bd = acc[v];
+                }
+        }
+        __syncthreads();
+    }
+    if (live) {
+        best[q] = bi;
+        bdist[q] = bd;
+    }
+}
+
 // Builds the packed (centroid, weight) rows from separate centroid / preference-mask arrays.
 __global__ void k_pack_cw(const double *__restrict__ cen, const uint64_t *__restrict__ mask, int64_t M, int D, int DP,
                           double wsel, double2 *__restrict__ cw) {

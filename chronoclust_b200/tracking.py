@@ -2,7 +2,8 @@
 
 Behavioural restatement of tracking/cluster_tracker.py:7-148 of the reference: lineage labels (A, B, A|1,
 (A,B), ...) from shared pcore ids, and historical association by nearest previous pcore MC.  The inner
-distance scan of the historical tracker is SURVEY 8f-1 ("next" row): here it is still the host loop.
+distance scan of the historical tracker is SURVEY 8f-1 ("next" row): from 65 536 (current, previous) pcore pairs on
+it runs on the device (ccb_assoc_nearest), below that it is the host loop; both give the same associations.
 """
 import string
 from collections import defaultdict, deque
@@ -78,6 +79,10 @@ class TrackByLineage(object):
 
 
 class TrackByHistoricalAssociation(object):
+    # the association scan moves to the device (ccb_assoc_nearest) from this many (current, previous) pcore pairs
+    # on; None keeps the host loop.  Below it the two host <-> device copies cost more than the loop.
+    device_scan_min_pairs = 1 << 16
+
     def __init__(self):
         self.current_clusters = []
         self.previous_timepoint_clusters = []
@@ -90,16 +95,50 @@ class TrackByHistoricalAssociation(object):
             for cluster in self.current_clusters:
                 cluster.add_historical_associate(None)
             return
-        for cluster in self.current_clusters:
-            for pcore in cluster.pcore_objects:
-                best_d, best_cluster, best_pcore = None, None, None
-                for prev in self.previous_timepoint_clusters:
-                    for prev_pcore in prev.pcore_objects:
-                        d = pcore.get_projected_dist_to_point(prev_pcore.cluster_centroids)
-                        if best_d is None or d < best_d:  # strict <: first wins
-                            best_d, best_cluster, best_pcore = d, prev.id, prev_pcore.id
-                cluster.add_historical_associate(best_cluster)
-                cluster.add_historical_associate_pcore(best_pcore)
+        cur = [(cluster, pcore) for cluster in self.current_clusters for pcore in cluster.pcore_objects]
+        prev = [(c.id, p) for c in self.previous_timepoint_clusters for p in c.pcore_objects]
+        if self.device_scan_min_pairs is not None and prev and len(cur) * len(prev) >= self.device_scan_min_pairs:
+            best = self._device_scan([p for _, p in cur], [p for _, p in prev])
+            for (cluster, _), j in zip(cur, best):
+                cluster.add_historical_associate(prev[j][0])
+                cluster.add_historical_associate_pcore(prev[j][1].id)
+            return
+        for cluster, pcore in cur:
+            best_d, best_cluster, best_pcore = None, None, None
+            for prev_id, prev_pcore in prev:
+                d = pcore.get_projected_dist_to_point(prev_pcore.cluster_centroids)
+                if best_d is None or d < best_d:  # strict <: first wins
+                    best_d, best_cluster, best_pcore = d, prev_id, prev_pcore.id
+            cluster.add_historical_associate(best_cluster)
+            cluster.add_historical_associate_pcore(best_pcore)
+
+    @staticmethod
+    def _device_scan(cur_pcores, prev_pcores, device=0):
+        """the O(P_cur * P_prev * D) scan on the device (ccb_assoc_nearest, kernel k_assoc) -- the same
+        argmin, bit for bit (sequential sum over d, the query's stored centroid / preference vector, first wins)."""
+        import numpy as np
+        import torch
+
+        from . import _lib
+
+        D = len(cur_pcores[0].cluster_centroids)
+        ccen = np.ascontiguousarray([p.cluster_centroids for p in cur_pcores], np.float64).reshape(len(cur_pcores), D)
+        pref = np.ascontiguousarray([p.preferred_dimension_vector for p in cur_pcores], np.float64).reshape(len(cur_pcores), D)
+        pcen = np.ascontiguousarray([p.cluster_centroids for p in prev_pcores], np.float64).reshape(len(prev_pcores), D)
+        ks = np.unique(pref[pref != 1.0])
+        if len(ks) > 1:
+            raise ValueError("preference vectors with more than one weight value")
+        k = float(ks[0]) if len(ks) else 1.0
+        mask = ((pref != 1.0) * (np.uint64(1) << np.arange(D, dtype=np.uint64))).sum(axis=1).astype(np.uint64)
+        dev = torch.device("cuda", device)
+        tc, tp = torch.from_numpy(ccen).to(dev), torch.from_numpy(pcen).to(dev)
+        tm = torch.from_numpy(mask.view(np.int64)).to(dev)
+        best = torch.empty(len(cur_pcores), dtype=torch.int32, device=dev)
+        dist = torch.empty(len(cur_pcores), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().ccb_assoc_nearest(device, None, tc.data_ptr(), tm.data_ptr(), len(cur_pcores), tp.data_ptr(),
+                                                len(prev_pcores), D, k, best.data_ptr(), dist.data_ptr()))
+        torch.cuda.synchronize(dev)
+        return best.cpu().numpy().tolist()
 
     def transfer_current_to_previous(self):
         self.previous_timepoint_clusters = self.current_clusters

@@ -199,6 +199,14 @@ int ccb_export_offline(ccb_handle *h, uint8_t *core, uint8_t *nbr, uint8_t *wnbr
 int ccb_nearest(int32_t device, void *stream, const double *X, int64_t N, int64_t ld, int32_t D, const double *cen,
                 const uint64_t *prefmask, int64_t M, double k, int32_t *slot, double *dist);
 
+/* Association scan (replaces the inner loops of TrackByHistoricalAssociation.track_cluster_history,
+ * tracking/cluster_tracker.py:127-144): for every CURRENT pcore microcluster q the index of the previous-timepoint
+ * pcore microcluster j, in scan order, that minimises q.get_projected_dist_to_point(prev_cen[j]) =
+ * sum_d ((prev_cen[j][d] - cur_cen[q][d])^2) / pref_q[d] (microcluster.py:167-181), first strictly smaller wins.
+ * cur_cen [Q][D], cur_prefmask [Q] (bit d set <=> pref_q[d] == k), prev_cen [P][D]; best [Q] (-1 if P == 0), dist [Q]. */
+int ccb_assoc_nearest(int32_t device, void *stream, const double *cur_cen, const uint64_t *cur_prefmask, int64_t Q,
+                      const double *prev_cen, int64_t P, int32_t D, double k, int32_t *best, double *dist);
+
 /* FP64 pipe microbenchmark for the roofline denominators: mode 0 = DFMA stream (2 flop/instr), mode 1 =
  * separate DMUL + DADD (1 flop/instr, the only form the parity contract allows).  Launches `blocks` CTAs of
  * 256 threads x 8 independent chains x iters; *flops_out = flops executed.  Time it with CUDA events. */

@@ -460,3 +460,111 @@ def test_cluster_growth_formulations_agree():
     assert (c0 == c1).all() and (o0 == o1).all() and (l0 == l1).all()
     sizes = np.diff(c0)
     assert (sizes > 1).sum() > 20 and (sizes == 0).sum() > 0 and (l0 < 0).sum() > 0  # the fixture exercises every case
+
+
+@pytest.mark.parametrize("D,Q,P,k", [(3, 7, 5, 4.0), (12, 300, 257, 4.0), (40, 130, 999, 16.0), (12, 64, 100, 3.0),
+                                     (5, 33, 1, 1.0)])
+def test_assoc_scan_bit_exact(D, Q, P, k):
+    """ccb_assoc_nearest against numpy's elementwise IEEE arithmetic (microcluster.py:167-181 ->
+    mc_functions.py:35-43 with the QUERY's centroid / preference vector), summed over d in index order, first wins."""
+    import torch
+    from chronoclust_b200 import _lib
+
+    rng = np.random.default_rng(D * 31 + Q + P)
+    cur, prev = rng.random((Q, D)), rng.random((P, D))
+    if P > 3:
+        prev[P // 2] = prev[1]  # exact tie: the earlier previous MC must win
+    prefbits = rng.random((Q, D)) < 0.5
+    pref = np.where(prefbits, k, 1.0)
+    masks = np.array([sum(1 << d for d in range(D) if prefbits[q, d] and k != 1.0) for q in range(Q)], np.uint64).view(np.int64)
+    tc, tp, tm = torch.from_numpy(cur).cuda(), torch.from_numpy(prev).cuda(), torch.from_numpy(masks).cuda()
+    best = torch.empty(Q, dtype=torch.int32, device="cuda")
+    dist = torch.empty(Q, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().ccb_assoc_nearest(0, None, tc.data_ptr(), tm.data_ptr(), Q, tp.data_ptr(), P, D, k,
+                                            best.data_ptr(), dist.data_ptr()))
+    torch.cuda.synchronize()
+    acc = np.zeros((Q, P))
+    for d in range(D):
+        t = prev[None, :, d] - cur[:, d, None]
+        acc = acc + (t * t) / pref[:, d, None]
+    exp = acc.argmin(axis=1)
+    assert (best.cpu().numpy() == exp).all()
+    assert bits_equal(dist.cpu().numpy(), acc[np.arange(Q), exp])
+
+
+def test_historical_association_device_scan_matches_host_loop():
+    """The tracker (tracking/cluster_tracker.py:127-144) with the scan on the device gives the associations of the
+    host loop, on clusters built from the C1 golden microclusters of two consecutive timepoints."""
+    from chronoclust_b200.objects import Cluster, Microcluster
+    from chronoclust_b200.tracking import TrackByHistoricalAssociation
+
+    z = load("c1.npz")
+
+    def clusters_at(t):
+        P = f"t{t}_p_"
+        mcs = {int(i): Microcluster(z[P + "cf1"][j], z[P + "cf2"][j], id=[int(i)], cumulative_weight=float(z[P + "w"][j]),
+                                    preferred_dimension_vector=z[P + "pref"][j], cluster_centroids=z[P + "cen"][j])
+               for j, i in enumerate(z[P + "ids"].tolist())}
+        off, idl = z[f"t{t}_cl_off"], z[f"t{t}_cl_idlist"]
+        out = []
+        for c in range(len(off) - 1):
+            cl = Cluster([int(i) for i in idl[off[c]:off[c + 1]]])
+            cl.id = f"K{t}_{c}"
+            cl.add_pcore_objects(mcs)
+            out.append(cl)
+        return out
+
+    res = []
+    for min_pairs in (None, 0):
+        tr = TrackByHistoricalAssociation()
+        tr.device_scan_min_pairs = min_pairs
+        tr.previous_timepoint_clusters = clusters_at(1)
+        cur = clusters_at(2)
+        tr.set_current_clusters(cur)
+        tr.track_cluster_history()
+        res.append([(sorted(c.historical_associates), sorted(c.historical_associates_pcores)) for c in cur])
+    assert res[0] == res[1] and any(a for a, _ in res[0])
+
+
+def test_full_size_c2_invariants():
+    """BASELINE config C2 at FULL size (1e6 cells x 12 markers, 2 timepoints) -- too big for the oracle in test time, so
+    the check is through properties that do not depend on the size:
+      * the engine's knobs never change results: the default run (32 768-cell blocks, CUDA graph) and a run with 6 000-cell
+        blocks on plain stream launches give bit-identical assignments, lists, statistics and clusters;
+      * conservation at t0 (nothing decays yet): every cell is absorbed exactly once, so the weights are integers that
+        sum to N, each MC's weight is the number of cells assigned to it, and sum(CF1) over all MCs equals the column
+        sums of X to 1e-9 relative (the summation ORDER differs, the set of addends does not);
+      * every per-cell uid names a live microcluster; created + upgraded counters agree with the list lengths."""
+    from chronoclust_b200.synth import CONFIGS, config_params, gen
+
+    N, D, _, Cn, seed, _, _ = CONFIGS["C2"]
+    cfg = config_params("C2")
+    Xs = gen(N, D, 2, Cn, seed)
+    a, b = make(cfg), make(cfg, chunk=6000, bsv_bmin=256, bsv_stream=1)
+    for t, X in enumerate(Xs):
+        a.online_microcluster_maintenance(X, t)
+        b.online_microcluster_maintenance(X, t)
+        assert (a.last_assignment == b.last_assignment).all() and (a.last_stage == b.last_stage).all()
+        for which in (0, 1):
+            ga, gb = a.export_arrays(which), b.export_arrays(which)
+            assert (ga[0] == gb[0]).all() and (ga[1] == gb[1]).all()
+            for x, y in zip(ga[2:], gb[2:]):
+                assert bits_equal(x, y)
+        ca, cb = clusters_of(a), clusters_of(b)
+        assert len(ca) == len(cb)
+        for (m1, w1, *r1), (m2, w2, *r2) in zip(ca, cb):
+            assert list(m1) == list(m2) and w1 == w2 and all(bits_equal(p, q) for p, q in zip(r1, r2))
+        if t == 0:
+            ids_p, uid_p, w_p, cf1_p = a.export_arrays(0)[:4]
+            ids_o, uid_o, w_o, cf1_o = a.export_arrays(1)[:4]
+            w, uid = np.concatenate([w_p, w_o]), np.concatenate([uid_p, uid_o])
+            assert (w == np.round(w)).all() and w.sum() == N
+            counts = np.bincount(a.last_assignment, minlength=int(uid.max()) + 1)
+            assert (counts[uid] == w).all() and counts.sum() == N
+            col = np.concatenate([cf1_p, cf1_o]).sum(axis=0)
+            assert np.allclose(col, X.sum(axis=0), rtol=1e-9, atol=0.0)
+        live = np.zeros(int(max(a.last_assignment.max(), 0)) + 2, bool)
+        live[np.concatenate([a.export_arrays(0)[1], a.export_arrays(1)[1]])] = True
+        assert live[a.last_assignment].all()
+    st = a.stats()
+    assert st["points"] == 2 * N and st["bsv_blocks"] > 0
