@@ -633,7 +633,7 @@ int launch_prologue(ccb_handle *h, const Eng &e, cudaStream_t s) {
     const int g_cells = (h->bs_bmax + BS_THREADS - 1) / BS_THREADS;
     Timed tm(h, CCB_CAT_SPEC);
     k_bs_begin<<<1, 1, 0, s>>>(e);
-    CCB_DISPATCH_DP(h->DP, { k_bs_spec<kDP><<<g_cells, BS_THREADS, 0, s>>>(e); })
+    CCB_DISPATCH_DP(h->DP, { k_bs_spec<kDP><<<g_cells * BS_SPLIT, BS_THREADS, 0, s>>>(e); })
     k_bs_need<<<1, BS_CTA1, 0, s>>>(e);
     CKL(h);
     return CCB_OK;
@@ -684,7 +684,7 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     }
     {
         Timed tm(h, CCB_CAT_CHAIN_O);
-        CCB_DISPATCH_DP(h->DP, { k_bs_chain_o<kDP><<<BS_RMAX, BS_THREADS, 0, s>>>(e); })
+        CCB_DISPATCH_DP(h->DP, { k_bs_chain_o<kDP><<<148 * 4, BS_THREADS, 0, s>>>(e); }) // CTAs loop over the keys
     }
     {
         Timed tm(h, CCB_CAT_DERIVE);
@@ -693,7 +693,7 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     {
         Timed tm(h, CCB_CAT_RESOLVE);
         CCB_DISPATCH_DP(h->DP, {
-            k_bs_verify_p<kDP><<<g_tiles, BS_THREADS, 0, s>>>(e);
+            k_bs_verify_p<kDP><<<B / 32 + 1, BS_THREADS, 0, s>>>(e);
             k_bs_verify_o<kDP><<<148 * 2, BS_THREADS, 0, s>>>(e);
         })
     }
@@ -919,7 +919,20 @@ int launch_off_neighbours(ccb_handle *h, cudaStream_t s, const double *cen, int 
         // rows x column slabs: at least ~4 waves of CTAs on 148 SMs so that the tail does not dominate
         const int gx = (r1 - r0 + OffCfg<kDP>::ROWS - 1) / OffCfg<kDP>::ROWS;
         const int ntiles = (M + OffCfg<kDP>::TM - 1) / OffCfg<kDP>::TM;
-        const int gy = gx > 0 ? std::max(1, std::min(ntiles, (148 * 2 * 4 + gx - 1) / gx)) : 1;
+        int gy = gx > 0 ? std::max(1, std::min(ntiles, (148 * 2 * 4 + gx - 1) / gx)) : 1;
+        if (gx > 0) { // ... and a slab count whose last wave is full (391 x 4 CTAs on 296 slots were 5.28 waves)
+            int occ = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_off_neighbours<kDP>, OFFN_THREADS, 0);
+            const double resident = 148.0 * std::max(occ, 1);
+            auto loss = [&](int sl) {
+                const double w = (double)gx * sl / resident;
+                return w <= 1.0 ? 0.0 : std::ceil(w) / w - 1.0;
+            };
+            int best = gy;
+            for (int sl = gy + 1; sl <= std::min(ntiles, gy + 7) && loss(best) > 0.03; ++sl)
+                if (loss(sl) < loss(best)) best = sl;
+            gy = best;
+        }
         if (gx > 0)
             k_off_neighbours<kDP><<<dim3(gx, gy), OFFN_THREADS, 0, s>>>(cen, M, D, r0, r1, E2, nbr, cnt, border, border_cap,
                                                                           n_border);
@@ -1607,8 +1620,7 @@ int ccb_offline(ccb_handle *h, int64_t *n_clusters) {
         const int64_t t = (int64_t)M * D;
         k_off_subspace<<<(unsigned)((t + 127) / 128), 128, 0, s>>>(P.cen, M, D, 0, M, nbr.p, cnt.p, h->prm.delta, submask.p);
         CKL(h);
-        const int64_t t2 = (int64_t)M * words;
-        k_off_weighted<<<(unsigned)((t2 + 127) / 128), 128, 0, s>>>(P.cen, M, D, 0, M, nbr.p, submask.p, h->prm.k, E2, wnbr.p);
+        k_off_weighted<<<(unsigned)((M + 3) / 4), OFFW_THREADS, 0, s>>>(P.cen, M, D, 0, M, nbr.p, submask.p, h->prm.k, E2, wnbr.p);
         CKL(h);
         int nl = 0, rc2;
         if ((rc2 = launch_off_clusters(h, s, M, wnbr.p, core.p, submask.p, h->cnt_gt1, h->pi, cls.p, queue.p, label.p, order.p,
@@ -1917,9 +1929,8 @@ int ccb_off_weighted(int32_t device, void *stream, const double *cen, int64_t M,
     if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     if (r1 == r0) return CCB_OK;
     const int words = (int)((M + 31) / 32);
-    const int64_t t = (r1 - r0) * words;
-    k_off_weighted<<<(unsigned)((t + 127) / 128), 128, 0, (cudaStream_t)stream>>>(cen, (int)M, D, (int)r0, (int)r1, nbr,
-                                                                                  submask_all, k, E2, wnbr);
+    k_off_weighted<<<(unsigned)((r1 - r0 + 3) / 4), OFFW_THREADS, 0, (cudaStream_t)stream>>>(cen, (int)M, D, (int)r0, (int)r1, nbr,
+                                                                                             submask_all, k, E2, wnbr);
     e = cudaGetLastError();
     return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "k_off_weighted: %s", cudaGetErrorString(e));
 }

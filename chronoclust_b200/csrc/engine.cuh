@@ -259,20 +259,39 @@ __global__ void k_bs_begin(Eng e) {
 // ---- S ----------------------------------------------------------------------------------------------
 constexpr int BS_THREADS = 128;
 
+// BS_SPLIT lanes share one cell: lane p of the group scans pcore MCs p, p + BS_SPLIT, ... and the group reduces
+// (distance, list position) lexicographically -- the first strictly smaller MC of the sequential scan.  The grid of
+// one block is small (32 768 cells); splitting the MC axis quadruples the warps that hide the dependent-add latency.
+constexpr int BS_SPLIT = 4;
+
+__device__ __forceinline__ void group_argmin(double &d, int &j) { // over BS_SPLIT adjacent lanes; j < 0: no candidate
+#pragma unroll
+    for (int o = 1; o < BS_SPLIT; o <<= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, d, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, j, o);
+        if (oj >= 0 && (j < 0 || od < d || (od == d && oj < j))) {
+            d = od;
+            j = oj;
+        }
+    }
+}
+
 template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_spec(Eng e) {
     e.fetch();
     const BsCtl *bc = e.bc;
     if (!bc->active) return;
-    const int i = blockIdx.x * BS_THREADS + threadIdx.x;
-    if (i >= bc->Bcur) return;
+    const int gt = blockIdx.x * BS_THREADS + threadIdx.x;
+    const int i = gt / BS_SPLIT, part = gt % BS_SPLIT;
+    if ((blockIdx.x * BS_THREADS + (threadIdx.x & ~31)) / BS_SPLIT >= bc->Bcur) return; // whole warps only (shuffles below)
+    const bool live = i < bc->Bcur;
     const Num nm = e.nm;
-    const int D = nm.D, Mp = bc->Mp;
+    const int D = nm.D, Mp = live ? bc->Mp : 0;
     double x[DP];
-    load_row<DP>(e.X + (bc->pos + i) * e.ld, D, x);
+    load_row<DP>(e.X + (bc->pos + (live ? i : 0)) * e.ld, D, x);
     int best = -1;
     double bd = 0.0;
-    for (int j = 0; j < Mp; ++j) {
+    for (int j = part; j < Mp; j += BS_SPLIT) {
         if (nm.pi_active && !feasible_regs<DP>(e.P.cf1 + (size_t)j * D, e.P.cf2 + (size_t)j * D, e.P.w[j], x, nm)) continue;
         const double dv = dist_regs<DP>(x, e.P.cen + (size_t)j * D, e.P.mask[j], nm);
         if (!(dv != dv) && (best < 0 || dv < bd)) {
@@ -280,6 +299,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_spec(Eng e) {
             bd = dv;
         }
     }
+    group_argmin(bd, best);
+    if (part != 0 || !live) return;
     int flag = 1;
     if (best >= 0) {
         double wn;
@@ -338,12 +359,39 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
     const int lo = min(B, tid * per), hi = min(B, lo + per);
     if (tid == 0) s_cut = B;
     int cnt = 0;
-    for (int i = lo; i < hi; ++i) cnt += e.ws.pflag[i];
+    // up to 32 cells per thread (blocks of <= 32 768 cells): their flags become one register mask, fetched with
+    // 16-byte loads; the slots are then handed out by walking the set bits
+    const bool small = per <= 32;
+    uint32_t fmask = 0u;
+    if (small) {
+        int i = lo;
+        if ((lo & 15) == 0)
+            for (; i + 16 <= hi; i += 16) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(e.ws.pflag + i);
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if ((w4[k4] >> (8 * b)) & 0xffu) fmask |= 1u << (i - lo + 4 * k4 + b);
+            }
+        for (; i < hi; ++i)
+            if (e.ws.pflag[i]) fmask |= 1u << (i - lo);
+        cnt = __popc(fmask);
+    } else {
+        for (int i = lo; i < hi; ++i) cnt += e.ws.pflag[i];
+    }
     int total;
     int base = block_exclusive_scan_1024(cnt, s_warp, total);
     const int32_t row0 = (int32_t)bc->pos;
     for (int i = lo; i < hi; ++i) {
-        if (!e.ws.pflag[i]) continue;
+        if (small) { // jump to the next flagged cell
+            if (!fmask) break;
+            i = lo + __ffs(fmask) - 1;
+            fmask &= fmask - 1;
+        } else if (!e.ws.pflag[i]) {
+            continue;
+        }
         if (base < BS_RMAX) {
             e.ws.tkpos[i] = base;
             e.ws.nrows[base] = row0 + i;
@@ -483,22 +531,34 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
         pos = e.ws.poff[c] + e.ws.tilecnt[(size_t)t * e.ws.mp_stride + c] + rank;
         e.ws.plist[pos] = i | (e.ws.pflag[i] ? (int)0x80000000 : 0);
     }
-    // the warp writes the 32 records together, lane = element of the record (coalesced rows)
+    // the warp writes the 32 records together, lane = element of the record (coalesced rows); four records are in
+    // flight at a time so that the row loads overlap instead of paying one global-memory latency per record
     const int D = e.nm.D, dp = e.ws.dp, lsp = e.ws.lsp;
     const double *Xt = e.X + (bc->pos + (int64_t)t * 32) * e.ld;
-    for (int q = 0; q < 32; ++q) {
-        const int pq = __shfl_sync(0xffffffffu, pos, q);
-        if (pq < 0) continue;
-        const double *src = Xt + (int64_t)q * e.ld;
-        double *dst = e.ws.xg + (size_t)pq * lsp;
-        for (int el = lane; el < lsp; el += 32) {
-            double v = 0.0;
-            if (el < D) v = src[el];
-            else if (el >= dp && el < dp + D) {
-                const double x = src[el - dp];
-                v = dmul(x, x);
-            } else if (el == 2 * dp) v = 1.0;
-            dst[el] = v;
+    constexpr int QU = 4;
+    for (int q0 = 0; q0 < 32; q0 += QU) {
+        int pq[QU];
+#pragma unroll
+        for (int u = 0; u < QU; ++u) pq[u] = __shfl_sync(0xffffffffu, pos, q0 + u);
+        for (int el0 = 0; el0 < lsp; el0 += 32) {
+            const int el = el0 + lane;
+            double v[QU];
+#pragma unroll
+            for (int u = 0; u < QU; ++u) {
+                v[u] = 0.0;
+                if (pq[u] >= 0 && el < lsp) {
+                    const double *src = Xt + (int64_t)(q0 + u) * e.ld;
+                    if (el < D) v[u] = src[el];
+                    else if (el >= dp && el < dp + D) v[u] = src[el - dp];
+                    else if (el == 2 * dp) v[u] = 1.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < QU; ++u)
+                if (pq[u] >= 0 && el < lsp) {
+                    const double x = v[u];
+                    e.ws.xg[(size_t)pq[u] * lsp + el] = (el >= dp && el < dp + D) ? dmul(x, x) : x;
+                }
         }
     }
 }
@@ -518,26 +578,21 @@ struct ChainCfg {
 };
 constexpr int BS_CHAIN_PRODUCERS = BS_THREADS - 32;
 
+// one key; every thread of the CTA passes the same 1 + (batches) barriers, so the caller may loop over keys
 template <int DP>
-__global__ void __launch_bounds__(BS_THREADS) k_bs_chain_o(Eng e) {
-    e.fetch();
+__device__ __forceinline__ void bs_chain_o_key(const Eng &e, const BsCtl *bc, int key_idx,
+                                               double (&xs)[2][ChainCfg<DP>::NB][DP], int (&mi)[2][ChainCfg<DP>::NB]) {
     constexpr int NB = ChainCfg<DP>::NB;
     constexpr int GS = 8;
     constexpr int NH = DP > 32 ? 2 : 1;
-    __shared__ __align__(16) double xs[2][NB][DP];
-    __shared__ int mi[2][NB];
-    const BsCtl *bc = e.bc;
-    if (!bc->active || bc->phase != 0) return;
     const Num nm = e.nm;
     const int D = nm.D;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Mp = bc->Mp, KNEW = bc->Mp + bc->Mo0;
-    const int key_idx = blockIdx.x;
     const int32_t *mem;
     int n;
     const double *s1 = nullptr, *s2 = nullptr;
     double w = 0.0;
-    if (key_idx >= bc->nh) return;
     mem = e.ws.omem + e.ws.hoff[key_idx];
     n = e.ws.hoff[key_idx + 1] - e.ws.hoff[key_idx];
     {
@@ -658,6 +713,17 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_chain_o(Eng e) {
         }
         __syncthreads();
     }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(BS_THREADS) k_bs_chain_o(Eng e) {
+    e.fetch();
+    __shared__ __align__(16) double xs[2][ChainCfg<DP>::NB][DP];
+    __shared__ int mi[2][ChainCfg<DP>::NB];
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const int nh = bc->nh;
+    for (int key_idx = blockIdx.x; key_idx < nh; key_idx += gridDim.x) bs_chain_o_key<DP>(e, bc, key_idx, xs, mi);
 }
 
 // k_bs_chain_p: PCORE keys (CONTESTED members take the exact radius test in place).  The candidates of a key lie
@@ -1147,15 +1213,20 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive(Eng e) {
 }
 
 // ---- V ----------------------------------------------------------------------------------------------
-// pcore stage, one warp per tile of 32 cells: for every pcore MC the version it had just before each cell =
-// the latest accepted member of its chain inside the tile (ballot) or before the tile (tbase).
+// pcore stage, one CTA per tile of 32 cells (lane = cell): for every pcore MC the version it had just before each cell =
+// the latest accepted member of its chain inside the tile (ballot) or before the tile (tbase).  The CTA's four warps
+// take the pcore MCs j = w, w + 4, ... and warp 0 reduces (distance, list position) lexicographically = the first
+// strictly smaller MC of the sequential scan; four times the warps to hide the dependent loads and adds.
 template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
     e.fetch();
+    constexpr int NW = BS_THREADS / 32;
+    __shared__ double s_bd[NW][32];
+    __shared__ int s_best[NW][32], s_prev[NW][32];
     BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return; // light round: eff / dec / pend of the pcore side stand
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int t = blockIdx.x;
     const int Beff = bc->Beff;
     if (t * 32 >= Beff) return;
     const Num nm = e.nm;
@@ -1168,12 +1239,12 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
     const bool myrej = live ? (e.ws.prej[i] != 0) : true;
     const int acc_key = (myc >= 0 && !myrej) ? myc : -1;
     const int eff = !live ? BS_KEY_NONE : (myrej ? e.ws.ospec[i] : myc);
-    if (live) e.ws.eff[i] = eff;
+    if (live && part == 0) e.ws.eff[i] = eff;
     int best = -1, bprev = -1;
     double bd = 0.0;
     const unsigned lt = lanemask_lt();
     const int32_t *tb = e.ws.tbase + (size_t)t * e.ws.mp_stride;
-    for (int j = 0; j < Mp; ++j) {
+    for (int j = part; j < Mp; j += NW) {
         const unsigned lower = __ballot_sync(0xffffffffu, acc_key == j) & lt;
         const int prev = lower ? (t * 32 + 31 - __clz(lower)) : tb[j];
         const double *cen = prev >= 0 ? e.ws.vcen + (size_t)prev * D : e.P.cen + (size_t)j * D;
@@ -1192,7 +1263,21 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
             bprev = prev;
         }
     }
-    if (!live) return;
+    s_bd[part][lane] = bd;
+    s_best[part][lane] = best;
+    s_prev[part][lane] = bprev;
+    __syncthreads();
+    if (part != 0 || !live) return;
+#pragma unroll
+    for (int p = 1; p < NW; ++p) {
+        const int ob = s_best[p][lane];
+        const double od = s_bd[p][lane];
+        if (ob >= 0 && (best < 0 || od < bd || (od == bd && ob < best))) {
+            best = ob;
+            bd = od;
+            bprev = s_prev[p][lane];
+        }
+    }
     bool acc = false;
     if (best >= 0) {
         if (eff == best) {
@@ -1358,19 +1443,35 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
     const int tid = threadIdx.x;
     const int Beff = bc->Beff, Mp = bc->Mp, KNEW = bc->Mp + bc->Mo0;
     // first cell whose exact decision differs from the speculation (threads stride the cells: coalesced)
+    // (the scans below fetch eight strides per step: a lone CTA pays the full memory latency for every dependent step,
+    // so the loads of one step must be independent of its comparisons)
+    constexpr int SU = 8;
     int m0 = Beff;
-    for (int i = tid; i < Beff; i += BS_CTA1)
-        if (e.ws.dec[i] != e.ws.eff[i]) {
-            m0 = i;
-            break;
+    for (int i0 = tid; i0 < Beff && m0 == Beff; i0 += BS_CTA1 * SU) {
+        int dv[SU], ev[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int i = i0 + u * BS_CTA1;
+            dv[u] = i < Beff ? e.ws.dec[i] : 0;
+            ev[u] = i < Beff ? e.ws.eff[i] : 0;
         }
+#pragma unroll
+        for (int u = SU - 1; u >= 0; --u)
+            if (dv[u] != ev[u]) m0 = i0 + u * BS_CTA1; // ends on the smallest u
+    }
     m0 = block_min_1024(m0, s_warp);
     int up = INT_MAX;
-    for (int i = tid; i < m0; i += BS_CTA1)
-        if (e.ws.upf[i]) {
-            up = i;
-            break;
+    for (int i0 = tid; i0 < m0 && up == INT_MAX; i0 += BS_CTA1 * SU) {
+        uint8_t uv[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int i = i0 + u * BS_CTA1;
+            uv[u] = i < m0 ? e.ws.upf[i] : 0;
         }
+#pragma unroll
+        for (int u = SU - 1; u >= 0; --u)
+            if (uv[u]) up = i0 + u * BS_CTA1;
+    }
     up = block_min_1024(up, s_warp);
     if (tid == 0) {
         int act = 0; // 0 refine, 1 commit
@@ -1410,57 +1511,48 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
     }
     // ---- refinement: the recomputed decisions of [m0, Beff) become the next speculation
     int cut = Beff;
-    for (int i = m0 + tid; i < Beff; i += BS_CTA1)
-        if (e.ws.dec[i] == BS_KEY_UNKNOWN) {
-            cut = i;
-            break;
+    for (int i0 = m0 + tid; i0 < Beff && cut == Beff; i0 += BS_CTA1 * SU) {
+        int dv[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int i = i0 + u * BS_CTA1;
+            dv[u] = i < Beff ? e.ws.dec[i] : 0;
         }
+#pragma unroll
+        for (int u = SU - 1; u >= 0; --u)
+            if (dv[u] == BS_KEY_UNKNOWN) cut = i0 + u * BS_CTA1;
+    }
     cut = block_min_1024(cut, s_warp);
-    // One ordered pass over [m0, cut), 1024 cells at a time.  Cells that need a (new) top-K slot get one in cell
-    // order: cells that reach the outlier stage without a list, and SAFE cells whose nearest pcore MC changed
-    // (they become CONTESTED, which needs a fallback outlier decision should the chain reject them).  The block
-    // is truncated at the first cell that finds the list full (cells behind it may already have been rewritten;
-    // they are outside the block from now on and every block starts from a fresh speculation).
-    const int nneed_old = bc->nneed;
-    const int32_t row0 = (int32_t)bc->pos;
-    int base = nneed_old;
     // A refinement that only moves cells between OUTLIER-SIDE keys leaves the pcore side of the next round exactly
     // as it is now (same candidates, flags, accepts, hence the same pcore versions, eff / dec of the accepted cells
     // and the same list of pcore-rejected cells): that round re-runs the outlier side only (bc->pclean).
-    int dirty = 0;
-    for (int c0 = m0; c0 < cut; c0 += BS_CTA1) {
-        const int i = c0 + tid;
-        int dc = 0, ef = 0;
-        bool diff = false, want = false;
-        if (i < cut) {
-            dc = e.ws.dec[i];
-            ef = e.ws.eff[i];
-            diff = dc != ef;
-            want = diff && (dc == BS_KEY_NEED || (dc >= 0 && dc < Mp && e.ws.pcand[i] != dc && !e.ws.pflag[i]));
+    //
+    // Pass 1, all threads striding, no barriers: every differing cell that does NOT need a new top-K slot takes its
+    // recomputed decision as the next speculation.  (If pass 2 truncates the block, cells behind the cut have been
+    // rewritten for nothing: they are outside the block from now on and every block starts from a fresh speculation.)
+    const int nneed_old = bc->nneed;
+    const int32_t row0 = (int32_t)bc->pos;
+    int base = nneed_old;
+    int dirty = 0, any_want = 0;
+    constexpr int PU = 4;
+    for (int i0 = m0 + tid; i0 < cut; i0 += BS_CTA1 * PU) {
+        int dv[PU], ev[PU];
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+            const int i = i0 + u * BS_CTA1;
+            dv[u] = i < cut ? e.ws.dec[i] : 0;
+            ev[u] = i < cut ? e.ws.eff[i] : 0;
         }
-        const int nwant = __syncthreads_count(want);
-        int slot = base;
-        if (nwant) {
-            int total;
-            slot = base + block_exclusive_scan_1024(want ? 1 : 0, s_warp, total);
-        }
-        if (want && slot >= BS_RMAX) atomicMin(&s_cut, i);
-        __syncthreads();
-        const bool fits = i < s_cut;
-        if (diff && fits) {
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+            const int i = i0 + u * BS_CTA1, dc = dv[u], ef = ev[u];
+            if (dc == ef) continue; // (also the padding past cut)
+            const bool want = dc == BS_KEY_NEED || (dc >= 0 && dc < Mp && e.ws.pcand[i] != dc && !e.ws.pflag[i]);
             if (want) {
-                e.ws.tkpos[i] = slot;
-                e.ws.nrows[slot] = row0 + i;
-                e.ws.ncell[slot] = i;
+                any_want = 1;
+                continue;
             }
-            if (dc == BS_KEY_NEED) {
-                e.ws.ospec[i] = KNEW + i; // provisional: create; the next round decides with the top-K list
-                e.ws.pflag[i] = 1;
-            } else if (dc < Mp) {
-                if (want) {
-                    e.ws.ospec[i] = KNEW + i;
-                    e.ws.pflag[i] = 1;
-                }
+            if (dc < Mp) {
                 e.ws.pcand[i] = dc;
             } else {
                 e.ws.ospec[i] = dc;
@@ -1468,6 +1560,36 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
             }
             if (ef >= Mp && dc >= Mp) e.ws.eff[i] = dc; // what k_bs_verify_p would record for this (rejected) cell
             else dirty = 1;
+        }
+    }
+    any_want = __syncthreads_or(any_want);
+    // Pass 2, only when some cell needs a (new) top-K slot -- a cell that reaches the outlier stage without a list, or a
+    // SAFE cell whose nearest pcore MC changed (it becomes CONTESTED, which needs a fallback outlier decision should the
+    // chain reject it): slots are handed out in cell order, 1024 cells at a time; the block is truncated at the first
+    // cell that finds the list full.
+    for (int c0 = m0; any_want && c0 < cut; c0 += BS_CTA1) {
+        const int i = c0 + tid;
+        int dc = 0;
+        bool want = false;
+        if (i < cut) {
+            dc = e.ws.dec[i];
+            want = dc != e.ws.eff[i] &&
+                   (dc == BS_KEY_NEED || (dc >= 0 && dc < Mp && e.ws.pcand[i] != dc && !e.ws.pflag[i]));
+        }
+        const int nwant = __syncthreads_count(want);
+        if (!nwant) continue; // uniform
+        int total;
+        const int slot = base + block_exclusive_scan_1024(want ? 1 : 0, s_warp, total);
+        if (want && slot >= BS_RMAX) atomicMin(&s_cut, i);
+        __syncthreads();
+        if (want && i < s_cut) {
+            e.ws.tkpos[i] = slot;
+            e.ws.nrows[slot] = row0 + i;
+            e.ws.ncell[slot] = i;
+            e.ws.ospec[i] = KNEW + i; // provisional: create; the next round decides with the top-K list
+            e.ws.pflag[i] = 1;
+            if (dc != BS_KEY_NEED) e.ws.pcand[i] = dc;
+            dirty = 1;
         }
         base += nwant;
         if (s_cut < Beff) break; // uniform: s_cut was read after the barrier
@@ -1499,15 +1621,9 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
 
 // ---- commit -----------------------------------------------------------------------------------------
 // one warp per key: the last version before m_commit becomes the stored state of the MC
-__global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
-    e.fetch();
-    const BsCtl *bc = e.bc;
-    if (!bc->active || bc->phase != 1) return;
-    const Num nm = e.nm;
+__device__ __forceinline__ void commit_row(const Eng &e, const BsCtl *bc, const Num &nm, int kidx, int lane, int Mp, int Mo0,
+                                           int KNEW, int m) {
     const int D = nm.D, DP = nm.DP;
-    const int lane = threadIdx.x & 31;
-    const int kidx = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
-    const int Mp = bc->Mp, Mo0 = bc->Mo0, KNEW = Mp + Mo0, m = bc->m_commit;
     if (kidx < Mp) {
         const int j = kidx, tm = m >> 5;
         const int i = tm * 32 + lane;
@@ -1560,6 +1676,17 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
             e.O.uid[slot] = (int32_t)id;
         }
     }
+}
+
+__global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
+    e.fetch();
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 1) return;
+    const Num nm = e.nm;
+    const int lane = threadIdx.x & 31;
+    const int Mp = bc->Mp, Mo0 = bc->Mo0, KNEW = Mp + Mo0, m = bc->m_commit;
+    const int kidx = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
+    commit_row(e, bc, nm, kidx, lane, Mp, Mo0, KNEW, m);
 }
 
 __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_cells(Eng e) {

@@ -223,38 +223,42 @@ __global__ void k_off_subspace(const double *__restrict__ cen, int M, int D, int
     if (var <= delta) atomicOr(reinterpret_cast<unsigned long long *>(&submask[row - r0]), 1ull << d); // delta, not delta^2
 }
 
-// ---- 4d: one thread per (row, word of the neighbour row) -----------------------------------------------
-__global__ void k_off_weighted(const double *__restrict__ cen, int M, int D, int r0, int r1,
-                               const uint32_t *__restrict__ nbr, const uint64_t *__restrict__ submask_all, double k,
-                               double E2, uint32_t *__restrict__ wnbr) {
+// ---- 4d: one WARP per row; lane l takes words l, l + 32, ... of the neighbour row ------------------------------------
+// (a thread per (row, word) launched M * M / 32 threads, nearly all of them for empty words: 2.4 M CTAs at M = 1e5)
+constexpr int OFFW_THREADS = 128;
+__global__ void __launch_bounds__(OFFW_THREADS)
+    k_off_weighted(const double *__restrict__ cen, int M, int D, int r0, int r1, const uint32_t *__restrict__ nbr,
+                   const uint64_t *__restrict__ submask_all, double k, double E2, uint32_t *__restrict__ wnbr) {
     const int words = (M + 31) / 32;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = r0 + (int)(t / words), wq = (int)(t % words);
+    const int lane = threadIdx.x & 31;
+    const int row = r0 + blockIdx.x * (OFFW_THREADS / 32) + (threadIdx.x >> 5);
     if (row >= r1) return;
-    uint32_t bits = nbr[(size_t)(row - r0) * words + wq];
-    uint32_t out = 0u;
     const double *cp = cen + (size_t)row * D;
     const uint64_t mp = submask_all[row];
-    while (bits) {
-        const int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int q = (wq << 5) + b;
-        const double *cq = cen + (size_t)q * D;
-        const uint64_t mq = submask_all[q];
-        double dpq = 0.0, dqp = 0.0; // calculate_weighted_dist_squared, predeconmc_functions.py:44-62
-        for (int d = 0; d < D; ++d) {
-            const double x = dsub(cp[d], cq[d]);
-            const double sq = dmul(x, x);
-            dpq = dadd(dpq, ((mp >> d) & 1ull) ? dmul(k, sq) : sq);
-            const double y = dsub(cq[d], cp[d]);
-            const double sy = dmul(y, y);
-            dqp = dadd(dqp, ((mq >> d) & 1ull) ? dmul(k, sy) : sy);
+    for (int wq = lane; wq < words; wq += 32) {
+        uint32_t bits = nbr[(size_t)(row - r0) * words + wq];
+        uint32_t out = 0u;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int q = (wq << 5) + b;
+            const double *cq = cen + (size_t)q * D;
+            const uint64_t mq = submask_all[q];
+            double dpq = 0.0, dqp = 0.0; // calculate_weighted_dist_squared, predeconmc_functions.py:44-62
+            for (int d = 0; d < D; ++d) {
+                const double x = dsub(cp[d], cq[d]);
+                const double sq = dmul(x, x);
+                dpq = dadd(dpq, ((mp >> d) & 1ull) ? dmul(k, sq) : sq);
+                const double y = dsub(cq[d], cp[d]);
+                const double sy = dmul(y, y);
+                dqp = dadd(dqp, ((mq >> d) & 1ull) ? dmul(k, sy) : sy);
+            }
+            double dist = dpq;
+            if (dqp > dpq) dist = dqp; // Python max(a, b)
+            if (dist <= E2) out |= 1u << b;
         }
-        double dist = dpq;
-        if (dqp > dpq) dist = dqp; // Python max(a, b)
-        if (dist <= E2) out |= 1u << b;
+        wnbr[(size_t)(row - r0) * words + wq] = out;
     }
-    wnbr[(size_t)(row - r0) * words + wq] = out;
 }
 
 // ---- 4e: ordered cluster growth ------------------------------------------------------------------------
