@@ -568,3 +568,59 @@ def test_full_size_c2_invariants():
         assert live[a.last_assignment].all()
     st = a.stats()
     assert st["points"] == 2 * N and st["bsv_blocks"] > 0
+
+
+EDGE_CFG = {"beta": 0.2, "delta": 0.05, "epsilon": 0.05, "lambda": 2, "k": 4, "mu": 0.01, "pi": 0, "omicron": 0.00000435,
+            "upsilon": 6.5}
+
+
+def _edge_series(kind):
+    rng = np.random.default_rng(7)
+    blob = lambda n, d: np.clip(0.5 + 0.02 * rng.standard_normal((n, d)), 0.0, 1.0)
+    if kind == "d1":
+        return EDGE_CFG, [blob(500, 1) for _ in range(3)]
+    if kind == "d64":  # the widest preference mask (64 bits)
+        return dict(EDGE_CFG, epsilon=0.2), [blob(300, 64) for _ in range(3)]
+    if kind == "single_cell":
+        return EDGE_CFG, [blob(1, 3) for _ in range(3)]
+    if kind == "empty_timepoint":
+        return EDGE_CFG, [blob(400, 3), np.zeros((0, 3)), blob(400, 3)]
+    if kind == "identical_cells":  # zero variance, every distance an exact tie
+        return EDGE_CFG, [np.full((257, 5), 0.25), np.full((64, 5), 0.25), np.full((300, 5), 0.75)]
+    if kind == "k1_default":  # reference default k = 1: every preference weight is 1, pdim is always 0
+        return dict(EDGE_CFG, k=1, pi=2), [blob(600, 4) for _ in range(3)]
+    if kind == "no_cluster":  # nothing ever reaches the pcore threshold (no_cluster_test.py of the reference)
+        return dict(EDGE_CFG, beta=1.0, mu=0.9), [rng.random((500, 3)) for _ in range(3)]
+    if kind == "two_far_blobs_gap":  # timestamps with a gap: decay by 2^(-lambda * 3)
+        return EDGE_CFG, [np.vstack([blob(300, 2), blob(300, 2) * 0.2]) for _ in range(3)]
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind", ["d1", "d64", "single_cell", "empty_timepoint", "identical_cells", "k1_default",
+                                  "no_cluster", "two_far_blobs_gap"])
+def test_edge_shapes_vs_oracle(kind):
+    """Edge cases of the hot path against the (reference-pinned) oracle, bit for bit: one marker, 64 markers, a single
+    cell, an empty timepoint, identical cells (exact ties), the default k = 1, a run in which no cluster ever forms,
+    and non-consecutive timestamps."""
+    from oracle.oracle import OracleHDDStream
+
+    cfg, Xs = _edge_series(kind)
+    stamps = [0, 3, 4] if kind == "two_far_blobs_gap" else list(range(len(Xs)))
+    h, o = make(cfg), OracleHDDStream(cfg)
+    for t, X in zip(stamps, Xs):
+        X = np.ascontiguousarray(X, np.float64)
+        h.online_microcluster_maintenance(X, t)
+        o.online_microcluster_maintenance(X, t)
+        if len(X):
+            assert (h.last_assignment == o.assign_uid).all() and (h.last_stage == o.stage).all()
+        for which in (0, 1):
+            e, got = o.export(which), h.export_arrays(which)
+            assert len(got[0]) == len(e.ids) and (got[0] == e.ids).all() and (got[1] == e.uids).all()
+            for g, x in zip(got[2:], (e.w, e.cf1, e.cf2, e.cen, e.pref)):
+                assert bits_equal(g, x)
+        oc, hc = o.clusters(), clusters_of(h)
+        assert len(oc) == len(hc)
+        for (m1, w1, *r1), (m2, w2, *r2) in zip(hc, oc):
+            assert list(m1) == list(m2) and w1 == w2 and all(bits_equal(p, q) for p, q in zip(r1, r2))
+    if kind == "no_cluster":
+        assert len(h.final_clusters) == 0
