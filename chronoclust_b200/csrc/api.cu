@@ -674,9 +674,20 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
         Timed tm(h, CCB_CAT_PCORE);
         CCB_DISPATCH_DP(h->DP, { k_bs_chain_p<kDP><<<std::max(mp_grid, 1), BS_CHAINP_THREADS, ChainPCfg<kDP>::SMEM, s>>>(e); })
     }
-    if (side) {
+    if (side) { // join: k_bs_olist needs the speculated outlier decisions, everything below the pcore replay
         CK(h, cudaEventRecord(h->ev_join, side));
         CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+        // second fork: pcore side of derive + verify next to the outlier-side lists / replay / derive (disjoint cells)
+        CK(h, cudaEventRecord(h->ev_fork, s));
+        CK(h, cudaStreamWaitEvent(side, h->ev_fork, 0));
+    }
+    {
+        Timed tm(h, CCB_CAT_DERIVE);
+        k_bs_derive_p<<<g_cells, BS_THREADS, 0, sa>>>(e);
+    }
+    {
+        Timed tm(h, CCB_CAT_RESOLVE);
+        CCB_DISPATCH_DP(h->DP, { k_bs_verify_p<kDP><<<B / 32 + 1, BS_THREADS, 0, sa>>>(e); })
     }
     {
         Timed tm(h, CCB_CAT_OLIST);
@@ -688,14 +699,15 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     }
     {
         Timed tm(h, CCB_CAT_DERIVE);
-        k_bs_derive<<<g_cells, BS_THREADS, 0, s>>>(e);
+        k_bs_derive_o<<<BS_RMAX / BS_THREADS, BS_THREADS, 0, s>>>(e);
+    }
+    if (side) {
+        CK(h, cudaEventRecord(h->ev_join, side));
+        CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     }
     {
         Timed tm(h, CCB_CAT_RESOLVE);
-        CCB_DISPATCH_DP(h->DP, {
-            k_bs_verify_p<kDP><<<B / 32 + 1, BS_THREADS, 0, s>>>(e);
-            k_bs_verify_o<kDP><<<148 * 2, BS_THREADS, 0, s>>>(e);
-        })
+        CCB_DISPATCH_DP(h->DP, { k_bs_verify_o<kDP><<<148 * 2, BS_THREADS, 0, s>>>(e); })
     }
     {
         Timed tm(h, CCB_CAT_DECIDE);
@@ -704,7 +716,7 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     CKL(h);
     return CCB_OK;
 }
-constexpr int BS_LAUNCHES_PROLOGUE = 3, BS_LAUNCHES_ROUND = 13, BS_LAUNCHES_COMMIT = 3;
+constexpr int BS_LAUNCHES_PROLOGUE = 3, BS_LAUNCHES_ROUND = 14, BS_LAUNCHES_COMMIT = 3;
 
 int launch_commit(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, cudaStream_t side = nullptr) {
     const int g_cells = (h->bs_bmax + BS_THREADS - 1) / BS_THREADS;

@@ -1174,25 +1174,8 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_olist(Eng e) {
 }
 
 // ---- D ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BS_THREADS) k_bs_derive(Eng e) {
-    e.fetch();
-    const BsCtl *bc = e.bc;
-    if (!bc->active || bc->phase != 0) return;
-    const int i = blockIdx.x * BS_THREADS + threadIdx.x;
-    if (!bc->pclean) {
-        // tbase[t][j] = latest ACCEPTED member of pcore chain j before tile t (t == ntiles: of the whole block)
-        const int Mp = bc->Mp, stride = e.ws.mp_stride, ntiles = (bc->Beff + 31) >> 5;
-        const int total = (ntiles + 1) * Mp;
-        for (int idx = i; idx < total; idx += gridDim.x * BS_THREADS) {
-            const int t = idx / Mp, j = idx - t * Mp;
-            const int lo = e.ws.poff[j];
-            int pos = lo + (t < ntiles ? e.ws.tilecnt[(size_t)t * stride + j] : e.ws.pcnt[j]);
-            while (pos > lo && e.ws.prej[e.ws.plist[pos - 1] & 0x7fffffff]) --pos;
-            e.ws.tbase[(size_t)t * stride + j] = pos > lo ? (e.ws.plist[pos - 1] & 0x7fffffff) : -1;
-        }
-    }
-    if (i >= bc->Beff) return;
-    const Num nm = e.nm;
+// centroid, preference mask and r^2 of VERSION i (two IEEE divisions per dimension, off the serial path)
+__device__ __forceinline__ void derive_version(const Eng &e, const Num &nm, int i) {
     const int D = nm.D;
     const double w = ver_w(e.ws, i);
     const double *c1 = ver_cf1(e.ws, i), *c2 = ver_cf2(e.ws, i);
@@ -1210,6 +1193,38 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive(Eng e) {
     }
     e.ws.vmask[i] = mk;
     e.ws.vr2[i] = s;
+}
+
+// PCORE side: the versions k_bs_chain_p left (accepted members of the pcore chains) and the per-tile bases.  Runs, with
+// k_bs_verify_p behind it, next to k_bs_olist -> k_bs_chain_o -> k_bs_derive_o (disjoint cells); skipped in a light round.
+__global__ void __launch_bounds__(BS_THREADS) k_bs_derive_p(Eng e) {
+    e.fetch();
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0 || bc->pclean) return;
+    const int i = blockIdx.x * BS_THREADS + threadIdx.x;
+    {
+        // tbase[t][j] = latest ACCEPTED member of pcore chain j before tile t (t == ntiles: of the whole block)
+        const int Mp = bc->Mp, stride = e.ws.mp_stride, ntiles = (bc->Beff + 31) >> 5;
+        const int total = (ntiles + 1) * Mp;
+        for (int idx = i; idx < total; idx += gridDim.x * BS_THREADS) {
+            const int t = idx / Mp, j = idx - t * Mp;
+            const int lo = e.ws.poff[j];
+            int pos = lo + (t < ntiles ? e.ws.tilecnt[(size_t)t * stride + j] : e.ws.pcnt[j]);
+            while (pos > lo && e.ws.prej[e.ws.plist[pos - 1] & 0x7fffffff]) --pos;
+            e.ws.tbase[(size_t)t * stride + j] = pos > lo ? (e.ws.plist[pos - 1] & 0x7fffffff) : -1;
+        }
+    }
+    if (i >= bc->Beff || e.ws.pcand[i] < 0 || e.ws.prej[i]) return; // not an accepted member of a pcore chain
+    derive_version(e, e.nm, i);
+}
+
+// OUTLIER side: the versions k_bs_chain_o left (members of the outlier-side keys, in omem)
+__global__ void __launch_bounds__(BS_THREADS) k_bs_derive_o(Eng e) {
+    e.fetch();
+    const BsCtl *bc = e.bc;
+    if (!bc->active || bc->phase != 0) return;
+    const int no = bc->no;
+    for (int t = blockIdx.x * BS_THREADS + threadIdx.x; t < no; t += gridDim.x * BS_THREADS) derive_version(e, e.nm, e.ws.omem[t]);
 }
 
 // ---- V ----------------------------------------------------------------------------------------------
