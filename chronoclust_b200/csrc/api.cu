@@ -844,7 +844,17 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
     io.ld = ld;
     io.assign = d_assign;
     io.stage = d_stage;
-    io.theta = 4.0 * h->prm.eps2; // CONTESTED above 4 eps^2: heuristic only, never affects results
+    // SAFE / CONTESTED split of the speculation -- a heuristic that never affects results, only how much of the replay
+    // takes the exact in-chain radius test and how often verification sends a block into another round.  SAFE = the
+    // snapshot says "absorbed" (radius^2 of the tentative MC <= kappa eps^2, kappa = 1) and the cell is not far out
+    // (snapshot distance <= theta eps^2, theta = 4).  Established MCs sit right at their radius limit, so a margin
+    // kappa < 1 marks almost every cell CONTESTED (r1p_safe_rule_experiment.md: 10x slower); the distance bound singles
+    // out the ~1 % background cells, which are exactly the ones whose radius test is open.
+    // (CCB_SAFE_KAPPA / CCB_SAFE_THETA: experiment knobs; theta <= 0 removes the distance condition.)
+    static const double kappa = getenv("CCB_SAFE_KAPPA") ? atof(getenv("CCB_SAFE_KAPPA")) : 1.0;
+    static const double theta_mult = getenv("CCB_SAFE_THETA") ? atof(getenv("CCB_SAFE_THETA")) : 4.0;
+    io.theta = theta_mult > 0.0 ? theta_mult * h->prm.eps2 : HUGE_VAL;
+    io.r2safe = kappa * h->prm.eps2;
     io.nm = make_num(h);
     if (graph) {
         *h->h_io = io;
@@ -872,7 +882,7 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
             CK(h, cudaGraphLaunch(h->bs_exec, s));
         } else {
             const Ctl &c = *h->h_ctl;
-            e.X = io.X, e.ld = io.ld, e.assign = io.assign, e.stage = io.stage, e.theta = io.theta, e.nm = io.nm;
+            e.X = io.X, e.ld = io.ld, e.assign = io.assign, e.stage = io.stage, e.theta = io.theta, e.r2safe = io.r2safe, e.nm = io.nm;
             for (int g = 0; g < G; ++g) {
                 const int mp_grid = c.n_pcore + g + 1;
                 const int mo_bound = (int)std::min<int64_t>(c.n_outlier + (int64_t)(g + 1) * BS_RMAX, h->O[h->ocur].cap);

@@ -91,7 +91,8 @@ struct EngIo {
     int64_t ld;
     int32_t *assign;
     uint8_t *stage;
-    double theta; // contested threshold on the snapshot distance
+    double theta; // SAFE needs: snapshot distance <= theta (+inf: no distance condition) ...
+    double r2safe; // ... and snapshot radius^2 of the tentative MC <= r2safe (a margin below eps^2)
     Num nm;
 };
 
@@ -105,7 +106,7 @@ struct Eng {
     BsWs ws;
     int32_t *assign;
     uint8_t *stage;
-    double theta;
+    double theta, r2safe;
     const EngIo *io;                 // nullptr: the fields above are current
     unsigned long long h_outer, h_inner; // cudaGraphConditionalHandle of the block loop / round loop, 0 = stream launches
     __device__ __forceinline__ void fetch() {
@@ -115,6 +116,7 @@ struct Eng {
             assign = io->assign;
             stage = io->stage;
             theta = io->theta;
+            r2safe = io->r2safe;
             nm = io->nm;
         }
     }
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_spec(Eng e) {
         double wn;
         uint64_t nmask;
         const double r2s = tent_regs<DP>(e.P.cf1 + (size_t)best * D, e.P.cf2 + (size_t)best * D, e.P.w[best], x, nm, wn, nmask);
-        if (bd <= e.theta && r2s <= nm.eps2) flag = 0;
+        if (bd <= e.theta && r2s <= e.r2safe) flag = 0;
     }
     e.ws.pcand[i] = best;
     e.ws.pflag[i] = (uint8_t)flag;
