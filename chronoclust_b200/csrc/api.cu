@@ -100,6 +100,7 @@ struct ccb_handle {
     cudaStream_t cap1 = nullptr, cap2 = nullptr, cap3 = nullptr; // capture streams: block loop, round loop, side branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t copy_stream = nullptr; // host -> device segments of ccb_ingest, ahead of the engine
+    double *d_scale = nullptr;          // [2][CCB_MAX_D] scale_ / min_ of ccb_ingest_scaled
     cudaEvent_t ev_seg[8] = {nullptr};
     Eng bs_graph_eng{};         // the pointers / capacities the graph was captured with
     EngIo *d_io = nullptr, *h_io = nullptr;
@@ -1159,6 +1160,7 @@ void ccb_destroy(ccb_handle *h) {
     if (h->cap2) cudaStreamDestroy(h->cap2);
     if (h->cap3) cudaStreamDestroy(h->cap3);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    cudaFree(h->d_scale);
     for (auto &ev : h->ev_seg)
         if (ev) cudaEventDestroy(ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1374,7 +1376,23 @@ int ccb_ingest_device(ccb_handle *h, const double *X_dev, int64_t N, int64_t ld,
                      : ingest_core_bsv(h, X_dev, N, ld, assign_uid_dev, stage_dev);
 }
 
+static int ingest_host(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *assign_uid, uint8_t *stage,
+                       const double *scale, const double *shift);
+
 int ccb_ingest(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *assign_uid, uint8_t *stage) {
+    return ingest_host(h, X, N, ld, assign_uid, stage, nullptr, nullptr);
+}
+
+int ccb_ingest_scaled(ccb_handle *h, const double *X_raw, int64_t N, int64_t ld, const double *scale, const double *min_,
+                      int32_t *assign_uid, uint8_t *stage) {
+    if (!scale || !min_) return fail(h, CCB_EINVAL, "null scaler vectors");
+    return ingest_host(h, X_raw, N, ld, assign_uid, stage, scale, min_);
+}
+
+// host buffers in, per-cell results out; scale != nullptr: the rows are min-max scaled on the device first
+// (X * scale + shift, two roundings: sklearn MinMaxScaler.transform), segment by segment behind their copies
+static int ingest_host(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *assign_uid, uint8_t *stage,
+                       const double *scale, const double *shift) {
     if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
     if (N < 0 || ld < h->D || (!X && N > 0) || (!assign_uid && N > 0)) return fail(h, CCB_EINVAL, "bad ingest arguments");
     if (N == 0) return CCB_OK;
@@ -1388,12 +1406,25 @@ int ccb_ingest(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *a
     }
     int rc = ensure_point_buffers(h, N);
     if (rc) return rc;
+    if (scale) {
+        if (!h->d_scale) CK(h, cudaMalloc(&h->d_scale, 2 * CCB_MAX_D * sizeof(double)));
+        CK(h, cudaMemcpyAsync(h->d_scale, scale, (size_t)h->D * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(h->d_scale + CCB_MAX_D, shift, (size_t)h->D * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    auto scale_rows = [&](int64_t r0, int64_t n) { // on the handle's stream, behind the wait for the rows' copy
+        if (!scale || n <= 0) return;
+        const int64_t total = n * h->D;
+        k_scale_rows<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, h->stream>>>(
+            h->d_X + r0 * ld, n, ld, h->D, h->d_scale, h->d_scale + CCB_MAX_D);
+        h->st.kernel_launches++;
+    };
     const int nseg = (h->engine || h->timing) ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(8, N / 131072));
     if (nseg == 1) {
         {
             Timed tm(h, CCB_CAT_COPY);
             CK(h, cudaMemcpyAsync(h->d_X, X, need * 8, cudaMemcpyHostToDevice, h->stream));
         }
+        scale_rows(0, N);
         rc = h->engine ? ingest_core(h, h->d_X, N, ld, h->d_assign, h->d_stage)
                        : ingest_core_bsv(h, h->d_X, N, ld, h->d_assign, h->d_stage);
         if (rc) return rc;
@@ -1425,6 +1456,7 @@ int ccb_ingest(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *a
             int64_t r0, n;
             seg_rows(k, r0, n);
             CK(h, cudaStreamWaitEvent(h->stream, h->ev_seg[k], 0));
+            scale_rows(r0, n);
             const std::function<int()> next = [&]() -> int { return k + 1 < nseg ? copy_seg(k + 1) : CCB_OK; };
             if ((rc = ingest_core_bsv(h, h->d_X + r0 * ld, n, ld, h->d_assign + r0, h->d_stage + r0, &next))) return rc;
         }
@@ -1908,6 +1940,27 @@ int ccb_assoc_nearest(int32_t device, void *stream, const double *cur_cen, const
     if (!ok) return fail(nullptr, CCB_ELIMIT, "unsupported dimensionality %d", D);
     e = cudaGetLastError();
     return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "k_assoc launch: %s", cudaGetErrorString(e));
+}
+
+int ccb_colminmax(int32_t device, void *stream, const double *X_dev, int64_t N, int64_t ld, int32_t D, double *min_dev,
+                  double *max_dev) {
+    if (D < 1 || D > CCB_MAX_D || N < 0 || ld < D) return fail(nullptr, CCB_EINVAL, "bad ccb_colminmax arguments");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaStream_t s = (cudaStream_t)stream;
+    tune_pool(device);
+    unsigned long long *okey = nullptr;
+    if ((e = cudaMallocAsync(&okey, 2 * (size_t)D * 8, s)) != cudaSuccess)
+        return fail(nullptr, CCB_ENOMEM, "scratch allocation: %s", cudaGetErrorString(e));
+    cudaMemsetAsync(okey, 0xff, (size_t)D * 8, s);   // running minima: largest key
+    cudaMemsetAsync(okey + D, 0x00, (size_t)D * 8, s); // running maxima: smallest key
+    const int64_t total = N * D;
+    if (total > 0)
+        k_colminmax<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, s>>>(X_dev, N, ld, D, okey);
+    k_colminmax_finish<<<1, 64, 0, s>>>(okey, D, min_dev, max_dev);
+    e = cudaGetLastError();
+    cudaFreeAsync(okey, s);
+    return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "k_colminmax: %s", cudaGetErrorString(e));
 }
 
 int ccb_off_neighbours(int32_t device, void *stream, const double *cen, int64_t M, int32_t D, int64_t r0, int64_t r1,

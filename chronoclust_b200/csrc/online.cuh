@@ -999,4 +999,72 @@ __global__ void k_repack_store(Store S, int n, int D, int DP, double wsel) {
     S.cw[i] = cv;
 }
 
+// ---- scaler (scaling/scaler.py:11-53 -> sklearn MinMaxScaler) ---------------------------------------
+// transform: X * scale_ + min_ as TWO roundings (sklearn: `X *= self.scale_; X += self.min_`), in place on the device
+// copy of a timepoint, so the host never makes the scaled pass over the data.  HBM-bound: 16 B per element.
+__global__ void k_scale_rows(double *__restrict__ X, int64_t N, int64_t ld, int D, const double *__restrict__ scale,
+                             const double *__restrict__ shift) {
+    const int64_t total = N * D;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / D;
+        const int d = (int)(e - r * D);
+        double *p = X + r * ld + d;
+        *p = dadd(dmul(*p, scale[d]), shift[d]);
+    }
+}
+
+// fit: column-wise minimum / maximum ignoring NaN (np.nanmin / np.nanmax, what MinMaxScaler.partial_fit uses).
+// Doubles are compared through the order-preserving map to unsigned integers, so that one atomicMin / atomicMax per
+// column and CTA settles the result exactly.  okey[D] / okey[D + d]: running min / max keys (initialised by the caller).
+__device__ __forceinline__ unsigned long long ordered_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void k_colminmax(const double *__restrict__ X, int64_t N, int64_t ld, int D, unsigned long long *okey) {
+    __shared__ unsigned long long s_min[CCB_MAX_D], s_max[CCB_MAX_D];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        s_min[d] = ~0ull;
+        s_max[d] = 0ull;
+    }
+    __syncthreads();
+    // a stride that is a multiple of D keeps every thread on one column
+    const int64_t total = N * D;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x + D - 1) / D * D;
+    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e0 < total) {
+        const int d = (int)(e0 % D);
+        unsigned long long lo = ~0ull, hi = 0ull;
+        for (int64_t e = e0; e < total; e += stride) {
+            const double v = X[(e / D) * ld + d];
+            if (v == v) { // not NaN
+                const unsigned long long k = ordered_key(v);
+                lo = k < lo ? k : lo;
+                hi = k > hi ? k : hi;
+            }
+        }
+        if (lo <= hi) {
+            atomicMin(&s_min[d], lo);
+            atomicMax(&s_max[d], hi);
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        if (s_min[d] <= s_max[d]) {
+            atomicMin(&okey[d], s_min[d]);
+            atomicMax(&okey[D + d], s_max[d]);
+        }
+    }
+}
+__global__ void k_colminmax_finish(const unsigned long long *okey, int D, double *mn, double *mx) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    auto back = [](unsigned long long k) {
+        const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+        return __longlong_as_double((long long)b);
+    };
+    const bool any = okey[d] <= okey[D + d];
+    mn[d] = any ? back(okey[d]) : __longlong_as_double(0x7ff8000000000000LL); // all-NaN column: NaN, like np.nanmin
+    mx[d] = any ? back(okey[D + d]) : __longlong_as_double(0x7ff8000000000000LL);
+}
+
 } // namespace ccb

@@ -28,13 +28,15 @@ class _PointsView(object):
         self.segments = []
         self._index = None
 
-    def add(self, X, assign):
-        self.segments.append((X, assign))
+    def add(self, X, assign, scaler=None):
+        """scaler = (scale_, min_): X holds RAW rows that were scaled on the device; the coordinates handed out are
+        X * scale_ + min_ of the requested rows (numpy's elementwise arithmetic = the device's two roundings)."""
+        self.segments.append((X, assign, scaler))
         self._index = None
 
     def _build(self):
         idx = {}
-        for si, (_, assign) in enumerate(self.segments):
+        for si, (_, assign, _sc) in enumerate(self.segments):
             order = np.argsort(assign, kind="stable")
             sa = assign[order]
             cuts = np.flatnonzero(np.diff(sa)) + 1
@@ -54,8 +56,12 @@ class _PointsView(object):
     def points_of(self, uid):
         out = {}
         for si, rows in self.rows_of(uid):
-            X = self.segments[si][0]
-            vals = X[rows].tolist()
+            X, _, sc = self.segments[si]
+            sel = X[rows]
+            if sc is not None:
+                sel = sel * sc[0]
+                sel = sel + sc[1]
+            vals = sel.tolist()
             for r, v in zip(rows.tolist(), vals):
                 out[r] = v
         return out
@@ -179,7 +185,10 @@ class HDDStream(object):
 
     # ------------------------------------------------------------------------------------------
     def online_microcluster_maintenance(self, input_dataset, input_dataset_daystamp, reset_param=True,
-                                        run_offline=True):
+                                        run_offline=True, scaler=None):
+        """scaler (extension): a fitted sklearn MinMaxScaler (or a (scale_, min_) pair) -- input_dataset then
+        holds RAW rows and the min-max transform x * scale_ + min_ runs on the device behind the host -> device copy
+        (ccb_ingest_scaled) instead of as a host pass; results are those of scaling on the host first, bit for bit."""
         X = np.ascontiguousarray(input_dataset, dtype=np.float64)
         if X.ndim != 2:
             raise ValueError("input_dataset must be 2-D")
@@ -210,8 +219,18 @@ class HDDStream(object):
         logger.info("Starting online microcluster maintenance for timepoint {}".format(input_dataset_daystamp))
         assign = np.empty(N, np.int32)
         stage = np.empty(N, np.uint8)
-        _lib.check(L.ccb_ingest(h, _lib.ptr(X), N, X.shape[1], _lib.ptr(assign), _lib.ptr(stage)), h)
-        self._views.add(X, assign)
+        if scaler is None:
+            _lib.check(L.ccb_ingest(h, _lib.ptr(X), N, X.shape[1], _lib.ptr(assign), _lib.ptr(stage)), h)
+            self._views.add(X, assign)
+        else:
+            sc, mn = (scaler.scale_, scaler.min_) if hasattr(scaler, "scale_") else scaler
+            sc = np.ascontiguousarray(sc, np.float64)
+            mn = np.ascontiguousarray(mn, np.float64)
+            if sc.shape != (X.shape[1],) or mn.shape != (X.shape[1],):
+                raise ValueError("scaler vectors must have one entry per marker")
+            _lib.check(L.ccb_ingest_scaled(h, _lib.ptr(X), N, X.shape[1], _lib.ptr(sc), _lib.ptr(mn), _lib.ptr(assign),
+                                           _lib.ptr(stage)), h)
+            self._views.add(X, assign, (sc, mn))
         self.last_assignment, self.last_stage = assign, stage
         self._lists = [None, None]
         logger.info("Finish online microcluster maintenance for timepoint {}".format(input_dataset_daystamp))

@@ -161,6 +161,11 @@ int ccb_begin_timepoint(ccb_handle *h, double mu, double omicron, int64_t pi, in
  * of the MC that absorbed row r; stage[r] (host, N, may be NULL): 0 pcore absorb, 1 outlier absorb,
  * 2 outlier absorb + upgrade, 3 new outlier MC. */
 int ccb_ingest(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *assign_uid, uint8_t *stage);
+/* The same for RAW rows: every row is min-max scaled on the device first, x * scale[d] + min_[d] as two roundings --
+ * exactly sklearn's MinMaxScaler.transform with its fitted scale_ / min_ (scaling/scaler.py:43-47) -- so the host never
+ * makes the scaled pass over the data.  scale, min_: host arrays [D]. */
+int ccb_ingest_scaled(ccb_handle *h, const double *X_raw, int64_t N, int64_t ld, const double *scale, const double *min_,
+                      int32_t *assign_uid, uint8_t *stage);
 /* Same with X, assign_uid and stage already resident on the handle's device (stage may be NULL). */
 int ccb_ingest_device(ccb_handle *h, const double *X_dev, int64_t N, int64_t ld, int32_t *assign_uid_dev,
                       uint8_t *stage_dev);
@@ -198,6 +203,12 @@ int ccb_export_offline(ccb_handle *h, uint8_t *core, uint8_t *nbr, uint8_t *wnbr
  * (bit d set <=> pref_d == k, else 1.0).  slot [N] (-1 if M == 0), dist [N]. */
 int ccb_nearest(int32_t device, void *stream, const double *X, int64_t N, int64_t ld, int32_t D, const double *cen,
                 const uint64_t *prefmask, int64_t M, double k, int32_t *slot, double *dist);
+
+/* Scaler (scaling/scaler.py:11-53 -> sklearn MinMaxScaler).  ccb_colminmax: column-wise minimum / maximum of
+ * a device-resident X [N][ld] ignoring NaN (np.nanmin / np.nanmax of partial_fit); min_dev / max_dev [D] on the device.
+ * The transform itself is part of ccb_ingest_scaled (below the handle API). */
+int ccb_colminmax(int32_t device, void *stream, const double *X_dev, int64_t N, int64_t ld, int32_t D, double *min_dev,
+                  double *max_dev);
 
 /* Association scan (replaces the inner loops of TrackByHistoricalAssociation.track_cluster_history,
  * tracking/cluster_tracker.py:127-144): for every CURRENT pcore microcluster q the index of the previous-timepoint

@@ -624,3 +624,45 @@ def test_edge_shapes_vs_oracle(kind):
             assert list(m1) == list(m2) and w1 == w2 and all(bits_equal(p, q) for p, q in zip(r1, r2))
     if kind == "no_cluster":
         assert len(h.final_clusters) == 0
+
+
+def test_device_scaler_matches_sklearn():
+    """SURVEY 8f-3.  (1) ccb_colminmax = np.nanmin / np.nanmax per column (what MinMaxScaler.partial_fit computes),
+    negative values, NaNs and a strided layout included.  (2) Feeding RAW rows with a fitted sklearn MinMaxScaler
+    (ccb_ingest_scaled: x * scale_ + min_ on the device, two roundings) gives bit for bit what scaling on the host first
+    gives -- assignments, both lists, clusters, and the per-MC `points` coordinates."""
+    import torch
+    from sklearn.preprocessing import MinMaxScaler
+    from chronoclust_b200 import _lib
+    from chronoclust_b200.synth import gen
+
+    rng = np.random.default_rng(3)
+    N, D, ld = 70001, 7, 9
+    buf = rng.normal(0.0, 50.0, size=(N, ld))
+    buf[rng.random((N, ld)) < 0.001] = np.nan
+    buf[:, 3] = 12.5  # constant column
+    t = torch.from_numpy(buf).cuda()
+    mn = torch.empty(D, dtype=torch.float64, device="cuda")
+    mx = torch.empty(D, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().ccb_colminmax(0, None, t.data_ptr(), N, ld, D, mn.data_ptr(), mx.data_ptr()))
+    torch.cuda.synchronize()
+    assert bits_equal(mn.cpu().numpy(), np.nanmin(buf[:, :D], axis=0))
+    assert bits_equal(mx.cpu().numpy(), np.nanmax(buf[:, :D], axis=0))
+
+    cfg = {"beta": 0.2, "delta": 0.05, "epsilon": 0.05, "lambda": 2, "k": 4, "mu": 0.01, "pi": 0, "omicron": 0.00000435,
+           "upsilon": 6.5}
+    raw = [x * np.array([3.0, 250.0, 0.01, 17.0, 1e4, 2.0]) - np.array([1.0, 100.0, 0.0, -4.0, 5e3, 0.5])
+           for x in gen(150001, 6, 2, 6, 5)]  # > 131 072 rows: the segmented copy path scales segment by segment
+    sk = MinMaxScaler().fit(np.concatenate(raw, axis=0))
+    a, b = make(cfg), make(cfg)
+    for ts, X in enumerate(raw):
+        a.online_microcluster_maintenance(sk.transform(X), ts)
+        b.online_microcluster_maintenance(X, ts, scaler=sk)
+        assert (a.last_assignment == b.last_assignment).all() and (a.last_stage == b.last_stage).all()
+        for which in (0, 1):
+            ga, gb = a.export_arrays(which), b.export_arrays(which)
+            assert (ga[0] == gb[0]).all() and all(bits_equal(x, y) for x, y in zip(ga[2:], gb[2:]))
+        ca, cb = clusters_of(a), clusters_of(b)
+        assert len(ca) == len(cb) and all(list(m1) == list(m2) and w1 == w2 for (m1, w1, *_), (m2, w2, *_) in zip(ca, cb))
+        pa, pb = a.pcore_MC[0].points, b.pcore_MC[0].points
+        assert list(pa.keys()) == list(pb.keys()) and pa[next(iter(pa))] == pb[next(iter(pb))]
