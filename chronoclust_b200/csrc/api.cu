@@ -563,7 +563,7 @@ int ensure_bs_ws(ccb_handle *h) {
         w.bmax = B;
 #define WSA(field, n) if ((rc = ws_alloc(h, w.field, (n)))) return rc
         WSA(pcand, B); WSA(ospec, B); WSA(tkpos, B); WSA(dec, B); WSA(eff, B); WSA(newrank, B); WSA(pend, B);
-        WSA(pflag, B); WSA(prej, B); WSA(upf, B); WSA(want, B);
+        WSA(pflag, B); WSA(prej, B); WSA(upf, B);
         w.dp = h->DP;
         w.lsp = 2 * h->DP + 2;
         WSA(ver, (size_t)B * w.lsp); WSA(vcen, (size_t)B * D + 2);
@@ -2003,7 +2003,6 @@ int ccb_off_weighted(int32_t device, void *stream, const double *cen, int64_t M,
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     if (r1 == r0) return CCB_OK;
-    const int words = (int)((M + 31) / 32);
     k_off_weighted<<<(unsigned)((r1 - r0 + 3) / 4), OFFW_THREADS, 0, (cudaStream_t)stream>>>(cen, (int)M, D, (int)r0, (int)r1, nbr,
                                                                                              submask_all, k, E2, wnbr);
     e = cudaGetLastError();

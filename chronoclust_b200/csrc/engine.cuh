@@ -59,13 +59,13 @@ struct BsCtl {
     int32_t need_grow, done;
     int32_t ticket; // k_bs_pscan: CTAs finished (last one computes the key offsets)
     int32_t pclean; // refinement round whose pcore side (candidates, CONTESTED flags, accepts) is that of the round before
-    int64_t blocks, iters, mismatches, cuts_unknown, cuts_iter, cuts_cap, tk_late, rejects, contested, replayed, pairs;
+    int64_t blocks, iters, mismatches, cuts_unknown, cuts_iter, cuts_cap, tk_late, rejects, replayed, pairs;
     int64_t rounds_light; // refinement rounds that re-ran the outlier side only
 };
 
 struct BsWs {
     int32_t *pcand, *ospec, *tkpos, *dec, *eff, *newrank, *pend, *plist;
-    uint8_t *pflag, *prej, *upf, *want;
+    uint8_t *pflag, *prej, *upf;
     double *ver;  // [bmax][lsp] VERSION records: CF1 at [0, D), CF2 at [dp, dp + D), W at [2 dp]; lsp = 2 dp + 2
     double *vcen, *vr2;
     uint64_t *vmask;

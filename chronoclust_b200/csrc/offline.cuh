@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(OFFC_THREADS, 1)
                    int32_t *queue /*[2M+2]*/, int32_t *label, int32_t *order, int32_t *cl_off, int32_t *n_cl) {
     __shared__ int s_warp[32];
     __shared__ int s_tot[2];
-    __shared__ int s_qt, s_nmem;
+    __shared__ int s_nmem;
     const int tid = threadIdx.x;
     const int words = (M + 31) / 32;
     for (int i = tid; i < M; i += OFFC_THREADS) label[i] = -1;
