@@ -856,6 +856,10 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
     static const double theta_mult = getenv("CCB_SAFE_THETA") ? atof(getenv("CCB_SAFE_THETA")) : 4.0;
     io.theta = theta_mult > 0.0 ? theta_mult * h->prm.eps2 : HUGE_VAL;
     io.r2safe = kappa * h->prm.eps2;
+    // CCB_SPEC_REJECT = m > 0: a cell whose tentative MC is more than (1 + m) eps^2 wide on the snapshot is speculated
+    // REJECTED without entering the pcore chain (0 / unset: every such cell takes the exact in-chain test)
+    static const double rej_margin = getenv("CCB_SPEC_REJECT") ? atof(getenv("CCB_SPEC_REJECT")) : 0.0;
+    io.r2rej = rej_margin > 0.0 ? (1.0 + rej_margin) * h->prm.eps2 : HUGE_VAL;
     io.nm = make_num(h);
     if (graph) {
         *h->h_io = io;
@@ -883,7 +887,7 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
             CK(h, cudaGraphLaunch(h->bs_exec, s));
         } else {
             const Ctl &c = *h->h_ctl;
-            e.X = io.X, e.ld = io.ld, e.assign = io.assign, e.stage = io.stage, e.theta = io.theta, e.r2safe = io.r2safe, e.nm = io.nm;
+            e.X = io.X, e.ld = io.ld, e.assign = io.assign, e.stage = io.stage, e.theta = io.theta, e.r2safe = io.r2safe, e.r2rej = io.r2rej, e.nm = io.nm;
             for (int g = 0; g < G; ++g) {
                 const int mp_grid = c.n_pcore + g + 1;
                 const int mo_bound = (int)std::min<int64_t>(c.n_outlier + (int64_t)(g + 1) * BS_RMAX, h->O[h->ocur].cap);

@@ -93,6 +93,7 @@ struct EngIo {
     uint8_t *stage;
     double theta; // SAFE needs: snapshot distance <= theta (+inf: no distance condition) ...
     double r2safe; // ... and snapshot radius^2 of the tentative MC <= r2safe (a margin below eps^2)
+    double r2rej;  // snapshot radius^2 above this: speculate REJECTED without entering the chain (+inf: never)
     Num nm;
 };
 
@@ -106,7 +107,7 @@ struct Eng {
     BsWs ws;
     int32_t *assign;
     uint8_t *stage;
-    double theta, r2safe;
+    double theta, r2safe, r2rej;
     const EngIo *io;                 // nullptr: the fields above are current
     unsigned long long h_outer, h_inner; // cudaGraphConditionalHandle of the block loop / round loop, 0 = stream launches
     __device__ __forceinline__ void fetch() {
@@ -117,6 +118,7 @@ struct Eng {
             stage = io->stage;
             theta = io->theta;
             r2safe = io->r2safe;
+            r2rej = io->r2rej;
             nm = io->nm;
         }
     }
@@ -309,6 +311,9 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_spec(Eng e) {
         uint64_t nmask;
         const double r2s = tent_regs<DP>(e.P.cf1 + (size_t)best * D, e.P.cf2 + (size_t)best * D, e.P.w[best], x, nm, wn, nmask);
         if (bd <= e.theta && r2s <= e.r2safe) flag = 0;
+        // far beyond the radius limit on the snapshot: speculate "rejected by the pcore stage" right away instead of
+        // sending the cell through the serial chain for an exact test; k_bs_verify_p checks it like everything else
+        else if (r2s > e.r2rej) best = -1;
     }
     e.ws.pcand[i] = best;
     e.ws.pflag[i] = (uint8_t)flag;
