@@ -17,21 +17,24 @@
 //       k_bs_spec_o    snapshot outlier list for them, speculated outlier decision
 //   then up to ITMAX rounds of
 //   L   k_bs_tilecnt / k_bs_pscan / k_bs_pscatter   ordered candidate list of every pcore MC
-//   C   k_bs_chain<P>  per pcore MC, its candidates in input order: CF1 += x, CF2 += x*x, W += 1 as dependent
+//   C   k_bs_chain_p   per pcore MC, its candidates in input order: CF1 += x, CF2 += x*x, W += 1 as dependent
 //                      fp64 adds (the only inherently serial work: ~1 DADD latency per cell); CONTESTED cells
 //                      take the exact radius test in place; the state after every absorb is kept (VERSION)
 //       k_bs_olist     sort (key, cell) of the pcore-rejected cells -> outlier-side chains
-//       k_bs_chain<O>  the same replay for modified snapshot outlier MCs and MCs created in this block
-//   D   k_bs_derive    centroid, preference mask, radius^2 of every version (cell-parallel)
+//       k_bs_chain_o   the same replay for modified snapshot outlier MCs and MCs created in this block
+//   D   k_bs_derive_p / k_bs_derive_o   centroid, preference mask, radius^2 of every version (cell-parallel)
 //   V   k_bs_verify_p  every cell recomputes its pcore decision against the version every pcore MC had just
 //       k_bs_verify_o  before it; rejected cells recompute the outlier decision (nearest unmodified snapshot
-//                      MC from the top-K list, every modified / created MC at its version)
+//                      MC from the top-K list -- or the bound its last entry gives when all of them are stale --
+//                      against every modified / created MC at its version)
 //   M   k_bs_decide    first cell whose exact decision differs from the speculation = end of the exact
 //                      prefix (induction: every earlier cell saw exact versions).  The recomputed decisions
-//                      become the next speculation; an upgrade ends the block at that cell.
+//                      become the next speculation; if they only move cells between outlier-side keys the next
+//                      round re-runs the outlier side alone (LIGHT round); an upgrade ends the block at that cell.
 //   and finally k_bs_commit_rows / k_bs_commit_cells / k_bs_finish write the exact prefix back.
-// All control flow lives in device memory (BsCtl): the host only enqueues kernels and polls once per batch
-// of blocks.
+// All control flow lives in device memory (BsCtl): the whole loop of one ingest call is one CUDA graph with two
+// device-driven WHILE nodes (api.cu: build_graph), inside which   kernel 1 + S_o  ||  L + C_p   and then
+// D_p + V_p  ||  olist + C_o + D_o   run as parallel branches (disjoint data).
 #pragma once
 #include <limits.h>
 
