@@ -652,7 +652,7 @@ def test_device_scaler_matches_sklearn():
     cfg = {"beta": 0.2, "delta": 0.05, "epsilon": 0.05, "lambda": 2, "k": 4, "mu": 0.01, "pi": 0, "omicron": 0.00000435,
            "upsilon": 6.5}
     raw = [x * np.array([3.0, 250.0, 0.01, 17.0, 1e4, 2.0]) - np.array([1.0, 100.0, 0.0, -4.0, 5e3, 0.5])
-           for x in gen(150001, 6, 2, 6, 5)]  # > 131 072 rows: the segmented copy path scales segment by segment
+           for x in gen(300001, 6, 2, 6, 5)]  # >= 2 x 131 072 rows: the segmented copy path scales segment by segment
     sk = MinMaxScaler().fit(np.concatenate(raw, axis=0))
     a, b = make(cfg), make(cfg)
     for ts, X in enumerate(raw):
