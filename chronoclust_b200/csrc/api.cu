@@ -1422,7 +1422,21 @@ static int ingest_host(ccb_handle *h, const double *X, int64_t N, int64_t ld, in
             h->d_X + r0 * ld, n, ld, h->D, h->d_scale, h->d_scale + CCB_MAX_D);
         h->st.kernel_launches++;
     };
-    const int nseg = (h->engine || h->timing) ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(8, N / 131072));
+    // segments of the input: one block's worth of rows first, then doubling, the last one takes the rest -- the engine
+    // starts after a 3 MB copy instead of a 24 MB one and the copies (5x faster than the engine) stay ahead of it
+    int64_t seg_end[8];
+    int nseg = 1;
+    seg_end[0] = N;
+    if (!h->engine && !h->timing && N >= 262144) {
+        int64_t len = h->bs_bmax, at = 0;
+        nseg = 0;
+        while (nseg < 7 && at + len + len < N) {
+            at += len;
+            seg_end[nseg++] = at;
+            len *= 2;
+        }
+        seg_end[nseg++] = N;
+    }
     if (nseg == 1) {
         {
             Timed tm(h, CCB_CAT_COPY);
@@ -1442,10 +1456,9 @@ static int ingest_host(ccb_handle *h, const double *X, int64_t N, int64_t ld, in
         }
         CK(h, cudaEventRecord(h->ev_seg[0], h->stream)); // earlier work on the handle's stream (previous readers of d_X)
         CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_seg[0], 0));
-        const int64_t per = (N + nseg - 1) / nseg;
         auto seg_rows = [&](int k, int64_t &r0, int64_t &n) {
-            r0 = std::min<int64_t>(N, (int64_t)k * per);
-            n = std::min<int64_t>(N, r0 + per) - r0;
+            r0 = k ? seg_end[k - 1] : 0;
+            n = seg_end[k] - r0;
         };
         auto copy_seg = [&](int k) -> int {
             int64_t r0, n;
