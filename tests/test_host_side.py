@@ -146,3 +146,23 @@ def test_historical_association():
     t.set_current_clusters([c])
     t.track_cluster_history()
     assert c.get_historical_associates_as_str() == "A&B"
+
+
+def test_points_view_applies_the_device_scaler_on_the_host_side():
+    """When raw rows were scaled on the device (ccb_ingest_scaled), Microcluster.points hands out x * scale_ + min_ of the
+    requested rows -- the same two roundings (scaling/scaler.py:43-47 -> MinMaxScaler.transform)."""
+    from sklearn.preprocessing import MinMaxScaler
+
+    from chronoclust_b200.hddstream import _PointsView
+
+    rng = np.random.default_rng(0)
+    X = rng.normal(0.0, 30.0, size=(50, 4))
+    sk = MinMaxScaler().fit(X)
+    assign = rng.integers(0, 3, size=50).astype(np.int32)
+    raw_view, scaled_view = _PointsView(), _PointsView()
+    raw_view.add(X, assign, (sk.scale_, sk.min_))
+    scaled_view.add(sk.transform(X), assign)
+    for uid in range(3):
+        a, b = raw_view.points_of(uid), scaled_view.points_of(uid)
+        assert list(a.keys()) == list(b.keys()) == sorted(a.keys())
+        assert a == b
