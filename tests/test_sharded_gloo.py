@@ -98,7 +98,7 @@ def _worker(rank, world, port, ret):
 
 def test_sharded_offline_gloo_world2():
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()  # no fork() of the (multi-threaded) pytest process
     ret = mgr.dict()
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
