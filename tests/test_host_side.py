@@ -166,3 +166,33 @@ def test_points_view_applies_the_device_scaler_on_the_host_side():
         a, b = raw_view.points_of(uid), scaled_view.points_of(uid)
         assert list(a.keys()) == list(b.keys()) == sorted(a.keys())
         assert a == b
+
+
+def test_streamed_scaler_fit_equals_one_fit_over_all_timepoints(tmp_path):
+    """Scaler fits file by file (partial_fit); the fitted vectors and the transform equal those of the reference's single
+    fit over the concatenation of all timepoints (scaling/scaler.py:27-36), bit for bit."""
+    from sklearn.preprocessing import MinMaxScaler
+
+    from chronoclust_b200.scaling import Scaler
+
+    rng = np.random.default_rng(4)
+    parts, files = [], []
+    for t in range(4):
+        X = rng.normal(10.0 * t, 40.0, size=(300 + 17 * t, 5))
+        X[:, 2] = 3.25  # a constant marker
+        parts.append(X)
+        f = tmp_path / f"d{t}.csv"
+        np.savetxt(f, X, delimiter=",", header="a,b,c,d,e", comments="", fmt="%.17g")
+        files.append(str(f))
+    s = Scaler(files)
+    import pandas as pd
+    parts = [pd.read_csv(f, header=0, sep=',').to_numpy() for f in files]  # what both implementations see
+    allc = np.concatenate(parts, axis=0)
+    ref = MinMaxScaler().fit(allc)
+    same = lambda a, b: (np.ascontiguousarray(a).view(np.uint64) == np.ascontiguousarray(b).view(np.uint64)).all()
+    assert same(s.scaler.scale_, ref.scale_) and same(s.scaler.min_, ref.min_)
+    assert same(s.scale_data(parts[1]), ref.transform(parts[1]))
+    assert same(s.reverse_scaling(ref.transform(parts[2])), ref.inverse_transform(ref.transform(parts[2])))
+    sc, mn = s.device_vectors()
+    assert same(parts[3] * sc + mn, ref.transform(parts[3]))
+    assert len(s.get_input_data()) == len(allc)
