@@ -19,14 +19,13 @@ vp = C.c_void_p
 
 class Params(C.Structure):
     _fields_ = [("D", i32), ("device", i32), ("eps2", f64), ("upsilon_eps", f64), ("upsilon_eps2", f64),
-                ("delta", f64), ("delta2", f64), ("beta", f64), ("k", f64), ("wave", i32), ("chunk", i32),
-                ("bsv_bmin", i32), ("bsv_iters", i32), ("bsv_stream", i32), ("reserved0", i32)]
+                ("delta", f64), ("delta2", f64), ("beta", f64), ("k", f64), ("chunk", i32),
+                ("bsv_bmin", i32), ("bsv_iters", i32), ("bsv_stream", i32), ("off_csr_min_m", i32), ("reserved0", i32)]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, i64) for n in (
-        "points", "chunks", "waves", "wave_rollbacks", "rejects", "resolver_calls", "resolver_cuts", "nearest_pairs",
-        "pcore_pairs", "upgrades", "created", "downgraded", "deleted", "kernel_launches", "borderline_pairs",
+        "points", "nearest_pairs", "upgrades", "created", "downgraded", "deleted", "kernel_launches", "borderline_pairs",
         "bsv_blocks", "bsv_rounds", "bsv_mismatches", "bsv_cuts_unknown", "bsv_cuts_rounds", "bsv_cuts_capacity",
         "bsv_late_topk", "bsv_outlier_stage_cells", "bsv_replayed_cells", "bsv_light_rounds")]
 
@@ -42,9 +41,6 @@ SYMBOLS = {
     "ccb_stream": (vp, [vp]),
     "ccb_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
     "ccb_reset": (C.c_int, [vp]),
-    "ccb_debug_phase_cycles": (C.c_int, [vp, C.POINTER(i64 * 8)]),
-    "ccb_debug_chain": (C.c_int, [vp, vp, i32]),
-    "ccb_debug_set": (C.c_int, [vp, i32]),
     "ccb_fp64_peak": (C.c_int, [i32, vp, i32, i32, i32, vp, C.POINTER(f64)]),
     "ccb_enable_timing": (C.c_int, [vp, i32]),
     "ccb_get_timing": (C.c_int, [vp, C.POINTER(f64 * 16), C.POINTER(i64 * 16), i32]),
@@ -68,7 +64,7 @@ SYMBOLS = {
     "ccb_off_patch": (C.c_int, [i32, vp, vp, vp, vp, vp, i32, i64, i64]),
     "ccb_off_subspace": (C.c_int, [i32, vp, vp, i64, i32, i64, i64, vp, vp, f64, vp]),
     "ccb_off_weighted": (C.c_int, [i32, vp, vp, i64, i32, i64, i64, vp, vp, f64, f64, vp]),
-    "ccb_off_clusters": (C.c_int, [i32, vp, i64, vp, vp, vp, f64, i64, vp, vp, vp, vp]),
+    "ccb_off_clusters": (C.c_int, [i32, vp, i64, vp, vp, vp, f64, i64, i32, vp, vp, vp, vp]),
 }
 
 

@@ -1,20 +1,31 @@
-"""Builds chronoclust_b200/libchronoclust_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Builds chronoclust_b200/libchronoclust_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python chronoclust_b200/build.py [--force] [--debug]
+
+--debug builds libchronoclust_b200_debug.so instead: the same sources with -DCCB_DEBUG, which adds the diagnostics of
+csrc/debug.h (per-key cycle counters of the replay kernel, switches that deliberately break results).  The product
+library never contains them.
+"""
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "api.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "common.cuh", "nearest.cuh", "online.cuh", "offline.cuh", "engine.cuh")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "common.cuh", "nearest.cuh", "online.cuh", "offline.cuh",
+                                                "engine.cuh", "debug.h")]
 DEPS.append(os.path.join(os.path.dirname(HERE), "include", "chronoclust_b200.h"))
 SO = os.path.join(HERE, "libchronoclust_b200.so")
+SO_DEBUG = os.path.join(HERE, "libchronoclust_b200_debug.so")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false",            # parity: the reference never contracts mul+add
     "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if os.environ.get("CCB_PTXAS_V") else "-O3",
-    "--split-compile", "0",   # optimise the kernels of this one translation unit on all host cores
+    # the kernels of this one translation unit are optimised in 8 groups -- a FIXED count, so that the binary does not
+    # depend on how many cores the build host has (`--split-compile 0` made it irreproducible)
+    "--split-compile", "8",
 ]
 
 
@@ -25,15 +36,16 @@ def nvcc():
     return "nvcc"
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in DEPS):
-        return SO
-    cmd = [nvcc()] + NVCC_FLAGS + ["-o", SO, SRC]
+def build(force=False, verbose=False, debug=False):
+    so = SO_DEBUG if debug else SO
+    if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in DEPS):
+        return so
+    cmd = [nvcc()] + NVCC_FLAGS + (["-DCCB_DEBUG"] if debug else []) + ["-o", so, SRC]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    return SO
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, debug="--debug" in sys.argv))

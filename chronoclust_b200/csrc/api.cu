@@ -3,6 +3,9 @@
 // pipeline, import/export.  One handle = one device + one stream.  No CPU fallback anywhere: every
 // numeric result is produced by the kernels in nearest.cuh / online.cuh / offline.cuh.
 #include "../../include/chronoclust_b200.h"
+#ifdef CCB_DEBUG
+#include "debug.h"
+#endif
 
 #include <cmath>
 #include <cstdarg>
@@ -49,17 +52,13 @@ bool is_pow2(double k) {
     return std::frexp(k, &e) == 0.5;
 }
 
-constexpr int TOPK = 4;
-constexpr int REJ_CAP = 2048;   // rejects per ordered-commit launch (also the dirty-list capacity)
 constexpr int MAX_SLABS = 148;
-constexpr size_t PCORE_SMEM_LIMIT = 200 * 1024;
 
 } // namespace
 
 struct ccb_handle {
     ccb_params prm{};
-    int D = 0, DP = 0, div_mode = 0, cnt_gt1 = 0, wave = 32;
-    int64_t chunk = 65536;
+    int D = 0, DP = 0, div_mode = 0, cnt_gt1 = 0;
     double wsel = 1.0;
     cudaStream_t stream = nullptr;
     Store P[2]{}, O[2]{};
@@ -74,16 +73,8 @@ struct ccb_handle {
     int32_t *d_assign = nullptr;
     uint8_t *d_stage = nullptr;
     size_t n_cap = 0;
-    int32_t *d_rej = nullptr;
-    double *d_tk_dist_slab = nullptr, *d_tk_dist = nullptr;
-    int32_t *d_tk_idx_slab = nullptr, *d_tk_idx = nullptr;
-    uint8_t *d_dirty = nullptr;
-    int32_t *d_dirty_list = nullptr;
-    int32_t *d_pnew = nullptr, *d_pfin = nullptr, *d_onew = nullptr;
-    double *d_dist_gmem = nullptr;
-    size_t dist_gmem_cap = 0;
+    int32_t *d_pnew = nullptr, *d_pfin = nullptr, *d_onew = nullptr; // kernel 3 plan codes
     // block-speculative engine (engine.cuh)
-    int engine = 0;             // 0: block-speculative versioned commit, 1: wave engine (kernels 2a/2b of online.cuh)
     int bs_bmax = 32768, bs_bmin = 1024, bs_iters = 3;
     BsCtl *d_bc = nullptr, *h_bc = nullptr;
     BsWs ws{};
@@ -109,9 +100,15 @@ struct ccb_handle {
     std::vector<int64_t> cl_off, cl_members;
     std::vector<double> cl_w, cl_cf1, cl_cf2, cl_cen, cl_pref;
     std::vector<int32_t> cl_label;
-    std::vector<uint8_t> off_core;
-    std::vector<uint32_t> off_nbr, off_wnbr;
-    std::vector<uint64_t> off_submask;
+    // offline workspace: grow-only device buffers, kept between calls (the white-box export reads them lazily)
+    struct OffBuf {
+        void *p = nullptr;
+        size_t bytes = 0;
+    };
+    enum { OB_CORE, OB_CLS, OB_NBR, OB_WNBR, OB_CNT, OB_BORDER, OB_NBORDER, OB_QUEUE, OB_LABEL, OB_ORDER, OB_CLOFF, OB_NCL,
+           OB_SUBMASK, OB_OMASK, OB_D1, OB_D2, OB_DC, OB_DW, OB_DEC, OB_COUNT };
+    OffBuf ob[OB_COUNT];
+    int off_csr_min_m = 0;
     ccb_stats st{};
     ccb_stats st_base{}; // device-side counters folded in by ccb_reset
     std::string err;
@@ -245,9 +242,7 @@ int grow_store(ccb_handle *h, Store (&S)[2], int cur, int n, int64_t want) {
 
 int realloc_aux_for_outlier_cap(ccb_handle *h) {
     const int cap = h->O[h->ocur].cap;
-    cudaFree(h->d_dirty);
     cudaFree(h->d_onew);
-    CK(h, cudaMalloc(&h->d_dirty, (size_t)cap));
     CK(h, cudaMalloc(&h->d_onew, (size_t)cap * 4));
     return CCB_OK;
 }
@@ -390,146 +385,6 @@ int ensure_point_buffers(ccb_handle *h, int64_t N) {
         CK(h, cudaMalloc(&h->d_stage, (size_t)N));
         h->n_cap = (size_t)N;
     }
-    return CCB_OK;
-}
-
-// the ordered loop over cells [0, N) of a device-resident X
-int ingest_core(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int32_t *d_assign, uint8_t *d_stage) {
-    if (!h->have_params) return fail(h, CCB_ESTATE, "ccb_begin_timepoint must precede ccb_ingest");
-    cudaStream_t s = h->stream;
-    const Num nm = make_num(h);
-    int rc;
-    if ((rc = sync_ctl(h))) return rc;
-    int64_t pos = 0;
-    while (pos < N) {
-        Ctl &c = *h->h_ctl;
-        // capacity for this chunk: at most REJ_CAP new outlier MCs and one upgrade
-        if ((int64_t)c.n_outlier + REJ_CAP + 1 > h->O[h->ocur].cap) {
-            if ((rc = grow_store(h, h->O, h->ocur, c.n_outlier, (int64_t)c.n_outlier + REJ_CAP + 1))) return rc;
-            if ((rc = realloc_aux_for_outlier_cap(h))) return rc;
-        }
-        if (c.n_pcore + 1 > h->P[h->pcur].cap) {
-            if ((rc = grow_store(h, h->P, h->pcur, c.n_pcore, c.n_pcore + 1))) return rc;
-            if ((rc = realloc_aux_for_pcore_cap(h))) return rc;
-        }
-        Store &P = h->P[h->pcur], &O = h->O[h->ocur];
-        const int Mp = c.n_pcore, Mo = c.n_outlier;
-
-        {
-            Timed tm(h, CCB_CAT_MISC);
-            k_max_w<<<1, 1024, 0, s>>>(O.w, h->d_ctl);
-        }
-        h->st.kernel_launches++;
-
-        PcoreArgs pa{};
-        pa.X = dX;
-        pa.ld = ld;
-        pa.start = pos;
-        pa.end = std::min<int64_t>(N, pos + h->chunk);
-        pa.P = P;
-        pa.nm = nm;
-        pa.ctl = h->d_ctl;
-        pa.assign = d_assign;
-        pa.stage = d_stage;
-        pa.rej_list = h->d_rej;
-        pa.rej_cap = REJ_CAP;
-        pa.wave = h->wave;
-        size_t smem = pcore_smem_bytes(h->D, Mp, true, true);
-        pa.state_in_smem = pa.dist_in_smem = 1;
-        if (smem > PCORE_SMEM_LIMIT) {
-            pa.dist_in_smem = 0;
-            smem = pcore_smem_bytes(h->D, Mp, true, false);
-            if (smem > PCORE_SMEM_LIMIT) {
-                pa.state_in_smem = 0;
-                smem = pcore_smem_bytes(h->D, Mp, false, false);
-            }
-            const size_t need = (size_t)Mp * XS;
-            if (need > h->dist_gmem_cap) {
-                cudaFree(h->d_dist_gmem);
-                h->dist_gmem_cap = 0;
-                CK(h, cudaMalloc(&h->d_dist_gmem, need * 2 * 8));
-                h->dist_gmem_cap = need * 2;
-            }
-        }
-        pa.dist_gmem = h->d_dist_gmem;
-        {
-            Timed tm(h, CCB_CAT_PCORE);
-            CCB_DISPATCH_DP(h->DP, { k_pcore_stage<kDP><<<1, PCORE_THREADS, smem, s>>>(pa); })
-        }
-        CKL(h);
-        h->st.kernel_launches++;
-        h->st.chunks++;
-
-        // outlier stage of the chunk's rejects
-        int q_snap = 0;
-        bool first = true;
-        for (;;) {
-            Store &Oc = h->O[h->ocur];
-            const int mo_snap = first ? Mo : h->h_ctl->n_outlier;
-            CK(h, cudaMemsetAsync(h->d_dirty, 0, (size_t)std::max(mo_snap, 1), s));
-            if (mo_snap > 0) {
-                Timed tm(h, CCB_CAT_NEAREST);
-                rc = launch_nearest<TOPK>(h, s, h->DP, h->div_mode, dX, h->d_rej, &h->d_ctl->n_rej, q_snap, REJ_CAP - q_snap,
-                                          ld, h->D, Oc.cw, mo_snap, h->d_tk_dist_slab, h->d_tk_idx_slab, h->d_tk_dist,
-                                          h->d_tk_idx, MAX_SLABS, nullptr);
-                if (rc) return rc;
-            } else {
-                CK(h, cudaMemsetAsync(h->d_tk_idx, 0xff, (size_t)REJ_CAP * TOPK * 4, s));
-            }
-            ResolveArgs ra{};
-            ra.X = dX;
-            ra.ld = ld;
-            ra.O = Oc;
-            ra.P = h->P[h->pcur];
-            ra.nm = nm;
-            ra.ctl = h->d_ctl;
-            ra.rej_list = h->d_rej;
-            ra.q_snap = q_snap;
-            ra.mo_snap = mo_snap;
-            ra.topk = TOPK;
-            ra.tk_dist = h->d_tk_dist;
-            ra.tk_idx = h->d_tk_idx;
-            ra.dirty = h->d_dirty;
-            ra.dirty_list = h->d_dirty_list;
-            ra.assign = d_assign;
-            ra.stage = d_stage;
-            {
-                Timed tm(h, CCB_CAT_RESOLVE);
-                k_resolve<<<1, RES_THREADS, 0, s>>>(ra);
-            }
-            CKL(h);
-            h->st.kernel_launches++;
-            h->st.resolver_calls++;
-            if ((rc = sync_ctl(h))) return rc;
-            Ctl &cc = *h->h_ctl;
-            if (first) {
-                h->st.rejects += cc.n_rej;
-                h->st.nearest_pairs += (int64_t)cc.n_rej * mo_snap;
-            } else {
-                h->st.nearest_pairs += (int64_t)(cc.n_rej - q_snap) * mo_snap;
-            }
-            first = false;
-            if (cc.res_reason == RES_CUT || cc.res_reason == RES_OCAP) {
-                if (cc.res_reason == RES_CUT) h->st.resolver_cuts++;
-                if (cc.res_reason == RES_OCAP) {
-                    if ((rc = grow_store(h, h->O, h->ocur, cc.n_outlier, (int64_t)cc.n_outlier + REJ_CAP + 1))) return rc;
-                    if ((rc = realloc_aux_for_outlier_cap(h))) return rc;
-                }
-                q_snap = cc.res_done;
-                // fresh snapshot: nothing is dirty any more
-                cc.n_dirty = 0;
-                CK(h, cudaMemcpyAsync(&h->d_ctl->n_dirty, &cc.n_dirty, sizeof(int32_t), cudaMemcpyHostToDevice, s));
-                continue;
-            }
-            if (cc.res_reason == RES_PCAP) return fail(h, CCB_ESTATE, "internal: pcore list capacity exhausted mid-chunk");
-            if (cc.res_reason == RES_UPGRADE && cc.res_done != cc.n_rej)
-                return fail(h, CCB_ESTATE, "internal: upgrade before the last reject of a chunk (%d of %d)", cc.res_done,
-                            cc.n_rej);
-            break;
-        }
-        pos = h->h_ctl->pos_end;
-    }
-    h->st.points += N;
     return CCB_OK;
 }
 
@@ -847,19 +702,14 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
     io.stage = d_stage;
     // SAFE / CONTESTED split of the speculation -- a heuristic that never affects results, only how much of the replay
     // takes the exact in-chain radius test and how often verification sends a block into another round.  SAFE = the
-    // snapshot says "absorbed" (radius^2 of the tentative MC <= kappa eps^2, kappa = 1) and the cell is not far out
-    // (snapshot distance <= theta eps^2, theta = 4).  Established MCs sit right at their radius limit, so a margin
-    // kappa < 1 marks almost every cell CONTESTED (r1p_safe_rule_experiment.md: 10x slower); the distance bound singles
-    // out the ~1 % background cells, which are exactly the ones whose radius test is open.
-    // (CCB_SAFE_KAPPA / CCB_SAFE_THETA: experiment knobs; theta <= 0 removes the distance condition.)
-    static const double kappa = getenv("CCB_SAFE_KAPPA") ? atof(getenv("CCB_SAFE_KAPPA")) : 1.0;
-    static const double theta_mult = getenv("CCB_SAFE_THETA") ? atof(getenv("CCB_SAFE_THETA")) : 4.0;
-    io.theta = theta_mult > 0.0 ? theta_mult * h->prm.eps2 : HUGE_VAL;
-    io.r2safe = kappa * h->prm.eps2;
-    // CCB_SPEC_REJECT = m > 0: a cell whose tentative MC is more than (1 + m) eps^2 wide on the snapshot is speculated
-    // REJECTED without entering the pcore chain (0 / unset: every such cell takes the exact in-chain test)
-    static const double rej_margin = getenv("CCB_SPEC_REJECT") ? atof(getenv("CCB_SPEC_REJECT")) : 0.0;
-    io.r2rej = rej_margin > 0.0 ? (1.0 + rej_margin) * h->prm.eps2 : HUGE_VAL;
+    // snapshot says "absorbed" (radius^2 of the tentative MC <= eps^2) and the cell is not far out (snapshot distance
+    // <= 4 eps^2).  Established MCs sit right at their radius limit, so a margin below eps^2 marks almost every cell
+    // CONTESTED (profiles/r1p_safe_rule_experiment.md: 10x slower); the distance bound singles out the ~1 % background
+    // cells, which are exactly the ones whose radius test is open.  Speculative rejection of far cells did not pay
+    // either (profiles/r1t_speculative_reject_experiment.md), so every CONTESTED cell takes the exact in-chain test.
+    io.theta = 4.0 * h->prm.eps2;
+    io.r2safe = h->prm.eps2;
+    io.r2rej = HUGE_VAL;
     io.nm = make_num(h);
     if (graph) {
         *h->h_io = io;
@@ -916,12 +766,6 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
     return CCB_OK;
 }
 
-int pcore_ids_host(ccb_handle *h, int n, std::vector<int64_t> &ids) {
-    ids.resize(n);
-    if (n) CK(h, cudaMemcpy(ids.data(), h->P[h->pcur].id, (size_t)n * 8, cudaMemcpyDeviceToHost));
-    return CCB_OK;
-}
-
 double builtin_nrm2(const double *x, int n) {
     // restatement of OpenBLAS' x86-64 dnrm2: squares, sum and square root in x87 extended precision
     long double s = 0.0L;
@@ -935,6 +779,22 @@ struct DevBuf {
     ~DevBuf() { cudaFree(p); }
     cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
 };
+
+// grow-only buffer of the handle's offline workspace (contents are NOT preserved across a growth)
+int off_buf(ccb_handle *h, int which, size_t bytes) {
+    ccb_handle::OffBuf &b = h->ob[which];
+    bytes = std::max<size_t>(bytes, 16);
+    if (bytes <= b.bytes) return CCB_OK;
+    CK(h, cudaStreamSynchronize(h->stream));
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t cap = 256;
+    while (cap < bytes) cap *= 2;
+    CK(h, cudaMalloc(&b.p, cap));
+    b.bytes = cap;
+    return CCB_OK;
+}
 
 int launch_off_neighbours(ccb_handle *h, cudaStream_t s, const double *cen, int M, int D, int r0, int r1, double E2,
                           uint32_t *nbr, int32_t *cnt, int32_t *border, int border_cap, int32_t *n_border) {
@@ -987,12 +847,11 @@ void tune_pool(int device) {
 // kernel 4e: ordered cluster growth.  Small M (the online hot path: tens of pcore MCs): the single-launch bit-row
 // kernel.  Large M (config C4): isolated MCs in parallel, CSR lists for the rest, clusters merged by seed rank
 // (offline.cuh).  Both produce identical label / order / cl_off / n_cl.  cls [M] and queue [2M + 2] are scratch.
-int g_off_csr_min_m = 2048; // ccb_debug_set(h, 1000 + m) moves the switch-over (the tests force either path)
-int off_csr_min_m() { return g_off_csr_min_m; }
+constexpr int OFF_CSR_MIN_M = 2048; // default switch-over; ccb_params.off_csr_min_m / the csr_min_m argument move it
 
 int launch_off_clusters(ccb_handle *h, cudaStream_t s, int M, const uint32_t *wnbr, const uint8_t *core,
                         const uint64_t *submask, int cnt_gt1, int64_t pi, uint8_t *cls, int32_t *queue, int32_t *label,
-                        int32_t *order, int32_t *cl_off, int32_t *n_cl, int *launches) {
+                        int32_t *order, int32_t *cl_off, int32_t *n_cl, int *launches, int csr_min_m) {
     const int words = (M + 31) / 32;
     *launches = 0;
     cudaMemsetAsync(cls, 0, (size_t)std::max(M, 1), s);
@@ -1002,7 +861,7 @@ int launch_off_clusters(ccb_handle *h, cudaStream_t s, int M, const uint32_t *wn
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? CCB_OK : fail(h, CCB_ECUDA, "k_off_clusters: %s", cudaGetErrorString(e));
     };
-    if (M < off_csr_min_m() || M == 0) return old_path();
+    if (M < (csr_min_m > 0 ? csr_min_m : OFF_CSR_MIN_M) || M == 0) return old_path();
     uint8_t *iso = nullptr;
     int32_t *i32 = nullptr, *col = nullptr;
     int64_t *off = nullptr;
@@ -1070,7 +929,6 @@ int ccb_create(const ccb_params *p, ccb_handle **out) {
     if (!p || !out) return fail(nullptr, CCB_EINVAL, "null argument");
     *out = nullptr;
     if (p->D < 1 || p->D > CCB_MAX_D) return fail(nullptr, CCB_ELIMIT, "D=%d outside 1..%d", p->D, CCB_MAX_D);
-    if (p->wave < 0 || p->wave > 32) return fail(nullptr, CCB_EINVAL, "wave=%d outside 0..32", p->wave);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -1082,13 +940,11 @@ int ccb_create(const ccb_params *p, ccb_handle **out) {
     h->prm = *p;
     h->D = p->D;
     h->DP = round_dp(p->D);
-    h->engine = p->wave ? 1 : 0; // wave == 0: block-speculative engine; wave >= 1: wave engine of that width
-    h->wave = p->wave ? p->wave : 32;
-    h->chunk = p->chunk > 0 ? p->chunk : 65536;
     if (p->chunk > 0) h->bs_bmax = std::max(32, (p->chunk + 31) / 32 * 32); // block length cap of the BSV engine
     if (p->bsv_bmin > 0) h->bs_bmin = p->bsv_bmin;
     if (p->bsv_iters > 0) h->bs_iters = std::min(p->bsv_iters, 16);
     h->bs_use_graph = p->bsv_stream == 0;
+    h->off_csr_min_m = p->off_csr_min_m;
     h->bs_bmax = std::min(h->bs_bmax, 1 << 20);
     const bool p2 = is_pow2(p->k);
     h->div_mode = p2 ? 0 : 1;
@@ -1110,10 +966,6 @@ int ccb_create(const ccb_params *p, ccb_handle **out) {
     CKC(cudaMemset(h->d_ctl, 0, sizeof(Ctl)));
     CKC(cudaMallocHost(&h->h_ctl, sizeof(Ctl)));
     memset(h->h_ctl, 0, sizeof(Ctl));
-    CCB_DISPATCH_DP(h->DP, {
-        CKC(cudaFuncSetAttribute(k_pcore_stage<kDP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)PCORE_SMEM_LIMIT + 8192));
-    })
     int rc = 0;
     for (int i = 0; i < 2 && !rc; ++i) rc = alloc_store(h, h->P[i], 256);
     for (int i = 0; i < 2 && !rc; ++i) rc = alloc_store(h, h->O[i], 8192);
@@ -1124,12 +976,6 @@ int ccb_create(const ccb_params *p, ccb_handle **out) {
         ccb_destroy(h);
         return rc;
     }
-    CKC(cudaMalloc(&h->d_rej, (size_t)REJ_CAP * 4));
-    CKC(cudaMalloc(&h->d_dirty_list, (size_t)(REJ_CAP + 8) * 4));
-    CKC(cudaMalloc(&h->d_tk_dist_slab, (size_t)REJ_CAP * MAX_SLABS * TOPK * 8));
-    CKC(cudaMalloc(&h->d_tk_idx_slab, (size_t)REJ_CAP * MAX_SLABS * TOPK * 4));
-    CKC(cudaMalloc(&h->d_tk_dist, (size_t)REJ_CAP * TOPK * 8));
-    CKC(cudaMalloc(&h->d_tk_idx, (size_t)REJ_CAP * TOPK * 4));
 #undef CKC
     *out = h;
     return CCB_OK;
@@ -1148,17 +994,9 @@ void ccb_destroy(ccb_handle *h) {
     cudaFree(h->d_X);
     cudaFree(h->d_assign);
     cudaFree(h->d_stage);
-    cudaFree(h->d_rej);
-    cudaFree(h->d_tk_dist_slab);
-    cudaFree(h->d_tk_idx_slab);
-    cudaFree(h->d_tk_dist);
-    cudaFree(h->d_tk_idx);
-    cudaFree(h->d_dirty);
-    cudaFree(h->d_dirty_list);
     cudaFree(h->d_pnew);
     cudaFree(h->d_pfin);
     cudaFree(h->d_onew);
-    cudaFree(h->d_dist_gmem);
     drop_graph(h);
     if (h->cap1) cudaStreamDestroy(h->cap1);
     if (h->cap2) cudaStreamDestroy(h->cap2);
@@ -1177,6 +1015,7 @@ void ccb_destroy(ccb_handle *h) {
     for (void *q : h->ws_tiles) cudaFree(q);
     cudaFree(h->ws.dbg);
     cudaFree(h->ws_first);
+    for (auto &b : h->ob) cudaFree(b.p);
     for (auto &e : h->ev_pending) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
@@ -1191,9 +1030,6 @@ int ccb_get_stats(const ccb_handle *h, ccb_stats *out) {
     // the device-side counters are as of the last control-block read-back (every chunk / ccb_counts)
     *out = h->st;
     const Ctl &c = *h->h_ctl;
-    out->waves = h->st_base.waves + c.waves;
-    out->wave_rollbacks = h->st_base.wave_rollbacks + c.rollbacks;
-    out->pcore_pairs = h->st_base.pcore_pairs + c.pcore_pairs;
     out->upgrades = h->st_base.upgrades + c.upgrades;
     out->created = h->st_base.created + c.created;
     out->downgraded = h->st_base.downgraded + c.downgraded;
@@ -1215,20 +1051,11 @@ int ccb_get_stats(const ccb_handle *h, ccb_stats *out) {
     return CCB_OK;
 }
 
-int ccb_debug_phase_cycles(ccb_handle *h, int64_t out[8]) {
-    if (!h || !out) return fail(nullptr, CCB_EINVAL, "null argument");
-    int rc = sync_ctl(h);
-    if (rc) return rc;
-    for (int i = 0; i < 8; ++i) out[i] = h->h_ctl->phase_cycles[i];
-    return CCB_OK;
-}
-
+#ifdef CCB_DEBUG
+// Diagnostics build only (python chronoclust_b200/build.py --debug -> libchronoclust_b200_debug.so, declared in
+// csrc/debug.h): neither symbol exists in the product library.
 int ccb_debug_set(ccb_handle *h, int32_t mode) {
     if (!h) return fail(h, CCB_EINVAL, "null argument");
-    if (mode >= 1000) { // not a diagnostic: which of the two (equivalent) cluster-growth paths serves M microclusters
-        g_off_csr_min_m = mode - 1000;
-        return CCB_OK;
-    }
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaMemcpyToSymbol(g_bs_dbg_mode, &mode, sizeof(int)));
     return CCB_OK;
@@ -1249,6 +1076,7 @@ int ccb_debug_chain(ccb_handle *h, int64_t *out, int32_t max_keys) {
     CK(h, cudaMemcpy(out, h->ws.dbg, (size_t)n * 8 * sizeof(int64_t), cudaMemcpyDeviceToHost));
     return CCB_OK;
 }
+#endif
 
 int ccb_reset(ccb_handle *h) {
     if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
@@ -1257,9 +1085,6 @@ int ccb_reset(ccb_handle *h) {
     if (rc) return rc;
     {
         const Ctl &c = *h->h_ctl;
-        h->st_base.waves += c.waves;
-        h->st_base.wave_rollbacks += c.rollbacks;
-        h->st_base.pcore_pairs += c.pcore_pairs;
         h->st_base.upgrades += c.upgrades;
         h->st_base.created += c.created;
         h->st_base.downgraded += c.downgraded;
@@ -1376,8 +1201,7 @@ int ccb_ingest_device(ccb_handle *h, const double *X_dev, int64_t N, int64_t ld,
     if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
     if (N < 0 || ld < h->D || (!X_dev && N > 0) || (!assign_uid_dev && N > 0)) return fail(h, CCB_EINVAL, "bad ingest arguments");
     CK(h, cudaSetDevice(h->prm.device));
-    return h->engine ? ingest_core(h, X_dev, N, ld, assign_uid_dev, stage_dev)
-                     : ingest_core_bsv(h, X_dev, N, ld, assign_uid_dev, stage_dev);
+    return ingest_core_bsv(h, X_dev, N, ld, assign_uid_dev, stage_dev);
 }
 
 static int ingest_host(ccb_handle *h, const double *X, int64_t N, int64_t ld, int32_t *assign_uid, uint8_t *stage,
@@ -1427,7 +1251,7 @@ static int ingest_host(ccb_handle *h, const double *X, int64_t N, int64_t ld, in
     int64_t seg_end[8];
     int nseg = 1;
     seg_end[0] = N;
-    if (!h->engine && !h->timing && N >= 262144) {
+    if (!h->timing && N >= 262144) {
         int64_t len = h->bs_bmax, at = 0;
         nseg = 0;
         while (nseg < 7 && at + len + len < N) {
@@ -1443,8 +1267,7 @@ static int ingest_host(ccb_handle *h, const double *X, int64_t N, int64_t ld, in
             CK(h, cudaMemcpyAsync(h->d_X, X, need * 8, cudaMemcpyHostToDevice, h->stream));
         }
         scale_rows(0, N);
-        rc = h->engine ? ingest_core(h, h->d_X, N, ld, h->d_assign, h->d_stage)
-                       : ingest_core_bsv(h, h->d_X, N, ld, h->d_assign, h->d_stage);
+        rc = ingest_core_bsv(h, h->d_X, N, ld, h->d_assign, h->d_stage);
         if (rc) return rc;
     } else {
         // The ordered engine consumes cells front to back, so the input travels in segments on a copy stream and the
@@ -1618,52 +1441,56 @@ int ccb_offline(ccb_handle *h, int64_t *n_clusters) {
     h->cl_cen.clear();
     h->cl_pref.clear();
     h->cl_label.assign(M, -1);
-    h->off_core.assign(M, 0);
-    h->off_nbr.assign((size_t)M * words, 0);
-    h->off_wnbr.assign((size_t)M * words, 0);
-    h->off_submask.assign(M, 0);
     if (n_clusters) *n_clusters = 0;
     if (M == 0) return CCB_OK;
 
     const double E2 = h->prm.upsilon_eps2;
     Timed tm_off(h, CCB_CAT_OFFLINE);
-    DevBuf<uint8_t> core, cls;
-    DevBuf<uint32_t> nbr, wnbr;
-    DevBuf<int32_t> cnt, border, nborder, queue, label, order, cloff, ncl;
-    DevBuf<uint64_t> submask, omask;
-    const int border_cap = 1 << 16;
-    CK(h, core.alloc(M));
-    CK(h, cls.alloc(M));
-    CK(h, nbr.alloc((size_t)M * words));
-    CK(h, wnbr.alloc((size_t)M * words));
-    CK(h, cnt.alloc(M));
-    CK(h, border.alloc(2 * (size_t)border_cap));
-    CK(h, nborder.alloc(1));
-    CK(h, queue.alloc(2 * (size_t)M + 2));
-    CK(h, label.alloc(M));
-    CK(h, order.alloc(M));
-    CK(h, cloff.alloc((size_t)M + 2));
-    CK(h, ncl.alloc(1));
-    CK(h, submask.alloc(M));
-    CK(h, cudaMemsetAsync(nborder.p, 0, 4, s));
-    CK(h, cudaMemsetAsync(submask.p, 0, (size_t)M * 8, s));
-    CK(h, cudaMemsetAsync(cls.p, 0, (size_t)M, s));
+    uint8_t *core, *cls;
+    uint32_t *nbr, *wnbr;
+    int32_t *cnt, *border, *nborder, *queue, *label, *order, *cloff, *ncl;
+    uint64_t *submask;
+    int border_cap = (int)std::max<size_t>(h->ob[ccb_handle::OB_BORDER].bytes / 8, (size_t)1 << 16);
+#define OBUF(var, which, n)                                                      \
+    if ((rc = off_buf(h, ccb_handle::which, (size_t)(n) * sizeof(*var)))) return rc; \
+    var = (decltype(var))h->ob[ccb_handle::which].p
+    OBUF(core, OB_CORE, M);
+    OBUF(cls, OB_CLS, M);
+    OBUF(nbr, OB_NBR, (size_t)M * words);
+    OBUF(wnbr, OB_WNBR, (size_t)M * words);
+    OBUF(cnt, OB_CNT, M);
+    OBUF(border, OB_BORDER, 2 * (size_t)border_cap);
+    OBUF(nborder, OB_NBORDER, 1);
+    OBUF(queue, OB_QUEUE, 2 * (size_t)M + 2);
+    OBUF(label, OB_LABEL, M);
+    OBUF(order, OB_ORDER, M);
+    OBUF(cloff, OB_CLOFF, (size_t)M + 2);
+    OBUF(ncl, OB_NCL, 1);
+    OBUF(submask, OB_SUBMASK, M);
+    CK(h, cudaMemsetAsync(submask, 0, (size_t)M * 8, s));
+    CK(h, cudaMemsetAsync(cls, 0, (size_t)M, s));
 
     k_off_core<<<(M + 127) / 128, 128, 0, s>>>(P.cf1, P.cf2, P.w, P.mask, M, D, h->prm.k, h->wsel, h->div_mode, h->cnt_gt1,
-                                               h->prm.eps2, h->mu, h->pi, core.p);
+                                               h->prm.eps2, h->mu, h->pi, core);
     CKL(h);
-    if ((rc = launch_off_neighbours(h, s, P.cen, M, D, 0, M, E2, nbr.p, cnt.p, border.p, border_cap, nborder.p))) return rc;
-    h->st.kernel_launches += 2;
+    h->st.kernel_launches++;
     int32_t nb = 0;
-    CK(h, cudaMemcpyAsync(&nb, nborder.p, 4, cudaMemcpyDeviceToHost, s));
-    CK(h, cudaStreamSynchronize(s));
-    if (nb > border_cap) return fail(h, CCB_ELIMIT, "%d borderline neighbour pairs exceed the resolver capacity", nb);
+    for (;;) { // the borderline list grows to whatever the data needs (e.g. many coincident centroids with upsilon = 0)
+        CK(h, cudaMemsetAsync(nborder, 0, 4, s));
+        if ((rc = launch_off_neighbours(h, s, P.cen, M, D, 0, M, E2, nbr, cnt, border, border_cap, nborder))) return rc;
+        h->st.kernel_launches++;
+        CK(h, cudaMemcpyAsync(&nb, nborder, 4, cudaMemcpyDeviceToHost, s));
+        CK(h, cudaStreamSynchronize(s));
+        if (nb <= border_cap) break;
+        border_cap = nb;
+        OBUF(border, OB_BORDER, 2 * (size_t)border_cap);
+    }
     if (nb > 0) {
         // settle the pairs inside the guard band with the BLAS dnrm2 the reference itself calls
         std::vector<int32_t> pairs(2 * (size_t)nb);
         std::vector<double> hc((size_t)M * D), x(D);
         std::vector<uint8_t> dec(nb);
-        CK(h, cudaMemcpy(pairs.data(), border.p, pairs.size() * 4, cudaMemcpyDeviceToHost));
+        CK(h, cudaMemcpy(pairs.data(), border, pairs.size() * 4, cudaMemcpyDeviceToHost));
         CK(h, cudaMemcpy(hc.data(), P.cen, hc.size() * 8, cudaMemcpyDeviceToHost));
         typedef double (*nrm2_fn)(int *, double *, int *);
         for (int i = 0; i < nb; ++i) {
@@ -1678,63 +1505,59 @@ int ccb_offline(ccb_handle *h, int64_t *n_clusters) {
             }
             dec[i] = r <= h->prm.upsilon_eps;
         }
-        DevBuf<uint8_t> ddec;
-        CK(h, ddec.alloc(nb));
-        CK(h, cudaMemcpy(ddec.p, dec.data(), nb, cudaMemcpyHostToDevice));
-        k_off_patch<<<(nb + 127) / 128, 128, 0, s>>>(nbr.p, cnt.p, border.p, ddec.p, nb, 0, words);
+        uint8_t *ddec;
+        OBUF(ddec, OB_DEC, nb);
+        CK(h, cudaMemcpyAsync(ddec, dec.data(), nb, cudaMemcpyHostToDevice, s));
+        k_off_patch<<<(nb + 127) / 128, 128, 0, s>>>(nbr, cnt, border, ddec, nb, 0, words);
         CKL(h);
-        CK(h, cudaStreamSynchronize(s));
+        CK(h, cudaStreamSynchronize(s)); // dec (host) is read by the copy above
         h->st.borderline_pairs += nb;
         h->st.kernel_launches++;
     }
     {
         const int64_t t = (int64_t)M * D;
-        k_off_subspace<<<(unsigned)((t + 127) / 128), 128, 0, s>>>(P.cen, M, D, 0, M, nbr.p, cnt.p, h->prm.delta, submask.p);
+        k_off_subspace<<<(unsigned)((t + 127) / 128), 128, 0, s>>>(P.cen, M, D, 0, M, nbr, cnt, h->prm.delta, submask);
         CKL(h);
-        k_off_weighted<<<(unsigned)((M + 3) / 4), OFFW_THREADS, 0, s>>>(P.cen, M, D, 0, M, nbr.p, submask.p, h->prm.k, E2, wnbr.p);
+        k_off_weighted<<<(unsigned)((M + 3) / 4), OFFW_THREADS, 0, s>>>(P.cen, M, D, 0, M, nbr, submask, h->prm.k, E2, wnbr);
         CKL(h);
         int nl = 0, rc2;
-        if ((rc2 = launch_off_clusters(h, s, M, wnbr.p, core.p, submask.p, h->cnt_gt1, h->pi, cls.p, queue.p, label.p, order.p,
-                                       cloff.p, ncl.p, &nl)))
+        if ((rc2 = launch_off_clusters(h, s, M, wnbr, core, submask, h->cnt_gt1, h->pi, cls, queue, label, order, cloff, ncl, &nl,
+                                       h->off_csr_min_m)))
             return rc2;
         h->st.kernel_launches += 2 + nl;
     }
     int32_t nc_raw = 0;
-    CK(h, cudaMemcpyAsync(&nc_raw, ncl.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(h, cudaMemcpyAsync(&nc_raw, ncl, 4, cudaMemcpyDeviceToHost, s));
     CK(h, cudaStreamSynchronize(s));
     std::vector<int32_t> hl(M), ho(M), hoff((size_t)nc_raw + 1);
     std::vector<double> kw(nc_raw), k1((size_t)nc_raw * D), k2((size_t)nc_raw * D), kc((size_t)nc_raw * D);
     std::vector<uint64_t> km(nc_raw);
     if (nc_raw > 0) {
-        DevBuf<double> d1, d2, dc, dw;
-        CK(h, d1.alloc((size_t)nc_raw * D));
-        CK(h, d2.alloc((size_t)nc_raw * D));
-        CK(h, dc.alloc((size_t)nc_raw * D));
-        CK(h, dw.alloc(nc_raw));
-        CK(h, omask.alloc(nc_raw));
-        k_off_cluster_cf<<<nc_raw, 64, 0, s>>>(P.cf1, P.cf2, P.w, D, order.p, cloff.p, h->prm.delta2, d1.p, d2.p, dc.p, omask.p,
-                                               dw.p);
+        double *d1, *d2, *dc, *dw;
+        uint64_t *omask;
+        OBUF(d1, OB_D1, (size_t)nc_raw * D);
+        OBUF(d2, OB_D2, (size_t)nc_raw * D);
+        OBUF(dc, OB_DC, (size_t)nc_raw * D);
+        OBUF(dw, OB_DW, nc_raw);
+        OBUF(omask, OB_OMASK, nc_raw);
+        k_off_cluster_cf<<<nc_raw, 64, 0, s>>>(P.cf1, P.cf2, P.w, D, order, cloff, h->prm.delta2, d1, d2, dc, omask, dw);
         CKL(h);
         h->st.kernel_launches++;
-        CK(h, cudaMemcpyAsync(kw.data(), dw.p, (size_t)nc_raw * 8, cudaMemcpyDeviceToHost, s));
-        CK(h, cudaMemcpyAsync(k1.data(), d1.p, k1.size() * 8, cudaMemcpyDeviceToHost, s));
-        CK(h, cudaMemcpyAsync(k2.data(), d2.p, k2.size() * 8, cudaMemcpyDeviceToHost, s));
-        CK(h, cudaMemcpyAsync(kc.data(), dc.p, kc.size() * 8, cudaMemcpyDeviceToHost, s));
-        CK(h, cudaMemcpyAsync(km.data(), omask.p, (size_t)nc_raw * 8, cudaMemcpyDeviceToHost, s));
-        CK(h, cudaStreamSynchronize(s));
+        CK(h, cudaMemcpyAsync(kw.data(), dw, (size_t)nc_raw * 8, cudaMemcpyDeviceToHost, s));
+        CK(h, cudaMemcpyAsync(k1.data(), d1, k1.size() * 8, cudaMemcpyDeviceToHost, s));
+        CK(h, cudaMemcpyAsync(k2.data(), d2, k2.size() * 8, cudaMemcpyDeviceToHost, s));
+        CK(h, cudaMemcpyAsync(kc.data(), dc, kc.size() * 8, cudaMemcpyDeviceToHost, s));
+        CK(h, cudaMemcpyAsync(km.data(), omask, (size_t)nc_raw * 8, cudaMemcpyDeviceToHost, s));
     }
+#undef OBUF
     tm_off.stop();
+    CK(h, cudaMemcpyAsync(hl.data(), label, (size_t)M * 4, cudaMemcpyDeviceToHost, s));
+    CK(h, cudaMemcpyAsync(ho.data(), order, (size_t)M * 4, cudaMemcpyDeviceToHost, s));
+    CK(h, cudaMemcpyAsync(hoff.data(), cloff, hoff.size() * 4, cudaMemcpyDeviceToHost, s));
+    std::vector<int64_t> ids(M);
+    CK(h, cudaMemcpyAsync(ids.data(), P.id, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
     CK(h, cudaStreamSynchronize(s));
     if (h->timing) drain_timing(h);
-    CK(h, cudaMemcpy(hl.data(), label.p, (size_t)M * 4, cudaMemcpyDeviceToHost));
-    CK(h, cudaMemcpy(ho.data(), order.p, (size_t)M * 4, cudaMemcpyDeviceToHost));
-    CK(h, cudaMemcpy(hoff.data(), cloff.p, hoff.size() * 4, cudaMemcpyDeviceToHost));
-    CK(h, cudaMemcpy(h->off_core.data(), core.p, (size_t)M, cudaMemcpyDeviceToHost));
-    CK(h, cudaMemcpy(h->off_nbr.data(), nbr.p, h->off_nbr.size() * 4, cudaMemcpyDeviceToHost));
-    CK(h, cudaMemcpy(h->off_wnbr.data(), wnbr.p, h->off_wnbr.size() * 4, cudaMemcpyDeviceToHost));
-    CK(h, cudaMemcpy(h->off_submask.data(), submask.p, (size_t)M * 8, cudaMemcpyDeviceToHost));
-    std::vector<int64_t> ids;
-    if ((rc = pcore_ids_host(h, M, ids))) return rc;
     // keep clusters whose weight is > 0 (predecon.py:83); relabel
     std::vector<int32_t> remap(nc_raw, -1);
     for (int c = 0; c < nc_raw; ++c) {
@@ -1783,15 +1606,26 @@ int ccb_export_clusters(ccb_handle *h, int64_t *off, int64_t *members, double *w
 int ccb_export_offline(ccb_handle *h, uint8_t *core, uint8_t *nbr, uint8_t *wnbr, double *subw) {
     if (!h) return fail(nullptr, CCB_EINVAL, "null handle");
     const int64_t M = h->off_M;
+    if (M == 0) return CCB_OK;
+    CK(h, cudaSetDevice(h->prm.device));
+    // read back from the offline workspace of the last ccb_offline (kept on the device until the next one)
     const int D = h->D, words = (int)((M + 31) / 32);
+    std::vector<uint8_t> hcore(M);
+    std::vector<uint32_t> hn((size_t)M * words), hw((size_t)M * words);
+    std::vector<uint64_t> hs(M);
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaMemcpy(hcore.data(), h->ob[ccb_handle::OB_CORE].p, (size_t)M, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(hn.data(), h->ob[ccb_handle::OB_NBR].p, hn.size() * 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(hw.data(), h->ob[ccb_handle::OB_WNBR].p, hw.size() * 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(hs.data(), h->ob[ccb_handle::OB_SUBMASK].p, (size_t)M * 8, cudaMemcpyDeviceToHost));
     for (int64_t p = 0; p < M; ++p) {
-        if (core) core[p] = h->off_core[p];
+        if (core) core[p] = hcore[p];
         for (int64_t q = 0; q < M; ++q) {
-            if (nbr) nbr[p * M + q] = (h->off_nbr[p * words + (q >> 5)] >> (q & 31)) & 1u;
-            if (wnbr) wnbr[p * M + q] = (h->off_wnbr[p * words + (q >> 5)] >> (q & 31)) & 1u;
+            if (nbr) nbr[p * M + q] = (hn[p * words + (q >> 5)] >> (q & 31)) & 1u;
+            if (wnbr) wnbr[p * M + q] = (hw[p * words + (q >> 5)] >> (q & 31)) & 1u;
         }
         if (subw)
-            for (int d = 0; d < D; ++d) subw[p * D + d] = ((h->off_submask[p] >> d) & 1ull) ? h->prm.k : 1.0;
+            for (int d = 0; d < D; ++d) subw[p * D + d] = ((hs[p] >> d) & 1ull) ? h->prm.k : 1.0;
     }
     return CCB_OK;
 }
@@ -2027,8 +1861,8 @@ int ccb_off_weighted(int32_t device, void *stream, const double *cen, int64_t M,
 }
 
 int ccb_off_clusters(int32_t device, void *stream, int64_t M, const uint32_t *wnbr, const uint8_t *core,
-                     const uint64_t *submask_all, double k, int64_t pi, int32_t *label, int32_t *order, int32_t *cl_off,
-                     int32_t *n_cl) {
+                     const uint64_t *submask_all, double k, int64_t pi, int32_t csr_min_m, int32_t *label, int32_t *order,
+                     int32_t *cl_off, int32_t *n_cl) {
     if (M < 0) return fail(nullptr, CCB_EINVAL, "bad arguments");
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
@@ -2041,7 +1875,7 @@ int ccb_off_clusters(int32_t device, void *stream, int64_t M, const uint32_t *wn
         return fail(nullptr, CCB_ENOMEM, "scratch allocation: %s", cudaGetErrorString(e));
     int nl = 0;
     const int rc = launch_off_clusters(nullptr, s, (int)M, wnbr, core, submask_all, k > 1.0, pi, cls, queue, label, order, cl_off,
-                                       n_cl, &nl);
+                                       n_cl, &nl, csr_min_m);
     cudaFreeAsync(cls, s);
     cudaFreeAsync(queue, s);
     return rc;

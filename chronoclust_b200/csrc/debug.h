@@ -1,0 +1,26 @@
+/*
+ * debug.h -- diagnostics of the DEBUG build (python chronoclust_b200/build.py --debug -> libchronoclust_b200_debug.so,
+ * compiled with -DCCB_DEBUG).  Not part of the product ABI: include/chronoclust_b200.h does not declare these symbols and
+ * libchronoclust_b200.so does not export them.
+ */
+#ifndef CHRONOCLUST_B200_DEBUG_H
+#define CHRONOCLUST_B200_DEBUG_H
+
+#include "../../include/chronoclust_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Per pcore key of the last k_bs_chain_p launch: out[key][8] = {members, replay cycles, replay waiting for data, replay in
+ * groups with a CONTESTED cell, CONTESTED cells, storer cycles, storer waiting, producer waiting}.  The first call
+ * switches the counters on. */
+int ccb_debug_chain(ccb_handle *h, int64_t *out, int32_t max_keys);
+/* Results become WRONG: 1 = the storer warps of k_bs_chain_p skip their global stores, 2 = skip the copies altogether
+ * (isolates the replay warp's own speed).  0 restores normal operation. */
+int ccb_debug_set(ccb_handle *h, int32_t mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -783,7 +783,12 @@ constexpr int BS_CHAINP_THREADS = 256;
 constexpr int BS_CHAINP_STORERS = 4; // warps 2, 3, 6, 7 (schedulers 2 and 3); warps 4 and 5 would share the replay
                                      // warp's / the producer's scheduler and exit at once
 
-__device__ int g_bs_dbg_mode = 0; // diagnostics only (ccb_debug_set): 1 = storers skip the global stores, 2 = skip the copies
+#ifdef CCB_DEBUG
+__device__ int g_bs_dbg_mode = 0; // diagnostics build only (csrc/debug.h): 1 = storers skip the global stores, 2 = skip the copies
+#define CCB_DBG(...) __VA_ARGS__
+#else
+#define CCB_DBG(...)
+#endif
 
 // Exact radius test of the tentative MC nv = v + a (mc_functions.py:45-56) for a CONTESTED cell, by the whole replay
 // warp (lane = record element).  Deliberately NOT inlined: the replay warp runs alone on its scheduler, so every cold
@@ -845,6 +850,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
     e.fetch();
     using Cfg = ChainPCfg<DP>;
     constexpr int NB = Cfg::NB, S = Cfg::S, GS = 8, NH = Cfg::NH, LSP = Cfg::LSP;
+    static_assert(NB == 32 || NB == 64, "the CONTESTED flags of a stage are gathered by one or two ballots");
     extern __shared__ __align__(128) unsigned char bs_smem[];
     double *xs = reinterpret_cast<double *>(bs_smem);              // [S][NB][LSP]
     int *ms = reinterpret_cast<int *>(xs + (size_t)S * NB * LSP);  // [S][NB]
@@ -876,13 +882,13 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
     __syncthreads();
     if (warp == 1) { // ---- producer
         if (lane == 0) {
-            long long tw = 0;
+            CCB_DBG(long long tw = 0;)
             for (int b = 0; b < nb; ++b) {
                 const int s = b % S;
                 if (b >= S) {
-                    const long long t0 = clock64();
+                    CCB_DBG(const long long t0 = clock64();)
                     mbar_wait(&empty[s], ((b / S) - 1) & 1);
-                    tw += clock64() - t0;
+                    CCB_DBG(tw += clock64() - t0;)
                 }
                 const int cnt = min(NB, n - b * NB);
                 const uint32_t bx = (uint32_t)cnt * LSP * 8u, bi = (uint32_t)((cnt + 3) & ~3) * 4u;
@@ -890,7 +896,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
                 tma_load_1d(xs + (size_t)s * NB * LSP, xg + (size_t)b * NB * LSP, bx, &full[s]);
                 tma_load_1d(ms + s * NB, pl + b * NB, bi, &full[s]);
             }
-            if (e.ws.dbg) e.ws.dbg[j * 8 + 7] = tw;
+            CCB_DBG(if (e.ws.dbg) e.ws.dbg[j * 8 + 7] = tw;)
         }
         return;
     }
@@ -910,17 +916,16 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         // The copy is instruction-bound (index arithmetic per element), hence four warps on the two other schedulers.
         constexpr int U = 4, L2 = LSP / 2, NST = BS_CHAINP_STORERS * 32; // records are L2 double2 wide
         const int st = (warp < 4 ? warp - 2 : warp - 4) * 32 + lane;
-        long long tw = 0;
-        const long long tbeg = clock64();
+        CCB_DBG(long long tw = 0; const long long tbeg = clock64();)
         for (int b = 0; b < nb; ++b) {
             const int s = b % S;
             {
-                const long long t0 = clock64();
+                CCB_DBG(const long long t0 = clock64();)
                 mbar_wait(&done[s], (b / S) & 1);
-                tw += clock64() - t0;
+                CCB_DBG(tw += clock64() - t0;)
             }
-            const int dbgm = g_bs_dbg_mode;
-            const int tot = dbgm == 2 ? 0 : min(NB, n - b * NB) * L2;
+            int tot = min(NB, n - b * NB) * L2;
+            CCB_DBG(const int dbgm = g_bs_dbg_mode; if (dbgm == 2) tot = 0;)
             const double2 *xb = reinterpret_cast<const double2 *>(xs + (size_t)s * NB * LSP);
             const int *mb = ms + s * NB;
             double2 *ver2 = reinterpret_cast<double2 *>(e.ws.ver);
@@ -939,20 +944,17 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if (e0 + NST * u < tot) {
-                        if (dbgm == 1) {
-                            if (val[u].x == 1.2345e300) ver2[off[u]] = val[u];
-                        } else {
-                            ver2[off[u]] = val[u];
-                        }
+                        CCB_DBG(if (dbgm == 1 && val[u].x != 1.2345e300) continue;)
+                        ver2[off[u]] = val[u];
                     }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
-        if (e.ws.dbg && warp == 2 && lane == 0) {
+        CCB_DBG(if (e.ws.dbg && warp == 2 && lane == 0) {
             e.ws.dbg[j * 8 + 5] = clock64() - tbeg;
             e.ws.dbg[j * 8 + 6] = tw;
-        }
+        })
         return;
     }
     // ---- replay (warp 0): lane owns elements lane + 32 h of the record
@@ -966,8 +968,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         else if (el == 2 * DP) x = e.P.w[j];
         v[h] = x;
     }
-    long long t_wait = 0, t_slow = 0, n_cont = 0;
-    const long long t_beg = clock64();
+    CCB_DBG(long long t_wait = 0, t_slow = 0, n_cont = 0; const long long t_beg = clock64();)
     // shared-window addresses as opaque registers: otherwise the compiler re-derives them from special registers
     // (S2UR / S2R, tens of cycles each) inside the loop, which a lone warp cannot hide
     uint32_t xs_lane = smem_u32(xs) + lane * 8, ms_base = smem_u32(ms);
@@ -976,95 +977,67 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
 #pragma unroll
     for (int h = 0; h < NH; ++h) st_ok[h] = lane + 32 * h < LSP;
 
-    constexpr int GF = NH == 1 ? 16 : 8; // cells per register batch of the clean-stage path
+    // ONE loop shape for every stage: groups of GS = 8 cells, the addends of group g + 1 are fetched from shared memory
+    // (two register sets) before the dependent adds of group g.  A group without CONTESTED cells is eight chained adds;
+    // a group with one takes its cells one by one from the same registers, the CONTESTED ones through the exact radius
+    // test on their tentative record -- a few hundred cycles for that cell and nothing extra for the rest of the stage.
+    // Loads are unguarded (a lane past the end of a record, or a group past the end of a ragged stage, reads stale data
+    // inside the ring); stores are predicated.
     for (int b = 0; b < nb; ++b) {
         const int s = b % S;
         {
-            const long long t0 = clock64();
+            CCB_DBG(const long long t0 = clock64();)
             mbar_wait(&full[s], (b / S) & 1);
-            t_wait += clock64() - t0;
+            CCB_DBG(t_wait += clock64() - t0;)
         }
         const int cnt = __shfl_sync(0xffffffffu, min(NB, n - b * NB), 0); // warp-uniform for the compiler, too
         const uint32_t xa = xs_lane + s * (NB * LSP * 8), ma = ms_base + s * (NB * 4);
-        // CONTESTED flags of the whole stage in one pass: lane l looks at cells 2 l and 2 l + 1
-        unsigned m_even, m_odd;
+        // CONTESTED flags of the whole stage: lane l looks at cells l and l + 32
+        unsigned c_lo, c_hi = 0u;
         {
-            int fx = 0, fy = 0;
-            if (2 * lane < NB) {
-                asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(fx), "=r"(fy) : "r"(ma + lane * 8));
-            }
-            m_even = __ballot_sync(0xffffffffu, fx < 0 && 2 * lane < cnt);
-            m_odd = __ballot_sync(0xffffffffu, fy < 0 && 2 * lane + 1 < cnt);
+            int f0, f1 = 0;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(f0) : "r"(ma + lane * 4));
+            if (NB > 32) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(f1) : "r"(ma + (lane + 32) * 4));
+            c_lo = __ballot_sync(0xffffffffu, f0 < 0 && lane < cnt);
+            if (NB > 32) c_hi = __ballot_sync(0xffffffffu, f1 < 0 && lane + 32 < cnt);
         }
-        if (cnt == NB && (m_even | m_odd) == 0u) {
-            // ---- CLEAN FULL STAGE: straight-line code, no branches.  Two register sets: the addends of batch k + 1
-            // are fetched from shared memory before the dependent adds of batch k.  Explicit shared-space accesses
-            // with immediate offsets; loads are unguarded (a lane past the end of a record reads its neighbour, always
-            // inside the ring), only the stores are predicated.
-            double A[GF][NH], B[GF][NH];
-            auto fetch = [&](double (&R)[GF][NH], int k) {
+        const int ng = (cnt + GS - 1) / GS;
+        double A[GS][NH], B[GS][NH];
+        auto fetch = [&](double (&R)[GS][NH], int g) {
+            const uint32_t ga = xa + g * (GS * LSP * 8);
 #pragma unroll
-                for (int q = 0; q < GF; ++q)
+            for (int q = 0; q < GS; ++q)
 #pragma unroll
-                    for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(xa + ((k * GF + q) * LSP + 32 * h) * 8);
-            };
-            auto chain = [&](double (&R)[GF][NH], int k) {
+                for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8);
+        };
+        auto chain = [&](double (&R)[GS][NH], int g) {
+            const uint32_t ga = xa + g * (GS * LSP * 8);
+            const unsigned cg = ((g < 4 ? c_lo : c_hi) >> (8 * (g & 3))) & 0xffu;
+            const int ncell = min(GS, cnt - g * GS);
+            if (cg == 0u && ncell == GS) {
 #pragma unroll
-                for (int q = 0; q < GF; ++q)
+                for (int q = 0; q < GS; ++q)
 #pragma unroll
                     for (int h = 0; h < NH; ++h) {
                         v[h] = dadd(v[h], R[q][h]);
-                        if (st_ok[h]) sts_f64(xa + ((k * GF + q) * LSP + 32 * h) * 8, v[h]);
+                        if (st_ok[h]) sts_f64(ga + (q * LSP + 32 * h) * 8, v[h]);
                     }
-            };
-            fetch(A, 0);
-#pragma unroll
-            for (int k = 0; k < NB / GF; k += 2) {
-                if (k + 1 < NB / GF) fetch(B, k + 1);
-                chain(A, k);
-                if (k + 1 < NB / GF) {
-                    if (k + 2 < NB / GF) fetch(A, k + 2);
-                    chain(B, k + 1);
-                }
+                return;
             }
-        } else {
-            // ---- stage with CONTESTED cells or a ragged tail, kept SMALL (one copy of each piece of code, see
-            // bs_radius_test): a clean full group of eight is a short chain through registers; any other group goes one
-            // cell at a time, and a CONTESTED cell takes the exact radius test on its tentative record
-            const long long t_s0 = clock64();
-            const int ng = (cnt + GS - 1) / GS;
-#pragma unroll 1
-            for (int g = 0; g < ng; ++g) {
-                const uint32_t ga = xa + g * (GS * LSP * 8);
-                const unsigned ge = (m_even >> (4 * g)) & 0xfu, go = (m_odd >> (4 * g)) & 0xfu;
-                const int ncell = min(GS, cnt - g * GS);
-                if ((ge | go) == 0u && ncell == GS) {
-                    double R[GS][NH];
+            CCB_DBG(const long long t_s0 = clock64();)
 #pragma unroll
-                    for (int q = 0; q < GS; ++q)
-#pragma unroll
-                        for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8);
-#pragma unroll
-                    for (int q = 0; q < GS; ++q)
-#pragma unroll
-                        for (int h = 0; h < NH; ++h) {
-                            v[h] = dadd(v[h], R[q][h]);
-                            if (st_ok[h]) sts_f64(ga + (q * LSP + 32 * h) * 8, v[h]);
-                        }
-                    continue;
-                }
-#pragma unroll 1
-                for (int q = 0; q < ncell; ++q) {
+            for (int q = 0; q < GS; ++q) {
+                if (q < ncell) { // warp-uniform
                     const uint32_t ra = ga + q * (LSP * 8);
                     double nv[NH];
 #pragma unroll
                     for (int h = 0; h < NH; ++h) {
-                        nv[h] = dadd(v[h], lds_f64(ra + 32 * h * 8));
+                        nv[h] = dadd(v[h], R[q][h]);
                         if (st_ok[h]) sts_f64(ra + 32 * h * 8, nv[h]);
                     }
                     bool keep = true;
-                    if ((((q & 1) ? go : ge) >> (q >> 1)) & 1u) {
-                        ++n_cont;
+                    if ((cg >> q) & 1u) {
+                        CCB_DBG(++n_cont;)
                         keep = bs_radius_test<DP, NH>(nv[0], ra, lane, D, nm.delta2, nm.eps2, nm.div_mode, nm.k, nm.wsel, scr);
                         if (lane == 0) {
                             int raw;
@@ -1078,18 +1051,28 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
                     }
                 }
             }
-            t_slow += clock64() - t_s0;
+            CCB_DBG(t_slow += clock64() - t_s0;)
+        };
+        fetch(A, 0);
+#pragma unroll 1
+        for (int g = 0; g < ng; g += 2) {
+            if (g + 1 < ng) fetch(B, g + 1);
+            chain(A, g);
+            if (g + 1 < ng) {
+                if (g + 2 < ng) fetch(A, g + 2);
+                chain(B, g + 1);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&done[s]); // release: the versions written above are visible to the storers
     }
-    if (e.ws.dbg && lane == 0) {
+    CCB_DBG(if (e.ws.dbg && lane == 0) {
         e.ws.dbg[j * 8 + 0] = n;
         e.ws.dbg[j * 8 + 1] = clock64() - t_beg;
         e.ws.dbg[j * 8 + 2] = t_wait;
         e.ws.dbg[j * 8 + 3] = t_slow;
         e.ws.dbg[j * 8 + 4] = n_cont;
-    }
+    })
 }
 
 // ---- outlier-side member lists: sort (key, cell) of the pcore-rejected cells --------------------------

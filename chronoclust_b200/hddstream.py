@@ -68,7 +68,11 @@ class _PointsView(object):
 
 
 class HDDStream(object):
-    def __init__(self, config, logger, device=0, wave=0, chunk=0, bsv_bmin=0, bsv_iters=0, bsv_stream=0):
+    # CUDA ordinal an unpickled instance comes back on (pickle cannot pass constructor arguments): app.run(device=n,
+    # restore_program=True) sets it before loading program_images/hddstream
+    restore_device = 0
+
+    def __init__(self, config, logger, device=0, chunk=0, bsv_bmin=0, bsv_iters=0, bsv_stream=0, off_csr_min_m=0):
         """config: dict with beta, delta, epsilon, lambda, k, mu, pi, omicron, upsilon (hddstream.py:30-67)."""
         self.config = config
         self.pi = None
@@ -89,10 +93,10 @@ class HDDStream(object):
         self.logger = logger if logger is not None else logging.getLogger("chronoclust_b200")
         self.dataset_size = 0
 
-        # engine knobs (never affect results): wave == 0 selects the block-speculative versioned commit, wave >= 1
-        # the single-CTA wave engine; chunk caps the block (or launch) length
-        self._device, self._wave, self._chunk = device, wave, chunk
-        self._bsv = (bsv_bmin, bsv_iters, bsv_stream)
+        # engine knobs (never affect results): chunk caps the block length of the ordered engine, bsv_* shape its blocks
+        # and rounds, off_csr_min_m moves the switch between the two formulations of the offline cluster growth
+        self._device, self._chunk = device, chunk
+        self._bsv = (bsv_bmin, bsv_iters, bsv_stream, off_csr_min_m)
         self._h = None
         self._views = _PointsView()
         self._lists = [None, None]  # cached Microcluster lists (pcore, outlier)
@@ -124,8 +128,9 @@ class HDDStream(object):
         self.config = state[18] if len(state) > 18 else None
         self.final_clusters = []
         self.logger = logging.getLogger("chronoclust_b200")
-        self._device, self._wave, self._chunk = 0, 0, 0
-        self._bsv = (0, 0, 0)
+        self._device = type(self).restore_device
+        self._chunk = 0
+        self._bsv = (0, 0, 0, 0)
         self._h = None
         self._views = _PointsView()
         self._lists = [None, None]
@@ -171,8 +176,8 @@ class HDDStream(object):
         L = _lib.lib()
         prm = _lib.Params(D=D, device=self._device, eps2=self.epsilon_squared, upsilon_eps=self.upsilon,
                           upsilon_eps2=self.upsilon ** 2, delta=self.delta, delta2=self.delta_squared, beta=self.beta,
-                          k=self.k, wave=self._wave, chunk=self._chunk, bsv_bmin=self._bsv[0], bsv_iters=self._bsv[1],
-                          bsv_stream=self._bsv[2])
+                          k=self.k, chunk=self._chunk, bsv_bmin=self._bsv[0], bsv_iters=self._bsv[1],
+                          bsv_stream=self._bsv[2], off_csr_min_m=self._bsv[3])
         h = C.c_void_p()
         rc = L.ccb_create(C.byref(prm), C.byref(h))
         if rc != 0:

@@ -79,14 +79,14 @@ class CudaStages:
         _lib.check(self.L.ccb_off_weighted(self.device, self.stream(), cen.data_ptr(), M, D, r0, r1, nbr.data_ptr(),
                                            submask_all.data_ptr(), k, E2, wnbr.data_ptr()))
 
-    def clusters(self, M, wnbr_all, core, submask_all, k, pi):
+    def clusters(self, M, wnbr_all, core, submask_all, k, pi, csr_min_m=0):
         t = self.torch
         label = t.empty(max(M, 1), dtype=t.int32, device=self.dev)
         order = t.empty(max(M, 1), dtype=t.int32, device=self.dev)
         cl_off = t.zeros(M + 2, dtype=t.int32, device=self.dev)
         ncl = t.zeros(1, dtype=t.int32, device=self.dev)
         _lib.check(self.L.ccb_off_clusters(self.device, self.stream(), M, wnbr_all.data_ptr(), core.data_ptr(),
-                                           submask_all.data_ptr(), k, pi, label.data_ptr(), order.data_ptr(),
+                                           submask_all.data_ptr(), k, pi, csr_min_m, label.data_ptr(), order.data_ptr(),
                                            cl_off.data_ptr(), ncl.data_ptr()))
         n = int(ncl.item())
         return label[:M].cpu().numpy(), order.cpu().numpy(), cl_off[:n + 1].cpu().numpy(), n

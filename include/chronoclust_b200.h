@@ -65,29 +65,23 @@ typedef struct {
     double delta2;       /* delta ** 2                            hddstream.py:49 */
     double beta;         /*                                       hddstream.py:50 */
     double k;            /*                                       hddstream.py:51 */
-    int32_t wave;        /* 0 = block-speculative versioned commit (default engine, csrc/engine.cuh);
-                            1..32 = single-CTA wave engine of that micro-batch width (1 = fully serial) */
-    int32_t chunk;       /* wave engine: max cells per ordered-commit launch; block-speculative engine: max cells
-                            per block; 0 = default */
-    int32_t bsv_bmin;    /* block-speculative engine: smallest block length; 0 = default (1024) */
-    int32_t bsv_iters;   /* block-speculative engine: refinement rounds per block before the exact prefix is committed;
+    int32_t chunk;       /* max cells per block of the ordered engine (rounded up to a multiple of 32); 0 = default 32768 */
+    int32_t bsv_bmin;    /* smallest block length; 0 = default (1024) */
+    int32_t bsv_iters;   /* refinement rounds per block before the exact prefix is committed;
                             0 = default (3 with stream launches, 8 inside the CUDA graph) */
-    int32_t bsv_stream;  /* block-speculative engine: 1 = plain stream launches instead of the CUDA graph with device-driven
-                            WHILE nodes (the graph is also bypassed while ccb_enable_timing is on) */
-    int32_t reserved0;
+    int32_t bsv_stream;  /* 1 = plain stream launches instead of the CUDA graph with device-driven WHILE nodes (the graph
+                            is also bypassed while ccb_enable_timing is on) */
+    int32_t off_csr_min_m; /* offline cluster growth: number of potential microclusters from which the CSR formulation
+                              (isolated microclusters in parallel, lists instead of bit rows) replaces the single-CTA
+                              bit-row scan; 0 = default (2048).  Both give identical results. */
+    int32_t reserved0;   /* must be 0 */
 } ccb_params;
 
-/* Counters since ccb_create (monotonic); all int64. */
+/* Counters since ccb_create (monotonic); all int64.  None of the engine knobs above ever changes a result; the
+ * bsv_* counters describe how the ordered engine got there. */
 typedef struct {
     int64_t points;          /* cells ingested */
-    int64_t chunks;          /* ordered-commit launches (kernel 2a) */
-    int64_t waves;           /* micro-batches executed inside kernel 2a */
-    int64_t wave_rollbacks;  /* micro-batches cut short by a failed verification */
-    int64_t rejects;         /* cells that went on to the outlier stage */
-    int64_t resolver_calls;  /* kernel 2b launches */
-    int64_t resolver_cuts;   /* times kernel 2b stopped because every snapshot candidate was stale */
     int64_t nearest_pairs;   /* (cell x outlier MC) distances evaluated by kernel 1 */
-    int64_t pcore_pairs;     /* (cell x pcore MC) distances evaluated by kernel 2a (incl. verification) */
     int64_t upgrades, created, downgraded, deleted;
     int64_t kernel_launches; /* every kernel this library launched */
     int64_t borderline_pairs; /* offline pairs resolved on the host through dnrm2 */
@@ -111,26 +105,14 @@ const char *ccb_last_error(const ccb_handle *h);
 /* cudaStream_t the handle launches on (for CUDA-event timing by the caller). */
 void *ccb_stream(ccb_handle *h);
 int ccb_get_stats(const ccb_handle *h, ccb_stats *out);
-/* Diagnostics: cycles thread 0 of kernel 2a spent in each phase (A, B, C, D, E, commit) since ccb_reset. */
-int ccb_debug_phase_cycles(ccb_handle *h, int64_t out[8]);
-/* Diagnostics of the block-speculative engine's pcore replay kernel (k_bs_chain_p), last launch, per pcore key:
- * out[key][8] = {members, replay cycles, replay waiting for data, replay in groups with a CONTESTED cell,
- * CONTESTED cells, storer cycles, storer waiting, producer waiting}.  The first call switches the counters on. */
-int ccb_debug_chain(ccb_handle *h, int64_t *out, int32_t max_keys);
-/* Diagnostics only, results become WRONG: 1 = the storer warps of k_bs_chain_p skip their global stores, 2 = skip the
- * copies altogether (isolates the replay warp's own speed).  0 restores normal operation.
- * mode >= 1000 is not a diagnostic: the offline cluster growth uses its CSR formulation (isolated microclusters in
- * parallel, lists instead of bit rows) for M >= mode - 1000 potential microclusters (default 2048; process-wide).
- * Both formulations give identical results; the tests run the reference's offline goldens through each. */
-int ccb_debug_set(ccb_handle *h, int32_t mode);
 /* Forgets every microcluster and both id counters (a new run on the same device / stream). */
 int ccb_reset(ccb_handle *h);
 
 /* Optional GPU timing per kernel category, taken with CUDA events on the handle's stream (this is
  * what bench.py reads for the live roofline).  ms / launches: arrays of CCB_NCAT. */
-#define CCB_CAT_PCORE 0   /* kernel 2   ordered replay of the pcore keys (k_bs_chain_p; wave engine: k_pcore_stage) */
+#define CCB_CAT_PCORE 0   /* kernel 2   ordered replay of the pcore keys (k_bs_chain_p) */
 #define CCB_CAT_NEAREST 1 /* kernel 1   k_nearest (+ merge) on the cells that may reach the outlier stage */
-#define CCB_CAT_RESOLVE 2 /* kernel 2   exact verification (k_bs_verify_p/o; wave engine: k_resolve) */
+#define CCB_CAT_RESOLVE 2 /* kernel 2   exact verification (k_bs_verify_p/o) */
 #define CCB_CAT_MAINT 3   /* kernel 3   k_maint_plan + k_maint_gather */
 #define CCB_CAT_OFFLINE 4 /* kernel 4   offline pipeline (device part) */
 #define CCB_CAT_MISC 5    /* small helpers */
@@ -242,10 +224,11 @@ int ccb_off_weighted(int32_t device, void *stream, const double *cen, int64_t M,
                      const uint32_t *nbr, const uint64_t *submask_all, double k, double E2, uint32_t *wnbr);
 /* Offline stage 4: ordered cluster growth over the full weighted-neighbour matrix wnbr [M][words].
  * label [M] (-1 none), order [M] = MC indices in claim order grouped by cluster, cl_off [M+1], n_cl [1].
+ * csr_min_m: as ccb_params.off_csr_min_m (0 = default).
  * Clusters whose accumulated weight is not > 0 are dropped by the caller (predecon.py:83). */
 int ccb_off_clusters(int32_t device, void *stream, int64_t M, const uint32_t *wnbr, const uint8_t *core,
-                     const uint64_t *submask_all, double k, int64_t pi, int32_t *label, int32_t *order, int32_t *cl_off,
-                     int32_t *n_cl);
+                     const uint64_t *submask_all, double k, int64_t pi, int32_t csr_min_m, int32_t *label, int32_t *order,
+                     int32_t *cl_off, int32_t *n_cl);
 
 #ifdef __cplusplus
 }

@@ -43,14 +43,8 @@ def run_against_golden(z, Xs, what, **kw):
     return h
 
 
-@pytest.mark.parametrize("wave", [32, 1, 7])
-@pytest.mark.parametrize("name", STRESS_NAMES)
-def test_stress_matches_reference(name, wave):
-    z = load(f"stress_{name}.npz")
-    run_against_golden(z, stress_inputs(z), f"{name}/wave{wave}", wave=wave)
-
-
-# block-speculative engine (wave == 0): block length cap / smallest block / refinement rounds never change results
+# the ordered engine's knobs -- block length cap / smallest block / refinement rounds / graph vs stream launches -- never
+# change results
 BSV_KNOBS = [dict(), dict(chunk=96, bsv_bmin=32, bsv_iters=1), dict(chunk=2048, bsv_bmin=64, bsv_iters=2),
              dict(chunk=512, bsv_bmin=512, bsv_iters=6), dict(bsv_stream=1), dict(chunk=300, bsv_bmin=16, bsv_stream=1)]
 
@@ -92,17 +86,7 @@ def test_offline_sets_match_predecon(csr_min_m):
     """24 randomised pcore sets pushed through the reference's PreDeCon.run (predecon.py:49-120): neighbourhoods,
     subspace vectors, weighted neighbourhoods and the ordered cluster growth -- the latter through both of its
     device formulations (bit-row scan for small M, isolated-MC pre-pass + CSR lists for large M)."""
-    from chronoclust_b200 import _lib as _l
-
-    z = load("offline_sets.npz")
-    try:
-        _run_offline_sets(z, csr_min_m)
-    finally:
-        hh = make({"beta": 0.0, "delta": 0.5, "epsilon": 1.0, "lambda": 0, "k": 4.0, "mu": 0.0, "pi": 0, "omicron": 0.0,
-                   "upsilon": 1.0})
-        hh.dataset_dimensionality = 3
-        hh._ensure_handle(3)
-        _l.check(_l.lib().ccb_debug_set(hh._h, 1000 + 2048), hh._h)
+    _run_offline_sets(load("offline_sets.npz"), csr_min_m)
 
 
 def _run_offline_sets(z, csr_min_m):
@@ -118,13 +102,12 @@ def _run_offline_sets(z, csr_min_m):
             mu = float((wc.min() + wn_.max()) / 2) if len(wc) and len(wn_) else (0.0 if len(wc) else 1e300)
         cfg = {"beta": 0.0, "delta": float(delta), "epsilon": 1e150, "lambda": 0, "k": float(k), "mu": 0.0, "pi": pi,
                "omicron": 0.0, "upsilon": float(E) / 1e150}
-        h = make(cfg)
+        h = make(cfg, off_csr_min_m=csr_min_m if csr_min_m else 1)
         assert h.upsilon == float(E), "test construction: upsilon*epsilon must reproduce E exactly"
         h.dataset_dimensionality = D
         h._ensure_handle(D)
         h.pi, h.mu, h.omicron = pi, mu, 0.0
         from chronoclust_b200 import _lib
-        _lib.check(_lib.lib().ccb_debug_set(h._h, 1000 + csr_min_m), h._h)
         _lib.check(_lib.lib().ccb_begin_timepoint(h._h, mu, 0.0, pi, 0, 1.0), h._h)
         h.import_arrays(0, ids, ids, w, cf1, cf2, cen, np.ones((M, D)))
         h.offline_clustering(0)
@@ -443,18 +426,10 @@ def test_cluster_growth_formulations_agree():
     st = CudaStages(0)
     twn = torch.from_numpy(wn.view(np.int32)).cuda()
     tcore, tsub = torch.from_numpy(core).cuda(), torch.from_numpy(sub).cuda()
-    h = make({"beta": 0.0, "delta": 0.5, "epsilon": 1.0, "lambda": 0, "k": 4.0, "mu": 0.0, "pi": 0, "omicron": 0.0,
-              "upsilon": 1.0})
-    h.dataset_dimensionality = 3
-    h._ensure_handle(3)
     res = []
-    try:
-        for min_m in (10 ** 8, 0):
-            _lib.check(_lib.lib().ccb_debug_set(h._h, 1000 + min_m), h._h)
-            lab, order, cl_off, ncl = st.clusters(M, twn, tcore, tsub, 4.0, pi)
-            res.append((lab.copy(), order[:cl_off[-1]].copy(), cl_off.copy(), ncl))
-    finally:
-        _lib.check(_lib.lib().ccb_debug_set(h._h, 1000 + 2048), h._h)
+    for min_m in (10 ** 8, 1):
+        lab, order, cl_off, ncl = st.clusters(M, twn, tcore, tsub, 4.0, pi, csr_min_m=min_m)
+        res.append((lab.copy(), order[:cl_off[-1]].copy(), cl_off.copy(), ncl))
     (l0, o0, c0, n0), (l1, o1, c1, n1) = res
     assert n0 == n1 and n0 > 100
     assert (c0 == c1).all() and (o0 == o1).all() and (l0 == l1).all()
@@ -666,3 +641,117 @@ def test_device_scaler_matches_sklearn():
         assert len(ca) == len(cb) and all(list(m1) == list(m2) and w1 == w2 for (m1, w1, *_), (m2, w2, *_) in zip(ca, cb))
         pa, pb = a.pcore_MC[0].points, b.pcore_MC[0].points
         assert list(pa.keys()) == list(pb.keys()) and pa[next(iter(pa))] == pb[next(iter(pb))]
+
+
+# ---- BASELINE sizes against the oracle (the benched configuration itself must be compared) -------------
+def _assert_same_as_oracle(h, o, what):
+    assert (h.last_assignment == o.assign_uid).all(), \
+        f"{what}: {(h.last_assignment != o.assign_uid).sum()} assignments differ, first at " \
+        f"{np.flatnonzero(h.last_assignment != o.assign_uid)[:5]}"
+    assert (h.last_stage == o.stage).all(), f"{what}: per-cell stage differs"
+    for which in (0, 1):
+        e, got = o.export(which), h.export_arrays(which)
+        assert len(got[0]) == len(e), f"{what}: list {which} has {len(got[0])} MCs, oracle {len(e)}"
+        assert (got[0] == e.ids).all() and (got[1] == e.uids).all(), f"{what}: list {which} ids / order differ"
+        for n, g, x in zip(("w", "cf1", "cf2", "cen", "pref"), got[2:], (e.w, e.cf1, e.cf2, e.cen, e.pref)):
+            assert bits_equal(g, x), f"{what}: list {which} {n} not bit-identical"
+    assert tuple(h.counts()[2:]) == tuple(o.counters), f"{what}: id counters differ"
+    oc, hc = o.clusters(), clusters_of(h)
+    assert len(oc) == len(hc), f"{what}: {len(hc)} clusters, oracle {len(oc)}"
+    for c, ((m1, w1, *r1), (m2, w2, *r2)) in enumerate(zip(hc, oc)):
+        assert list(m1) == list(m2) and w1 == w2, f"{what}: cluster {c} members / weight differ"
+        assert all(bits_equal(p, q) for p, q in zip(r1, r2)), f"{what}: cluster {c} statistics not bit-identical"
+
+
+@pytest.mark.parametrize("cfgname,T,scale,over", [
+    ("C2", 5, 1.0, {}),                 # BASELINE configs[1] at full size: 1e6 cells x 12 markers x 5 timepoints
+    ("C3", 2, 1.0, {}),                 # BASELINE configs[2] at full N: 2e6 cells x 40 markers (2 timepoints: oracle ~30 s)
+    ("C2", 2, 0.5, {"epsilon": 0.04}),  # BASELINE configs[4] corner: the saturated regime (round / capacity cuts); the
+                                        # oracle needs 45 s for ONE full timepoint there, hence 5e5 cells x 2
+    ("C2", 2, 1.0, {"epsilon": 0.045, "upsilon": 4, "beta": 0.8}),  # another grid corner: late upgrades, long cold start
+], ids=["C2-full", "C3-fullN-2tp", "C5-eps0.04", "C5-beta0.8"])
+def test_baseline_sizes_vs_oracle(cfgname, T, scale, over):
+    """The CUDA path against the (reference-pinned) oracle at BASELINE.json's own sizes, bit for bit after every
+    timepoint: per-cell assignment and stage, both lists (order, ids, W / CF1 / CF2 / centroid / preference vector), id
+    counters, every cluster (claim order, sums).  These sizes reach what the fixtures cannot: 20-35 k outlier MCs,
+    kernel 1 over > 32 slabs, store growth inside the graph loop, need-list growth relaunches, capacity / round cuts."""
+    from chronoclust_b200.synth import CONFIGS, config_params, gen
+    from oracle.oracle import OracleHDDStream
+
+    N, D, _, Cn, seed, _, _ = CONFIGS[cfgname]
+    N = int(N * scale)
+    cfg = dict(config_params(cfgname), **over)
+    Xs = gen(N, D, T, Cn, seed)
+    h, o = make(cfg), OracleHDDStream(cfg)
+    for t, X in enumerate(Xs):
+        h.online_microcluster_maintenance(X, t)
+        o.online_microcluster_maintenance(X, t)
+        _assert_same_as_oracle(h, o, f"{cfgname}{over} t{t}")
+    st = h.stats()
+    print(cfgname, over, {k: v for k, v in st.items() if v})
+    assert st["points"] == N * T
+
+
+def test_offline_c4_shape_vs_oracle():
+    """The offline phase at M = 8192 potential microclusters x 40 markers from the C4 generator against the
+    oracle's PreDeCon restatement: column slabs of kernel 4b, the guard band on real data, CSR growth with thousands of
+    clusters, claim order and merged sums -- through ccb_offline, i.e. what HDDStream.offline_clustering calls."""
+    from chronoclust_b200 import _lib
+    from chronoclust_b200.synth import gen_offline_stress
+    from oracle.oracle import OracleHDDStream, _p
+    from oracle.oracle import lib as olib
+
+    M, D = 8192, 40
+    cen, w, _core = gen_offline_stress(M, D)
+    rng = np.random.default_rng(11)
+    cf1 = cen * w[:, None]
+    cf2 = (cen * cen + rng.uniform(1e-5, 4e-3, size=(M, D))) * w[:, None]  # variances on both sides of delta^2
+    ids = np.arange(M, dtype=np.int64)
+    cfg = {"beta": 0.0, "delta": 0.05, "epsilon": 1e150, "lambda": 0, "k": 4.0, "mu": 0.0, "pi": D, "omicron": 0.0,
+           "upsilon": 0.3 / 1e150}
+    mu = 20.0
+    o = OracleHDDStream(cfg)
+    o._ensure(D)
+    L = olib()
+    for i in range(M):
+        L.cco_import_mc(o._h, 0, int(ids[i]), int(ids[i]), float(w[i]), _p(np.ascontiguousarray(cf1[i])),
+                        _p(np.ascontiguousarray(cf2[i])), _p(np.ascontiguousarray(cen[i])), _p(np.ones(D)))
+    L.cco_set_thresholds(o._h, mu, 0.0, D)
+    o.offline_clustering()
+    oc = o.clusters()
+    for csr in (0, 10 ** 8):  # CSR formulation (default at this M) and the bit-row scan
+        h = make(cfg, off_csr_min_m=csr)
+        assert h.upsilon == 0.3
+        h.dataset_dimensionality = D
+        h._ensure_handle(D)
+        h.pi, h.mu, h.omicron = D, mu, 0.0
+        _lib.check(_lib.lib().ccb_begin_timepoint(h._h, mu, 0.0, D, 0, 1.0), h._h)
+        h.import_arrays(0, ids, ids, w, cf1, cf2, cen, np.ones((M, D)))
+        h.offline_clustering(0)
+        hc = clusters_of(h)
+        assert len(hc) == len(oc) and len(hc) > 1000
+        for c, ((m1, w1, *r1), (m2, w2, *r2)) in enumerate(zip(hc, oc)):
+            assert list(m1) == list(m2) and w1 == w2, f"cluster {c} (csr_min_m={csr})"
+            assert all(bits_equal(p, q) for p, q in zip(r1, r2)), f"cluster {c} statistics (csr_min_m={csr})"
+    assert max(len(m) for m, *_ in oc) > 1
+
+
+def test_colminmax_covers_every_element():
+    """with D = 12 / D = 40 and N * D far above the grid size, every flat index must be visited -- the extreme
+    values are planted exactly where a stride rounded UP to a multiple of D would skip (indices [threads, stride))."""
+    import torch
+    from chronoclust_b200 import _lib
+
+    threads = 148 * 8 * 256
+    for D, N in ((12, 200_003), (40, 100_001), (7, 70_001)):
+        X = np.random.default_rng(D).uniform(-1.0, 1.0, size=(N, D))
+        up = (threads + D - 1) // D * D
+        for w in range(3):  # a few stride windows
+            for e in range(threads + w * up, min(up + w * up, N * D)):
+                X[e // D, e % D] = 5.0 + e if (e % 2) else -5.0 - e
+        t = torch.from_numpy(X).cuda()
+        mn = torch.empty(D, dtype=torch.float64, device="cuda")
+        mx = torch.empty(D, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().ccb_colminmax(0, None, t.data_ptr(), N, D, D, mn.data_ptr(), mx.data_ptr()))
+        torch.cuda.synchronize()
+        assert bits_equal(mn.cpu().numpy(), X.min(axis=0)) and bits_equal(mx.cpu().numpy(), X.max(axis=0)), f"D={D}"
