@@ -79,7 +79,7 @@ struct ccb_handle {
     BsCtl *d_bc = nullptr, *h_bc = nullptr;
     BsWs ws{};
     std::vector<void *> ws_allocs;
-    void *ws_tiles[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *ws_tiles[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int32_t *ws_first = nullptr;
     int ws_first_cap = 0;
     double *d_bs_tk_dist_slab = nullptr;
@@ -417,7 +417,7 @@ int ensure_bs_ws(ccb_handle *h) {
         BsWs &w = h->ws;
         w.bmax = B;
 #define WSA(field, n) if ((rc = ws_alloc(h, w.field, (n)))) return rc
-        WSA(pcand, B); WSA(ospec, B); WSA(tkpos, B); WSA(dec, B); WSA(eff, B); WSA(newrank, B); WSA(pend, B);
+        WSA(pcand, B); WSA(ospec, B); WSA(tkpos, B); WSA(dec, B); WSA(eff, B); WSA(newrank, B); WSA(pend, B); WSA(vpos, B);
         WSA(pflag, B); WSA(prej, B); WSA(upf, B);
         w.dp = h->DP;
         w.lsp = 2 * h->DP + 2;
@@ -426,6 +426,7 @@ int ensure_bs_ws(ccb_handle *h) {
         WSA(nrows, BS_RMAX); WSA(ncell, BS_RMAX);
         WSA(tk_dist, (size_t)BS_RMAX * BS_TOPK); WSA(tk_idx, (size_t)BS_RMAX * BS_TOPK);
         WSA(hkey, BS_RMAX + 1); WSA(hoff, BS_RMAX + 2); WSA(omem, BS_RMAX + 1); WSA(hrank, BS_RMAX + 2);
+        WSA(hfirst, BS_RMAX + 1);
 #undef WSA
         if ((rc = ws_alloc(h, h->d_bs_tk_dist_slab, (size_t)BS_RMAX * BS_MAX_SLABS * BS_TOPK))) return rc;
         if ((rc = ws_alloc(h, h->d_bs_tk_idx_slab, (size_t)BS_RMAX * BS_MAX_SLABS * BS_TOPK))) return rc;
@@ -446,12 +447,14 @@ int ensure_bs_ws(ccb_handle *h) {
         CK(h, cudaMalloc(&h->ws_tiles[3], ((size_t)stride + 2) * 4));
         CK(h, cudaMalloc(&h->ws_tiles[4], npl * 4));
         CK(h, cudaMalloc(&h->ws_tiles[5], npl * ds * 8));
+        CK(h, cudaMalloc(&h->ws_tiles[6], npl * ds * 8));
         h->ws.tilecnt = (int32_t *)h->ws_tiles[0];
         h->ws.tbase = (int32_t *)h->ws_tiles[1];
         h->ws.poff = (int32_t *)h->ws_tiles[2];
         h->ws.pcnt = (int32_t *)h->ws_tiles[3];
         h->ws.plist = (int32_t *)h->ws_tiles[4];
         h->ws.xg = (double *)h->ws_tiles[5];
+        h->ws.verp = (double *)h->ws_tiles[6];
         h->ws.mp_stride = stride;
         if (h->ws.dbg) {
             cudaFree(h->ws.dbg);
@@ -563,7 +566,7 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     }
     {
         Timed tm(h, CCB_CAT_RESOLVE);
-        CCB_DISPATCH_DP(h->DP, { k_bs_verify_o<kDP><<<148 * 2, BS_THREADS, 0, s>>>(e); })
+        CCB_DISPATCH_DP(h->DP, { k_bs_verify_o<kDP><<<148 * 4, BS_THREADS, 0, s>>>(e); })
     }
     {
         Timed tm(h, CCB_CAT_DECIDE);
@@ -1046,6 +1049,7 @@ int ccb_get_stats(const ccb_handle *h, ccb_stats *out) {
         out->bsv_outlier_stage_cells = bb.rejects + b.rejects;
         out->bsv_replayed_cells = bb.replayed + b.replayed;
         out->bsv_light_rounds = bb.rounds_light + b.rounds_light;
+        out->bsv_serial_cells = bb.serial_cells + b.serial_cells;
         out->nearest_pairs += bb.pairs + b.pairs;
     }
     return CCB_OK;
@@ -1100,7 +1104,7 @@ int ccb_reset(ccb_handle *h) {
         BsCtl &bb = h->bc_base;
         bb.blocks += b.blocks, bb.iters += b.iters, bb.mismatches += b.mismatches, bb.cuts_unknown += b.cuts_unknown;
         bb.cuts_iter += b.cuts_iter, bb.cuts_cap += b.cuts_cap, bb.tk_late += b.tk_late, bb.rejects += b.rejects;
-        bb.replayed += b.replayed, bb.pairs += b.pairs, bb.rounds_light += b.rounds_light;
+        bb.replayed += b.replayed, bb.pairs += b.pairs, bb.rounds_light += b.rounds_light, bb.serial_cells += b.serial_cells;
         const int32_t keep_B = b.next_B;
         memset(h->h_bc, 0, sizeof(BsCtl));
         h->h_bc->next_B = keep_B;

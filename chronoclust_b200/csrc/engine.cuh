@@ -62,8 +62,11 @@ struct BsCtl {
     int32_t need_grow, done;
     int32_t ticket; // k_bs_pscan: CTAs finished (last one computes the key offsets)
     int32_t pclean; // refinement round whose pcore side (candidates, CONTESTED flags, accepts) is that of the round before
+    int32_t m0, up0; // this round: first cell whose exact decision differs from the speculation / first upgrading cell
+                     // (atomicMin by the verify kernels, consumed and reset by k_bs_decide; INT_MAX = none)
     int64_t blocks, iters, mismatches, cuts_unknown, cuts_iter, cuts_cap, tk_late, rejects, replayed, pairs;
     int64_t rounds_light; // refinement rounds that re-ran the outlier side only
+    int64_t serial_cells; // sum over the pcore replays of the LONGEST chain's members: the dependent-add floor of kernel 2
 };
 
 struct BsWs {
@@ -75,10 +78,13 @@ struct BsWs {
     int32_t *tilecnt, *tbase, *poff; // [ntiles + 1][mp_stride], [ntiles + 1][mp_stride], [mp_stride + 1]
     int32_t *pcnt;                   // [mp_stride + 1] candidates of every pcore key (poff is padded to multiples of 4)
     double *xg;                      // [bmax + 4 * mp_stride][lsp] ADDEND records in plist order: x, x*x, 1.0 (layout of ver)
+    double *verp;                    // [bmax + 4 * mp_stride][lsp] VERSION records of the pcore chains, in plist order
+    int32_t *vpos;                   // [bmax] plist position of every pcore candidate
     int32_t *nrows, *ncell;          // [BS_RMAX] absolute row / block-relative cell of the need list
     double *tk_dist;
     int32_t *tk_idx; // [BS_RMAX][BS_TOPK]
     int32_t *hkey, *hoff, *omem, *hrank; // hrank[q]: real creations before key hnew0 + q
+    int32_t *hfirst;                     // [BS_RMAX + 1] first member of every outlier-side key
     int32_t *firstmember; // [O.cap], INT_MAX = unmodified in this block
     int64_t *dbg; // optional [mp_stride][8] per-key cycle counters of k_bs_chain_p (diagnostics), or nullptr
     int32_t mp_stride, bmax, dp, lsp;
@@ -228,6 +234,7 @@ __global__ void k_bs_begin(Eng e) {
     BsCtl *bc = e.bc;
     bc->active = 0;
     bc->tk_lo = bc->tk_hi = 0; // an idle block must not leave kernel 1 any work
+    bc->m0 = bc->up0 = INT_MAX;
     do {
         if (bc->done || bc->need_grow) break;
         if (bc->pos >= bc->N) {
@@ -482,7 +489,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_tilecnt(Eng e) {
 __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
     e.fetch();
     __shared__ int s_warp[33];
-    __shared__ int s_last;
+    __shared__ int s_last, s_max;
     BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return;
     const int Mp = bc->Mp, stride = e.ws.mp_stride;
@@ -509,17 +516,25 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
     // exclusive scan of the totals, each rounded up to a multiple of 4 entries so that every key's segment of
     // plist / xg starts 16-byte aligned (bulk-copy requirement of the chain kernel)
     carry = 0;
+    if (threadIdx.x == 0) s_max = 0;
+    int mx = 0;
     for (int j0 = 0; j0 < Mp; j0 += BS_CTA1) {
         const int jj = j0 + threadIdx.x;
-        const int v = jj < Mp ? ((((volatile int32_t *)e.ws.pcnt)[jj] + 3) & ~3) : 0;
+        const int raw = jj < Mp ? ((volatile int32_t *)e.ws.pcnt)[jj] : 0;
+        mx = max(mx, raw);
+        const int v = (raw + 3) & ~3;
         int total;
         const int ex = block_exclusive_scan_1024(v, s_warp, total);
         if (jj < Mp) e.ws.poff[jj] = carry + ex;
         carry += total;
     }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&s_max, mx);
+    __syncthreads();
     if (threadIdx.x == 0) {
         e.ws.poff[Mp] = carry;
         bc->ticket = 0;
+        bc->serial_cells += s_max;
     }
 }
 
@@ -540,6 +555,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
         const int rank = __popc(peers & lanemask_lt());
         pos = e.ws.poff[c] + e.ws.tilecnt[(size_t)t * e.ws.mp_stride + c] + rank;
         e.ws.plist[pos] = i | (e.ws.pflag[i] ? (int)0x80000000 : 0);
+        e.ws.vpos[i] = pos;
     }
     // the warp writes the 32 records together, lane = element of the record (coalesced rows); four records are in
     // flight at a time so that the row loads overlap instead of paying one global-memory latency per record
@@ -744,10 +760,10 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_chain_o(Eng e) {
 //             (cp.async.bulk + mbarrier complete_tx);
 //   replay    warp 0, lane = record element: a <- LDS, v += a, v -> STS over the addend it just consumed (the stage
 //             now holds the VERSION after every cell);
-//   storers   two warps copy every version record to ver[cell] (scattered 16 D + 16 byte rows: plain coalesced
-//             stores -- one bulk TMA store per record caps the kernel at the TMA unit's per-operation rate) and
-//             release the stage.
-// A single warp cannot hide instruction latency, so everything that is not the dependent add lives in the other two.
+//   store     one thread sends every finished stage -- 64 consecutive VERSION records of the key -- to verp[plist position]
+//             with ONE bulk TMA store and releases the stage (k_bs_derive_p hands the records on to ver[cell], cell-parallel).
+// A single warp cannot hide instruction latency, so everything that is not the dependent add lives elsewhere, and the
+// replay code itself is written for in-order issue: one LDS and one STS hide in the shadow of every dependent DADD.
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -779,9 +795,9 @@ struct ChainPCfg {
     static constexpr int S = DP <= 48 ? 8 : 6;
     static constexpr size_t SMEM = (size_t)S * NB * (LSP * 8 + 4) + 3 * S * 8 + 2 * DP * 8 + 128;
 };
-constexpr int BS_CHAINP_THREADS = 256;
-constexpr int BS_CHAINP_STORERS = 4; // warps 2, 3, 6, 7 (schedulers 2 and 3); warps 4 and 5 would share the replay
-                                     // warp's / the producer's scheduler and exit at once
+// warp 0 replays, lane 0 of warp 1 streams the addends in, lane 0 of warp 2 streams the versions out, warp 4 (the replay
+// warp's scheduler) warms the instruction cache of the rare path and exits; warp 3 only fills the CTA up
+constexpr int BS_CHAINP_THREADS = 160;
 
 #ifdef CCB_DEBUG
 __device__ int g_bs_dbg_mode = 0; // diagnostics build only (csrc/debug.h): 1 = storers skip the global stores, 2 = skip the copies
@@ -845,18 +861,61 @@ __device__ __noinline__ bool bs_radius_test(double nv0, uint32_t rec_addr, int l
     return r2 <= eps2;
 }
 
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// one group of GS = 8 cells that holds a CONTESTED cell or is the ragged tail of the key: cell by cell, kept out of line
+// (one copy; see bs_radius_test)
+template <int NH>
+struct ChainRec {
+    double v[NH];
+};
+template <int DP, int NH>
+__device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint32_t ga, uint32_t ma_g, unsigned cg, int ncell,
+                                                         int lane, int D, double delta2, double eps2, int div_mode, double k,
+                                                         double wsel, double *scr, uint8_t *prej) {
+    constexpr int LSP = 2 * DP + 2;
+    double(&v)[NH] = rec.v;
+    bool st_ok[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) st_ok[h] = lane + 32 * h < LSP;
+#pragma unroll 1
+    for (int q = 0; q < ncell; ++q) {
+        const uint32_t ra = ga + q * (LSP * 8);
+        double nv[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            nv[h] = dadd(v[h], lds_f64(ra + 32 * h * 8));
+            if (st_ok[h]) sts_f64(ra + 32 * h * 8, nv[h]);
+        }
+        bool keep = true;
+        if ((cg >> q) & 1u) {
+            keep = bs_radius_test<DP, NH>(nv[0], ra, lane, D, delta2, eps2, div_mode, k, wsel, scr);
+            if (lane == 0) {
+                int raw;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + q * 4));
+                prej[raw & 0x7fffffff] = keep ? 0 : 1;
+            }
+        }
+        if (keep) { // the record of a rejected cell is never read as a version
+#pragma unroll
+            for (int h = 0; h < NH; ++h) v[h] = nv[h];
+        }
+    }
+    return rec;
+}
+
 template <int DP>
 __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
     e.fetch();
     using Cfg = ChainPCfg<DP>;
-    constexpr int NB = Cfg::NB, S = Cfg::S, GS = 8, NH = Cfg::NH, LSP = Cfg::LSP;
+    constexpr int NB = Cfg::NB, S = Cfg::S, GS = 8, NH = Cfg::NH, LSP = Cfg::LSP, NG = NB / GS;
     static_assert(NB == 32 || NB == 64, "the CONTESTED flags of a stage are gathered by one or two ballots");
     extern __shared__ __align__(128) unsigned char bs_smem[];
     double *xs = reinterpret_cast<double *>(bs_smem);              // [S][NB][LSP]
     int *ms = reinterpret_cast<int *>(xs + (size_t)S * NB * LSP);  // [S][NB]
     uint64_t *full = reinterpret_cast<uint64_t *>(ms + S * NB);    // [S] producer -> replay
-    uint64_t *done = full + S;                                     // [S] replay -> storer
-    uint64_t *empty = done + S;                                    // [S] storer -> producer
+    uint64_t *done = full + S;                                     // [S] replay -> store thread
+    uint64_t *empty = done + S;                                    // [S] store thread -> producer
     double *scr = reinterpret_cast<double *>(empty + S);           // [DP] radius terms of a CONTESTED cell
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return;
@@ -875,7 +934,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&done[s], 1);
-            mbar_init(&empty[s], BS_CHAINP_STORERS);
+            mbar_init(&empty[s], 1);
         }
         mbar_fence_init();
     }
@@ -900,61 +959,42 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         }
         return;
     }
-    if (warp == 4 || warp == 5) { // same schedulers as the replay warp / the producer: leave their issue slots alone
+    if (warp == 2) { // ---- store thread: verp[plist position] <- the versions left in the stage, one bulk copy per stage
+        if (lane == 0) {
+            CCB_DBG(long long tw = 0; const long long tbeg = clock64();)
+            double *vp = e.ws.verp + (size_t)p0 * LSP;
+            for (int b = 0; b < nb; ++b) {
+                const int s = b % S;
+                {
+                    CCB_DBG(const long long t0 = clock64();)
+                    mbar_wait(&done[s], (b / S) & 1);
+                    CCB_DBG(tw += clock64() - t0;)
+                }
+                const int cnt = min(NB, n - b * NB);
+                CCB_DBG(if (g_bs_dbg_mode == 0))
+                tma_store_1d(vp + (size_t)b * NB * LSP, xs + (size_t)s * NB * LSP, (uint32_t)cnt * LSP * 8u);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (b > 0) { // the copy before this one has read its stage: hand that stage back to the producer
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    mbar_arrive(&empty[(b - 1) % S]);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the copies
+            CCB_DBG(if (e.ws.dbg) {
+                e.ws.dbg[j * 8 + 5] = clock64() - tbeg;
+                e.ws.dbg[j * 8 + 6] = tw;
+            })
+        }
+        return;
+    }
+    if (warp != 0) {
         if (warp == 4) { // (the replay warp's scheduler: it is still waiting for its first stage)
-            // ... after one pass through the rare-path code on dummy data: its instruction-cache lines are then on this
-            // SM before the replay warp (which cannot hide a miss) meets its first CONTESTED cell
+            // one pass through the rare-path code on dummy data: its instruction-cache lines are then on this SM before the
+            // replay warp (which cannot hide a miss) meets its first CONTESTED cell
             const bool r = bs_radius_test<DP, NH>(1.0, smem_u32(xs) + lane * 8, lane, D, nm.delta2, nm.eps2, nm.div_mode, nm.k,
                                                   nm.wsel, scr + DP);
             if (r && D < 0) e.ws.prej[0] = 1; // never taken; keeps the call alive
         }
-        return;
-    }
-    if (warp >= 2) { // ---- storers: ver[cell] <- the version left in the stage
-        // the stage is one flat array of cnt * LSP doubles: lane = element, four elements in flight per lane
-        // (index and value loads first, then the stores) so that the shared-memory latency is paid once per four.
-        // The copy is instruction-bound (index arithmetic per element), hence four warps on the two other schedulers.
-        constexpr int U = 4, L2 = LSP / 2, NST = BS_CHAINP_STORERS * 32; // records are L2 double2 wide
-        const int st = (warp < 4 ? warp - 2 : warp - 4) * 32 + lane;
-        CCB_DBG(long long tw = 0; const long long tbeg = clock64();)
-        for (int b = 0; b < nb; ++b) {
-            const int s = b % S;
-            {
-                CCB_DBG(const long long t0 = clock64();)
-                mbar_wait(&done[s], (b / S) & 1);
-                CCB_DBG(tw += clock64() - t0;)
-            }
-            int tot = min(NB, n - b * NB) * L2;
-            CCB_DBG(const int dbgm = g_bs_dbg_mode; if (dbgm == 2) tot = 0;)
-            const double2 *xb = reinterpret_cast<const double2 *>(xs + (size_t)s * NB * LSP);
-            const int *mb = ms + s * NB;
-            double2 *ver2 = reinterpret_cast<double2 *>(e.ws.ver);
-            for (int e0 = st; e0 < tot; e0 += NST * U) {
-                double2 val[U];
-                size_t off[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int el = e0 + NST * u;
-                    if (el < tot) {
-                        const int row = el / L2;
-                        off[u] = (size_t)(mb[row] & 0x7fffffff) * L2 + (el - row * L2);
-                        val[u] = xb[el];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (e0 + NST * u < tot) {
-                        CCB_DBG(if (dbgm == 1 && val[u].x != 1.2345e300) continue;)
-                        ver2[off[u]] = val[u];
-                    }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
-        CCB_DBG(if (e.ws.dbg && warp == 2 && lane == 0) {
-            e.ws.dbg[j * 8 + 5] = clock64() - tbeg;
-            e.ws.dbg[j * 8 + 6] = tw;
-        })
         return;
     }
     // ---- replay (warp 0): lane owns elements lane + 32 h of the record
@@ -969,20 +1009,16 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         v[h] = x;
     }
     CCB_DBG(long long t_wait = 0, t_slow = 0, n_cont = 0; const long long t_beg = clock64();)
-    // shared-window addresses as opaque registers: otherwise the compiler re-derives them from special registers
-    // (S2UR / S2R, tens of cycles each) inside the loop, which a lone warp cannot hide
+    // The replay warp issues in order and is alone on its scheduler: every dependent instruction costs its full latency.
+    // Everything below is arranged for that.  Addresses and the lane number are held in OPAQUE registers (otherwise the
+    // compiler re-derives them from special registers -- S2R / S2UR, tens of cycles each -- inside the loop).
     uint32_t xs_lane = smem_u32(xs) + lane * 8, ms_base = smem_u32(ms);
-    asm volatile("" : "+r"(xs_lane), "+r"(ms_base));
+    int lane_o = lane;
+    asm volatile("" : "+r"(xs_lane), "+r"(ms_base), "+r"(lane_o));
     bool st_ok[NH];
 #pragma unroll
-    for (int h = 0; h < NH; ++h) st_ok[h] = lane + 32 * h < LSP;
+    for (int h = 0; h < NH; ++h) st_ok[h] = lane_o + 32 * h < LSP;
 
-    // ONE loop shape for every stage: groups of GS = 8 cells, the addends of group g + 1 are fetched from shared memory
-    // (two register sets) before the dependent adds of group g.  A group without CONTESTED cells is eight chained adds;
-    // a group with one takes its cells one by one from the same registers, the CONTESTED ones through the exact radius
-    // test on their tentative record -- a few hundred cycles for that cell and nothing extra for the rest of the stage.
-    // Loads are unguarded (a lane past the end of a record, or a group past the end of a ragged stage, reads stale data
-    // inside the ring); stores are predicated.
     for (int b = 0; b < nb; ++b) {
         const int s = b % S;
         {
@@ -991,80 +1027,90 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
             CCB_DBG(t_wait += clock64() - t0;)
         }
         const int cnt = __shfl_sync(0xffffffffu, min(NB, n - b * NB), 0); // warp-uniform for the compiler, too
-        const uint32_t xa = xs_lane + s * (NB * LSP * 8), ma = ms_base + s * (NB * 4);
+        uint32_t xa = xs_lane + s * (NB * LSP * 8), ma = ms_base + s * (NB * 4);
+        asm volatile("" : "+r"(xa), "+r"(ma));
         // CONTESTED flags of the whole stage: lane l looks at cells l and l + 32
         unsigned c_lo, c_hi = 0u;
         {
             int f0, f1 = 0;
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(f0) : "r"(ma + lane * 4));
-            if (NB > 32) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(f1) : "r"(ma + (lane + 32) * 4));
-            c_lo = __ballot_sync(0xffffffffu, f0 < 0 && lane < cnt);
-            if (NB > 32) c_hi = __ballot_sync(0xffffffffu, f1 < 0 && lane + 32 < cnt);
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(f0) : "r"(ma + lane_o * 4));
+            if (NB > 32) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(f1) : "r"(ma + (lane_o + 32) * 4));
+            c_lo = __ballot_sync(0xffffffffu, f0 < 0 && lane_o < cnt);
+            if (NB > 32) c_hi = __ballot_sync(0xffffffffu, f1 < 0 && lane_o + 32 < cnt);
         }
-        const int ng = (cnt + GS - 1) / GS;
-        double A[GS][NH], B[GS][NH];
-        auto fetch = [&](double (&R)[GS][NH], int g) {
-            const uint32_t ga = xa + g * (GS * LSP * 8);
+        if (cnt == NB && (c_lo | c_hi) == 0u) {
+            // ---- CLEAN FULL STAGE: straight-line code with immediate offsets.  Cell c: the dependent add, then -- in its
+            // latency shadow -- the store of the version cell c - 1 left and the load of an addend one batch ahead.
+            double R[2][GS][NH];
 #pragma unroll
             for (int q = 0; q < GS; ++q)
 #pragma unroll
-                for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8);
-        };
-        auto chain = [&](double (&R)[GS][NH], int g) {
-            const uint32_t ga = xa + g * (GS * LSP * 8);
-            const unsigned cg = ((g < 4 ? c_lo : c_hi) >> (8 * (g & 3))) & 0xffu;
-            const int ncell = min(GS, cnt - g * GS);
-            if (cg == 0u && ncell == GS) {
+                for (int h = 0; h < NH; ++h) R[0][q][h] = lds_f64(xa + (q * LSP + 32 * h) * 8);
 #pragma unroll
-                for (int q = 0; q < GS; ++q)
+            for (int k = 0; k < NG; ++k) {
 #pragma unroll
-                    for (int h = 0; h < NH; ++h) {
-                        v[h] = dadd(v[h], R[q][h]);
-                        if (st_ok[h]) sts_f64(ga + (q * LSP + 32 * h) * 8, v[h]);
-                    }
-                return;
-            }
-            CCB_DBG(const long long t_s0 = clock64();)
-#pragma unroll
-            for (int q = 0; q < GS; ++q) {
-                if (q < ncell) { // warp-uniform
-                    const uint32_t ra = ga + q * (LSP * 8);
+                for (int q = 0; q < GS; ++q) {
                     double nv[NH];
 #pragma unroll
-                    for (int h = 0; h < NH; ++h) {
-                        nv[h] = dadd(v[h], R[q][h]);
-                        if (st_ok[h]) sts_f64(ra + 32 * h * 8, nv[h]);
-                    }
-                    bool keep = true;
-                    if ((cg >> q) & 1u) {
-                        CCB_DBG(++n_cont;)
-                        keep = bs_radius_test<DP, NH>(nv[0], ra, lane, D, nm.delta2, nm.eps2, nm.div_mode, nm.k, nm.wsel, scr);
-                        if (lane == 0) {
-                            int raw;
-                            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma + (g * GS + q) * 4));
-                            e.ws.prej[raw & 0x7fffffff] = keep ? 0 : 1;
-                        }
-                    }
-                    if (keep) { // the record of a rejected cell is never read as a version
+                    for (int h = 0; h < NH; ++h) nv[h] = dadd(v[h], R[k & 1][q][h]);
+                    if (k + q > 0) {
 #pragma unroll
-                        for (int h = 0; h < NH; ++h) v[h] = nv[h];
+                        for (int h = 0; h < NH; ++h)
+                            if (st_ok[h]) sts_f64(xa + ((k * GS + q - 1) * LSP + 32 * h) * 8, v[h]);
                     }
+                    if (k + 1 < NG) {
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) R[(k + 1) & 1][q][h] = lds_f64(xa + (((k + 1) * GS + q) * LSP + 32 * h) * 8);
+                    }
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) v[h] = nv[h];
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < NH; ++h)
+                if (st_ok[h]) sts_f64(xa + ((NB - 1) * LSP + 32 * h) * 8, v[h]);
+        } else {
+            // ---- stage with CONTESTED cells or the ragged tail: group by group; a clean full group is eight chained adds
+            // through registers, any other group goes cell by cell (out of line), CONTESTED cells through the exact radius
+            // test on their tentative record
+            CCB_DBG(const long long t_s0 = clock64(); n_cont += __popc(c_lo) + __popc(c_hi);)
+            const int ng = (cnt + GS - 1) / GS;
+#pragma unroll 1
+            for (int g = 0; g < ng; ++g) {
+                uint32_t ga = xa + g * (GS * LSP * 8);
+                asm volatile("" : "+r"(ga));
+                const unsigned cg = ((g < 4 ? c_lo : c_hi) >> (8 * (g & 3))) & 0xffu;
+                const int ncell = min(GS, cnt - g * GS);
+                if (cg == 0u && ncell == GS) {
+                    double R[GS][NH];
+#pragma unroll
+                    for (int q = 0; q < GS; ++q)
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8);
+#pragma unroll
+                    for (int q = 0; q < GS; ++q)
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) {
+                            v[h] = dadd(v[h], R[q][h]);
+                            if (st_ok[h]) sts_f64(ga + (q * LSP + 32 * h) * 8, v[h]);
+                        }
+                } else {
+                    ChainRec<NH> rec;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) rec.v[h] = v[h];
+                    rec = bs_chain_slow_group<DP, NH>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
+                                                      nm.div_mode, nm.k, nm.wsel, scr, e.ws.prej);
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) v[h] = rec.v[h];
                 }
             }
             CCB_DBG(t_slow += clock64() - t_s0;)
-        };
-        fetch(A, 0);
-#pragma unroll 1
-        for (int g = 0; g < ng; g += 2) {
-            if (g + 1 < ng) fetch(B, g + 1);
-            chain(A, g);
-            if (g + 1 < ng) {
-                if (g + 2 < ng) fetch(A, g + 2);
-                chain(B, g + 1);
-            }
         }
+        // the versions were written through the generic proxy; the bulk copy reads them through the async proxy
         __syncwarp();
-        if (lane == 0) mbar_arrive(&done[s]); // release: the versions written above are visible to the storers
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane_o == 0) mbar_arrive(&done[s]);
     }
     CCB_DBG(if (e.ws.dbg && lane == 0) {
         e.ws.dbg[j * 8 + 0] = n;
@@ -1142,6 +1188,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_olist(Eng e) {
         if ((t == 0) || ((keys[t] >> 32) != (keys[t - 1] >> 32))) {
             e.ws.hkey[h] = key;
             e.ws.hoff[h] = t;
+            e.ws.hfirst[h] = i;
             if (key < KNEW) e.ws.firstmember[key - Mp] = i;
             else atomicMin(&bc->hnew0, h);
             ++h;
@@ -1167,23 +1214,32 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_olist(Eng e) {
 }
 
 // ---- D ----------------------------------------------------------------------------------------------
-// centroid, preference mask and r^2 of VERSION i (two IEEE divisions per dimension, off the serial path)
-__device__ __forceinline__ void derive_version(const Eng &e, const Num &nm, int i) {
-    const int D = nm.D;
-    const double w = ver_w(e.ws, i);
-    const double *c1 = ver_cf1(e.ws, i), *c2 = ver_cf2(e.ws, i);
+// centroid, preference mask and r^2 of VERSION i (two IEEE divisions per dimension, off the serial path).  rec: where the
+// chain kernel left the record -- ver[i] itself (outlier side), or verp[plist position] (pcore side), which is handed on
+// to ver[i] here so that every later reader finds a version under its cell
+__device__ __forceinline__ void derive_version(const Eng &e, const Num &nm, int i, const double *rec) {
+    const int D = nm.D, dp = e.ws.dp;
+    double *out = e.ws.ver + (size_t)i * e.ws.lsp;
+    const bool copy = rec != out;
+    const double w = rec[2 * dp];
     double *cen = e.ws.vcen + (size_t)i * D;
     double s = 0.0;
     uint64_t mk = 0ull;
     for (int d = 0; d < D; ++d) {
-        const double a = ddiv(c2[d], w);
-        const double c = ddiv(c1[d], w);
+        const double c1 = rec[d], c2 = rec[dp + d];
+        if (copy) {
+            out[d] = c1;
+            out[dp + d] = c2;
+        }
+        const double a = ddiv(c2, w);
+        const double c = ddiv(c1, w);
         cen[d] = c;
         const double var = dsub(a, dmul(c, c));
         const bool bit = var <= nm.delta2;
         mk |= (uint64_t)bit << d;
         s = dadd(s, bit ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var);
     }
+    if (copy) out[2 * dp] = w;
     e.ws.vmask[i] = mk;
     e.ws.vr2[i] = s;
 }
@@ -1208,7 +1264,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_p(Eng e) {
         }
     }
     if (i >= bc->Beff || e.ws.pcand[i] < 0 || e.ws.prej[i]) return; // not an accepted member of a pcore chain
-    derive_version(e, e.nm, i);
+    derive_version(e, e.nm, i, e.ws.verp + (size_t)e.ws.vpos[i] * e.ws.lsp);
 }
 
 // OUTLIER side: the versions k_bs_chain_o left (members of the outlier-side keys, in omem)
@@ -1217,7 +1273,10 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_o(Eng e) {
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const int no = bc->no;
-    for (int t = blockIdx.x * BS_THREADS + threadIdx.x; t < no; t += gridDim.x * BS_THREADS) derive_version(e, e.nm, e.ws.omem[t]);
+    for (int t = blockIdx.x * BS_THREADS + threadIdx.x; t < no; t += gridDim.x * BS_THREADS) {
+        const int i = e.ws.omem[t];
+        derive_version(e, e.nm, i, e.ws.ver + (size_t)i * e.ws.lsp);
+    }
 }
 
 // ---- V ----------------------------------------------------------------------------------------------
@@ -1300,70 +1359,78 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
         }
     }
     e.ws.upf[i] = 0;
+    int mm = INT_MAX;
     if (acc) {
         e.ws.dec[i] = best;
-    } else {
+        if (best != eff) mm = i;
+    } else { // decided by k_bs_verify_o, which also reports its mismatch
         e.ws.dec[i] = BS_KEY_PENDING;
         e.ws.pend[atomicAdd(&bc->npend, 1)] = i;
     }
+    // first cell of the tile whose exact decision differs from the speculation -> one atomicMin per tile
+    const unsigned am = __activemask();
+    mm = __reduce_min_sync(am, mm);
+    if (mm != INT_MAX && lane == __ffs(am) - 1) atomicMin(&bc->m0, mm);
 }
 
-// outlier stage of the cells the pcore stage rejected: one warp per cell
+// outlier stage of the cells the pcore stage rejected: one CTA per cell (the scan over the modified / created keys is a
+// chain of dependent loads per key -- member list, version, centroid -- so it is spread over 128 threads, not 32)
 template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
     e.fetch();
-    const BsCtl *bc = e.bc;
+    constexpr int NW = BS_THREADS / 32;
+    __shared__ double s_bd[NW], s_f[2];
+    __shared__ int s_bkey[NW], s_bver[NW], s_i[3];
+    BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const Num nm = e.nm;
     const int D = nm.D, Mp = bc->Mp, Mo0 = bc->Mo0, KNEW = Mp + Mo0;
-    const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5), nw = gridDim.x * (BS_THREADS / 32);
-    const int npend = bc->npend, nh = bc->nh;
-    for (int pidx = gw; pidx < npend; pidx += nw) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int npend = bc->npend, nh = bc->nh, Beff = bc->Beff;
+    for (int pidx = blockIdx.x; pidx < npend; pidx += gridDim.x) {
         const int i = e.ws.pend[pidx];
         double x[DP];
         load_row<DP>(e.X + (bc->pos + i) * e.ld, D, x);
         // (1) nearest snapshot MC not modified before cell i, from the top-K list.  If every listed candidate is
         // stale the nearest clean MC is unknown, but no clean MC is nearer than the last list entry (BOUND): the
         // decision still stands when a modified / created MC, at its exact version, beats that bound.
-        double bd = 0.0, bound = 0.0;
-        int bkey = INT_MAX, bver = -1, status = 0, bounded = 0; // status 2: NEED
-        if (lane == 0 && Mo0 > 0) {
-            const int tk = e.ws.tkpos[i];
-            if (tk < 0) {
-                status = 2;
-            } else {
-                int s = 0;
-                for (; s < BS_TOPK; ++s) {
-                    const int o = e.ws.tk_idx[(size_t)tk * BS_TOPK + s];
-                    if (o < 0) break;
-                    if (e.ws.firstmember[o] >= i) {
-                        bd = e.ws.tk_dist[(size_t)tk * BS_TOPK + s];
-                        bkey = Mp + o;
-                        break;
+        if (tid == 0) {
+            double bd0 = 0.0, bound = 0.0;
+            int bkey0 = INT_MAX, status = 0, bounded = 0; // status 2: NEED
+            if (Mo0 > 0) {
+                const int tk = e.ws.tkpos[i];
+                if (tk < 0) {
+                    status = 2;
+                } else {
+                    int s = 0;
+                    for (; s < BS_TOPK; ++s) {
+                        const int o = e.ws.tk_idx[(size_t)tk * BS_TOPK + s];
+                        if (o < 0) break;
+                        if (e.ws.firstmember[o] >= i) {
+                            bd0 = e.ws.tk_dist[(size_t)tk * BS_TOPK + s];
+                            bkey0 = Mp + o;
+                            break;
+                        }
+                    }
+                    if (s == BS_TOPK) {
+                        bounded = 1;
+                        bound = e.ws.tk_dist[(size_t)tk * BS_TOPK + BS_TOPK - 1];
                     }
                 }
-                if (s == BS_TOPK) {
-                    bounded = 1;
-                    bound = e.ws.tk_dist[(size_t)tk * BS_TOPK + BS_TOPK - 1];
-                }
             }
+            s_f[0] = bd0;
+            s_f[1] = bound;
+            s_i[0] = bkey0;
+            s_i[1] = status;
+            s_i[2] = bounded;
         }
-        status = __shfl_sync(0xffffffffu, status, 0);
-        if (status) {
-            if (lane == 0) {
-                e.ws.dec[i] = BS_KEY_NEED;
-                e.ws.upf[i] = 0;
-            }
-            continue;
-        }
-        bounded = __shfl_sync(0xffffffffu, bounded, 0);
-        bound = __shfl_sync(0xffffffffu, bound, 0);
         // (2) every MC modified or created earlier in the block, at its version just before cell i
-        for (int h = lane; h < nh; h += 32) {
-            const int32_t *mem = e.ws.omem + e.ws.hoff[h];
-            if (mem[0] >= i) continue;
-            const int v = latest_before(mem, e.ws.hoff[h + 1] - e.ws.hoff[h], i);
+        double bd = 0.0;
+        int bkey = INT_MAX, bver = -1;
+        for (int h = tid; h < nh; h += BS_THREADS) {
+            if (e.ws.hfirst[h] >= i) continue;
+            const int off = e.ws.hoff[h], cnt = e.ws.hoff[h + 1] - off;
+            const int v = cnt == 1 ? e.ws.omem[off] : latest_before(e.ws.omem + off, cnt, i);
             const double dv = dist_regs<DP>(x, e.ws.vcen + (size_t)v * D, e.ws.vmask[v], nm);
             const int key = e.ws.hkey[h];
             if (!(dv != dv) && (bkey == INT_MAX || dv < bd || (dv == bd && key < bkey))) {
@@ -1383,49 +1450,77 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
                 bver = ov;
             }
         }
-        if (bounded && !(bkey != INT_MAX && bd < bound)) { // warp-uniform after the reduction
-            if (lane == 0) {
-                e.ws.dec[i] = BS_KEY_UNKNOWN;
-                e.ws.upf[i] = 0;
-            }
-            continue;
-        }
-        int dec = KNEW + i, up = 0;
-        if (bkey != INT_MAX) {
-            const double *c1, *c2;
-            double w;
-            if (bver >= 0) {
-                c1 = ver_cf1(e.ws, bver);
-                c2 = ver_cf2(e.ws, bver);
-                w = ver_w(e.ws, bver);
-            } else {
-                const int o = bkey - Mp;
-                c1 = e.O.cf1 + (size_t)o * D;
-                c2 = e.O.cf2 + (size_t)o * D;
-                w = e.O.w[o];
-            }
-            LaneMc m, o2;
-            double xl[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int d = lane + 32 * h;
-                m.cf1[h] = d < D ? c1[d] : 1.0;
-                m.cf2[h] = d < D ? c2[d] : 1.0;
-                m.cen[h] = 0.0;
-                xl[h] = d < D ? e.X[(bc->pos + i) * e.ld + d] : 0.0;
-            }
-            double wn;
-            uint64_t nmask;
-            if (tentative_absorb_t<DP>(m, w, xl, nm, o2, wn, nmask)) {
-                dec = bkey;
-                const int pd = nm.cnt_gt1 ? popc64(nmask) : 0;
-                up = (wn >= nm.beta_mu) && ((int64_t)pd <= nm.pi); // hddstream.py:413-418
-            }
-        }
         if (lane == 0) {
-            e.ws.dec[i] = dec;
-            e.ws.upf[i] = (uint8_t)up;
+            s_bd[warp] = bd;
+            s_bkey[warp] = bkey;
+            s_bver[warp] = bver;
         }
+        __syncthreads();
+        if (warp == 0) { // the rest is one warp's work (lane = dimension in the tentative absorb)
+            const int status = s_i[1], bounded = s_i[2];
+            const double bound = s_f[1];
+            bd = s_f[0];
+            bkey = s_i[0];
+            bver = -1;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const double od = s_bd[w];
+                const int ok = s_bkey[w];
+                if (ok != INT_MAX && (bkey == INT_MAX || od < bd || (od == bd && ok < bkey))) {
+                    bd = od;
+                    bkey = ok;
+                    bver = s_bver[w];
+                }
+            }
+            int dec, up = 0;
+            if (status) {
+                dec = BS_KEY_NEED;
+            } else if (bounded && !(bkey != INT_MAX && bd < bound)) {
+                dec = BS_KEY_UNKNOWN;
+            } else {
+                dec = KNEW + i;
+                if (bkey != INT_MAX) {
+                    const double *c1, *c2;
+                    double w;
+                    if (bver >= 0) {
+                        c1 = ver_cf1(e.ws, bver);
+                        c2 = ver_cf2(e.ws, bver);
+                        w = ver_w(e.ws, bver);
+                    } else {
+                        const int o = bkey - Mp;
+                        c1 = e.O.cf1 + (size_t)o * D;
+                        c2 = e.O.cf2 + (size_t)o * D;
+                        w = e.O.w[o];
+                    }
+                    LaneMc m, o2;
+                    double xl[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int d = lane + 32 * h;
+                        m.cf1[h] = d < D ? c1[d] : 1.0;
+                        m.cf2[h] = d < D ? c2[d] : 1.0;
+                        m.cen[h] = 0.0;
+                        xl[h] = d < D ? e.X[(bc->pos + i) * e.ld + d] : 0.0;
+                    }
+                    double wn;
+                    uint64_t nmask;
+                    if (tentative_absorb_t<DP>(m, w, xl, nm, o2, wn, nmask)) {
+                        dec = bkey;
+                        const int pd = nm.cnt_gt1 ? popc64(nmask) : 0;
+                        up = (wn >= nm.beta_mu) && ((int64_t)pd <= nm.pi); // hddstream.py:413-418
+                    }
+                }
+            }
+            if (lane == 0) {
+                e.ws.dec[i] = dec;
+                e.ws.upf[i] = (uint8_t)up;
+                if (i < Beff) { // (a light round after a truncation still lists cells behind the cut)
+                    if (dec != e.ws.eff[i]) atomicMin(&bc->m0, i);
+                    if (up) atomicMin(&bc->up0, i);
+                }
+            }
+        }
+        __syncthreads(); // the shared slots are reused by the next cell
     }
 }
 
@@ -1450,37 +1545,18 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
     if (!bc->active || bc->phase != 0) return;
     const int tid = threadIdx.x;
     const int Beff = bc->Beff, Mp = bc->Mp, KNEW = bc->Mp + bc->Mo0;
-    // first cell whose exact decision differs from the speculation (threads stride the cells: coalesced)
-    // (the scans below fetch eight strides per step: a lone CTA pays the full memory latency for every dependent step,
-    // so the loads of one step must be independent of its comparisons)
+    // first cell whose exact decision differs from the speculation, first upgrade inside the exact prefix: both were
+    // reduced with atomicMin by the verify kernels; consume and re-arm them
+    __shared__ int s_m0, s_up;
+    if (tid == 0) {
+        s_m0 = min(bc->m0, Beff);
+        s_up = bc->up0;
+        bc->m0 = bc->up0 = INT_MAX;
+    }
+    __syncthreads();
+    const int m0 = s_m0;
+    const int up = s_up < m0 ? s_up : INT_MAX;
     constexpr int SU = 8;
-    int m0 = Beff;
-    for (int i0 = tid; i0 < Beff && m0 == Beff; i0 += BS_CTA1 * SU) {
-        int dv[SU], ev[SU];
-#pragma unroll
-        for (int u = 0; u < SU; ++u) {
-            const int i = i0 + u * BS_CTA1;
-            dv[u] = i < Beff ? e.ws.dec[i] : 0;
-            ev[u] = i < Beff ? e.ws.eff[i] : 0;
-        }
-#pragma unroll
-        for (int u = SU - 1; u >= 0; --u)
-            if (dv[u] != ev[u]) m0 = i0 + u * BS_CTA1; // ends on the smallest u
-    }
-    m0 = block_min_1024(m0, s_warp);
-    int up = INT_MAX;
-    for (int i0 = tid; i0 < m0 && up == INT_MAX; i0 += BS_CTA1 * SU) {
-        uint8_t uv[SU];
-#pragma unroll
-        for (int u = 0; u < SU; ++u) {
-            const int i = i0 + u * BS_CTA1;
-            uv[u] = i < m0 ? e.ws.upf[i] : 0;
-        }
-#pragma unroll
-        for (int u = SU - 1; u >= 0; --u)
-            if (uv[u]) up = i0 + u * BS_CTA1;
-    }
-    up = block_min_1024(up, s_warp);
     if (tid == 0) {
         int act = 0; // 0 refine, 1 commit
         bc->iters += 1;

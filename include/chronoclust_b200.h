@@ -96,6 +96,8 @@ typedef struct {
     int64_t bsv_outlier_stage_cells; /* cells given a top-K list up front (not SAFE) */
     int64_t bsv_replayed_cells;      /* cells replayed by the chain kernels, summed over rounds */
     int64_t bsv_light_rounds;        /* refinement rounds that re-ran the outlier side only (pcore side unchanged) */
+    int64_t bsv_serial_cells;        /* sum over the pcore replays of the longest chain's member count: x one dependent-add
+                                        latency = the serial floor of kernel 2 (what the reference's ordering forces) */
 } ccb_stats;
 
 int ccb_create(const ccb_params *params, ccb_handle **out);
