@@ -58,6 +58,7 @@ SYMBOLS = {
     "ccb_export_offline": (C.c_int, [vp] + [vp] * 4),
     "ccb_nearest": (C.c_int, [i32, vp, vp, i64, i64, i32, vp, vp, i64, f64, vp, vp]),
     "ccb_assoc_nearest": (C.c_int, [i32, vp, vp, vp, i64, vp, i64, i32, f64, vp, vp]),
+    "ccb_assoc_nearest2": (C.c_int, [i32, vp, vp, vp, i64, vp, i64, i32, f64, vp, vp, vp]),
     "ccb_colminmax": (C.c_int, [i32, vp, vp, i64, i64, i32, vp, vp]),
     "ccb_ingest_scaled": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp]),
     "ccb_off_neighbours": (C.c_int, [i32, vp, vp, i64, i32, i64, i64, f64, vp, vp, vp, i32, vp]),

@@ -17,6 +17,8 @@ DEPS = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "common.cuh", "nearest
 DEPS.append(os.path.join(os.path.dirname(HERE), "include", "chronoclust_b200.h"))
 SO = os.path.join(HERE, "libchronoclust_b200.so")
 SO_DEBUG = os.path.join(HERE, "libchronoclust_b200_debug.so")
+HOSTIO_SRC = os.path.join(HERE, "csrc", "hostio.c")
+HOSTIO_SO = os.path.join(HERE, "libccb_hostio.so")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -47,5 +49,17 @@ def build(force=False, verbose=False, debug=False):
     return so
 
 
+def build_hostio(force=False, verbose=False):
+    """The host-side CSV writer (plain C, pthreads; no CUDA): chronoclust_b200/libccb_hostio.so."""
+    if not force and os.path.exists(HOSTIO_SO) and os.path.getmtime(HOSTIO_SO) >= os.path.getmtime(HOSTIO_SRC):
+        return HOSTIO_SO
+    cmd = ["gcc", "-O2", "-std=gnu11", "-fPIC", "-shared", "-pthread", "-o", HOSTIO_SO, HOSTIO_SRC, "-lm"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return HOSTIO_SO
+
+
 if __name__ == "__main__":
+    print(build_hostio(force="--force" in sys.argv, verbose=True))
     print(build(force="--force" in sys.argv, verbose=True, debug="--debug" in sys.argv))

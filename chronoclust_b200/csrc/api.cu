@@ -920,6 +920,79 @@ int launch_off_clusters(ccb_handle *h, cudaStream_t s, int M, const uint32_t *wn
     return e == cudaSuccess ? CCB_OK : fail(h, CCB_ECUDA, "offline cluster growth: %s", cudaGetErrorString(e));
 }
 
+// Probes of the pcore replay pattern (mode 3 of ccb_fp64_peak): one warp runs the CLEAN-stage schedule of k_bs_chain_p over
+// a ring of records in shared memory -- per cell one dependent DADD, the store of the previous version, the load of an
+// addend one batch ahead -- under different conditions; sink[8 + v] = cycles per cell of variant v:
+//   0 DADD chain only (addends in registers)      1 + addends from LDS      2 + STS of every version
+//   3 as 2, while two other warps spin on mbarrier try_wait (the producer / store threads of the kernel)
+//   4 as 2 with 64-bit accesses replaced by lane-strided 8-byte accesses of a 26-element record (the real layout)
+template <int VAR>
+__device__ __forceinline__ double chain_probe_run(double *sm, int lane, long long &cyc) {
+    constexpr int LSP = 26, NB = 64, GS = 8, NG = NB / GS, REP = 32;
+    double v = 1.0 + lane * 1e-9;
+    uint32_t xa = smem_u32(sm) + (lane < LSP ? lane : 0) * 8;
+    asm volatile("" : "+r"(xa));
+    const bool st_ok = lane < LSP;
+    const long long t0 = clock64();
+    for (int rep = 0; rep < REP; ++rep) {
+        double R[2][GS];
+#pragma unroll
+        for (int q = 0; q < GS; ++q) R[0][q] = VAR >= 1 ? lds_f64(xa + (q * LSP) * 8) : 1e-12 * q;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+#pragma unroll
+            for (int q = 0; q < GS; ++q) {
+                const double nv = ccb::dadd(v, R[k & 1][q]);
+                if (VAR >= 2 && k + q > 0 && st_ok) sts_f64(xa + ((k * GS + q - 1) * LSP) * 8, v);
+                if (k + 1 < NG) R[(k + 1) & 1][q] = VAR >= 1 ? lds_f64(xa + (((k + 1) * GS + q) * LSP) * 8) : 1e-12 * q;
+                v = nv;
+            }
+        }
+        if (VAR >= 2 && st_ok) sts_f64(xa + ((NB - 1) * LSP) * 8, v);
+    }
+    cyc = clock64() - t0;
+    return v;
+}
+__global__ void k_chain_probe(double *sink) {
+    __shared__ __align__(16) double sm[64 * 26 + 32];
+    __shared__ uint64_t bar;
+    __shared__ volatile int stop;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 64 * 26 + 32; i += blockDim.x) sm[i] = 1e-9 * (i % 97);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        stop = 0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        long long c0, c1, c2, c3;
+        double a = chain_probe_run<0>(sm, lane, c0);
+        a += chain_probe_run<1>(sm, lane, c1);
+        a += chain_probe_run<2>(sm, lane, c2);
+        if (lane == 0) stop = 1; // phase 1 over: spinners start
+        __syncwarp();
+        for (volatile int w = 0; w < 2000; ++w) {}
+        a += chain_probe_run<2>(sm, lane, c3);
+        if (lane == 0) {
+            const double cells = 32.0 * 64.0;
+            sink[8] = c0 / cells;
+            sink[9] = c1 / cells;
+            sink[10] = c2 / cells;
+            sink[11] = c3 / cells;
+            sink[7] = a;
+            stop = 2;
+            mbar_arrive(&bar);
+        }
+        return;
+    }
+    // warps 1, 2: idle until phase 1 is over, then lane 0 spins on the mbarrier like the producer / store thread do
+    if (lane == 0) {
+        while (stop == 0) {}
+        mbar_wait(&bar, 0);
+    }
+}
+
 } // namespace
 
 // =====================================================================================================
@@ -1714,6 +1787,13 @@ int ccb_fp64_peak(int32_t device, void *stream, int32_t mode, int32_t iters, int
                   double *flops_out) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    if (mode == 3) { // probes of the replay pattern: sink[8..11] = cycles per cell (see k_chain_probe)
+        k_chain_probe<<<1, 96, 0, (cudaStream_t)stream>>>(sink);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "k_chain_probe: %s", cudaGetErrorString(e));
+        if (flops_out) *flops_out = 0.0;
+        return CCB_OK;
+    }
     if (mode == 2) { // latency probes: sink[1..5] = cycles per dependent DADD, DMUL, DFMA, replay step, FADD
         k_fp64_latency<<<1, 32, 0, (cudaStream_t)stream>>>(sink);
         e = cudaGetLastError();
@@ -1773,6 +1853,11 @@ int ccb_nearest(int32_t device, void *stream, const double *X, int64_t N, int64_
 
 int ccb_assoc_nearest(int32_t device, void *stream, const double *cur_cen, const uint64_t *cur_prefmask, int64_t Q,
                       const double *prev_cen, int64_t P, int32_t D, double k, int32_t *best, double *dist) {
+    return ccb_assoc_nearest2(device, stream, cur_cen, cur_prefmask, Q, prev_cen, P, D, k, best, dist, nullptr);
+}
+
+int ccb_assoc_nearest2(int32_t device, void *stream, const double *cur_cen, const uint64_t *cur_prefmask, int64_t Q,
+                       const double *prev_cen, int64_t P, int32_t D, double k, int32_t *best, double *dist, double *dist2) {
     if (D < 1 || D > CCB_MAX_D || Q < 0 || P < 0 || Q >= ((int64_t)1 << 31) || P >= ((int64_t)1 << 31))
         return fail(nullptr, CCB_EINVAL, "bad ccb_assoc_nearest arguments");
     cudaError_t e = cudaSetDevice(device);
@@ -1788,8 +1873,8 @@ int ccb_assoc_nearest(int32_t device, void *stream, const double *cur_cen, const
     int ok = 0;
     CCB_DISPATCH_DP(DP, {
         const int gx = (int)((Q + ASSOC_THREADS - 1) / ASSOC_THREADS);
-        if (p2) k_assoc<kDP, false><<<gx, ASSOC_THREADS, 0, s>>>(cur_cen, cur_prefmask, (int)Q, prev_cen, (int)P, D, k, 1.0 / k, best, dist);
-        else k_assoc<kDP, true><<<gx, ASSOC_THREADS, 0, s>>>(cur_cen, cur_prefmask, (int)Q, prev_cen, (int)P, D, k, k, best, dist);
+        if (p2) k_assoc<kDP, false><<<gx, ASSOC_THREADS, 0, s>>>(cur_cen, cur_prefmask, (int)Q, prev_cen, (int)P, D, k, 1.0 / k, best, dist, dist2);
+        else k_assoc<kDP, true><<<gx, ASSOC_THREADS, 0, s>>>(cur_cen, cur_prefmask, (int)Q, prev_cen, (int)P, D, k, k, best, dist, dist2);
         ok = 1;
     })
     if (!ok) return fail(nullptr, CCB_ELIMIT, "unsupported dimensionality %d", D);

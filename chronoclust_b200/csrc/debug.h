@@ -12,12 +12,12 @@
 extern "C" {
 #endif
 
-/* Per pcore key of the last k_bs_chain_p launch: out[key][8] = {members, replay cycles, replay waiting for data, replay in
- * groups with a CONTESTED cell, CONTESTED cells, storer cycles, storer waiting, producer waiting}.  The first call
- * switches the counters on. */
+/* Per pcore key of the last k_bs_chain_p launch: out[key][8] = {members, replay cycles, replay waiting for data, cycles in
+ * stages with a CONTESTED cell or a ragged tail, CONTESTED cells, cycles at the head of the stages (flags), cycles at
+ * their tail (proxy fence + arrive), clean full stages}.  The first call switches the counters on. */
 int ccb_debug_chain(ccb_handle *h, int64_t *out, int32_t max_keys);
-/* Results become WRONG: 1 = the storer warps of k_bs_chain_p skip their global stores, 2 = skip the copies altogether
- * (isolates the replay warp's own speed).  0 restores normal operation. */
+/* Results may become WRONG: 1 = the store thread of k_bs_chain_p skips its bulk copies, 4 = the replay warp skips the
+ * proxy fence before handing a stage to the store thread (timing experiments).  0 restores normal operation. */
 int ccb_debug_set(ccb_handle *h, int32_t mode);
 
 #ifdef __cplusplus

@@ -811,60 +811,66 @@ __device__ int g_bs_dbg_mode = 0; // diagnostics build only (csrc/debug.h): 1 = 
 // instruction-cache line it touches is a full miss it cannot hide; one small shared copy keeps the footprint of the
 // rare path at a few hundred instructions.  NH == 1: the record is one register per lane (nv0); otherwise it is read
 // back from the stage at rec_addr (this lane's element 0 of the record, shared-window address).
+// Lane d computes the d-th term (two IEEE divisions, off each other's critical path); the D terms are then summed in index
+// order by every lane from warp shuffles -- no memory round trip; with D == DP the sum is a straight chain of D adds.
 template <int DP, int NH>
 __device__ __noinline__ bool bs_radius_test(double nv0, uint32_t rec_addr, int lane, int D, double delta2, double eps2,
-                                            int div_mode, double k, double wsel, double *scr) {
-    double wn, c1[2], c2[2];
+                                            int div_mode, double k, double wsel) {
+    constexpr int NT = DP > 32 ? 2 : 1; // terms per lane
+    double wn, c1[NT], c2[NT];
     if (NH == 1) { // fetch CF2', W' by shuffle
         wn = __shfl_sync(0xffffffffu, nv0, 2 * DP);
         c1[0] = nv0;
         c2[0] = __shfl_sync(0xffffffffu, nv0, (lane + DP) & 31);
-        c1[1] = c2[1] = 1.0;
     } else {
         __syncwarp();
         wn = lds_f64(rec_addr - lane * 8 + 2 * DP * 8);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int d = lane + 32 * h;
-            const bool rd = (h == 0 || DP > 32) && d < D;
+        for (int h = 0; h < NT; ++h) {
+            const bool rd = lane + 32 * h < D;
             c1[h] = rd ? lds_f64(rec_addr + 32 * h * 8) : 1.0;
             c2[h] = rd ? lds_f64(rec_addr + (DP + 32 * h) * 8) : 1.0;
         }
     }
-    double term[2] = {0.0, 0.0};
+    double term[NT];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        if (h == 0 || DP > 32) {
-            const int d = lane + 32 * h;
-            const bool act = d < D;
-            // idle lanes carry 1.0: their (discarded) quotients stay on the fast path of the division
-            const double q2 = ddiv(act ? c2[h] : 1.0, wn);
-            const double c = ddiv(act ? c1[h] : 1.0, wn);
-            const double var = dsub(q2, dmul(c, c));
-            const bool bit = act && (var <= delta2);
-            term[h] = bit ? (div_mode ? ddiv(var, k) : dmul(var, wsel)) : var;
+    for (int h = 0; h < NT; ++h) {
+        const bool act = lane + 32 * h < D;
+        // idle lanes carry 1.0: their (discarded) quotients stay on the fast path of the division
+        const double q2 = ddiv(act ? c2[h] : 1.0, wn);
+        const double c = ddiv(act ? c1[h] : 1.0, wn);
+        const double var = dsub(q2, dmul(c, c));
+        const bool bit = act && (var <= delta2);
+        double t = var;
+        if (div_mode) { // warp-uniform; a real branch, so that a power-of-two k never pays for this division
+            asm volatile("");
+            const double tq = ddiv(var, k);
+            t = bit ? tq : var;
+        } else {
+            t = bit ? dmul(var, wsel) : var;
+        }
+        term[h] = t;
+    }
+    double r2 = 0.0;
+    if (D == DP) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) r2 = dadd(r2, __shfl_sync(0xffffffffu, term[d >> 5], d & 31));
+    } else {
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) {
+            const double t0 = __shfl_sync(0xffffffffu, term[0], d & 31);
+            const double t1 = NT > 1 ? __shfl_sync(0xffffffffu, term[NT - 1], d & 31) : 0.0;
+            r2 = dadd(r2, d < 32 ? t0 : t1);
         }
     }
-    // the D terms are summed in index order by every lane from shared memory (broadcast LDS.128)
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-        if ((h == 0 || DP > 32) && lane + 32 * h < DP) scr[lane + 32 * h] = term[h];
-    __syncwarp();
-    double r2 = 0.0;
-#pragma unroll
-    for (int d = 0; d < DP; d += 2) {
-        const double2 t2 = *reinterpret_cast<const double2 *>(scr + d);
-        if (d < D) r2 = dadd(r2, t2.x);
-        if (d + 1 < D) r2 = dadd(r2, t2.y);
-    }
-    __syncwarp();
     return r2 <= eps2;
 }
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// one group of GS = 8 cells that holds a CONTESTED cell or is the ragged tail of the key: cell by cell, kept out of line
-// (one copy; see bs_radius_test)
+// one group of GS = 8 cells that holds a CONTESTED cell or is the ragged tail of the key: its addends are fetched up
+// front, then the cells go one by one, the CONTESTED ones through the exact radius test on their tentative record.  Kept
+// out of line (one copy; see bs_radius_test).
 template <int NH>
 struct ChainRec {
     double v[NH];
@@ -872,33 +878,40 @@ struct ChainRec {
 template <int DP, int NH>
 __device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint32_t ga, uint32_t ma_g, unsigned cg, int ncell,
                                                          int lane, int D, double delta2, double eps2, int div_mode, double k,
-                                                         double wsel, double *scr, uint8_t *prej) {
-    constexpr int LSP = 2 * DP + 2;
+                                                         double wsel, uint8_t *prej) {
+    constexpr int LSP = 2 * DP + 2, GS = 8;
     double(&v)[NH] = rec.v;
     bool st_ok[NH];
 #pragma unroll
     for (int h = 0; h < NH; ++h) st_ok[h] = lane + 32 * h < LSP;
-#pragma unroll 1
-    for (int q = 0; q < ncell; ++q) {
-        const uint32_t ra = ga + q * (LSP * 8);
-        double nv[NH];
+    double R[GS][NH];
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            nv[h] = dadd(v[h], lds_f64(ra + 32 * h * 8));
-            if (st_ok[h]) sts_f64(ra + 32 * h * 8, nv[h]);
-        }
-        bool keep = true;
-        if ((cg >> q) & 1u) {
-            keep = bs_radius_test<DP, NH>(nv[0], ra, lane, D, delta2, eps2, div_mode, k, wsel, scr);
-            if (lane == 0) {
-                int raw;
-                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + q * 4));
-                prej[raw & 0x7fffffff] = keep ? 0 : 1;
+    for (int q = 0; q < GS; ++q)
+#pragma unroll
+        for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8); // (stale past ncell: never used)
+#pragma unroll
+    for (int q = 0; q < GS; ++q) {
+        if (q < ncell) { // warp-uniform
+            const uint32_t ra = ga + q * (LSP * 8);
+            double nv[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                nv[h] = dadd(v[h], R[q][h]);
+                if (st_ok[h]) sts_f64(ra + 32 * h * 8, nv[h]);
             }
-        }
-        if (keep) { // the record of a rejected cell is never read as a version
+            bool keep = true;
+            if ((cg >> q) & 1u) {
+                keep = bs_radius_test<DP, NH>(nv[0], ra, lane, D, delta2, eps2, div_mode, k, wsel);
+                if (lane == 0) {
+                    int raw;
+                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + q * 4));
+                    prej[raw & 0x7fffffff] = keep ? 0 : 1;
+                }
+            }
+            if (keep) { // the record of a rejected cell is never read as a version
 #pragma unroll
-            for (int h = 0; h < NH; ++h) v[h] = nv[h];
+                for (int h = 0; h < NH; ++h) v[h] = nv[h];
+            }
         }
     }
     return rec;
@@ -916,7 +929,6 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
     uint64_t *full = reinterpret_cast<uint64_t *>(ms + S * NB);    // [S] producer -> replay
     uint64_t *done = full + S;                                     // [S] replay -> store thread
     uint64_t *empty = done + S;                                    // [S] store thread -> producer
-    double *scr = reinterpret_cast<double *>(empty + S);           // [DP] radius terms of a CONTESTED cell
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return;
     const Num nm = e.nm;
@@ -955,7 +967,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
                 tma_load_1d(xs + (size_t)s * NB * LSP, xg + (size_t)b * NB * LSP, bx, &full[s]);
                 tma_load_1d(ms + s * NB, pl + b * NB, bi, &full[s]);
             }
-            CCB_DBG(if (e.ws.dbg) e.ws.dbg[j * 8 + 7] = tw;)
+            CCB_DBG((void)tw;)
         }
         return;
     }
@@ -971,7 +983,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
                     CCB_DBG(tw += clock64() - t0;)
                 }
                 const int cnt = min(NB, n - b * NB);
-                CCB_DBG(if (g_bs_dbg_mode == 0))
+                CCB_DBG(if (!(g_bs_dbg_mode & 1)))
                 tma_store_1d(vp + (size_t)b * NB * LSP, xs + (size_t)s * NB * LSP, (uint32_t)cnt * LSP * 8u);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 if (b > 0) { // the copy before this one has read its stage: hand that stage back to the producer
@@ -980,10 +992,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
                 }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the copies
-            CCB_DBG(if (e.ws.dbg) {
-                e.ws.dbg[j * 8 + 5] = clock64() - tbeg;
-                e.ws.dbg[j * 8 + 6] = tw;
-            })
+            CCB_DBG((void)tw; (void)tbeg;)
         }
         return;
     }
@@ -992,7 +1001,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
             // one pass through the rare-path code on dummy data: its instruction-cache lines are then on this SM before the
             // replay warp (which cannot hide a miss) meets its first CONTESTED cell
             const bool r = bs_radius_test<DP, NH>(1.0, smem_u32(xs) + lane * 8, lane, D, nm.delta2, nm.eps2, nm.div_mode, nm.k,
-                                                  nm.wsel, scr + DP);
+                                                  nm.wsel);
             if (r && D < 0) e.ws.prej[0] = 1; // never taken; keeps the call alive
         }
         return;
@@ -1008,7 +1017,8 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         else if (el == 2 * DP) x = e.P.w[j];
         v[h] = x;
     }
-    CCB_DBG(long long t_wait = 0, t_slow = 0, n_cont = 0; const long long t_beg = clock64();)
+    CCB_DBG(long long t_wait = 0, t_slow = 0, n_cont = 0, t_head = 0, t_tail = 0, n_clean = 0; const long long t_beg = clock64();
+            const int dbgm = g_bs_dbg_mode;)
     // The replay warp issues in order and is alone on its scheduler: every dependent instruction costs its full latency.
     // Everything below is arranged for that.  Addresses and the lane number are held in OPAQUE registers (otherwise the
     // compiler re-derives them from special registers -- S2R / S2UR, tens of cycles each -- inside the loop).
@@ -1026,6 +1036,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
             mbar_wait(&full[s], (b / S) & 1);
             CCB_DBG(t_wait += clock64() - t0;)
         }
+        CCB_DBG(const long long t_h0 = clock64();)
         const int cnt = __shfl_sync(0xffffffffu, min(NB, n - b * NB), 0); // warp-uniform for the compiler, too
         uint32_t xa = xs_lane + s * (NB * LSP * 8), ma = ms_base + s * (NB * 4);
         asm volatile("" : "+r"(xa), "+r"(ma));
@@ -1038,7 +1049,9 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
             c_lo = __ballot_sync(0xffffffffu, f0 < 0 && lane_o < cnt);
             if (NB > 32) c_hi = __ballot_sync(0xffffffffu, f1 < 0 && lane_o + 32 < cnt);
         }
+        CCB_DBG(t_head += clock64() - t_h0;)
         if (cnt == NB && (c_lo | c_hi) == 0u) {
+            CCB_DBG(++n_clean;)
             // ---- CLEAN FULL STAGE: straight-line code with immediate offsets.  Cell c: the dependent add, then -- in its
             // latency shadow -- the store of the version cell c - 1 left and the load of an addend one batch ahead.
             double R[2][GS][NH];
@@ -1099,7 +1112,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
 #pragma unroll
                     for (int h = 0; h < NH; ++h) rec.v[h] = v[h];
                     rec = bs_chain_slow_group<DP, NH>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
-                                                      nm.div_mode, nm.k, nm.wsel, scr, e.ws.prej);
+                                                      nm.div_mode, nm.k, nm.wsel, e.ws.prej);
 #pragma unroll
                     for (int h = 0; h < NH; ++h) v[h] = rec.v[h];
                 }
@@ -1107,10 +1120,13 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
             CCB_DBG(t_slow += clock64() - t_s0;)
         }
         // the versions were written through the generic proxy; the bulk copy reads them through the async proxy
+        CCB_DBG(const long long t_t0 = clock64();)
         __syncwarp();
+        CCB_DBG(if (!(dbgm & 4)))
         fence_proxy_async_smem();
         __syncwarp();
         if (lane_o == 0) mbar_arrive(&done[s]);
+        CCB_DBG(t_tail += clock64() - t_t0;)
     }
     CCB_DBG(if (e.ws.dbg && lane == 0) {
         e.ws.dbg[j * 8 + 0] = n;
@@ -1118,6 +1134,9 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         e.ws.dbg[j * 8 + 2] = t_wait;
         e.ws.dbg[j * 8 + 3] = t_slow;
         e.ws.dbg[j * 8 + 4] = n_cont;
+        e.ws.dbg[j * 8 + 5] = t_head;  // (the store thread's slots: it only waits)
+        e.ws.dbg[j * 8 + 6] = t_tail;
+        e.ws.dbg[j * 8 + 7] = n_clean;
     })
 }
 

@@ -390,7 +390,8 @@ struct AssocCfg {
 template <int DP, bool DIV>
 __global__ void __launch_bounds__(ASSOC_THREADS)
     k_assoc(const double *__restrict__ qcen, const uint64_t *__restrict__ qmask, int Q, const double *__restrict__ pcen, int P,
-            int D, double k, double wsel, int32_t *__restrict__ best, double *__restrict__ bdist) {
+            int D, double k, double wsel, int32_t *__restrict__ best, double *__restrict__ bdist,
+            double *__restrict__ bdist2) {
     constexpr int TM = AssocCfg<DP>::TM, JU = ASSOC_JU;
     __shared__ __align__(128) double tile[2][TM * DP];
     __shared__ __align__(8) uint64_t bar[2];
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS)
     };
     if (threadIdx.x == 0 && ntiles > 0) issue(0);
     int bi = -1;
-    double bd = 0.0;
+    double bd = 0.0, bd2 = __longlong_as_double(0x7ff0000000000000LL); // runner-up distance (+inf: none)
     for (int t = 0; t < ntiles; ++t) {
         if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1);
         mbar_wait(&bar[t & 1], (t >> 1) & 1);
@@ -462,17 +463,23 @@ __global__ void __launch_bounds__(ASSOC_THREADS)
                 }
             }
 #pragma unroll
-            for (int v = 0; v < JU; ++v)
-                if (j0 + v < n && (bi < 0 || acc[v] < bd)) { // strict <: the first scanned MC keeps a tie
+            for (int v = 0; v < JU; ++v) {
+                if (j0 + v >= n) continue;
+                if (bi < 0 || acc[v] < bd) { // strict <: the first scanned MC keeps a tie
+                    if (bi >= 0) bd2 = bd;
                     bi = jt + j0 + v;
                     bd = acc[v];
+                } else if (acc[v] < bd2) {
+                    bd2 = acc[v];
                 }
+            }
         }
         __syncthreads();
     }
     if (live) {
         best[q] = bi;
         bdist[q] = bd;
+        if (bdist2) bdist2[q] = bd2;
     }
 }
 

@@ -18,7 +18,9 @@ from .objects import FinalCluster, Microcluster
 
 
 class _PointsView(object):
-    """Per-timepoint cell -> MC assignment; builds Microcluster.points dicts on demand."""
+    """Per-timepoint cell -> MC assignment; builds Microcluster.points dicts on demand.  The input arrays are BORROWED, not
+    copied (the reference copies every row into a Python list, microcluster.py:149): a caller that overwrites its array
+    in place after the call changes what `points` hands out."""
 
     def __init__(self):
         self.segments = []  # [(X, assign_uid)] since the last reset (hddstream.py:208-213)
@@ -217,7 +219,9 @@ class HDDStream(object):
             logger.info("Decaying and downgrading microclusters")
             interval = input_dataset_daystamp - self.last_data_timestamp
             factor = 2 ** (-self.lambbda * interval)  # hddstream.py:283, Python float power
-            self._views.reset()
+            # a NEW view per timepoint (hddstream.py:208-213 clears the points): Microcluster copies kept by the trackers
+            # stay bound to the view -- cells and assignment -- of the timepoint they were made in
+            self._views = _PointsView()
         _lib.check(L.ccb_begin_timepoint(h, float(self.mu), float(self.omicron), int(self.pi), int(decay),
                                          float(factor)), h)
         N = X.shape[0]
@@ -281,7 +285,7 @@ class HDDStream(object):
         """Forgets all microclusters and counters (a new run with the same parameters and device)."""
         if self._h is not None:
             _lib.check(_lib.lib().ccb_reset(self._h), self._h)
-        self._views.reset()
+        self._views = _PointsView()
         self._lists = [None, None]
         self.final_clusters = []
         self.last_data_timestamp = 0

@@ -83,6 +83,8 @@ class TrackByHistoricalAssociation(object):
     # on; None keeps the host loop.  Below it the two host <-> device copies cost more than the loop.
     device_scan_min_pairs = 1 << 16
 
+    device = 0  # CUDA ordinal of the association scan (app.run sets it to its own `device`)
+
     def __init__(self):
         self.current_clusters = []
         self.previous_timepoint_clusters = []
@@ -97,8 +99,9 @@ class TrackByHistoricalAssociation(object):
             return
         cur = [(cluster, pcore) for cluster in self.current_clusters for pcore in cluster.pcore_objects]
         prev = [(c.id, p) for c in self.previous_timepoint_clusters for p in c.pcore_objects]
-        if self.device_scan_min_pairs is not None and prev and len(cur) * len(prev) >= self.device_scan_min_pairs:
-            best = self._device_scan([p for _, p in cur], [p for _, p in prev])
+        if self.device_scan_min_pairs is not None and prev and len(cur) * len(prev) >= self.device_scan_min_pairs \
+                and self._cuda_ready():
+            best = self._device_scan([p for _, p in cur], [p for _, p in prev], self.device)
             for (cluster, _), j in zip(cur, best):
                 cluster.add_historical_associate(prev[j][0])
                 cluster.add_historical_associate_pcore(prev[j][1].id)
@@ -111,6 +114,16 @@ class TrackByHistoricalAssociation(object):
                     best_d, best_cluster, best_pcore = d, prev_id, prev_pcore.id
             cluster.add_historical_associate(best_cluster)
             cluster.add_historical_associate_pcore(best_pcore)
+
+    @staticmethod
+    def _cuda_ready():
+        """The device scan needs torch (device buffers) and a CUDA device; without them the host loop below runs."""
+        try:
+            import torch
+
+            return torch.cuda.is_available()
+        except ImportError:
+            return False
 
     @staticmethod
     def _device_scan(cur_pcores, prev_pcores, device=0):

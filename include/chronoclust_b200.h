@@ -201,6 +201,13 @@ int ccb_colminmax(int32_t device, void *stream, const double *X_dev, int64_t N, 
  * cur_cen [Q][D], cur_prefmask [Q] (bit d set <=> pref_q[d] == k), prev_cen [P][D]; best [Q] (-1 if P == 0), dist [Q]. */
 int ccb_assoc_nearest(int32_t device, void *stream, const double *cur_cen, const uint64_t *cur_prefmask, int64_t Q,
                       const double *prev_cen, int64_t P, int32_t D, double k, int32_t *best, double *dist);
+/* The same scan, also returning the runner-up distance dist2 [Q] (+inf if P < 2).  Used for the gating label of every
+ * cluster (replaces the loop of find_closest_gating, app.py:497-512, over Cluster.get_projected_dist_to_point,
+ * objects/cluster.py:94-104): that reference expression squares with Python's float `** 2` (libm pow), which may differ
+ * from the IEEE product in the last bit, so the caller accepts the device's argmin only when dist2 - dist clears a guard
+ * band and re-evaluates the few near-ties with the reference expression itself. */
+int ccb_assoc_nearest2(int32_t device, void *stream, const double *cur_cen, const uint64_t *cur_prefmask, int64_t Q,
+                       const double *prev_cen, int64_t P, int32_t D, double k, int32_t *best, double *dist, double *dist2);
 
 /* FP64 pipe microbenchmark for the roofline denominators: mode 0 = DFMA stream (2 flop/instr), mode 1 =
  * separate DMUL + DADD (1 flop/instr, the only form the parity contract allows).  Launches `blocks` CTAs of

@@ -196,3 +196,53 @@ def test_streamed_scaler_fit_equals_one_fit_over_all_timepoints(tmp_path):
     sc, mn = s.device_vectors()
     assert same(parts[3] * sc + mn, ref.transform(parts[3]))
     assert len(s.get_input_data()) == len(allc)
+
+
+def test_hostio_repr_is_python_repr():
+    """csrc/hostio.c formats float64 exactly like repr(float) (= what pandas' to_csv writes): shortest round-trip digits,
+    positional / exponent notation switch at 1e-4 and 1e16, '.0' on integers, subnormals, signed zero, infinities."""
+    import ctypes as C
+
+    from chronoclust_b200 import _hostio
+
+    L = _hostio.lib()
+    buf = C.create_string_buffer(64)
+    rng = np.random.default_rng(4)
+    vals = [0.1, 5.0, 1e-5, 0.0001, 1e15, 1e16, 1e17, 1.5e-7, 123456789.0, 1e22, -0.0, 0.0, 1 / 3, 2 / 3, 1e-310, 5e-324,
+            1.7976931348623157e308, float("inf"), -float("inf"), 9.999999999999999e15, 0.00011, 9.5e-5, 2.5e-4,
+            1234567890123456.0, 12345678901234567.0, 2.2250738585072014e-308, 2.225073858507201e-308, 1e100, -1e-100]
+    vals += rng.random(3000).tolist() + (rng.random(3000) * 1e6).tolist() + (rng.standard_normal(3000) * 1e-6).tolist()
+    vals += np.exp(rng.uniform(-740, 709, 3000)).tolist() + np.round(rng.random(1000), 3).tolist()
+    vals += rng.integers(-1000, 1000, 500).astype(float).tolist()
+    for v in vals:
+        n = L.ccbio_repr(v, buf)
+        assert buf.raw[:n].decode() == repr(v), (repr(v), buf.raw[:n])
+    assert L.ccbio_repr(float("nan"), buf) == 0  # an empty field, pandas' na_rep
+
+
+def test_hostio_table_is_byte_identical_to_pandas(tmp_path):
+    """The native multi-threaded writer of cluster_points_D{t}.csv against DataFrame.to_csv(index=False): same bytes,
+    including quoted labels (merged lineage ids contain commas), quoted column names, NaN cells and a strided input."""
+    import pandas as pd
+
+    from chronoclust_b200 import _hostio
+
+    rng = np.random.default_rng(9)
+    N, D = 50_003, 7
+    wide = rng.random((N, D + 2)) * np.array([1e-6, 1e-3, 1.0, 10.0, 1e3, 1e7, 1e17, 1.0, 1.0])
+    X = wide[:, :D]  # row stride != D
+    X[5, 3] = np.nan
+    X[7, 0] = 1e-310
+    X[9, 2] = -0.0
+    labels = ["None", "A", "B|1", "(A,B)", 'q"x', "((A,B),C)|2"]
+    li = rng.integers(0, len(labels), N).astype(np.int32)
+    names = ["FSC-A", "x,y"] + [f"m{j}" for j in range(2, D)]
+    cols = {"id": np.arange(N), "cluster_id": np.array(labels, dtype=object)[li]}
+    for j in range(D):
+        cols[names[j]] = X[:, j]
+    pd.DataFrame(cols).to_csv(tmp_path / "pandas.csv", index=False)
+    for threads in (0, 1, 3):
+        _hostio.write_points_csv(tmp_path / "native.csv", ["id", "cluster_id"] + names, X, li, labels, threads=threads)
+        assert open(tmp_path / "native.csv", "rb").read() == open(tmp_path / "pandas.csv", "rb").read()
+    _hostio.write_points_csv(tmp_path / "empty.csv", ["id", "cluster_id"] + names, np.zeros((0, D)), np.zeros(0, np.int32), labels)
+    assert open(tmp_path / "empty.csv").read() == ",".join(["id", "cluster_id", "FSC-A", '"x,y"'] + names[2:]) + "\n"

@@ -29,14 +29,20 @@ with tempfile.TemporaryDirectory() as tmp:
         np.savetxt(f, X, delimiter=",", header=",".join(f"m{d}" for d in range(D)), comments="", fmt="%.17g")
         files.append(f)
     t_write = time.perf_counter() - t0
-    out = os.path.join(tmp, "out")
-    os.makedirs(out)
-    t0 = time.perf_counter()
-    app.run(data=files, output_directory=out, normalise_data=False, param_beta=cfg["beta"], param_delta=cfg["delta"],
-            param_epsilon=cfg["epsilon"], param_lambda=cfg["lambda"], param_k=cfg["k"], param_mu=cfg["mu"],
-            param_pi=cfg["pi"], param_omicron=cfg["omicron"], param_upsilon=cfg["upsilon"])
-    wall = time.perf_counter() - t0
-    nres = sum(1 for _ in open(os.path.join(out, "result.csv"))) - 1
-    print(json.dumps({"metric": "app.run wall time, everything included", "cells": N * T, "seconds": wall,
-                      "cells_per_s": N * T / wall, "input_csv_write_s": t_write, "result_rows": nres,
+    res = {}
+    for normalise in (False, True, False):  # (the first pass also pays the one-time costs: CUDA context, library load)
+        out = os.path.join(tmp, f"out{len(res)}_{int(normalise)}")
+        os.makedirs(out)
+        t0 = time.perf_counter()
+        app.run(data=files, output_directory=out, normalise_data=normalise, param_beta=cfg["beta"], param_delta=cfg["delta"],
+                param_epsilon=cfg["epsilon"], param_lambda=cfg["lambda"], param_k=cfg["k"], param_mu=cfg["mu"],
+                param_pi=cfg["pi"], param_omicron=cfg["omicron"], param_upsilon=cfg["upsilon"])
+        wall = time.perf_counter() - t0
+        nres = sum(1 for _ in open(os.path.join(out, "result.csv"))) - 1
+        name = ("first_run_" if not res else "") + ("normalise" if normalise else "no_normalise")
+        res[name] = {"seconds": wall, "cells_per_s": N * T / wall, "result_rows": nres,
+                     "output_bytes": sum(os.path.getsize(os.path.join(out, f)) for f in os.listdir(out)
+                                         if f.endswith(".csv"))}
+    print(json.dumps({"metric": "app.run wall time, everything included", "cells": N * T, "runs": res,
+                      "input_csv_write_s": t_write, "host_cores": os.cpu_count(),
                       "workload": f"C2 at scale {scale}: {N} cells x {D} markers x {T} timepoints as CSV files"}))
