@@ -66,6 +66,9 @@ SYMBOLS = {
     "ccb_off_subspace": (C.c_int, [i32, vp, vp, i64, i32, i64, i64, vp, vp, f64, vp]),
     "ccb_off_weighted": (C.c_int, [i32, vp, vp, i64, i32, i64, i64, vp, vp, f64, f64, vp]),
     "ccb_off_clusters": (C.c_int, [i32, vp, i64, vp, vp, vp, f64, i64, i32, vp, vp, vp, vp]),
+    "ccb_offc_rowinfo": (C.c_int, [i32, vp, vp, i64, i64, i64, vp, vp]),
+    "ccb_offc_fill": (C.c_int, [i32, vp, vp, i64, i64, i64, vp, vp, vp]),
+    "ccb_off_clusters_csr": (C.c_int, [i32, vp, i64, vp, vp, vp, vp, vp, f64, i64, vp, vp, vp, vp]),
 }
 
 

@@ -852,6 +852,28 @@ void tune_pool(int device) {
 // (offline.cuh).  Both produce identical label / order / cl_off / n_cl.  cls [M] and queue [2M + 2] are scratch.
 constexpr int OFF_CSR_MIN_M = 2048; // default switch-over; ccb_params.off_csr_min_m / the csr_min_m argument move it
 
+// The ordered growth over a CSR of the weighted neighbourhoods and the merge with the isolated microclusters' clusters by
+// seed rank (offline.cuh).  i32: scratch of 7 M + 16 int32; cls [M] zeroed; queue [2 M + 2].
+void offc_grow_and_merge(cudaStream_t s, int M, const int64_t *off, const int32_t *col, const uint8_t *core, const uint8_t *iso,
+                         const uint64_t *submask, int cnt_gt1, int64_t pi, uint8_t *cls, int32_t *queue, int32_t *i32,
+                         int32_t *label, int32_t *order, int32_t *cl_off, int32_t *n_cl) {
+    const size_t m = (size_t)M;
+    int32_t *order_s = i32, *cl_off_s = order_s + m, *seed_of = cl_off_s + m + 1, *n_cl_s = seed_of + m + 1,
+            *seedflag = n_cl_s + 1, *size_by_node = seedflag + m, *rank = size_by_node + m, *size_by_cluster = rank + m + 1;
+    const int tgrid = (M + 255) / 256;
+    k_offc_grow<<<1, OFFG_THREADS, 0, s>>>(M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, order_s, cl_off_s, seed_of,
+                                           n_cl_s);
+    k_offc_seeds<<<tgrid, 256, 0, s>>>(M, iso, core, submask, cnt_gt1, pi, seed_of, cl_off_s, n_cl_s, seedflag, size_by_node,
+                                       label);
+    k_offc_seeds_serial<<<tgrid, 256, 0, s>>>(seed_of, cl_off_s, n_cl_s, seedflag, size_by_node);
+    k_offc_scan<int32_t><<<1, OFFG_THREADS, 0, s>>>(seedflag, M, rank);
+    cudaMemsetAsync(size_by_cluster, 0, m * 4, s);
+    k_offc_sizes<<<tgrid, 256, 0, s>>>(M, seedflag, rank, size_by_node, size_by_cluster, n_cl);
+    k_offc_scan<int32_t><<<1, OFFG_THREADS, 0, s>>>(size_by_cluster, M, cl_off);
+    k_offc_scatter_iso<<<tgrid, 256, 0, s>>>(M, iso, seedflag, rank, size_by_node, cl_off, order, label);
+    k_offc_scatter_serial<<<148, 256, 0, s>>>(seed_of, cl_off_s, n_cl_s, order_s, rank, cl_off, order, label);
+}
+
 int launch_off_clusters(ccb_handle *h, cudaStream_t s, int M, const uint32_t *wnbr, const uint8_t *core,
                         const uint64_t *submask, int cnt_gt1, int64_t pi, uint8_t *cls, int32_t *queue, int32_t *label,
                         int32_t *order, int32_t *cl_off, int32_t *n_cl, int *launches, int csr_min_m) {
@@ -876,16 +898,15 @@ int launch_off_clusters(ccb_handle *h, cudaStream_t s, int M, const uint32_t *wn
     if ((e = cudaMallocAsync(&iso, m, s)) != cudaSuccess || (e = cudaMallocAsync(&i32, n32 * 4, s)) != cudaSuccess ||
         (e = cudaMallocAsync(&off, (m + 1) * 8, s)) != cudaSuccess)
         return fail(h, CCB_ENOMEM, "offline scratch: %s", cudaGetErrorString(e));
-    int32_t *nnz = i32, *order_s = nnz + m, *cl_off_s = order_s + m, *seed_of = cl_off_s + m + 1, *n_cl_s = seed_of + m + 1,
-            *seedflag = n_cl_s + 1, *size_by_node = seedflag + m, *rank = size_by_node + m, *size_by_cluster = rank + m + 1;
+    int32_t *nnz = i32; // the remaining 7 m + 16 entries are the scratch of offc_grow_and_merge
     auto release = [&]() {
         cudaFreeAsync(iso, s);
         cudaFreeAsync(i32, s);
         cudaFreeAsync(off, s);
         if (col) cudaFreeAsync(col, s);
     };
-    const int wgrid = (M + 3) / 4, tgrid = (M + 255) / 256;
-    k_offc_rowinfo<<<wgrid, 128, 0, s>>>(wnbr, M, words, iso, nnz);
+    const int wgrid = (M + 3) / 4;
+    k_offc_rowinfo<<<wgrid, 128, 0, s>>>(wnbr, 0, M, words, iso, nnz);
     k_offc_scan<int64_t><<<1, OFFG_THREADS, 0, s>>>(nnz, M, off);
     *launches += 2;
     int64_t total = 0;
@@ -902,19 +923,10 @@ int launch_off_clusters(ccb_handle *h, cudaStream_t s, int M, const uint32_t *wn
         release();
         return fail(h, CCB_ENOMEM, "offline CSR (%lld entries): %s", (long long)total, cudaGetErrorString(e));
     }
-    k_offc_fill<<<wgrid, 128, 0, s>>>(wnbr, M, words, iso, off, col);
-    k_offc_grow<<<1, OFFG_THREADS, 0, s>>>(M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, order_s, cl_off_s, seed_of,
-                                           n_cl_s);
-    k_offc_seeds<<<tgrid, 256, 0, s>>>(M, iso, core, submask, cnt_gt1, pi, seed_of, cl_off_s, n_cl_s, seedflag, size_by_node,
-                                       label);
-    k_offc_seeds_serial<<<tgrid, 256, 0, s>>>(seed_of, cl_off_s, n_cl_s, seedflag, size_by_node);
-    k_offc_scan<int32_t><<<1, OFFG_THREADS, 0, s>>>(seedflag, M, rank);
-    cudaMemsetAsync(size_by_cluster, 0, m * 4, s);
-    k_offc_sizes<<<tgrid, 256, 0, s>>>(M, seedflag, rank, size_by_node, size_by_cluster, n_cl);
-    k_offc_scan<int32_t><<<1, OFFG_THREADS, 0, s>>>(size_by_cluster, M, cl_off);
-    k_offc_scatter_iso<<<tgrid, 256, 0, s>>>(M, iso, seedflag, rank, size_by_node, cl_off, order, label);
-    k_offc_scatter_serial<<<148, 256, 0, s>>>(seed_of, cl_off_s, n_cl_s, order_s, rank, cl_off, order, label);
-    *launches += 9;
+    k_offc_fill<<<wgrid, 128, 0, s>>>(wnbr, 0, M, words, iso, off, col);
+    *launches += 1;
+    offc_grow_and_merge(s, M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, i32 + m, label, order, cl_off, n_cl);
+    *launches += 8;
     e = cudaGetLastError();
     release();
     return e == cudaSuccess ? CCB_OK : fail(h, CCB_ECUDA, "offline cluster growth: %s", cudaGetErrorString(e));
@@ -1968,6 +1980,58 @@ int ccb_off_clusters(int32_t device, void *stream, int64_t M, const uint32_t *wn
     cudaFreeAsync(cls, s);
     cudaFreeAsync(queue, s);
     return rc;
+}
+
+int ccb_offc_rowinfo(int32_t device, void *stream, const uint32_t *wnbr_rows, int64_t M, int64_t r0, int64_t r1, uint8_t *iso,
+                     int32_t *nnz) {
+    if (M < 0 || r0 < 0 || r1 < r0 || r1 > M) return fail(nullptr, CCB_EINVAL, "bad arguments");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    if (r1 > r0)
+        k_offc_rowinfo<<<(unsigned)((r1 - r0 + 3) / 4), 128, 0, (cudaStream_t)stream>>>(wnbr_rows, (int)r0, (int)r1,
+                                                                                       (int)((M + 31) / 32), iso, nnz);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "k_offc_rowinfo: %s", cudaGetErrorString(e));
+}
+
+int ccb_offc_fill(int32_t device, void *stream, const uint32_t *wnbr_rows, int64_t M, int64_t r0, int64_t r1,
+                  const uint8_t *iso_all, const int64_t *off_all, int32_t *col) {
+    if (M < 0 || r0 < 0 || r1 < r0 || r1 > M) return fail(nullptr, CCB_EINVAL, "bad arguments");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    if (r1 > r0)
+        k_offc_fill<<<(unsigned)((r1 - r0 + 3) / 4), 128, 0, (cudaStream_t)stream>>>(wnbr_rows, (int)r0, (int)r1,
+                                                                                    (int)((M + 31) / 32), iso_all, off_all, col);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "k_offc_fill: %s", cudaGetErrorString(e));
+}
+
+int ccb_off_clusters_csr(int32_t device, void *stream, int64_t M, const int64_t *off, const int32_t *col, const uint8_t *iso,
+                         const uint8_t *core, const uint64_t *submask_all, double k, int64_t pi, int32_t *label, int32_t *order,
+                         int32_t *cl_off, int32_t *n_cl) {
+    if (M < 0 || M >= ((int64_t)1 << 31)) return fail(nullptr, CCB_EINVAL, "bad arguments");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CCB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaStream_t s = (cudaStream_t)stream;
+    tune_pool(device);
+    if (M == 0) {
+        cudaMemsetAsync(n_cl, 0, 4, s);
+        cudaMemsetAsync(cl_off, 0, 4, s);
+        return CCB_OK;
+    }
+    uint8_t *cls = nullptr;
+    int32_t *queue = nullptr, *i32 = nullptr;
+    const size_t m = (size_t)M;
+    if ((e = cudaMallocAsync(&cls, m, s)) != cudaSuccess || (e = cudaMallocAsync(&queue, (2 * m + 2) * 4, s)) != cudaSuccess ||
+        (e = cudaMallocAsync(&i32, (7 * m + 16) * 4, s)) != cudaSuccess)
+        return fail(nullptr, CCB_ENOMEM, "scratch allocation: %s", cudaGetErrorString(e));
+    cudaMemsetAsync(cls, 0, m, s);
+    offc_grow_and_merge(s, (int)M, off, col, core, iso, submask_all, k > 1.0, pi, cls, queue, i32, label, order, cl_off, n_cl);
+    e = cudaGetLastError();
+    cudaFreeAsync(cls, s);
+    cudaFreeAsync(queue, s);
+    cudaFreeAsync(i32, s);
+    return e == cudaSuccess ? CCB_OK : fail(nullptr, CCB_ECUDA, "offline cluster growth (CSR): %s", cudaGetErrorString(e));
 }
 
 } // extern "C"

@@ -416,12 +416,13 @@ __device__ __forceinline__ int offc_block_min(int v, int *s_warp) {
     return v;
 }
 
-// warp per row: |WN(row)|, isolated flag, CSR entries the row will need (0 for isolated rows)
-__global__ void k_offc_rowinfo(const uint32_t *__restrict__ wnbr, int M, int words, uint8_t *iso, int32_t *nnz) {
+// warp per row of [r0, r1): |WN(row)|, isolated flag, CSR entries the row will need (0 for isolated rows).  wnbr holds the
+// rows from r0 on (a rank's own rows in the sharded path); iso / nnz are indexed from r0, too.
+__global__ void k_offc_rowinfo(const uint32_t *__restrict__ wnbr, int r0, int r1, int words, uint8_t *iso, int32_t *nnz) {
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= M) return;
-    const uint32_t *r = wnbr + (size_t)row * words;
+    const int row = r0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= r1) return;
+    const uint32_t *r = wnbr + (size_t)(row - r0) * words;
     int c = 0;
     for (int w = lane; w < words; w += 32) c += __popc(r[w]);
 #pragma unroll
@@ -429,8 +430,8 @@ __global__ void k_offc_rowinfo(const uint32_t *__restrict__ wnbr, int M, int wor
     if (lane == 0) {
         const bool self = (r[row >> 5] >> (row & 31)) & 1u;
         const bool is = (c == 1 && self);
-        iso[row] = is;
-        nnz[row] = is ? 0 : c;
+        iso[row - r0] = is;
+        nnz[row - r0] = is ? 0 : c;
     }
 }
 
@@ -451,13 +452,14 @@ __global__ void __launch_bounds__(OFFG_THREADS, 1) k_offc_scan(const int32_t *__
     if (threadIdx.x == 0) out[n] = carry;
 }
 
-// warp per non-isolated row: column indices of its set bits, ascending
-__global__ void k_offc_fill(const uint32_t *__restrict__ wnbr, int M, int words, const uint8_t *__restrict__ iso,
+// warp per non-isolated row of [r0, r1): column indices of its set bits, ascending.  wnbr holds the rows from r0 on; iso and
+// off are indexed by the GLOBAL row, col is the global CSR (a rank fills the segment of its own rows).
+__global__ void k_offc_fill(const uint32_t *__restrict__ wnbr, int r0, int r1, int words, const uint8_t *__restrict__ iso,
                             const int64_t *__restrict__ off, int32_t *__restrict__ col) {
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= M || iso[row]) return;
-    const uint32_t *r = wnbr + (size_t)row * words;
+    const int row = r0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= r1 || iso[row]) return;
+    const uint32_t *r = wnbr + (size_t)(row - r0) * words;
     int64_t o = off[row];
     for (int w0 = 0; w0 < words; w0 += 32) {
         const int w = w0 + lane;

@@ -239,6 +239,21 @@ int ccb_off_clusters(int32_t device, void *stream, int64_t M, const uint32_t *wn
                      const uint64_t *submask_all, double k, int64_t pi, int32_t csr_min_m, int32_t *label, int32_t *order,
                      int32_t *cl_off, int32_t *n_cl);
 
+/* Offline stage 4, sharded form (config C4): instead of all-gathering the weighted-neighbour BIT ROWS (M^2 / 8 bytes), every
+ * rank turns its own rows [r0, r1) into CSR form and only the lists travel.
+ * ccb_offc_rowinfo: per own row the isolated flag (WN(p) = {p}) and the number of CSR entries it needs (0 if isolated);
+ *   wnbr_rows [(r1-r0)][words], iso / nnz [(r1-r0)].
+ * ccb_offc_fill: column indices of the own non-isolated rows into the GLOBAL CSR col at off_all[row] (iso_all [M], off_all
+ *   [M + 1] = exclusive prefix of the gathered nnz; the caller merges the ranks' disjoint segments, e.g. by an all-reduce).
+ * ccb_off_clusters_csr: the ordered cluster growth of ccb_off_clusters over that CSR (same outputs). */
+int ccb_offc_rowinfo(int32_t device, void *stream, const uint32_t *wnbr_rows, int64_t M, int64_t r0, int64_t r1, uint8_t *iso,
+                     int32_t *nnz);
+int ccb_offc_fill(int32_t device, void *stream, const uint32_t *wnbr_rows, int64_t M, int64_t r0, int64_t r1,
+                  const uint8_t *iso_all, const int64_t *off_all, int32_t *col);
+int ccb_off_clusters_csr(int32_t device, void *stream, int64_t M, const int64_t *off, const int32_t *col, const uint8_t *iso,
+                         const uint8_t *core, const uint64_t *submask_all, double k, int64_t pi, int32_t *label, int32_t *order,
+                         int32_t *cl_off, int32_t *n_cl);
+
 #ifdef __cplusplus
 }
 #endif

@@ -755,3 +755,88 @@ def test_colminmax_covers_every_element():
         _lib.check(_lib.lib().ccb_colminmax(0, None, t.data_ptr(), N, D, D, mn.data_ptr(), mx.data_ptr()))
         torch.cuda.synchronize()
         assert bits_equal(mn.cpu().numpy(), X.min(axis=0)) and bits_equal(mx.cpu().numpy(), X.max(axis=0)), f"D={D}"
+
+
+def _nccl_offline_worker(rank, world, port, M, ret):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        from chronoclust_b200 import _lib
+        from chronoclust_b200.offline_sharded import CudaStages, sharded_offline
+        from chronoclust_b200.synth import gen_offline_stress
+
+        D, E = 40, 0.3
+        cen, w, core = gen_offline_stress(M, D)
+        tc = torch.from_numpy(cen).cuda(rank)
+        tcore = torch.from_numpy(core.astype(np.uint8)).cuda(rank)
+        st = CudaStages(rank, dnrm2_ptr=_lib.scipy_dnrm2_pointer())
+        out = {}
+        for name, stages in (("csr", st), ("bitrows", _WithoutCsr(st))):
+            lab, order, cl_off, ncl, info = sharded_offline(stages, tc, tcore, M, D, 4.0, D, 0.05, E, E ** 2, dist=dist)
+            out[name] = (lab.copy(), order[:cl_off[-1]].copy(), cl_off.copy(), int(ncl), info["exchange"], info["gather_bytes"])
+        l1, o1, c1, n1, _ = sharded_offline(st, tc, tcore, M, D, 4.0, D, 0.05, E, E ** 2, dist=None)  # this rank alone
+        ok = True
+        for name, (lab, order, cl_off, ncl, exch, nbytes) in out.items():
+            ok = ok and exch == name and ncl == n1 and (lab == l1).all() and (cl_off == c1).all() and (order == o1[:c1[-1]]).all()
+        ret[rank] = (bool(ok), int(n1), out["csr"][5], out["bitrows"][5], l1.tolist() if rank == 0 else None,
+                     o1[:c1[-1]].tolist() if rank == 0 else None, c1.tolist() if rank == 0 else None)
+    finally:
+        dist.destroy_process_group()
+
+
+class _WithoutCsr:
+    """A stage object without the CSR methods: sharded_offline then all-gathers the bit rows."""
+
+    def __init__(self, st):
+        self._st, self.torch = st, st.torch
+
+    def __getattr__(self, name):
+        if name in ("rowinfo", "fill", "clusters_csr"):
+            raise AttributeError(name)
+        return getattr(self._st, name)
+
+
+def test_sharded_offline_nccl_matches_single_rank_and_oracle():
+    """The row-sharded offline phase on 2 GPUs over NCCL -- both exchanges: per-rank CSR lists merged by an all-reduce, and
+    the all-gather of the bit rows -- against (i) the same phase on one rank and (ii) the oracle's PreDeCon restatement:
+    labels, claim order and cluster offsets identical.  Skipped on a box with fewer than 2 GPUs (run it with
+    `gpurun --gpus 2`; the log of that run is committed under profiles/)."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from chronoclust_b200.synth import gen_offline_stress
+    from oracle.oracle import OracleHDDStream, _p
+    from oracle.oracle import lib as olib
+
+    M, D = 6000, 40
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    mp.spawn(_nccl_offline_worker, args=(world, 29700 + os.getpid() % 200, M, ret), nprocs=world, join=True)
+    assert all(ret[r][0] for r in range(world)), {r: ret[r][:4] for r in range(world)}
+    assert ret[0][2] < ret[0][3], "the CSR exchange must move fewer bytes than the bit rows"
+    # oracle: same microclusters (any CF consistent with the centroids; only centroids / weights / core flags matter here)
+    cen, w, core = gen_offline_stress(M, D)
+    cfg = {"beta": 0.0, "delta": 0.05, "epsilon": 1e150, "lambda": 0, "k": 4.0, "mu": 0.0, "pi": D, "omicron": 0.0,
+           "upsilon": 0.3 / 1e150}
+    o = OracleHDDStream(cfg)
+    o._ensure(D)
+    L = olib()
+    cf1, cf2 = cen * w[:, None], (cen * cen) * w[:, None]  # zero variance: every MC passes the radius test of the core flag
+    for i in range(M):
+        L.cco_import_mc(o._h, 0, i, i, float(w[i]), _p(np.ascontiguousarray(cf1[i])), _p(np.ascontiguousarray(cf2[i])),
+                        _p(np.ascontiguousarray(cen[i])), _p(np.ones(D)))
+    L.cco_set_thresholds(o._h, 20.0, 0.0, D)  # core <=> W >= 20, the generator's flag
+    o.offline_clustering()
+    lab, order, cl_off = np.array(ret[0][4]), np.array(ret[0][5]), np.array(ret[0][6])
+    members = [order[cl_off[c]:cl_off[c + 1]].tolist() for c in range(len(cl_off) - 1)]
+    members = [m for m in members if m]  # (clusters without members have weight 0 and are dropped, predecon.py:83)
+    oc = [list(m) for m, *_ in o.clusters()]
+    assert members == oc, "2-GPU clusters differ from the oracle's"

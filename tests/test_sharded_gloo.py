@@ -1,6 +1,7 @@
-"""world_size-2 gloo test (CPU) of the row-sharded offline path's host logic: row partitioning, padding,
-all-gathers and the replicated cluster stage.  The compute stages are injected: here they are backed by
-the oracle's full-matrix intermediates (test infrastructure), on the GPU by the C-ABI kernels."""
+"""world_size-2 gloo test (CPU) of the row-sharded offline path's host logic: row partitioning, padding, the all-gathers,
+the CSR exchange (per-rank lists merged by an all-reduce) and the replicated cluster stage.  The compute stages are
+injected: here they are backed by the oracle's full-matrix intermediates (test infrastructure), on the GPU by the C-ABI
+kernels (tests/test_gpu_parity.py::test_sharded_offline_nccl_matches_single_rank runs those on 2 GPUs)."""
 import os
 import sys
 
@@ -49,12 +50,50 @@ class OracleStages:
         words = (M + 31) // 32
         wnbr[:r1 - r0] = torch.from_numpy(self._pack(self.wn[r0:r1], words))
 
+    def rowinfo(self, wn_rows, M, r0, r1, iso, nnz):
+        rows = self.wn[r0:r1].astype(bool)
+        c = rows.sum(1)
+        lone = (c == 1) & rows[np.arange(r1 - r0), np.arange(r0, r1)]
+        iso[:r1 - r0] = torch.from_numpy(lone.astype(np.uint8))
+        nnz[:r1 - r0] = torch.from_numpy(np.where(lone, 0, c).astype(np.int32))
+
+    def fill(self, wn_rows, M, r0, r1, iso_all, off_all, col):
+        for row in range(r0, r1):
+            if not int(iso_all[row]):
+                cols = np.flatnonzero(self.wn[row]).astype(np.int32)
+                o = int(off_all[row])
+                assert int(off_all[row + 1]) - o == len(cols)
+                col[o:o + len(cols)] = torch.from_numpy(cols)
+
+    def clusters_csr(self, M, off_all, col, iso_all, core, submask_all, k, pi):
+        # the merged CSR must be the CSR of the oracle's full matrix without its isolated rows
+        full = self.wn.astype(bool)
+        lone = (full.sum(1) == 1) & full[np.arange(M), np.arange(M)]
+        assert (iso_all[:M].numpy().astype(bool) == lone).all(), "gathered isolated flags differ"
+        exp = np.concatenate([np.flatnonzero(full[r]) for r in range(M) if not lone[r]] + [np.zeros(0, np.int64)])
+        assert int(off_all[M]) == len(exp) and (col[:len(exp)].numpy() == exp).all(), "merged CSR differs"
+        self.used_csr = True
+        return self.labels, np.arange(M, dtype=np.int32), np.zeros(1, np.int32), 0
+
     def clusters(self, M, wnbr_all, core, submask_all, k, pi):
         # the gathered matrix must equal the oracle's full one: that is what this test is about
         words = (M + 31) // 32
         full = self._pack(self.wn, words)
         assert (wnbr_all[:M].numpy() == full).all(), "gathered WN rows differ from the full matrix"
         return self.labels, np.arange(M, dtype=np.int32), np.zeros(1, np.int32), 0
+
+
+class _NoCsr:
+    """View of a stage object without the CSR methods (forces the bit-row all-gather)."""
+
+    def __init__(self, st):
+        self._st = st
+        self.torch = st.torch
+
+    def __getattr__(self, name):
+        if name in ("rowinfo", "fill", "clusters_csr"):
+            raise AttributeError(name)
+        return getattr(self._st, name)
 
 
 def _worker(rank, world, port, ret):
@@ -91,6 +130,12 @@ def _worker(rank, world, port, ret):
             R, r0, r1 = row_range(M, world, rank)
             ok = ok and info["rows"] == (r0, r1) and (lab == labels).all()
             ok = ok and info["neighbour_count"] == int(nbr[r0:r1].sum())
+            ok = ok and info["exchange"] in ("csr", "bitrows") and (info["exchange"] == "bitrows" or st.used_csr)
+            # the same through the bit-row exchange (what a stage object without the CSR methods gets)
+            st2 = OracleStages(core, nbr, wn, subw, float(k), labels)
+            lab2, *_rest, info2 = sharded_offline(_NoCsr(st2), torch.from_numpy(cen), torch.from_numpy(core), M, D, float(k), pi,
+                                                  float(delta), float(E), float(E) ** 2, group=None, dist=dist)
+            ok = ok and info2["exchange"] == "bitrows" and (lab2 == labels).all()
         ret[rank] = ok
     finally:
         dist.destroy_process_group()
