@@ -88,6 +88,10 @@ def main():
                           "n_gpus": world, "configs": len(grid), "cells_per_config": N * T, "seconds": sec,
                           "wall_s": wall, "scaling": "strong", "partition": "config i -> rank i mod G, no collective",
                           "clusters_min_max": [min(r["clusters"] for r in res), max(r["clusters"] for r in res)],
+                          "seconds_per_run_min_median_max": [min(r["seconds"] for r in res),
+                                                             sorted(r["seconds"] for r in res)[len(res) // 2],
+                                                             max(r["seconds"] for r in res)],
+                          "slowest_over_fastest": max(r["seconds"] for r in res) / max(min(r["seconds"] for r in res), 1e-9),
                           "runs": res}))
     if dist is not None:
         dist.destroy_process_group()
