@@ -709,7 +709,9 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
     // <= 4 eps^2).  Established MCs sit right at their radius limit, so a margin below eps^2 marks almost every cell
     // CONTESTED (profiles/r1p_safe_rule_experiment.md: 10x slower); the distance bound singles out the ~1 % background
     // cells, which are exactly the ones whose radius test is open.  Speculative rejection of far cells did not pay
-    // either (profiles/r1t_speculative_reject_experiment.md), so every CONTESTED cell takes the exact in-chain test.
+    // either (profiles/r1t_speculative_reject_experiment.md), nor did calling every cell SAFE whose tentative MC keeps a
+    // margin below eps^2 whatever its distance (profiles/r2h_slack_rule_experiment.md): every CONTESTED cell takes the
+    // exact in-chain test.
     io.theta = 4.0 * h->prm.eps2;
     io.r2safe = h->prm.eps2;
     io.r2rej = HUGE_VAL;
@@ -856,13 +858,18 @@ constexpr int OFF_CSR_MIN_M = 2048; // default switch-over; ccb_params.off_csr_m
 // seed rank (offline.cuh).  i32: scratch of 7 M + 16 int32; cls [M] zeroed; queue [2 M + 2].
 void offc_grow_and_merge(cudaStream_t s, int M, const int64_t *off, const int32_t *col, const uint8_t *core, const uint8_t *iso,
                          const uint64_t *submask, int cnt_gt1, int64_t pi, uint8_t *cls, int32_t *queue, int32_t *i32,
-                         int32_t *label, int32_t *order, int32_t *cl_off, int32_t *n_cl) {
+                         int32_t *label, int32_t *order, int32_t *cl_off, int32_t *n_cl, int64_t total_nnz) {
     const size_t m = (size_t)M;
     int32_t *order_s = i32, *cl_off_s = order_s + m, *seed_of = cl_off_s + m + 1, *n_cl_s = seed_of + m + 1,
             *seedflag = n_cl_s + 1, *size_by_node = seedflag + m, *rank = size_by_node + m, *size_by_cluster = rank + m + 1;
     const int tgrid = (M + 255) / 256;
-    k_offc_grow<<<1, OFFG_THREADS, 0, s>>>(M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, order_s, cl_off_s, seed_of,
-                                           n_cl_s);
+    // short lists (a sparse graph): one warp, no block barriers; long lists: the 1024-thread walk.  total_nnz < 0 = unknown
+    if (total_nnz >= 0 && total_nnz <= (int64_t)M * 16)
+        k_offc_grow_warp<<<1, 32, 0, s>>>(M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, order_s, cl_off_s, seed_of,
+                                          n_cl_s);
+    else
+        k_offc_grow<<<1, OFFG_THREADS, 0, s>>>(M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, order_s, cl_off_s,
+                                               seed_of, n_cl_s);
     k_offc_seeds<<<tgrid, 256, 0, s>>>(M, iso, core, submask, cnt_gt1, pi, seed_of, cl_off_s, n_cl_s, seedflag, size_by_node,
                                        label);
     k_offc_seeds_serial<<<tgrid, 256, 0, s>>>(seed_of, cl_off_s, n_cl_s, seedflag, size_by_node);
@@ -925,7 +932,7 @@ int launch_off_clusters(ccb_handle *h, cudaStream_t s, int M, const uint32_t *wn
     }
     k_offc_fill<<<wgrid, 128, 0, s>>>(wnbr, 0, M, words, iso, off, col);
     *launches += 1;
-    offc_grow_and_merge(s, M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, i32 + m, label, order, cl_off, n_cl);
+    offc_grow_and_merge(s, M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, i32 + m, label, order, cl_off, n_cl, total);
     *launches += 8;
     e = cudaGetLastError();
     release();
@@ -2026,7 +2033,11 @@ int ccb_off_clusters_csr(int32_t device, void *stream, int64_t M, const int64_t 
         (e = cudaMallocAsync(&i32, (7 * m + 16) * 4, s)) != cudaSuccess)
         return fail(nullptr, CCB_ENOMEM, "scratch allocation: %s", cudaGetErrorString(e));
     cudaMemsetAsync(cls, 0, m, s);
-    offc_grow_and_merge(s, (int)M, off, col, core, iso, submask_all, k > 1.0, pi, cls, queue, i32, label, order, cl_off, n_cl);
+    int64_t total = -1; // list lengths decide between the one-warp and the 1024-thread walk
+    if (cudaMemcpyAsync(&total, off + M, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+        total = -1;
+    offc_grow_and_merge(s, (int)M, off, col, core, iso, submask_all, k > 1.0, pi, cls, queue, i32, label, order, cl_off, n_cl,
+                        total);
     e = cudaGetLastError();
     cudaFreeAsync(cls, s);
     cudaFreeAsync(queue, s);

@@ -868,10 +868,9 @@ __device__ __noinline__ bool bs_radius_test(double nv0, uint32_t rec_addr, int l
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// one group of GS = 8 cells that holds a CONTESTED cell or is the ragged tail of the key: cell by cell, the CONTESTED ones
-// through the exact radius test on their tentative record.  Out of line and ROLLED: together with bs_radius_test and the
-// group loop of the kernel the whole replay path has to stay inside the ~6 KB L0 instruction cache of its scheduler -- a
-// lone warp pays every instruction-cache miss in full.
+// one group of GS = 8 cells that holds a CONTESTED cell or is the ragged tail of the key: its addends are fetched up
+// front, then the cells go one by one, the CONTESTED ones through the exact radius test on their tentative record.  Kept
+// out of line (one copy; see bs_radius_test).
 template <int NH>
 struct ChainRec {
     double v[NH];
@@ -880,32 +879,39 @@ template <int DP, int NH>
 __device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint32_t ga, uint32_t ma_g, unsigned cg, int ncell,
                                                          int lane, int D, double delta2, double eps2, int div_mode, double k,
                                                          double wsel, uint8_t *prej) {
-    constexpr int LSP = 2 * DP + 2;
+    constexpr int LSP = 2 * DP + 2, GS = 8;
     double(&v)[NH] = rec.v;
     bool st_ok[NH];
 #pragma unroll
     for (int h = 0; h < NH; ++h) st_ok[h] = lane + 32 * h < LSP;
-#pragma unroll 1
-    for (int q = 0; q < ncell; ++q) {
-        const uint32_t ra = ga + q * (LSP * 8);
-        double nv[NH];
+    double R[GS][NH];
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            nv[h] = dadd(v[h], lds_f64(ra + 32 * h * 8));
-            if (st_ok[h]) sts_f64(ra + 32 * h * 8, nv[h]);
-        }
-        bool keep = true;
-        if ((cg >> q) & 1u) {
-            keep = bs_radius_test<DP, NH>(nv[0], ra, lane, D, delta2, eps2, div_mode, k, wsel);
-            if (lane == 0) {
-                int raw;
-                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + q * 4));
-                prej[raw & 0x7fffffff] = keep ? 0 : 1;
+    for (int q = 0; q < GS; ++q)
+#pragma unroll
+        for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8); // (stale past ncell: never used)
+#pragma unroll
+    for (int q = 0; q < GS; ++q) {
+        if (q < ncell) { // warp-uniform
+            const uint32_t ra = ga + q * (LSP * 8);
+            double nv[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                nv[h] = dadd(v[h], R[q][h]);
+                if (st_ok[h]) sts_f64(ra + 32 * h * 8, nv[h]);
             }
-        }
-        if (keep) { // the record of a rejected cell is never read as a version
+            bool keep = true;
+            if ((cg >> q) & 1u) {
+                keep = bs_radius_test<DP, NH>(nv[0], ra, lane, D, delta2, eps2, div_mode, k, wsel);
+                if (lane == 0) {
+                    int raw;
+                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + q * 4));
+                    prej[raw & 0x7fffffff] = keep ? 0 : 1;
+                }
+            }
+            if (keep) { // the record of a rejected cell is never read as a version
 #pragma unroll
-            for (int h = 0; h < NH; ++h) v[h] = nv[h];
+                for (int h = 0; h < NH; ++h) v[h] = nv[h];
+            }
         }
     }
     return rec;
@@ -1044,76 +1050,75 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
             if (NB > 32) c_hi = __ballot_sync(0xffffffffu, f1 < 0 && lane_o + 32 < cnt);
         }
         CCB_DBG(t_head += clock64() - t_h0;)
-        // ONE compact loop shape for every stage (straight-line code for a whole stage would not fit the L0 instruction
-        // cache next to the rare path): groups of GS = 8 cells; the addends of group g + 1 are fetched (two register sets)
-        // before the dependent adds of group g; inside a group every add is followed, in its latency shadow, by the store of
-        // the version the cell before it left.  A group with a CONTESTED cell, or the ragged tail, goes out of line.
-        unsigned slow; // bit g: group g needs the cell-by-cell path
-        {
-            auto nz_bytes = [](unsigned x) { // bit b of the result <=> byte b of x is non-zero
-                x |= x >> 4;
-                x |= x >> 2;
-                x |= x >> 1;
-                x &= 0x01010101u;
-                return (x * 0x01020408u) >> 24;
-            };
-            slow = nz_bytes(c_lo) | (NB > 32 ? nz_bytes(c_hi) << 4 : 0u);
-            if (cnt & (GS - 1)) slow |= 1u << (cnt >> 3);
-        }
-        CCB_DBG(if (slow == 0u) ++n_clean; const long long t_s0 = clock64(); n_cont += __popc(c_lo) + __popc(c_hi);)
-        const int ng = (cnt + GS - 1) / GS;
-        double A[GS][NH], B[GS][NH];
-        auto fetch = [&](double (&R)[GS][NH], int g) {
-            uint32_t ga = xa + g * (GS * LSP * 8);
-            asm volatile("" : "+r"(ga));
+        if (cnt == NB && (c_lo | c_hi) == 0u) {
+            CCB_DBG(++n_clean;)
+            // ---- CLEAN FULL STAGE: straight-line code with immediate offsets.  Cell c: the dependent add, then -- in its
+            // latency shadow -- the store of the version cell c - 1 left and the load of an addend one batch ahead.
+            double R[2][GS][NH];
 #pragma unroll
             for (int q = 0; q < GS; ++q)
 #pragma unroll
-                for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8);
-        };
-        auto run = [&](double (&R)[GS][NH], int g) {
-            uint32_t ga = xa + g * (GS * LSP * 8);
-            asm volatile("" : "+r"(ga));
-            if (!((slow >> g) & 1u)) {
+                for (int h = 0; h < NH; ++h) R[0][q][h] = lds_f64(xa + (q * LSP + 32 * h) * 8);
+#pragma unroll
+            for (int k = 0; k < NG; ++k) {
 #pragma unroll
                 for (int q = 0; q < GS; ++q) {
                     double nv[NH];
 #pragma unroll
-                    for (int h = 0; h < NH; ++h) nv[h] = dadd(v[h], R[q][h]);
-                    if (q > 0) {
+                    for (int h = 0; h < NH; ++h) nv[h] = dadd(v[h], R[k & 1][q][h]);
+                    if (k + q > 0) {
 #pragma unroll
                         for (int h = 0; h < NH; ++h)
-                            if (st_ok[h]) sts_f64(ga + ((q - 1) * LSP + 32 * h) * 8, v[h]);
+                            if (st_ok[h]) sts_f64(xa + ((k * GS + q - 1) * LSP + 32 * h) * 8, v[h]);
+                    }
+                    if (k + 1 < NG) {
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) R[(k + 1) & 1][q][h] = lds_f64(xa + (((k + 1) * GS + q) * LSP + 32 * h) * 8);
                     }
 #pragma unroll
                     for (int h = 0; h < NH; ++h) v[h] = nv[h];
                 }
-#pragma unroll
-                for (int h = 0; h < NH; ++h)
-                    if (st_ok[h]) sts_f64(ga + ((GS - 1) * LSP + 32 * h) * 8, v[h]);
-            } else {
-                const unsigned cg = ((g < 4 ? c_lo : c_hi) >> (8 * (g & 3))) & 0xffu;
-                ChainRec<NH> rec;
-#pragma unroll
-                for (int h = 0; h < NH; ++h) rec.v[h] = v[h];
-                rec = bs_chain_slow_group<DP, NH>(rec, ga, ma + g * (GS * 4), cg, min(GS, cnt - g * GS), lane_o, D, nm.delta2,
-                                                  nm.eps2, nm.div_mode, nm.k, nm.wsel, e.ws.prej);
-#pragma unroll
-                for (int h = 0; h < NH; ++h) v[h] = rec.v[h];
             }
-        };
-        fetch(A, 0);
+#pragma unroll
+            for (int h = 0; h < NH; ++h)
+                if (st_ok[h]) sts_f64(xa + ((NB - 1) * LSP + 32 * h) * 8, v[h]);
+        } else {
+            // ---- stage with CONTESTED cells or the ragged tail: group by group; a clean full group is eight chained adds
+            // through registers, any other group goes cell by cell (out of line), CONTESTED cells through the exact radius
+            // test on their tentative record
+            CCB_DBG(const long long t_s0 = clock64(); n_cont += __popc(c_lo) + __popc(c_hi);)
+            const int ng = (cnt + GS - 1) / GS;
 #pragma unroll 1
-        for (int g = 0; g < ng; g += 2) {
-            const bool second = g + 1 < ng;
-            if (second) fetch(B, g + 1);
-            run(A, g);
-            if (second) {
-                if (g + 2 < ng) fetch(A, g + 2);
-                run(B, g + 1);
+            for (int g = 0; g < ng; ++g) {
+                uint32_t ga = xa + g * (GS * LSP * 8);
+                asm volatile("" : "+r"(ga));
+                const unsigned cg = ((g < 4 ? c_lo : c_hi) >> (8 * (g & 3))) & 0xffu;
+                const int ncell = min(GS, cnt - g * GS);
+                if (cg == 0u && ncell == GS) {
+                    double R[GS][NH];
+#pragma unroll
+                    for (int q = 0; q < GS; ++q)
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) R[q][h] = lds_f64(ga + (q * LSP + 32 * h) * 8);
+#pragma unroll
+                    for (int q = 0; q < GS; ++q)
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) {
+                            v[h] = dadd(v[h], R[q][h]);
+                            if (st_ok[h]) sts_f64(ga + (q * LSP + 32 * h) * 8, v[h]);
+                        }
+                } else {
+                    ChainRec<NH> rec;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) rec.v[h] = v[h];
+                    rec = bs_chain_slow_group<DP, NH>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
+                                                      nm.div_mode, nm.k, nm.wsel, e.ws.prej);
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) v[h] = rec.v[h];
+                }
             }
+            CCB_DBG(t_slow += clock64() - t_s0;)
         }
-        CCB_DBG(if (slow != 0u) t_slow += clock64() - t_s0;)
         // the versions were written through the generic proxy; the bulk copy reads them through the async proxy
         CCB_DBG(const long long t_t0 = clock64();)
         __syncwarp();

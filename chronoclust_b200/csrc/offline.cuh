@@ -481,6 +481,82 @@ __global__ void k_offc_fill(const uint32_t *__restrict__ wnbr, int r0, int r1, i
     }
 }
 
+// The same ordered growth by ONE WARP: when the lists are short (a sparse weighted-neighbour graph: config C4 has ~2 entries
+// per non-isolated row) the 1024-thread version below spends its time in block barriers -- two per seed scan step, one per
+// popped microcluster; a warp needs none.  Seeds are scanned 32 at a time, lists are compacted with ballots in index
+// order.  Identical output; the launcher picks by the mean list length.
+__global__ void __launch_bounds__(32, 1)
+    k_offc_grow_warp(int M, const int64_t *__restrict__ off, const int32_t *__restrict__ col, const uint8_t *__restrict__ core,
+                     const uint8_t *__restrict__ iso, const uint64_t *__restrict__ submask, int cnt_gt1, int64_t pi,
+                     uint8_t *cls /*[M] zeroed*/, int32_t *queue /*[2M+2]*/, int32_t *order_s, int32_t *cl_off_s,
+                     int32_t *seed_of, int32_t *n_cl_s) {
+    const int lane = threadIdx.x;
+    const unsigned lt = (1u << lane) - 1u;
+    int ncl = 0, nmem = 0;
+    if (lane == 0) cl_off_s[0] = 0;
+    int base = 0;
+    while (base < M) {
+        const int i = base + lane;
+        int c = 1;
+        bool isc = false;
+        if (i < M && !iso[i]) {
+            c = cls[i];
+            isc = core[i] != 0;
+        }
+        const unsigned seeds = __ballot_sync(0xffffffffu, c == 0 && isc);
+        const int fl = seeds ? __ffs(seeds) - 1 : 32; // first unclassified core MC of this window
+        if (c == 0 && !isc && lane < fl) cls[i] = 2;   // an unclassified non-core MC reached by the seed loop becomes noise
+        if (!seeds) {
+            base += 32;
+            continue;
+        }
+        const int fc = base + fl;
+        // ---- expand(fc): the queue starts as a copy of WN(seed), unfiltered (predecon.py:103)
+        const int64_t o0 = off[fc];
+        const int len0 = (int)(off[fc + 1] - o0);
+        for (int t = lane; t < len0; t += 32) queue[t] = col[o0 + t];
+        int qt = len0, qh = 0;
+        __syncwarp();
+        while (qh < qt) {
+            const int q = queue[qh++];
+            if (!core[q]) continue; // _find_directly_reachable_points: point_is_core
+            const int64_t o = off[q];
+            const int len = (int)(off[q + 1] - o);
+            for (int c0 = 0; c0 < len; c0 += 32) {
+                const int t = c0 + lane;
+                int x = -1;
+                bool enq = false, claim = false;
+                if (t < len) {
+                    x = col[o + t];
+                    const int pd = cnt_gt1 ? popc64(submask[x]) : 0;
+                    if ((int64_t)pd <= pi) {
+                        const int cx = cls[x];
+                        enq = cx == 0;
+                        claim = cx == 0 || cx == 2;
+                    }
+                }
+                const unsigned be = __ballot_sync(0xffffffffu, enq), bc = __ballot_sync(0xffffffffu, claim);
+                if (enq) queue[qt + __popc(be & lt)] = x;
+                if (claim) {
+                    order_s[nmem + __popc(bc & lt)] = x;
+                    cls[x] = 1;
+                }
+                qt += __popc(be);
+                nmem += __popc(bc);
+                __syncwarp(); // the next chunk / pop reads cls and the queue written above
+            }
+        }
+        if (lane == 0) {
+            seed_of[ncl] = fc;
+            cl_off_s[ncl + 1] = nmem;
+        }
+        ncl += 1; // emitted even if empty; the host drops clusters whose weight is not > 0 (predecon.py:83)
+        base = fc + 1;
+        __syncwarp();
+    }
+    if (lane == 0) *n_cl_s = ncl;
+}
+
 // the ordered growth over the non-isolated MCs (PreDeCon.run / _expand, predecon.py:62-120, 242-267)
 __global__ void __launch_bounds__(OFFG_THREADS, 1)
     k_offc_grow(int M, const int64_t *__restrict__ off, const int32_t *__restrict__ col, const uint8_t *__restrict__ core,

@@ -9,6 +9,10 @@ sys.path.insert(0, ".")
 from chronoclust_b200.hddstream import HDDStream
 from chronoclust_b200.synth import CONFIGS, config_params, gen
 
+if "--debuglib" in sys.argv:  # experiment knobs (CCB_SLACK, ...) only exist in the debug build
+    sys.argv.remove("--debuglib")
+    from chronoclust_b200 import _lib as _l0, build as _b0
+    _l0.SO_PATH = _b0.build(debug=True)
 name = sys.argv[1] if len(sys.argv) > 1 else "C2"
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 N, D, T, Cn, seed, eps, pi = CONFIGS[name]
