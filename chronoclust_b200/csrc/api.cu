@@ -863,13 +863,19 @@ void offc_grow_and_merge(cudaStream_t s, int M, const int64_t *off, const int32_
     int32_t *order_s = i32, *cl_off_s = order_s + m, *seed_of = cl_off_s + m + 1, *n_cl_s = seed_of + m + 1,
             *seedflag = n_cl_s + 1, *size_by_node = seedflag + m, *rank = size_by_node + m, *size_by_cluster = rank + m + 1;
     const int tgrid = (M + 255) / 256;
-    // short lists (a sparse graph): one warp, no block barriers; long lists: the 1024-thread walk.  total_nnz < 0 = unknown
-    if (total_nnz >= 0 && total_nnz <= (int64_t)M * 16)
-        k_offc_grow_warp<<<1, 32, 0, s>>>(M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, order_s, cl_off_s, seed_of,
-                                          n_cl_s);
-    else
+    // short lists (a sparse graph): one warp over the compacted non-isolated microclusters, no block barriers; long lists:
+    // the 1024-thread walk.  total_nnz < 0 = unknown.  (cand / its flags / ranks live in buffers the later kernels rewrite.)
+    if (total_nnz >= 0 && total_nnz <= (int64_t)M * 16) {
+        int32_t *candflag = seedflag, *candrank = rank, *cand = size_by_node;
+        k_offc_candflag<<<tgrid, 256, 0, s>>>(M, iso, candflag);
+        k_offc_scan<int32_t><<<1, OFFG_THREADS, 0, s>>>(candflag, M, candrank);
+        k_offc_candscatter<<<tgrid, 256, 0, s>>>(M, candflag, candrank, cand);
+        k_offc_grow_warp<<<1, 32, 0, s>>>(cand, candrank + M, off, col, core, submask, cnt_gt1, pi, cls, queue, order_s, cl_off_s,
+                                          seed_of, n_cl_s);
+    } else {
         k_offc_grow<<<1, OFFG_THREADS, 0, s>>>(M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, order_s, cl_off_s,
                                                seed_of, n_cl_s);
+    }
     k_offc_seeds<<<tgrid, 256, 0, s>>>(M, iso, core, submask, cnt_gt1, pi, seed_of, cl_off_s, n_cl_s, seedflag, size_by_node,
                                        label);
     k_offc_seeds_serial<<<tgrid, 256, 0, s>>>(seed_of, cl_off_s, n_cl_s, seedflag, size_by_node);

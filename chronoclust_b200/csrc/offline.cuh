@@ -481,25 +481,38 @@ __global__ void k_offc_fill(const uint32_t *__restrict__ wnbr, int r0, int r1, i
     }
 }
 
-// The same ordered growth by ONE WARP: when the lists are short (a sparse weighted-neighbour graph: config C4 has ~2 entries
-// per non-isolated row) the 1024-thread version below spends its time in block barriers -- two per seed scan step, one per
-// popped microcluster; a warp needs none.  Seeds are scanned 32 at a time, lists are compacted with ballots in index
-// order.  Identical output; the launcher picks by the mean list length.
+// The same ordered growth by ONE WARP over the compacted list of NON-ISOLATED microclusters: when the lists are short (a
+// sparse weighted-neighbour graph: config C4 has ~2 entries per non-isolated row and 98 % isolated rows) the 1024-thread
+// version below spends its time in block barriers and in scanning all M flags for the next seed; a warp needs no barrier
+// and only visits the candidates (cand [ncand], ascending; isolated microclusters never take part in the growth).  Seeds
+// are scanned 32 candidates at a time, lists are compacted with ballots in index order.  Identical output; the launcher
+// picks by the mean list length.
+__global__ void k_offc_candflag(int M, const uint8_t *__restrict__ iso, int32_t *__restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) flag[i] = iso[i] ? 0 : 1;
+}
+__global__ void k_offc_candscatter(int M, const int32_t *__restrict__ flag, const int32_t *__restrict__ rank,
+                                   int32_t *__restrict__ cand) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M && flag[i]) cand[rank[i]] = i;
+}
 __global__ void __launch_bounds__(32, 1)
-    k_offc_grow_warp(int M, const int64_t *__restrict__ off, const int32_t *__restrict__ col, const uint8_t *__restrict__ core,
-                     const uint8_t *__restrict__ iso, const uint64_t *__restrict__ submask, int cnt_gt1, int64_t pi,
-                     uint8_t *cls /*[M] zeroed*/, int32_t *queue /*[2M+2]*/, int32_t *order_s, int32_t *cl_off_s,
-                     int32_t *seed_of, int32_t *n_cl_s) {
+    k_offc_grow_warp(const int32_t *__restrict__ cand, const int32_t *__restrict__ ncand_p, const int64_t *__restrict__ off,
+                     const int32_t *__restrict__ col, const uint8_t *__restrict__ core, const uint64_t *__restrict__ submask,
+                     int cnt_gt1, int64_t pi, uint8_t *cls /*[M] zeroed*/, int32_t *queue /*[2M+2]*/, int32_t *order_s,
+                     int32_t *cl_off_s, int32_t *seed_of, int32_t *n_cl_s) {
     const int lane = threadIdx.x;
     const unsigned lt = (1u << lane) - 1u;
+    const int ncand = *ncand_p;
     int ncl = 0, nmem = 0;
     if (lane == 0) cl_off_s[0] = 0;
     int base = 0;
-    while (base < M) {
-        const int i = base + lane;
+    while (base < ncand) {
+        const int ci = base + lane;
+        const int i = ci < ncand ? cand[ci] : -1;
         int c = 1;
         bool isc = false;
-        if (i < M && !iso[i]) {
+        if (i >= 0) {
             c = cls[i];
             isc = core[i] != 0;
         }
@@ -510,7 +523,7 @@ __global__ void __launch_bounds__(32, 1)
             base += 32;
             continue;
         }
-        const int fc = base + fl;
+        const int fc = __shfl_sync(0xffffffffu, i, fl);
         // ---- expand(fc): the queue starts as a copy of WN(seed), unfiltered (predecon.py:103)
         const int64_t o0 = off[fc];
         const int len0 = (int)(off[fc + 1] - o0);
@@ -551,7 +564,7 @@ __global__ void __launch_bounds__(32, 1)
             cl_off_s[ncl + 1] = nmem;
         }
         ncl += 1; // emitted even if empty; the host drops clusters whose weight is not > 0 (predecon.py:83)
-        base = fc + 1;
+        base = base + fl + 1;
         __syncwarp();
     }
     if (lane == 0) *n_cl_s = ncl;
