@@ -870,8 +870,16 @@ void offc_grow_and_merge(cudaStream_t s, int M, const int64_t *off, const int32_
         k_offc_candflag<<<tgrid, 256, 0, s>>>(M, iso, candflag);
         k_offc_scan<int32_t><<<1, OFFG_THREADS, 0, s>>>(candflag, M, candrank);
         k_offc_candscatter<<<tgrid, 256, 0, s>>>(M, candflag, candrank, cand);
-        k_offc_grow_warp<<<1, 32, 0, s>>>(cand, candrank + M, off, col, core, submask, cnt_gt1, pi, cls, queue, order_s, cl_off_s,
-                                          seed_of, n_cl_s);
+        // (a non-isolated microcluster owns >= 1 CSR entry, so total_nnz bounds the number of candidates, too)
+        const size_t smem = (size_t)total_nnz * 22 + 64;
+        if (smem <= 200 * 1024) { // the whole non-isolated graph fits one CTA's shared memory: walk it there
+            cudaFuncSetAttribute(k_offc_grow_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            k_offc_grow_smem<<<1, 1024, smem, s>>>(cand, candrank, M, off, col, core, submask, cnt_gt1, pi, order_s, cl_off_s,
+                                                   seed_of, n_cl_s, (int)total_nnz + 1, (int)total_nnz + 1);
+        } else {
+            k_offc_grow_warp<<<1, 32, 0, s>>>(cand, candrank + M, off, col, core, submask, cnt_gt1, pi, cls, queue, order_s,
+                                              cl_off_s, seed_of, n_cl_s);
+        }
     } else {
         k_offc_grow<<<1, OFFG_THREADS, 0, s>>>(M, off, col, core, iso, submask, cnt_gt1, pi, cls, queue, order_s, cl_off_s,
                                                seed_of, n_cl_s);

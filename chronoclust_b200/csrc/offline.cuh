@@ -435,17 +435,29 @@ __global__ void k_offc_rowinfo(const uint32_t *__restrict__ wnbr, int r0, int r1
     }
 }
 
-// single-CTA exclusive scan of n int32 values into n + 1 outputs (T = int64_t offsets or int32_t ranks)
+// single-CTA exclusive scan of n int32 values into n + 1 outputs (T = int64_t offsets or int32_t ranks); every thread owns
+// 8 consecutive values per step, so M = 1e5 takes 13 steps of three block barriers instead of 98
 template <typename T>
 __global__ void __launch_bounds__(OFFG_THREADS, 1) k_offc_scan(const int32_t *__restrict__ in, int n, T *__restrict__ out) {
+    constexpr int E = 8;
     __shared__ int s_warp[32];
     __shared__ int s_tot;
     T carry = 0;
-    for (int b = 0; b < n; b += OFFG_THREADS) {
-        const int i = b + threadIdx.x;
-        const int v = i < n ? in[i] : 0;
-        const int ex = block_excl_scan(v, s_warp, &s_tot);
-        if (i < n) out[i] = carry + (T)ex;
+    for (int b = 0; b < n; b += OFFG_THREADS * E) {
+        const int i0 = b + threadIdx.x * E;
+        int v[E], sum = 0;
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+            v[u] = i0 + u < n ? in[i0 + u] : 0;
+            sum += v[u];
+        }
+        const int ex = block_excl_scan(sum, s_warp, &s_tot);
+        T run = carry + (T)ex;
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+            if (i0 + u < n) out[i0 + u] = run;
+            run += (T)v[u];
+        }
         carry += (T)s_tot;
         __syncthreads();
     }
@@ -565,6 +577,121 @@ __global__ void __launch_bounds__(32, 1)
         }
         ncl += 1; // emitted even if empty; the host drops clusters whose weight is not > 0 (predecon.py:83)
         base = base + fl + 1;
+        __syncwarp();
+    }
+    if (lane == 0) *n_cl_s = ncl;
+}
+
+// The one-warp walk with its whole working set in SHARED memory: the walk is a chain of dependent loads (candidate ->
+// class -> core flag -> list bounds -> list -> class of every entry ...), ~0.7 us each from L2, ~4 us per seed; config C4
+// has ~850 seeds and that was 3 of the 3.5 ms of the whole growth.  When the non-isolated part of the graph is small
+// (22 bytes per CSR entry fit the CTA's shared memory: nnz <= ~9 000) the CTA first copies it -- candidates, local CSR
+// (neighbour ids remapped to candidate positions through `rank`), core / pdim flags -- and warp 0 then walks it at
+// shared-memory latency.  Outputs as k_offc_grow_warp (global ids).
+__global__ void __launch_bounds__(1024, 1)
+    k_offc_grow_smem(const int32_t *__restrict__ cand, const int32_t *__restrict__ rank, int M, const int64_t *__restrict__ off,
+                     const int32_t *__restrict__ col, const uint8_t *__restrict__ core, const uint64_t *__restrict__ submask,
+                     int cnt_gt1, int64_t pi, int32_t *order_s, int32_t *cl_off_s, int32_t *seed_of, int32_t *n_cl_s,
+                     int cap_nodes, int cap_nnz) {
+    extern __shared__ __align__(16) unsigned char offc_smem[];
+    const int ncand = rank[M];
+    int32_t *gid = reinterpret_cast<int32_t *>(offc_smem); // [cap_nodes]
+    int32_t *loff = gid + cap_nodes;                       // [cap_nodes + 1]
+    int32_t *queue = loff + cap_nodes + 1;                 // [2 cap_nodes + 2]
+    int32_t *lcol = queue + 2 * cap_nodes + 2;             // [cap_nnz]
+    uint8_t *flags = reinterpret_cast<uint8_t *>(lcol + cap_nnz); // [cap_nodes] bit 0 core, bit 1 pdim <= pi
+    uint8_t *cls = flags + cap_nodes;                             // [cap_nodes] 0 unclassified, 1 classified, 2 noise
+    const int tid = threadIdx.x;
+    if (ncand > cap_nodes) { // cannot happen (the launcher sizes by nnz >= ncand); leave a marker instead of corrupting memory
+        if (tid == 0) *n_cl_s = -1;
+        return;
+    }
+    for (int c = tid; c < ncand; c += blockDim.x) {
+        const int g = cand[c];
+        gid[c] = g;
+        const int pd = cnt_gt1 ? popc64(submask[g]) : 0;
+        flags[c] = (uint8_t)((core[g] ? 1 : 0) | (((int64_t)pd <= pi) ? 2 : 0));
+        cls[c] = 0;
+    }
+    __syncthreads();
+    // local CSR: the lists of the candidates are contiguous in the global CSR in candidate order (isolated rows own none)
+    const int64_t o_first = ncand ? off[gid[0]] : 0;
+    if (ncand == 0) {
+        if (tid == 0) {
+            cl_off_s[0] = 0;
+            *n_cl_s = 0;
+        }
+        return;
+    }
+    for (int c = tid; c <= ncand; c += blockDim.x)
+        loff[c] = c < ncand ? (int)(off[gid[c]] - o_first) : (int)(off[gid[ncand - 1] + 1] - o_first);
+    __syncthreads();
+    const int nnz = ncand ? loff[ncand] : 0;
+    if (nnz > cap_nnz) {
+        if (tid == 0) *n_cl_s = -1;
+        return;
+    }
+    for (int t = tid; t < nnz; t += blockDim.x) lcol[t] = rank[col[o_first + t]];
+    __syncthreads();
+    if (tid >= 32) return;
+    const int lane = tid;
+    const unsigned lt = (1u << lane) - 1u;
+    int ncl = 0, nmem = 0;
+    if (lane == 0) cl_off_s[0] = 0;
+    int base = 0;
+    while (base < ncand) {
+        const int ci = base + lane;
+        int c = 1;
+        bool isc = false;
+        if (ci < ncand) {
+            c = cls[ci];
+            isc = flags[ci] & 1;
+        }
+        const unsigned seeds = __ballot_sync(0xffffffffu, c == 0 && isc);
+        const int fl = seeds ? __ffs(seeds) - 1 : 32;
+        if (c == 0 && !isc && lane < fl) cls[ci] = 2; // an unclassified non-core MC reached by the seed loop becomes noise
+        if (!seeds) {
+            base += 32;
+            continue;
+        }
+        const int fc = base + fl; // candidate position of the seed
+        const int o0 = loff[fc], len0 = loff[fc + 1] - o0;
+        for (int t = lane; t < len0; t += 32) queue[t] = lcol[o0 + t];
+        int qt = len0, qh = 0;
+        __syncwarp();
+        while (qh < qt) {
+            const int q = queue[qh++];
+            if (!(flags[q] & 1)) continue; // _find_directly_reachable_points: point_is_core
+            const int o = loff[q], len = loff[q + 1] - o;
+            for (int c0 = 0; c0 < len; c0 += 32) {
+                const int t = c0 + lane;
+                int x = -1;
+                bool enq = false, claim = false;
+                if (t < len) {
+                    x = lcol[o + t];
+                    if (flags[x] & 2) {
+                        const int cx = cls[x];
+                        enq = cx == 0;
+                        claim = cx == 0 || cx == 2;
+                    }
+                }
+                const unsigned be = __ballot_sync(0xffffffffu, enq), bc = __ballot_sync(0xffffffffu, claim);
+                if (enq) queue[qt + __popc(be & lt)] = x;
+                if (claim) {
+                    order_s[nmem + __popc(bc & lt)] = gid[x];
+                    cls[x] = 1;
+                }
+                qt += __popc(be);
+                nmem += __popc(bc);
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            seed_of[ncl] = gid[fc];
+            cl_off_s[ncl + 1] = nmem;
+        }
+        ncl += 1;
+        base = fc + 1;
         __syncwarp();
     }
     if (lane == 0) *n_cl_s = ncl;
