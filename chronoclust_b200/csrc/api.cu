@@ -711,7 +711,7 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
     // cells, which are exactly the ones whose radius test is open.  Speculative rejection of far cells did not pay
     // either (profiles/r1t_speculative_reject_experiment.md), nor did calling every cell SAFE whose tentative MC keeps a
     // margin below eps^2 whatever its distance (profiles/r2h_slack_rule_experiment.md): every CONTESTED cell takes the
-    // exact in-chain test.
+    // exact in-chain test.  The distance bound is flat between 2 and 8 eps^2 (profiles/r2l_theta_experiment.md).
     io.theta = 4.0 * h->prm.eps2;
     io.r2safe = h->prm.eps2;
     io.r2rej = HUGE_VAL;

@@ -840,3 +840,25 @@ def test_sharded_offline_nccl_matches_single_rank_and_oracle():
     members = [m for m in members if m]  # (clusters without members have weight 0 and are dropped, predecon.py:83)
     oc = [list(m) for m, *_ in o.clusters()]
     assert members == oc, "2-GPU clusters differ from the oracle's"
+
+
+def test_gating_scan_on_device_matches_reference_expression():
+    """the (clusters x gates) scan of app.closest_gates on the device (ccb_assoc_nearest2) gives the labels of
+    the reference's own loop (find_closest_gating, app.py:497-512), with and without a scaler, including an exact tie
+    between two gates (settled by the guard band + the reference expression: the first gate in dict order wins)."""
+    from sklearn.preprocessing import MinMaxScaler
+
+    from chronoclust_b200 import app
+    from chronoclust_b200.scaling import Scaler
+    from test_host_side import _gating_case
+
+    for k in (4.0, 3.0, 1.0):
+        gates, clusters = _gating_case(seed=int(k), Q=300, P=40, D=12, k=k)
+        scan = app._device_gate_scan(np.array([c.centroid for c in clusters]),
+                                     np.array([c.preferred_dimensions for c in clusters]),
+                                     np.array([list(g) for g in gates]), k, 0)
+        assert scan is not None and (scan[1] <= scan[2]).all()
+        assert app.closest_gates(gates, clusters, None, k) == [app.find_closest_gating(gates, c, None) for c in clusters]
+        sc = Scaler()
+        sc.scaler = MinMaxScaler().fit(np.random.default_rng(1).random((50, 12)) * 7.0 - 2.0)
+        assert app.closest_gates(gates, clusters, sc, k) == [app.find_closest_gating(gates, c, sc) for c in clusters]

@@ -246,3 +246,42 @@ def test_hostio_table_is_byte_identical_to_pandas(tmp_path):
         assert open(tmp_path / "native.csv", "rb").read() == open(tmp_path / "pandas.csv", "rb").read()
     _hostio.write_points_csv(tmp_path / "empty.csv", ["id", "cluster_id"] + names, np.zeros((0, D)), np.zeros(0, np.int32), labels)
     assert open(tmp_path / "empty.csv").read() == ",".join(["id", "cluster_id", "FSC-A", '"x,y"'] + names[2:]) + "\n"
+
+
+def _gating_case(seed=3, Q=37, P=11, D=6, k=4.0):
+    from chronoclust_b200.objects import Cluster
+
+    rng = np.random.default_rng(seed)
+    gates = {tuple(rng.random(D).tolist()): f"pop{j}" for j in range(P)}
+    clusters = []
+    for q in range(Q):
+        pref = np.where(rng.random(D) < 0.5, k, 1.0)
+        clusters.append(Cluster([q], rng.random(D), 1.0, pref))
+    first = next(iter(gates))
+    clusters[0].centroid = np.array(first) + 1e-3   # a clear winner
+    twin = tuple((np.array(first) + 2e-3).tolist())  # ... and an exact tie between two gates for cluster 1
+    gates[twin] = "twin"
+    clusters[1].centroid = np.array(first) + 1e-3
+    clusters[1].preferred_dimensions = np.ones(D)
+    return gates, clusters
+
+
+def test_closest_gates_without_cuda_uses_the_reference_expression():
+    """SURVEY 8f-4 host side: with no CUDA device the gating labels come from the reference's own scan
+    (find_closest_gating, app.py:497-512): first strictly smaller distance wins, dict order."""
+    from chronoclust_b200 import app
+
+    gates, clusters = _gating_case()
+    got = app.closest_gates(gates, clusters, None, 4.0)
+    exp = []
+    for c in clusters:
+        best, lab = None, None
+        for cen, name in gates.items():
+            d = 0.0
+            for ci, pi_, di in zip(c.centroid, cen, c.preferred_dimensions):
+                d += ((float(pi_) - float(ci)) ** 2) / float(di)
+            if best is None or d < best:
+                best, lab = d, name
+        exp.append(lab)
+    assert got == exp and got[0] == "pop0"
+    assert app.closest_gates(gates, [], None, 4.0) == []
