@@ -289,7 +289,7 @@ Num make_num(const ccb_handle *h) {
 // one (13 % for the dense 1e6 x 4096 benchmark at one slab); a few slabs make the waves finer.
 template <int kDP, int K>
 void nearest_static_split(int div_mode, int64_t nrows_max, int M, int max_slabs, int &gx, int &slab_mcs, int &nslab) {
-    using Cfg = NearestCfg<kDP>;
+    using Cfg = NearestCfg<kDP, K>;
     gx = (int)((nrows_max + Cfg::CELLS - 1) / Cfg::CELLS);
     int want = gx > 0 ? (2 * 148 + gx - 1) / gx : 1;
     if (want > max_slabs) want = max_slabs;
@@ -358,7 +358,7 @@ int launch_nearest_dyn(ccb_handle *h, cudaStream_t s, int DP, int div_mode, cons
                        const XRef *xref) {
     int launched = 0;
     CCB_DISPATCH_DP(DP, {
-        using Cfg = NearestCfg<kDP>;
+        using Cfg = NearestCfg<kDP, K>;
         if (div_mode)
             k_nearest<kDP, K, true><<<NEAREST_DYN_GRID, NEAREST_THREADS, 0, s>>>(X, rows, nullptr, 0, 0, ld, D, cw, M_bound, 0,
                                                                                  slab_dist, slab_idx, range_dev, M_dev, max_slabs, xref);
@@ -389,7 +389,7 @@ int ensure_point_buffers(ccb_handle *h, int64_t N) {
 }
 
 // ---- block-speculative engine: workspace and block enqueue ------------------------------------------
-constexpr int BS_MAX_SLABS = 128;
+constexpr int BS_MAX_SLABS = 256; // (k_topk_merge_dyn: a lane walks up to 8 slab lists)
 
 template <typename T>
 int ws_alloc(ccb_handle *h, T *&p, size_t n) {
@@ -527,7 +527,7 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
         Timed tm(h, CCB_CAT_LISTS);
         k_bs_tilecnt<<<g_tiles, BS_THREADS, 0, s>>>(e);
         k_bs_pscan<<<std::max(mp_grid, 1), BS_CTA1, 0, s>>>(e);
-        k_bs_pscatter<<<g_tiles, BS_THREADS, 0, s>>>(e);
+        k_bs_pscatter<<<B / 32 + 1, BS_THREADS, 0, s>>>(e);
     }
     {
         Timed tm(h, CCB_CAT_PCORE);
@@ -546,7 +546,7 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     }
     {
         Timed tm(h, CCB_CAT_RESOLVE);
-        CCB_DISPATCH_DP(h->DP, { k_bs_verify_p<kDP><<<B / 32 + 1, BS_THREADS, 0, sa>>>(e); })
+        CCB_DISPATCH_DP(h->DP, { k_bs_verify_p<kDP><<<B / 32 + 1, BS_VP_THREADS, 0, sa>>>(e); })
     }
     {
         Timed tm(h, CCB_CAT_OLIST);

@@ -92,6 +92,8 @@ struct BsWs {
 __device__ __forceinline__ double *ver_cf1(const BsWs &w, int i) { return w.ver + (size_t)i * w.lsp; }
 __device__ __forceinline__ double *ver_cf2(const BsWs &w, int i) { return w.ver + (size_t)i * w.lsp + w.dp; }
 __device__ __forceinline__ double &ver_w(const BsWs &w, int i) { return w.ver[(size_t)i * w.lsp + 2 * w.dp]; }
+// VERSION record of a member of a PCORE chain: where k_bs_chain_p's bulk store left it (plist order)
+__device__ __forceinline__ const double *pver(const BsWs &w, int i) { return w.verp + (size_t)w.vpos[i] * w.lsp; }
 
 // What changes from one ccb_ingest call to the next.  Stream launches pass it inside Eng; CUDA-graph launches (whose
 // kernel arguments are baked in) read it from device memory through Eng::io.
@@ -291,7 +293,7 @@ __device__ __forceinline__ void group_argmin(double &d, int &j) { // over BS_SPL
 }
 
 template <int DP>
-__global__ void __launch_bounds__(BS_THREADS) k_bs_spec(Eng e) {
+__global__ void __launch_bounds__(BS_THREADS, DP <= 16 ? 7 : 1) k_bs_spec(Eng e) {
     e.fetch();
     const BsCtl *bc = e.bc;
     if (!bc->active) return;
@@ -538,34 +540,40 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
     }
 }
 
-// plist[pos] = cell | CONTESTED << 31 and xg[pos] = the cell's ADDEND record (x, x*x, 1.0), pos in (key, cell) order
+// plist[pos] = cell | CONTESTED << 31 and xg[pos] = the cell's ADDEND record (x, x*x, 1.0), pos in (key, cell) order.
+// One CTA per tile of 32 cells: warp 0 places the cells (lane = cell), then each of the four warps writes eight of the
+// records, lane = element of the record (coalesced rows), four records in flight at a time so that the row loads overlap
+// instead of paying one global-memory latency per record.
 __global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
     e.fetch();
+    __shared__ int s_pos[32];
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return;
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x;
     const int ntiles = (bc->Beff + 31) >> 5;
     if (t >= ntiles) return;
-    const int i = t * 32 + lane;
-    const int c = i < bc->Beff ? e.ws.pcand[i] : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, c);
-    int pos = -1;
-    if (c >= 0) {
-        const int rank = __popc(peers & lanemask_lt());
-        pos = e.ws.poff[c] + e.ws.tilecnt[(size_t)t * e.ws.mp_stride + c] + rank;
-        e.ws.plist[pos] = i | (e.ws.pflag[i] ? (int)0x80000000 : 0);
-        e.ws.vpos[i] = pos;
+    if (warp == 0) {
+        const int i = t * 32 + lane;
+        const int c = i < bc->Beff ? e.ws.pcand[i] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        int pos = -1;
+        if (c >= 0) {
+            const int rank = __popc(peers & lanemask_lt());
+            pos = e.ws.poff[c] + e.ws.tilecnt[(size_t)t * e.ws.mp_stride + c] + rank;
+            e.ws.plist[pos] = i | (e.ws.pflag[i] ? (int)0x80000000 : 0);
+            e.ws.vpos[i] = pos;
+        }
+        s_pos[lane] = pos;
     }
-    // the warp writes the 32 records together, lane = element of the record (coalesced rows); four records are in
-    // flight at a time so that the row loads overlap instead of paying one global-memory latency per record
+    __syncthreads();
     const int D = e.nm.D, dp = e.ws.dp, lsp = e.ws.lsp;
     const double *Xt = e.X + (bc->pos + (int64_t)t * 32) * e.ld;
-    constexpr int QU = 4;
-    for (int q0 = 0; q0 < 32; q0 += QU) {
+    constexpr int QU = 4, PER = 32 / (BS_THREADS / 32);
+    for (int q0 = warp * PER; q0 < (warp + 1) * PER; q0 += QU) {
         int pq[QU];
 #pragma unroll
-        for (int u = 0; u < QU; ++u) pq[u] = __shfl_sync(0xffffffffu, pos, q0 + u);
+        for (int u = 0; u < QU; ++u) pq[u] = s_pos[q0 + u];
         for (int el0 = 0; el0 < lsp; el0 += 32) {
             const int el = el0 + lane;
             double v[QU];
@@ -1167,6 +1175,20 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_olist(Eng e) {
     }
     __syncthreads();
     const int n = s_n;
+    if (n <= BS_CTA1) {
+        // the usual case (a few hundred rejected cells): RANK SORT -- the composite (key, cell) values are distinct, so the
+        // sorted position of an entry is the number of smaller entries; every thread counts for its own entry over the
+        // shared array (broadcast reads, no barrier per step) instead of log^2 n barrier-separated bitonic steps
+        unsigned long long mine = ~0ull;
+        int rank = 0;
+        if (tid < n) {
+            mine = keys[tid];
+            for (int j = 0; j < n; ++j) rank += keys[j] < mine;
+        }
+        __syncthreads();
+        if (tid < n) keys[rank] = mine;
+        __syncthreads();
+    } else {
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     for (int t = n + tid; t < np2; t += BS_CTA1) keys[t] = ~0ull;
@@ -1186,6 +1208,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_olist(Eng e) {
             }
             __syncthreads();
         }
+    }
     }
     // heads of the key segments, in key order (= list order: snapshot slots, then creations by creator)
     const int per = (n + BS_CTA1 - 1) / BS_CTA1;
@@ -1234,31 +1257,22 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_olist(Eng e) {
 
 // ---- D ----------------------------------------------------------------------------------------------
 // centroid, preference mask and r^2 of VERSION i (two IEEE divisions per dimension, off the serial path).  rec: where the
-// chain kernel left the record -- ver[i] itself (outlier side), or verp[plist position] (pcore side), which is handed on
-// to ver[i] here so that every later reader finds a version under its cell
+// chain kernel left the record -- ver[i] (outlier side) or verp[plist position] (pcore side, see pver)
 __device__ __forceinline__ void derive_version(const Eng &e, const Num &nm, int i, const double *rec) {
     const int D = nm.D, dp = e.ws.dp;
-    double *out = e.ws.ver + (size_t)i * e.ws.lsp;
-    const bool copy = rec != out;
     const double w = rec[2 * dp];
     double *cen = e.ws.vcen + (size_t)i * D;
     double s = 0.0;
     uint64_t mk = 0ull;
     for (int d = 0; d < D; ++d) {
-        const double c1 = rec[d], c2 = rec[dp + d];
-        if (copy) {
-            out[d] = c1;
-            out[dp + d] = c2;
-        }
-        const double a = ddiv(c2, w);
-        const double c = ddiv(c1, w);
+        const double a = ddiv(rec[dp + d], w);
+        const double c = ddiv(rec[d], w);
         cen[d] = c;
         const double var = dsub(a, dmul(c, c));
         const bool bit = var <= nm.delta2;
         mk |= (uint64_t)bit << d;
         s = dadd(s, bit ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var);
     }
-    if (copy) out[2 * dp] = w;
     e.ws.vmask[i] = mk;
     e.ws.vr2[i] = s;
 }
@@ -1283,7 +1297,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_p(Eng e) {
         }
     }
     if (i >= bc->Beff || e.ws.pcand[i] < 0 || e.ws.prej[i]) return; // not an accepted member of a pcore chain
-    derive_version(e, e.nm, i, e.ws.verp + (size_t)e.ws.vpos[i] * e.ws.lsp);
+    derive_version(e, e.nm, i, pver(e.ws, i));
 }
 
 // OUTLIER side: the versions k_bs_chain_o left (members of the outlier-side keys, in omem)
@@ -1303,10 +1317,11 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_o(Eng e) {
 // the latest accepted member of its chain inside the tile (ballot) or before the tile (tbase).  The CTA's four warps
 // take the pcore MCs j = w, w + 4, ... and warp 0 reduces (distance, list position) lexicographically = the first
 // strictly smaller MC of the sequential scan; four times the warps to hide the dependent loads and adds.
+constexpr int BS_VP_THREADS = 128; // (eight warps with two MCs in flight were measured slower: 37.6 vs 27.2 us, r2m)
 template <int DP>
-__global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
+__global__ void __launch_bounds__(BS_VP_THREADS, DP <= 16 ? 5 : 1) k_bs_verify_p(Eng e) {
     e.fetch();
-    constexpr int NW = BS_THREADS / 32;
+    constexpr int NW = BS_VP_THREADS / 32, U = 1;
     __shared__ double s_bd[NW][32];
     __shared__ int s_best[NW][32], s_prev[NW][32];
     BsCtl *bc = e.bc;
@@ -1330,23 +1345,42 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
     double bd = 0.0;
     const unsigned lt = lanemask_lt();
     const int32_t *tb = e.ws.tbase + (size_t)t * e.ws.mp_stride;
-    for (int j = part; j < Mp; j += NW) {
-        const unsigned lower = __ballot_sync(0xffffffffu, acc_key == j) & lt;
-        const int prev = lower ? (t * 32 + 31 - __clz(lower)) : tb[j];
-        const double *cen = prev >= 0 ? e.ws.vcen + (size_t)prev * D : e.P.cen + (size_t)j * D;
-        const uint64_t mask = prev >= 0 ? e.ws.vmask[prev] : e.P.mask[j];
-        bool feas = true;
-        if (nm.pi_active) {
-            const double *c1 = prev >= 0 ? ver_cf1(e.ws, prev) : e.P.cf1 + (size_t)j * D;
-            const double *c2 = prev >= 0 ? ver_cf2(e.ws, prev) : e.P.cf2 + (size_t)j * D;
-            const double w = prev >= 0 ? ver_w(e.ws, prev) : e.P.w[j];
-            feas = feasible_regs<DP>(c1, c2, w, x, nm);
+    for (int j0 = part; j0 < Mp; j0 += NW * U) {
+        int prev[U];
+        const double *cen[U];
+        uint64_t mask[U];
+        bool on[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + u * NW;
+            on[u] = j < Mp; // warp-uniform
+            const unsigned lower = __ballot_sync(0xffffffffu, on[u] && acc_key == j) & lt;
+            prev[u] = lower ? (t * 32 + 31 - __clz(lower)) : (on[u] ? tb[j] : -1);
         }
-        const double dv = dist_regs<DP>(x, cen, mask, nm);
-        if (feas && !(dv != dv) && (best < 0 || dv < bd)) {
-            best = j;
-            bd = dv;
-            bprev = prev;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = on[u] ? j0 + u * NW : 0;
+            cen[u] = prev[u] >= 0 ? e.ws.vcen + (size_t)prev[u] * D : e.P.cen + (size_t)j * D;
+            mask[u] = prev[u] >= 0 ? e.ws.vmask[prev[u]] : e.P.mask[j];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!on[u]) continue;
+            const int j = j0 + u * NW;
+            bool feas = true;
+            if (nm.pi_active) {
+                const double *rec = prev[u] >= 0 ? pver(e.ws, prev[u]) : nullptr;
+                const double *c1 = rec ? rec : e.P.cf1 + (size_t)j * D;
+                const double *c2 = rec ? rec + e.ws.dp : e.P.cf2 + (size_t)j * D;
+                const double w = rec ? rec[2 * e.ws.dp] : e.P.w[j];
+                feas = feasible_regs<DP>(c1, c2, w, x, nm);
+            }
+            const double dv = dist_regs<DP>(x, cen[u], mask[u], nm);
+            if (feas && !(dv != dv) && (best < 0 || dv < bd)) { // (j ascends within the warp: strict < keeps the first)
+                best = j;
+                bd = dv;
+                bprev = prev[u];
+            }
         }
     }
     s_bd[part][lane] = bd;
@@ -1369,9 +1403,10 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_p(Eng e) {
         if (eff == best) {
             acc = e.ws.vr2[i] <= nm.eps2; // this very absorb is version i of the chain
         } else {
-            const double *c1 = bprev >= 0 ? ver_cf1(e.ws, bprev) : e.P.cf1 + (size_t)best * D;
-            const double *c2 = bprev >= 0 ? ver_cf2(e.ws, bprev) : e.P.cf2 + (size_t)best * D;
-            const double w = bprev >= 0 ? ver_w(e.ws, bprev) : e.P.w[best];
+            const double *rec = bprev >= 0 ? pver(e.ws, bprev) : nullptr;
+            const double *c1 = rec ? rec : e.P.cf1 + (size_t)best * D;
+            const double *c2 = rec ? rec + e.ws.dp : e.P.cf2 + (size_t)best * D;
+            const double w = rec ? rec[2 * e.ws.dp] : e.P.w[best];
             double wn;
             uint64_t nmask;
             acc = tent_regs<DP>(c1, c2, w, x, nm, wn, nmask) <= nm.eps2;
@@ -1734,13 +1769,14 @@ __device__ __forceinline__ void commit_row(const Eng &e, const BsCtl *bc, const 
         const unsigned mk = __ballot_sync(0xffffffffu, accd);
         const int v = mk ? (tm * 32 + 31 - __clz(mk)) : e.ws.tbase[(size_t)tm * e.ws.mp_stride + j];
         if (v < 0) return;
+        const double *rec = pver(e.ws, v);
         for (int d = lane; d < D; d += 32) {
-            e.P.cf1[(size_t)j * D + d] = ver_cf1(e.ws, v)[d];
-            e.P.cf2[(size_t)j * D + d] = ver_cf2(e.ws, v)[d];
+            e.P.cf1[(size_t)j * D + d] = rec[d];
+            e.P.cf2[(size_t)j * D + d] = rec[e.ws.dp + d];
             e.P.cen[(size_t)j * D + d] = e.ws.vcen[(size_t)v * D + d];
         }
         if (lane == 0) {
-            e.P.w[j] = ver_w(e.ws, v);
+            e.P.w[j] = rec[2 * e.ws.dp];
             e.P.mask[j] = e.ws.vmask[v];
         }
         return;

@@ -28,9 +28,11 @@ namespace ccb {
 constexpr int NEAREST_THREADS = 128;
 constexpr int NEAREST_JU = 4;
 
-template <int DP>
+// K > 1 is the in-engine use (a few hundred cells x 1e4 microclusters per launch): there the kernel is bound by the
+// instruction stream of a single warp per work item, so a thread owns ONE cell and the split makes more, smaller items
+template <int DP, int K = 1>
 struct NearestCfg {
-    static constexpr int PPT = (DP <= 40) ? 2 : 1;
+    static constexpr int PPT = (K == 1 && DP <= 40) ? 2 : 1;
     // tile of TM microclusters, ~12-16 KB per buffer, TM a multiple of JU
     static constexpr int TM = ((1024 / DP) < 8 ? 8 : (1024 / DP)) / NEAREST_JU * NEAREST_JU;
     static constexpr int CELLS = NEAREST_THREADS * PPT;
@@ -86,9 +88,9 @@ template <int DP, int K, bool DIV>
 __device__ __forceinline__ void nearest_item(const double *__restrict__ X, const int32_t *__restrict__ rows, int64_t row_off,
                                              int64_t nrows, int64_t ld, int D, const double2 *__restrict__ cw, int64_t cell0,
                                              int j0, int j1, double *__restrict__ out_dist, int32_t *__restrict__ out_idx,
-                                             int64_t out_off, int out_stride, int out_slab, double2 (*tile)[NearestCfg<DP>::TM * DP],
+                                             int64_t out_off, int out_stride, int out_slab, double2 (*tile)[NearestCfg<DP, K>::TM * DP],
                                              uint64_t *bar, uint32_t &seq) {
-    using Cfg = NearestCfg<DP>;
+    using Cfg = NearestCfg<DP, K>;
     constexpr int PPT = Cfg::PPT, TM = Cfg::TM, JU = NEAREST_JU;
     // ---- this thread's cells -> registers (row-contiguous 16-byte loads; every fetched sector is used)
     double p[PPT][DP];
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS)
               int64_t row_off, int64_t nrows, int64_t ld, int D, const double2 *__restrict__ cw, int M, int slab_mcs,
               double *__restrict__ out_dist, int32_t *__restrict__ out_idx, const int32_t *__restrict__ range_dev,
               const int32_t *__restrict__ M_dev, int dyn_max_slabs, const XRef *__restrict__ xref) {
-    using Cfg = NearestCfg<DP>;
+    using Cfg = NearestCfg<DP, K>;
     __shared__ __align__(128) double2 tile[2][Cfg::TM * DP];
     __shared__ __align__(8) uint64_t bar[2];
 
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(128) k_topk_merge_dyn(const double *__restrict
                                                         const int32_t *__restrict__ range_dev, const int32_t *__restrict__ M_dev,
                                                         int M, int target, int max_slabs, int tm, int cells,
                                                         double *__restrict__ out_dist, int32_t *__restrict__ out_idx) {
-    constexpr int QMAX = 4; // max_slabs <= 128
+    constexpr int QMAX = 8; // max_slabs <= 256
     const int lane = threadIdx.x & 31;
     const int R = range_dev[1] - range_dev[0];
     if (M_dev) M = min(M, *M_dev);
