@@ -426,7 +426,7 @@ int ensure_bs_ws(ccb_handle *h) {
         WSA(nrows, BS_RMAX); WSA(ncell, BS_RMAX);
         WSA(tk_dist, (size_t)BS_RMAX * BS_TOPK); WSA(tk_idx, (size_t)BS_RMAX * BS_TOPK);
         WSA(hkey, BS_RMAX + 1); WSA(hoff, BS_RMAX + 2); WSA(omem, BS_RMAX + 1); WSA(hrank, BS_RMAX + 2);
-        WSA(hfirst, BS_RMAX + 1);
+        WSA(hfirst, BS_RMAX + 1); WSA(okeys, BS_RMAX);
 #undef WSA
         if ((rc = ws_alloc(h, h->d_bs_tk_dist_slab, (size_t)BS_RMAX * BS_MAX_SLABS * BS_TOPK))) return rc;
         if ((rc = ws_alloc(h, h->d_bs_tk_idx_slab, (size_t)BS_RMAX * BS_MAX_SLABS * BS_TOPK))) return rc;
@@ -550,7 +550,7 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     }
     {
         Timed tm(h, CCB_CAT_OLIST);
-        k_bs_olist<<<1, BS_CTA1, 0, s>>>(e);
+        k_bs_olist<<<BS_OL_CTAS, BS_OL_THREADS, 0, s>>>(e);
     }
     {
         Timed tm(h, CCB_CAT_CHAIN_O);
@@ -1169,6 +1169,18 @@ int ccb_debug_set(ccb_handle *h, int32_t mode) {
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaMemcpyToSymbol(g_bs_dbg_mode, &mode, sizeof(int)));
     return CCB_OK;
+}
+
+int64_t ccb_debug_trace(ccb_handle *h, int64_t *out, int64_t max_records) {
+    if (!h || !out) return -1;
+    cudaStreamSynchronize(h->stream);
+    int n = 0;
+    cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(int));
+    const int64_t m = std::min<int64_t>(std::min<int64_t>(n, CCB_TRACE_MAX), max_records);
+    if (m > 0) cudaMemcpyFromSymbol(out, g_trace, (size_t)m * CCB_TRACE_WORDS * sizeof(long long));
+    const int zero = 0;
+    cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(int));
+    return n;
 }
 
 int ccb_debug_chain(ccb_handle *h, int64_t *out, int32_t max_keys) {

@@ -59,6 +59,27 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  : "memory");
 }
 
+// ---- diagnostics build only: per-round timeline of the engine (csrc/debug.h: ccb_debug_trace) -------
+#ifdef CCB_DEBUG
+constexpr int CCB_TRACE_SLOTS = 24, CCB_TRACE_WORDS = 48, CCB_TRACE_MAX = 1 << 14;
+__device__ long long g_trace_ts[CCB_TRACE_SLOTS];               // start of every kernel of the current round (globaltimer, ns)
+__device__ long long g_trace[CCB_TRACE_MAX][CCB_TRACE_WORDS];   // one record per round (k_bs_decide) / block (k_bs_finish)
+__device__ int g_trace_n;
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CCB_DBG(...) __VA_ARGS__
+#define CCB_TS(slot)                                                                    \
+    do {                                                                                \
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_trace_ts[slot] = globaltimer_ns();   \
+    } while (0)
+#else
+#define CCB_DBG(...)
+#define CCB_TS(slot)
+#endif
+
 // ---- small utilities ------------------------------------------------------------------------------
 __device__ __forceinline__ int popc64(uint64_t m) { return __popcll(m); }
 

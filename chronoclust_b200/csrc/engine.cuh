@@ -61,6 +61,8 @@ struct BsCtl {
     int32_t m_commit, upgrade;
     int32_t need_grow, done;
     int32_t ticket; // k_bs_pscan: CTAs finished (last one computes the key offsets)
+    int32_t ticket_o; // k_bs_olist: likewise (the last one builds the key segments)
+    int32_t m_exact;  // cells below this are exact since an earlier round of the block (first mismatch of the previous round)
     int32_t pclean; // refinement round whose pcore side (candidates, CONTESTED flags, accepts) is that of the round before
     int32_t m0, up0; // this round: first cell whose exact decision differs from the speculation / first upgrading cell
                      // (atomicMin by the verify kernels, consumed and reset by k_bs_decide; INT_MAX = none)
@@ -85,6 +87,7 @@ struct BsWs {
     int32_t *tk_idx; // [BS_RMAX][BS_TOPK]
     int32_t *hkey, *hoff, *omem, *hrank; // hrank[q]: real creations before key hnew0 + q
     int32_t *hfirst;                     // [BS_RMAX + 1] first member of every outlier-side key
+    unsigned long long *okeys;           // [BS_RMAX] (key, cell) of the pcore-rejected cells, sorted (k_bs_olist)
     int32_t *firstmember; // [O.cap], INT_MAX = unmodified in this block
     int64_t *dbg; // optional [mp_stride][8] per-key cycle counters of k_bs_chain_p (diagnostics), or nullptr
     int32_t mp_stride, bmax, dp, lsp;
@@ -233,6 +236,7 @@ __global__ void k_bs_init(BsCtl *bc, int64_t N, int32_t itmax, int32_t bmin, int
 
 __global__ void k_bs_begin(Eng e) {
     e.fetch();
+    CCB_TS(0);
     BsCtl *bc = e.bc;
     bc->active = 0;
     bc->tk_lo = bc->tk_hi = 0; // an idle block must not leave kernel 1 any work
@@ -265,6 +269,7 @@ __global__ void k_bs_begin(Eng e) {
         bc->m_commit = 0;
         bc->upgrade = 0;
         bc->pclean = 0;
+        bc->m_exact = 0;
         bc->active = 1;
     } while (0);
     // graph launches: the round loop runs iff the block is active; an idle block also ends the block loop
@@ -295,6 +300,7 @@ __device__ __forceinline__ void group_argmin(double &d, int &j) { // over BS_SPL
 template <int DP>
 __global__ void __launch_bounds__(BS_THREADS, DP <= 16 ? 7 : 1) k_bs_spec(Eng e) {
     e.fetch();
+    CCB_TS(1);
     const BsCtl *bc = e.bc;
     if (!bc->active) return;
     const int gt = blockIdx.x * BS_THREADS + threadIdx.x;
@@ -369,6 +375,7 @@ __device__ __forceinline__ int block_exclusive_scan_1024(int v, int *s_warp, int
 
 __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
     e.fetch();
+    CCB_TS(2);
     __shared__ int s_warp[33];
     __shared__ int s_cut;
     BsCtl *bc = e.bc;
@@ -434,6 +441,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
 // speculated outlier-stage decision of the need list: nearest snapshot MC + radius test on the snapshot state
 __global__ void __launch_bounds__(BS_THREADS) k_bs_spec_o(Eng e) {
     e.fetch();
+    CCB_TS(5);
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->it != 0) return; // first round of a block only
     const int t = blockIdx.x * BS_THREADS + threadIdx.x;
@@ -465,6 +473,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_spec_o(Eng e) {
 // per (tile of 32 cells, pcore key): number of candidates
 __global__ void __launch_bounds__(BS_THREADS) k_bs_tilecnt(Eng e) {
     e.fetch();
+    CCB_TS(6);
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return;
     const int lane = threadIdx.x & 31;
@@ -490,6 +499,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_tilecnt(Eng e) {
 // finish turns the totals into the (padded) key offsets
 __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
     e.fetch();
+    CCB_TS(7);
     __shared__ int s_warp[33];
     __shared__ int s_last, s_max;
     BsCtl *bc = e.bc;
@@ -537,6 +547,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
         e.ws.poff[Mp] = carry;
         bc->ticket = 0;
         bc->serial_cells += s_max;
+        CCB_DBG(g_trace_ts[21] = s_max;)
     }
 }
 
@@ -546,6 +557,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
 // instead of paying one global-memory latency per record.
 __global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
     e.fetch();
+    CCB_TS(8);
     __shared__ int s_pos[32];
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return;
@@ -752,6 +764,7 @@ __device__ __forceinline__ void bs_chain_o_key(const Eng &e, const BsCtl *bc, in
 template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_chain_o(Eng e) {
     e.fetch();
+    CCB_TS(13);
     __shared__ __align__(16) double xs[2][ChainCfg<DP>::NB][DP];
     __shared__ int mi[2][ChainCfg<DP>::NB];
     const BsCtl *bc = e.bc;
@@ -809,9 +822,6 @@ constexpr int BS_CHAINP_THREADS = 160;
 
 #ifdef CCB_DEBUG
 __device__ int g_bs_dbg_mode = 0; // diagnostics build only (csrc/debug.h): 1 = storers skip the global stores, 2 = skip the copies
-#define CCB_DBG(...) __VA_ARGS__
-#else
-#define CCB_DBG(...)
 #endif
 
 // Exact radius test of the tentative MC nv = v + a (mc_functions.py:45-56) for a CONTESTED cell, by the whole replay
@@ -874,6 +884,81 @@ __device__ __noinline__ bool bs_radius_test(double nv0, uint32_t rec_addr, int l
     return r2 <= eps2;
 }
 
+// FAST radius test of a CONTESTED cell: the same decision from ~1/5 of the latency, or "undecided".  Returns 1 (radius^2 of
+// the tentative MC <= eps^2: absorbed), 0 (rejected) or 2 (too close to call: the caller runs bs_radius_test).
+// Multiplied through by W'^2 the test of mc_functions.py:45-56 reads  sum_d w_d (CF2'_d W' - CF1'_d^2)  <=  eps^2 W'^2
+// with w_d = 1/k where CF2'_d W' - CF1'_d^2 <= delta^2 W'^2, else 1 -- no division.  Lane d evaluates its term in fp64 (one
+// DMUL + one DFMA), scales it so that the right-hand side is at most TH = 2^25 (2^23 for D > 16), rounds it to an integer and
+// the warp adds the integers with ONE redux.sync instead of a chain of D shuffles and dependent adds.  The approximation
+// differs from the reference's rounding sequence by a few ulp of the terms; with coordinates of magnitude <= ~1e3 eps that
+// is far below one integer unit, and the decision is only taken when the sum is D + 8 units clear of the threshold and no
+// variance is within 2^-24 (relative) of delta^2; anything else -- including NaNs -- is "undecided".  The approximation
+// cannot corrupt results in any case: k_bs_verify_p recomputes every decision of the chain with the reference's exact
+// arithmetic (a wrong one would merely cost a round), and the first member of every chain always takes the exact test, so
+// every block advances.  D > 16: the integer is split into a high and a low part (two redux.sync) to keep 2^-20 units.
+struct ChainFast {
+    double F;    // TH / Wmax^2, Wmax = W at the start of the chain + its members + 1 (>= every W' of the chain)
+    double fs;   // F / eps^2: scale of the terms
+    double invk; // weight of a preferred dimension (approximate for a k that is not a power of two)
+    double delta2;
+    double mg;   // D + 8 integer units: clearance a decision needs
+};
+template <int DP, int NH>
+__device__ __forceinline__ int bs_radius_fast(double nv0, uint32_t rec_addr, int lane, int D, const ChainFast cf) {
+    constexpr int NT = DP > 32 ? 2 : 1; // terms per lane
+    constexpr bool SPLIT = DP > 16;
+    constexpr int CL = SPLIT ? (1 << 24) : (1 << 26);
+    double wn, c1[NT], c2[NT];
+    if (NH == 1) {
+        wn = __shfl_sync(0xffffffffu, nv0, 2 * DP);
+        c1[0] = nv0;
+        c2[0] = __shfl_sync(0xffffffffu, nv0, (lane + DP) & 31);
+    } else {
+        __syncwarp();
+        wn = lds_f64(rec_addr - lane * 8 + 2 * DP * 8);
+#pragma unroll
+        for (int h = 0; h < NT; ++h) {
+            const bool rd = lane + 32 * h < D;
+            c1[h] = rd ? lds_f64(rec_addr + 32 * h * 8) : 0.0;
+            c2[h] = rd ? lds_f64(rec_addr + (DP + 32 * h) * 8) : 0.0;
+        }
+    }
+    const double wn2 = dmul(wn, wn);
+    const double thr = dmul(wn2, cf.F);
+    const double d2w = dmul(cf.delta2, wn2);
+    const double tol = dmul(d2w, 0x1p-24);
+    // integer thresholds, off the critical path (they depend on W' only): absorbed below t_lo, rejected above t_hi
+    const int t_lo = __double2int_rd(dsub(thr, cf.mg)), t_hi = __double2int_ru(dadd(thr, cf.mg));
+    int hi_sum = 0, lo_sum = 0;
+    bool amb = false;
+#pragma unroll
+    for (int h = 0; h < NT; ++h) {
+        const bool act = lane + 32 * h < D;
+        const double t = __fma_rn(-c1[h], c1[h], dmul(c2[h], wn));
+        const double diff = dsub(t, d2w);
+        amb = amb || (act && !(fabs(diff) > tol));
+        const double tk = dmul(t, cf.invk);
+        const double v = dmul(diff <= 0.0 ? tk : t, cf.fs);
+        int hi = __double2int_rn(v); // saturates; NaN -> 0 (caught by amb above)
+        hi = max(min(hi, CL), -(1 << 20));
+        hi_sum += act ? hi : 0;
+        if (SPLIT) {
+            const int lo = __double2int_rn(dmul(dsub(v, (double)hi), 0x1p20));
+            lo_sum += act ? max(min(lo, 1 << 20), -(1 << 20)) : 0;
+        }
+    }
+    const int S = __reduce_add_sync(0xffffffffu, hi_sum);
+    if (__any_sync(0xffffffffu, amb)) return 2;
+    if (SPLIT) {
+        const int L = __reduce_add_sync(0xffffffffu, lo_sum);
+        const double tot = dadd((double)S, dmul((double)L, 0x1p-20));
+        if (tot < dsub(thr, 0.01)) return 1;
+        if (tot > dadd(thr, 0.01)) return 0;
+        return 2;
+    }
+    return S < t_lo ? 1 : (S > t_hi ? 0 : 2);
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // one group of GS = 8 cells that holds a CONTESTED cell or is the ragged tail of the key: its addends are fetched up
@@ -886,7 +971,7 @@ struct ChainRec {
 template <int DP, int NH>
 __device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint32_t ga, uint32_t ma_g, unsigned cg, int ncell,
                                                          int lane, int D, double delta2, double eps2, int div_mode, double k,
-                                                         double wsel, uint8_t *prej) {
+                                                         double wsel, uint8_t *prej, const ChainFast cf, int exact_first) {
     constexpr int LSP = 2 * DP + 2, GS = 8;
     double(&v)[NH] = rec.v;
     bool st_ok[NH];
@@ -909,7 +994,9 @@ __device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint3
             }
             bool keep = true;
             if ((cg >> q) & 1u) {
-                keep = bs_radius_test<DP, NH>(nv[0], ra, lane, D, delta2, eps2, div_mode, k, wsel);
+                int r = (q == 0 && exact_first) ? 2 : bs_radius_fast<DP, NH>(nv[0], ra, lane, D, cf);
+                if (r == 2) r = bs_radius_test<DP, NH>(nv[0], ra, lane, D, delta2, eps2, div_mode, k, wsel) ? 1 : 0;
+                keep = r != 0;
                 if (lane == 0) {
                     int raw;
                     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + q * 4));
@@ -928,6 +1015,7 @@ __device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint3
 template <int DP>
 __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
     e.fetch();
+    CCB_TS(9);
     using Cfg = ChainPCfg<DP>;
     constexpr int NB = Cfg::NB, S = Cfg::S, GS = 8, NH = Cfg::NH, LSP = Cfg::LSP, NG = NB / GS;
     static_assert(NB == 32 || NB == 64, "the CONTESTED flags of a stage are gathered by one or two ballots");
@@ -1025,6 +1113,16 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         else if (el == 2 * DP) x = e.P.w[j];
         v[h] = x;
     }
+    ChainFast cfast;
+    {
+        constexpr double TH = DP > 16 ? 0x1p23 : 0x1p25;
+        const double wmax = dadd(e.P.w[j], (double)(n + 1));
+        cfast.F = ddiv(TH, dmul(wmax, wmax));
+        cfast.fs = ddiv(cfast.F, nm.eps2);
+        cfast.invk = nm.div_mode ? ddiv(1.0, nm.k) : nm.wsel;
+        cfast.delta2 = nm.delta2;
+        cfast.mg = (double)(D + 8);
+    }
     CCB_DBG(long long t_wait = 0, t_slow = 0, n_cont = 0, t_head = 0, t_tail = 0, n_clean = 0; const long long t_beg = clock64();
             const int dbgm = g_bs_dbg_mode;)
     // The replay warp issues in order and is alone on its scheduler: every dependent instruction costs its full latency.
@@ -1120,7 +1218,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
 #pragma unroll
                     for (int h = 0; h < NH; ++h) rec.v[h] = v[h];
                     rec = bs_chain_slow_group<DP, NH>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
-                                                      nm.div_mode, nm.k, nm.wsel, e.ws.prej);
+                                                      nm.div_mode, nm.k, nm.wsel, e.ws.prej, cfast, (b | g) == 0);
 #pragma unroll
                     for (int h = 0; h < NH; ++h) v[h] = rec.v[h];
                 }
@@ -1136,6 +1234,7 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         if (lane_o == 0) mbar_arrive(&done[s]);
         CCB_DBG(t_tail += clock64() - t_t0;)
     }
+    CCB_DBG(if (lane == 0) atomicMax((unsigned long long *)&g_trace_ts[20], (unsigned long long)globaltimer_ns());)
     CCB_DBG(if (e.ws.dbg && lane == 0) {
         e.ws.dbg[j * 8 + 0] = n;
         e.ws.dbg[j * 8 + 1] = clock64() - t_beg;
@@ -1149,78 +1248,118 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
 }
 
 // ---- outlier-side member lists: sort (key, cell) of the pcore-rejected cells --------------------------
-__global__ void __launch_bounds__(BS_CTA1, 1) k_bs_olist(Eng e) {
+// RANK SORT over the whole GPU.  The composite (key, cell) values are distinct, so the sorted position of an entry is the
+// number of smaller entries.  Every CTA compacts the same entry list into its shared memory (a few thousand slots of the
+// need list at most), then ranks its own slice of the entries -- BS_OL_TPE threads per entry, each counting over a strided
+// part of the array (broadcast reads) -- and writes the entries to their places in global memory; the last CTA to finish
+// (ticket) turns the sorted array into the key segments.  A single CTA spent 55 us in a bitonic sort of 4096 entries;
+// 148 CTAs need ~2 us for the 16.7 M comparisons.
+constexpr int BS_OL_THREADS = 512, BS_OL_TPE = 16, BS_OL_CTAS = 148;
+
+template <int NT>
+__device__ __forceinline__ int block_exclusive_scan_t(int v, int *s_warp, int &total) { // NT threads, NT / 32 <= 32 warps
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = lane < NT / 32 ? s_warp[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    const int r = s_warp[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(BS_OL_THREADS, 1) k_bs_olist(Eng e) {
     e.fetch();
+    CCB_TS(12);
+    constexpr int NT = BS_OL_THREADS, TPE = BS_OL_TPE, EPP = NT / TPE; // entries ranked per pass
     __shared__ unsigned long long keys[BS_RMAX];
     __shared__ int s_warp[33];
-    __shared__ int s_n;
+    __shared__ int s_last;
     BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const int tid = threadIdx.x;
     const int Mp = bc->Mp, KNEW = bc->Mp + bc->Mo0;
+    const int nneed = bc->nneed, Beff = bc->Beff;
+    // ---- every CTA: the entry list, in need-list order (the same in every CTA)
+    constexpr int SPT = BS_RMAX / NT; // slots per thread
+    unsigned long long mine[SPT];
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < SPT; ++u) {
+        const int t = tid * SPT + u;
+        mine[u] = ~0ull;
+        if (t < nneed) {
+            const int i = e.ws.ncell[t];
+            if (i < Beff && e.ws.prej[i]) {
+                const int sp = e.ws.ospec[i];
+                if (sp >= 0) {
+                    mine[u] = ((unsigned long long)(unsigned)sp << 32) | (unsigned)i;
+                    ++cnt;
+                }
+            }
+        }
+    }
+    int n;
+    int pos = block_exclusive_scan_t<NT>(cnt, s_warp, n);
+#pragma unroll
+    for (int u = 0; u < SPT; ++u)
+        if (mine[u] != ~0ull) keys[pos++] = mine[u];
+    __syncthreads();
+    // ---- rank of this CTA's slice
+    const int sub = tid % TPE, slot = tid / TPE;
+    for (int e0 = blockIdx.x * EPP; e0 < n; e0 += gridDim.x * EPP) { // (block-uniform bounds)
+        const int en = e0 + slot;
+        const unsigned long long my = en < n ? keys[en] : 0ull;
+        int rank = 0;
+        if (en < n)
+            for (int q = sub; q < n; q += TPE) rank += keys[q] < my;
+#pragma unroll
+        for (int o = TPE / 2; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+        if (en < n && sub == 0) e.ws.okeys[rank] = my;
+    }
+    // ---- the last CTA to get here builds the segments
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&bc->ticket_o, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int t = tid; t < n; t += NT) keys[t] = ((volatile unsigned long long *)e.ws.okeys)[t];
     // forget the modified-flags of the previous round
-    for (int h = tid; h < bc->nh; h += BS_CTA1) {
+    for (int h = tid; h < bc->nh; h += NT) {
         const int key = e.ws.hkey[h];
         if (key < KNEW) e.ws.firstmember[key - Mp] = INT_MAX;
     }
-    if (tid == 0) s_n = 0;
     __syncthreads();
-    const int nneed = bc->nneed, Beff = bc->Beff;
-    for (int t = tid; t < nneed; t += BS_CTA1) {
-        const int i = e.ws.ncell[t];
-        if (i < Beff && e.ws.prej[i] && e.ws.ospec[i] >= 0) {
-            const int slot = atomicAdd(&s_n, 1);
-            keys[slot] = ((unsigned long long)(unsigned)e.ws.ospec[i] << 32) | (unsigned)i;
-        }
-    }
-    __syncthreads();
-    const int n = s_n;
-    if (n <= BS_CTA1) {
-        // the usual case (a few hundred rejected cells): RANK SORT -- the composite (key, cell) values are distinct, so the
-        // sorted position of an entry is the number of smaller entries; every thread counts for its own entry over the
-        // shared array (broadcast reads, no barrier per step) instead of log^2 n barrier-separated bitonic steps
-        unsigned long long mine = ~0ull;
-        int rank = 0;
-        if (tid < n) {
-            mine = keys[tid];
-            for (int j = 0; j < n; ++j) rank += keys[j] < mine;
-        }
-        __syncthreads();
-        if (tid < n) keys[rank] = mine;
-        __syncthreads();
-    } else {
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    for (int t = n + tid; t < np2; t += BS_CTA1) keys[t] = ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < np2; t += BS_CTA1) {
-                const int p = t ^ j;
-                if (p > t) {
-                    const unsigned long long a = keys[t], b = keys[p];
-                    const bool up = (t & k) == 0;
-                    if ((a > b) == up) {
-                        keys[t] = b;
-                        keys[p] = a;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    }
     // heads of the key segments, in key order (= list order: snapshot slots, then creations by creator)
-    const int per = (n + BS_CTA1 - 1) / BS_CTA1;
+    const int per = (n + NT - 1) / NT;
     const int lo = min(n, tid * per), hi = min(n, lo + per);
-    int cnt = 0;
+    cnt = 0;
     for (int t = lo; t < hi; ++t) cnt += (t == 0) || ((keys[t] >> 32) != (keys[t - 1] >> 32));
     int total;
-    int h = block_exclusive_scan_1024(cnt, s_warp, total);
+    int h = block_exclusive_scan_t<NT>(cnt, s_warp, total);
     if (tid == 0) {
         bc->nh = total;
         bc->no = n;
         bc->hnew0 = total; // lowered below by the first created-in-block key
+        bc->ticket_o = 0;
         e.ws.hoff[total] = n;
     }
     __syncthreads();
@@ -1241,12 +1380,12 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_olist(Eng e) {
     // its first member is its creator; a stale speculation can leave phantom keys (members, but the creator
     // decided otherwise) -- those lie beyond the first mismatch and get no rank.
     const int nh = bc->nh, hnew0 = bc->hnew0;
-    const int nk = nh - hnew0, per2 = (nk + BS_CTA1 - 1) / BS_CTA1;
+    const int nk = nh - hnew0, per2 = (nk + NT - 1) / NT;
     const int k0 = min(nk, tid * per2), k1 = min(nk, k0 + per2);
     int creal = 0;
     for (int q = k0; q < k1; ++q) creal += e.ws.omem[e.ws.hoff[hnew0 + q]] == e.ws.hkey[hnew0 + q] - KNEW;
     int rtotal;
-    int rk = block_exclusive_scan_1024(creal, s_warp, rtotal);
+    int rk = block_exclusive_scan_t<NT>(creal, s_warp, rtotal);
     for (int q = k0; q < k1; ++q) {
         const int creator = e.ws.hkey[hnew0 + q] - KNEW;
         e.ws.hrank[q] = rk; // real creations before key hnew0 + q
@@ -1281,6 +1420,7 @@ __device__ __forceinline__ void derive_version(const Eng &e, const Num &nm, int 
 // k_bs_verify_p behind it, next to k_bs_olist -> k_bs_chain_o -> k_bs_derive_o (disjoint cells); skipped in a light round.
 __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_p(Eng e) {
     e.fetch();
+    CCB_TS(10);
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return;
     const int i = blockIdx.x * BS_THREADS + threadIdx.x;
@@ -1303,6 +1443,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_p(Eng e) {
 // OUTLIER side: the versions k_bs_chain_o left (members of the outlier-side keys, in omem)
 __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_o(Eng e) {
     e.fetch();
+    CCB_TS(14);
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const int no = bc->no;
@@ -1321,6 +1462,7 @@ constexpr int BS_VP_THREADS = 128; // (eight warps with two MCs in flight were m
 template <int DP>
 __global__ void __launch_bounds__(BS_VP_THREADS, DP <= 16 ? 5 : 1) k_bs_verify_p(Eng e) {
     e.fetch();
+    CCB_TS(11);
     constexpr int NW = BS_VP_THREADS / 32, U = 1;
     __shared__ double s_bd[NW][32];
     __shared__ int s_best[NW][32], s_prev[NW][32];
@@ -1330,6 +1472,7 @@ __global__ void __launch_bounds__(BS_VP_THREADS, DP <= 16 ? 5 : 1) k_bs_verify_p
     const int t = blockIdx.x;
     const int Beff = bc->Beff;
     if (t * 32 >= Beff) return;
+    if (t * 32 + 32 <= bc->m_exact) return; // exact since an earlier round: eff / dec of these cells stand
     const Num nm = e.nm;
     const int D = nm.D, Mp = bc->Mp;
     const int i = t * 32 + lane;
@@ -1427,94 +1570,186 @@ __global__ void __launch_bounds__(BS_VP_THREADS, DP <= 16 ? 5 : 1) k_bs_verify_p
     if (mm != INT_MAX && lane == __ffs(am) - 1) atomicMin(&bc->m0, mm);
 }
 
-// outlier stage of the cells the pcore stage rejected: one CTA per cell (the scan over the modified / created keys is a
-// chain of dependent loads per key -- member list, version, centroid -- so it is spread over 128 threads, not 32)
+// outlier stage of the cells the pcore stage rejected.  Two layouts of the same work: with few pending cells (the steady
+// state: a few hundred per block) one CTA per cell -- the scan over the modified / created keys is a chain of dependent
+// loads per key (member list, version, centroid), so it is spread over 128 threads; with thousands of pending cells (cold
+// start, saturated parameter corners) one WARP per cell, no block barriers.  Cells below the exact prefix of the previous
+// rounds (bc->m_exact) are final and skipped.
+
+// (1) nearest snapshot MC not modified before cell i, from the top-K list, by one warp: lane s looks at entry s.  If every
+// listed candidate is stale the nearest clean MC is unknown, but no clean MC is nearer than the last list entry (BOUND):
+// the decision still stands when a modified / created MC, at its exact version, beats that bound.
+__device__ __forceinline__ void bs_vo_topk(const Eng &e, int i, int Mp, int Mo0, int lane, double &bd0, int &bkey0, int &status,
+                                           int &bounded, double &bound) {
+    bd0 = 0.0, bound = 0.0;
+    bkey0 = INT_MAX, status = 0, bounded = 0; // status 2: NEED
+    if (Mo0 <= 0) return;
+    const int tk = e.ws.tkpos[i];
+    if (tk < 0) {
+        status = 2;
+        return;
+    }
+    int o = -1;
+    double dv = 0.0;
+    bool clean = false;
+    if (lane < BS_TOPK) {
+        o = e.ws.tk_idx[(size_t)tk * BS_TOPK + lane];
+        dv = e.ws.tk_dist[(size_t)tk * BS_TOPK + lane];
+        clean = o >= 0 && e.ws.firstmember[o] >= i;
+    }
+    const unsigned valid = __ballot_sync(0xffffffffu, lane < BS_TOPK && o >= 0); // a prefix of the list
+    const unsigned cl = __ballot_sync(0xffffffffu, clean);
+    if (cl) {
+        const int s = __ffs(cl) - 1;
+        bd0 = __shfl_sync(0xffffffffu, dv, s);
+        bkey0 = Mp + __shfl_sync(0xffffffffu, o, s);
+    } else if (valid == (1u << BS_TOPK) - 1u) {
+        bounded = 1;
+        bound = __shfl_sync(0xffffffffu, dv, BS_TOPK - 1);
+    }
+}
+
+// (2) lanes [sub, sub + step, ...) of the hot keys: every MC modified or created earlier in the block, at its version just
+// before cell i
+template <int DP>
+__device__ __forceinline__ void bs_vo_scan(const Eng &e, const Num &nm, const double (&x)[DP], int i, int nh, int sub, int step,
+                                           double &bd, int &bkey, int &bver) {
+    const int D = nm.D;
+    bd = 0.0;
+    bkey = INT_MAX, bver = -1;
+    for (int h = sub; h < nh; h += step) {
+        if (e.ws.hfirst[h] >= i) continue;
+        const int off = e.ws.hoff[h], cnt = e.ws.hoff[h + 1] - off;
+        const int v = cnt == 1 ? e.ws.omem[off] : latest_before(e.ws.omem + off, cnt, i);
+        const double dv = dist_regs<DP>(x, e.ws.vcen + (size_t)v * D, e.ws.vmask[v], nm);
+        const int key = e.ws.hkey[h];
+        if (!(dv != dv) && (bkey == INT_MAX || dv < bd || (dv == bd && key < bkey))) {
+            bd = dv;
+            bkey = key;
+            bver = v;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bkey, o);
+        const int ov = __shfl_xor_sync(0xffffffffu, bver, o);
+        if (ok != INT_MAX && (bkey == INT_MAX || od < bd || (od == bd && ok < bkey))) {
+            bd = od;
+            bkey = ok;
+            bver = ov;
+        }
+    }
+}
+
+// (3) the decision, by one warp (lane = dimension in the tentative absorb)
+template <int DP>
+__device__ __forceinline__ void bs_vo_decide(const Eng &e, BsCtl *bc, const Num &nm, int i, int lane, int Mp, int KNEW, int Beff,
+                                             int status, int bounded, double bound, double bd, int bkey, int bver) {
+    const int D = nm.D;
+    int dec, up = 0;
+    if (status) {
+        dec = BS_KEY_NEED;
+    } else if (bounded && !(bkey != INT_MAX && bd < bound)) {
+        dec = BS_KEY_UNKNOWN;
+    } else {
+        dec = KNEW + i;
+        if (bkey != INT_MAX) {
+            const double *c1, *c2;
+            double w;
+            if (bver >= 0) {
+                c1 = ver_cf1(e.ws, bver);
+                c2 = ver_cf2(e.ws, bver);
+                w = ver_w(e.ws, bver);
+            } else {
+                const int o = bkey - Mp;
+                c1 = e.O.cf1 + (size_t)o * D;
+                c2 = e.O.cf2 + (size_t)o * D;
+                w = e.O.w[o];
+            }
+            LaneMc m, o2;
+            double xl[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int d = lane + 32 * h;
+                m.cf1[h] = d < D ? c1[d] : 1.0;
+                m.cf2[h] = d < D ? c2[d] : 1.0;
+                m.cen[h] = 0.0;
+                xl[h] = d < D ? e.X[(bc->pos + i) * e.ld + d] : 0.0;
+            }
+            double wn;
+            uint64_t nmask;
+            if (tentative_absorb_t<DP>(m, w, xl, nm, o2, wn, nmask)) {
+                dec = bkey;
+                const int pd = nm.cnt_gt1 ? popc64(nmask) : 0;
+                up = (wn >= nm.beta_mu) && ((int64_t)pd <= nm.pi); // hddstream.py:413-418
+            }
+        }
+    }
+    if (lane == 0) {
+        e.ws.dec[i] = dec;
+        e.ws.upf[i] = (uint8_t)up;
+        if (i < Beff) { // (a light round after a truncation still lists cells behind the cut)
+            if (dec != e.ws.eff[i]) atomicMin(&bc->m0, i);
+            if (up) atomicMin(&bc->up0, i);
+        }
+    }
+}
+
 template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
     e.fetch();
+    CCB_TS(15);
     constexpr int NW = BS_THREADS / 32;
-    __shared__ double s_bd[NW], s_f[2];
-    __shared__ int s_bkey[NW], s_bver[NW], s_i[3];
+    __shared__ double s_bd[NW];
+    __shared__ int s_bkey[NW], s_bver[NW];
     BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const Num nm = e.nm;
     const int D = nm.D, Mp = bc->Mp, Mo0 = bc->Mo0, KNEW = Mp + Mo0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int npend = bc->npend, nh = bc->nh, Beff = bc->Beff;
+    const int npend = bc->npend, nh = bc->nh, Beff = bc->Beff, m_exact = bc->m_exact;
+    if (npend > (int)gridDim.x) {
+        // ---- one warp per cell
+        for (int pidx = blockIdx.x * NW + warp; pidx < npend; pidx += gridDim.x * NW) {
+            const int i = e.ws.pend[pidx];
+            if (i < m_exact) continue;
+            double x[DP];
+            load_row<DP>(e.X + (bc->pos + i) * e.ld, D, x);
+            double bd0, bound, bd;
+            int bkey0, status, bounded, bkey, bver;
+            bs_vo_topk(e, i, Mp, Mo0, lane, bd0, bkey0, status, bounded, bound);
+            bs_vo_scan<DP>(e, nm, x, i, nh, lane, 32, bd, bkey, bver);
+            if (!(bkey != INT_MAX && (bkey0 == INT_MAX || bd < bd0 || (bd == bd0 && bkey < bkey0)))) {
+                bd = bd0;
+                bkey = bkey0;
+                bver = -1;
+            }
+            bs_vo_decide<DP>(e, bc, nm, i, lane, Mp, KNEW, Beff, status, bounded, bound, bd, bkey, bver);
+        }
+        return;
+    }
+    // ---- one CTA per cell
     for (int pidx = blockIdx.x; pidx < npend; pidx += gridDim.x) {
         const int i = e.ws.pend[pidx];
+        if (i < m_exact) continue; // (block-uniform)
         double x[DP];
         load_row<DP>(e.X + (bc->pos + i) * e.ld, D, x);
-        // (1) nearest snapshot MC not modified before cell i, from the top-K list.  If every listed candidate is
-        // stale the nearest clean MC is unknown, but no clean MC is nearer than the last list entry (BOUND): the
-        // decision still stands when a modified / created MC, at its exact version, beats that bound.
-        if (tid == 0) {
-            double bd0 = 0.0, bound = 0.0;
-            int bkey0 = INT_MAX, status = 0, bounded = 0; // status 2: NEED
-            if (Mo0 > 0) {
-                const int tk = e.ws.tkpos[i];
-                if (tk < 0) {
-                    status = 2;
-                } else {
-                    int s = 0;
-                    for (; s < BS_TOPK; ++s) {
-                        const int o = e.ws.tk_idx[(size_t)tk * BS_TOPK + s];
-                        if (o < 0) break;
-                        if (e.ws.firstmember[o] >= i) {
-                            bd0 = e.ws.tk_dist[(size_t)tk * BS_TOPK + s];
-                            bkey0 = Mp + o;
-                            break;
-                        }
-                    }
-                    if (s == BS_TOPK) {
-                        bounded = 1;
-                        bound = e.ws.tk_dist[(size_t)tk * BS_TOPK + BS_TOPK - 1];
-                    }
-                }
-            }
-            s_f[0] = bd0;
-            s_f[1] = bound;
-            s_i[0] = bkey0;
-            s_i[1] = status;
-            s_i[2] = bounded;
-        }
-        // (2) every MC modified or created earlier in the block, at its version just before cell i
-        double bd = 0.0;
-        int bkey = INT_MAX, bver = -1;
-        for (int h = tid; h < nh; h += BS_THREADS) {
-            if (e.ws.hfirst[h] >= i) continue;
-            const int off = e.ws.hoff[h], cnt = e.ws.hoff[h + 1] - off;
-            const int v = cnt == 1 ? e.ws.omem[off] : latest_before(e.ws.omem + off, cnt, i);
-            const double dv = dist_regs<DP>(x, e.ws.vcen + (size_t)v * D, e.ws.vmask[v], nm);
-            const int key = e.ws.hkey[h];
-            if (!(dv != dv) && (bkey == INT_MAX || dv < bd || (dv == bd && key < bkey))) {
-                bd = dv;
-                bkey = key;
-                bver = v;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-            const int ok = __shfl_xor_sync(0xffffffffu, bkey, o);
-            const int ov = __shfl_xor_sync(0xffffffffu, bver, o);
-            if (ok != INT_MAX && (bkey == INT_MAX || od < bd || (od == bd && ok < bkey))) {
-                bd = od;
-                bkey = ok;
-                bver = ov;
-            }
-        }
+        double bd0 = 0.0, bound = 0.0;
+        int bkey0 = INT_MAX, status = 0, bounded = 0;
+        if (warp == 0) bs_vo_topk(e, i, Mp, Mo0, lane, bd0, bkey0, status, bounded, bound);
+        double bd;
+        int bkey, bver;
+        bs_vo_scan<DP>(e, nm, x, i, nh, tid, BS_THREADS, bd, bkey, bver);
         if (lane == 0) {
             s_bd[warp] = bd;
             s_bkey[warp] = bkey;
             s_bver[warp] = bver;
         }
         __syncthreads();
-        if (warp == 0) { // the rest is one warp's work (lane = dimension in the tentative absorb)
-            const int status = s_i[1], bounded = s_i[2];
-            const double bound = s_f[1];
-            bd = s_f[0];
-            bkey = s_i[0];
+        if (warp == 0) { // the rest is one warp's work
+            bd = bd0;
+            bkey = bkey0;
             bver = -1;
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
@@ -1526,59 +1761,43 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
                     bver = s_bver[w];
                 }
             }
-            int dec, up = 0;
-            if (status) {
-                dec = BS_KEY_NEED;
-            } else if (bounded && !(bkey != INT_MAX && bd < bound)) {
-                dec = BS_KEY_UNKNOWN;
-            } else {
-                dec = KNEW + i;
-                if (bkey != INT_MAX) {
-                    const double *c1, *c2;
-                    double w;
-                    if (bver >= 0) {
-                        c1 = ver_cf1(e.ws, bver);
-                        c2 = ver_cf2(e.ws, bver);
-                        w = ver_w(e.ws, bver);
-                    } else {
-                        const int o = bkey - Mp;
-                        c1 = e.O.cf1 + (size_t)o * D;
-                        c2 = e.O.cf2 + (size_t)o * D;
-                        w = e.O.w[o];
-                    }
-                    LaneMc m, o2;
-                    double xl[2];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int d = lane + 32 * h;
-                        m.cf1[h] = d < D ? c1[d] : 1.0;
-                        m.cf2[h] = d < D ? c2[d] : 1.0;
-                        m.cen[h] = 0.0;
-                        xl[h] = d < D ? e.X[(bc->pos + i) * e.ld + d] : 0.0;
-                    }
-                    double wn;
-                    uint64_t nmask;
-                    if (tentative_absorb_t<DP>(m, w, xl, nm, o2, wn, nmask)) {
-                        dec = bkey;
-                        const int pd = nm.cnt_gt1 ? popc64(nmask) : 0;
-                        up = (wn >= nm.beta_mu) && ((int64_t)pd <= nm.pi); // hddstream.py:413-418
-                    }
-                }
-            }
-            if (lane == 0) {
-                e.ws.dec[i] = dec;
-                e.ws.upf[i] = (uint8_t)up;
-                if (i < Beff) { // (a light round after a truncation still lists cells behind the cut)
-                    if (dec != e.ws.eff[i]) atomicMin(&bc->m0, i);
-                    if (up) atomicMin(&bc->up0, i);
-                }
-            }
+            bs_vo_decide<DP>(e, bc, nm, i, lane, Mp, KNEW, Beff, status, bounded, bound, bd, bkey, bver);
         }
         __syncthreads(); // the shared slots are reused by the next cell
     }
 }
 
 // ---- M ----------------------------------------------------------------------------------------------
+#ifdef CCB_DEBUG
+// diagnostics build: one record per round / per block (see tools/trace_rounds.py for the layout)
+__device__ void bs_trace_round(const BsCtl *bc, int kind, int m0, int Beff_in, int nneed_in) {
+    const int r = atomicAdd(&g_trace_n, 1);
+    if (r < CCB_TRACE_MAX) {
+        long long *t = g_trace[r];
+        t[0] = kind; // 0 refine, 1 commit decided, 2 block finished
+        t[1] = bc->pos;
+        t[2] = bc->Bcur;
+        t[3] = Beff_in;
+        t[4] = bc->it;
+        t[5] = nneed_in;
+        t[6] = bc->npend;
+        t[7] = bc->nh;
+        t[8] = bc->no;
+        t[9] = m0;
+        t[10] = bc->upgrade;
+        t[11] = bc->pclean; // (of the NEXT round when kind == 0)
+        t[12] = bc->m_commit;
+        t[13] = bc->Mp;
+        t[14] = bc->Mo0;
+        t[15] = bc->hnew0;
+        t[16] = bc->nneed;
+        t[17] = bc->Beff;
+        t[18] = globaltimer_ns();
+        for (int k = 0; k < CCB_TRACE_SLOTS; ++k) t[20 + k] = g_trace_ts[k];
+    }
+    for (int k = 3; k < CCB_TRACE_SLOTS; ++k) g_trace_ts[k] = 0;
+}
+#endif
 __device__ __forceinline__ int block_min_1024(int v, int *s_warp) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -1593,6 +1812,7 @@ __device__ __forceinline__ int block_min_1024(int v, int *s_warp) {
 
 __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
     e.fetch();
+    CCB_TS(16);
     __shared__ int s_warp[33];
     __shared__ int s_act, s_cut;
     BsCtl *bc = e.bc;
@@ -1644,6 +1864,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
             bc->phase = 1;
             bc->tk_lo = bc->tk_hi = 0;
             if (e.h_inner) cudaGraphSetConditional(e.h_inner, 0u);
+            CCB_DBG(bs_trace_round(bc, 1, m0, Beff, bc->nneed);)
         }
         return;
     }
@@ -1748,12 +1969,14 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
             bc->tk_late += nneed_new - nneed_old;
             bc->pairs += (int64_t)(nneed_new - nneed_old) * bc->Mo0;
             bc->Beff = Bnew;
+            bc->m_exact = m0; // every cell before the first mismatch saw exact versions: final from here on
             bc->it += 1;
             bc->pclean = dirty ? 0 : 1;
             if (dirty) bc->npend = 0; // a light round keeps the list of pcore-rejected cells
             else bc->rounds_light += 1;
         }
         if (e.h_inner) cudaGraphSetConditional(e.h_inner, bc->phase == 0 ? 1u : 0u);
+        CCB_DBG(bs_trace_round(bc, 0, m0, Beff, nneed_old);)
     }
 }
 
@@ -1819,6 +2042,7 @@ __device__ __forceinline__ void commit_row(const Eng &e, const BsCtl *bc, const 
 
 __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
     e.fetch();
+    CCB_TS(17);
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 1) return;
     const Num nm = e.nm;
@@ -1830,6 +2054,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
 
 __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_cells(Eng e) {
     e.fetch();
+    CCB_TS(18);
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 1) return;
     const int i = blockIdx.x * BS_THREADS + threadIdx.x;
@@ -1858,6 +2083,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_commit_cells(Eng e) {
 // upgrade (hddstream.py:397-430), list lengths, id counters, next block length
 __global__ void __launch_bounds__(BS_THREADS) k_bs_finish(Eng e) {
     e.fetch();
+    CCB_TS(19);
     __shared__ int s_ncreated;
     BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 1) return;
@@ -1915,6 +2141,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_finish(Eng e) {
         bc->blocks += 1;
         if (m == bc->Bcur) bc->next_B = min(bc->next_B * 2, bc->Bmax);
         else if (!bc->upgrade) bc->next_B = max(bc->next_B / 2, bc->Bmin);
+        CCB_DBG(bs_trace_round(bc, 2, m, ncreated, bc->nneed);)
         bc->nh = 0;
         bc->active = 0;
         if (bc->pos >= bc->N) bc->done = 1;

@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS)
         X = xref->X;
         ld = xref->ld;
     }
+    CCB_TS(3);
     if (nrows_dev) nrows = (int64_t)(*nrows_dev) - row_off;
     if (M_dev) M = min(M, *M_dev);
     if (range_dev) {
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(128) k_topk_merge_dyn(const double *__restrict
                                                         int M, int target, int max_slabs, int tm, int cells,
                                                         double *__restrict__ out_dist, int32_t *__restrict__ out_idx) {
     constexpr int QMAX = 8; // max_slabs <= 256
+    CCB_TS(4);
     const int lane = threadIdx.x & 31;
     const int R = range_dev[1] - range_dev[0];
     if (M_dev) M = min(M, *M_dev);
