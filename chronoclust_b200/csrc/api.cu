@@ -86,8 +86,12 @@ struct ccb_handle {
     int32_t *d_bs_tk_idx_slab = nullptr;
     BsCtl bc_base{}; // counters folded in by ccb_reset
     bool bs_use_graph = true;   // CUDA graph with device-driven WHILE nodes (stream launches when per-kernel timing is on)
-    cudaGraph_t bs_graph = nullptr;
-    cudaGraphExec_t bs_exec = nullptr;
+    // Two cached graphs: the double-buffered stores flip at every ccb_begin_timepoint with decay, so consecutive timepoints
+    // alternate between two sets of (baked-in) pointers -- with one slot the graph was re-captured and re-instantiated at
+    // every timepoint (~1 ms each).
+    cudaGraph_t bs_graph = nullptr, bs_graph_alt = nullptr;
+    cudaGraphExec_t bs_exec = nullptr, bs_exec_alt = nullptr;
+    Eng bs_graph_eng_alt{};
     cudaStream_t cap1 = nullptr, cap2 = nullptr, cap3 = nullptr; // capture streams: block loop, round loop, side branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t copy_stream = nullptr; // host -> device segments of ccb_ingest, ahead of the engine
@@ -366,7 +370,8 @@ int launch_nearest_dyn(ccb_handle *h, cudaStream_t s, int DP, int div_mode, cons
             k_nearest<kDP, K, false><<<NEAREST_DYN_GRID, NEAREST_THREADS, 0, s>>>(X, rows, nullptr, 0, 0, ld, D, cw, M_bound, 0,
                                                                                   slab_dist, slab_idx, range_dev, M_dev, max_slabs, xref);
         k_topk_merge_dyn<K><<<std::min(NEAREST_DYN_GRID, (rows_max + 3) / 4), 128, 0, s>>>(
-            slab_dist, slab_idx, range_dev, M_dev, M_bound, NEAREST_DYN_GRID, max_slabs, Cfg::TM, Cfg::CELLS, out_dist, out_idx);
+            slab_dist, slab_idx, range_dev, M_dev, M_bound, NEAREST_DYN_GRID, max_slabs, Cfg::TM, Cfg::CELLS,
+            Cfg::CAN_SPLIT ? Cfg::TMS : 0, out_dist, out_idx);
         launched = 2;
     })
     if (!launched) return fail(h, CCB_ELIMIT, "unsupported padded dimensionality %d", DP);
@@ -487,7 +492,7 @@ int sync_bc(ccb_handle *h) { // both control blocks -> pinned host mirrors
 // control block, so a converged (or finished) block turns the remaining launches into no-ops.  The three pieces are
 // launched either on the handle's stream (bs_iters rounds enqueued per block; used when per-kernel timing is on) or
 // captured once into a CUDA graph whose block loop and round loop are WHILE conditional nodes driven from the
-// device (k_bs_begin / k_bs_decide / k_bs_finish call cudaGraphSetConditional): no idle launches, no host round trip.
+// device (k_bs_begin / k_bs_decide / k_bs_commit call cudaGraphSetConditional): no idle launches, no host round trip.
 int launch_prologue(ccb_handle *h, const Eng &e, cudaStream_t s) {
     const int g_cells = (h->bs_bmax + BS_THREADS - 1) / BS_THREADS;
     Timed tm(h, CCB_CAT_SPEC);
@@ -575,22 +580,14 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     CKL(h);
     return CCB_OK;
 }
-constexpr int BS_LAUNCHES_PROLOGUE = 3, BS_LAUNCHES_ROUND = 14, BS_LAUNCHES_COMMIT = 3;
+constexpr int BS_LAUNCHES_PROLOGUE = 3, BS_LAUNCHES_ROUND = 14, BS_LAUNCHES_COMMIT = 1;
 
 int launch_commit(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, cudaStream_t side = nullptr) {
+    (void)side;
     const int g_cells = (h->bs_bmax + BS_THREADS - 1) / BS_THREADS;
+    const int rows_ctas = (mp_grid + BS_RMAX + 3) / 4;
     Timed tm(h, CCB_CAT_COMMIT);
-    if (side) { // rows and cells write disjoint data (stores vs. per-cell results)
-        CK(h, cudaEventRecord(h->ev_fork, s));
-        CK(h, cudaStreamWaitEvent(side, h->ev_fork, 0));
-    }
-    k_bs_commit_rows<<<(mp_grid + BS_RMAX + 3) / 4, BS_THREADS, 0, s>>>(e);
-    k_bs_commit_cells<<<g_cells, BS_THREADS, 0, side ? side : s>>>(e);
-    if (side) {
-        CK(h, cudaEventRecord(h->ev_join, side));
-        CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
-    }
-    k_bs_finish<<<1, BS_THREADS, 0, s>>>(e);
+    k_bs_commit<<<rows_ctas + g_cells, BS_THREADS, 0, s>>>(e, rows_ctas); // rows | cells | (last CTA) finish
     CKL(h);
     return CCB_OK;
 }
@@ -606,7 +603,7 @@ Eng make_eng(ccb_handle *h) {
 }
 
 // ---- CUDA graph of the whole ordered loop: WHILE(block) { prologue; WHILE(round) { round }; commit } ----------
-void drop_graph(ccb_handle *h) {
+void drop_graph(ccb_handle *h) { // (the current slot)
     if (h->bs_exec) cudaGraphExecDestroy(h->bs_exec);
     if (h->bs_graph) cudaGraphDestroy(h->bs_graph);
     h->bs_exec = nullptr;
@@ -616,9 +613,14 @@ void drop_graph(ccb_handle *h) {
 int build_graph(ccb_handle *h, const Eng &base) {
     drop_graph(h);
     if (!h->cap1) {
-        CK(h, cudaStreamCreateWithFlags(&h->cap1, cudaStreamNonBlocking));
-        CK(h, cudaStreamCreateWithFlags(&h->cap2, cudaStreamNonBlocking));
-        CK(h, cudaStreamCreateWithFlags(&h->cap3, cudaStreamNonBlocking));
+        // the main line of a round (lists, replay, outlier-side lists ...) is the critical path: its kernels are captured
+        // from high-priority streams, the side branches (kernel 1, pcore-side derive / verify) from a low-priority one, so
+        // that a small critical kernel is not queued behind the thousand CTAs of a side kernel running next to it
+        int prio_lo = 0, prio_hi = 0;
+        CK(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(h, cudaStreamCreateWithPriority(&h->cap1, cudaStreamNonBlocking, prio_hi));
+        CK(h, cudaStreamCreateWithPriority(&h->cap2, cudaStreamNonBlocking, prio_hi));
+        CK(h, cudaStreamCreateWithPriority(&h->cap3, cudaStreamNonBlocking, prio_lo));
         CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     }
@@ -737,8 +739,14 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
         const int64_t pos0 = b.pos;
         const int64_t blocks0 = b.blocks, iters0 = b.iters;
         if (graph) {
-            if (!h->bs_exec || memcmp(&h->bs_graph_eng, &e, sizeof(Eng)) != 0)
-                if ((rc = build_graph(h, e))) return rc;
+            if (!h->bs_exec || memcmp(&h->bs_graph_eng, &e, sizeof(Eng)) != 0) {
+                // not the current slot: the other one? (swap); otherwise rebuild the older slot
+                std::swap(h->bs_graph, h->bs_graph_alt);
+                std::swap(h->bs_exec, h->bs_exec_alt);
+                std::swap(h->bs_graph_eng, h->bs_graph_eng_alt);
+                if (!h->bs_exec || memcmp(&h->bs_graph_eng, &e, sizeof(Eng)) != 0)
+                    if ((rc = build_graph(h, e))) return rc;
+            }
             CK(h, cudaGraphLaunch(h->bs_exec, s));
         } else {
             const Ctl &c = *h->h_ctl;
@@ -1106,6 +1114,9 @@ void ccb_destroy(ccb_handle *h) {
     cudaFree(h->d_pnew);
     cudaFree(h->d_pfin);
     cudaFree(h->d_onew);
+    drop_graph(h);
+    std::swap(h->bs_graph, h->bs_graph_alt);
+    std::swap(h->bs_exec, h->bs_exec_alt);
     drop_graph(h);
     if (h->cap1) cudaStreamDestroy(h->cap1);
     if (h->cap2) cudaStreamDestroy(h->cap2);

@@ -61,7 +61,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 
 // ---- diagnostics build only: per-round timeline of the engine (csrc/debug.h: ccb_debug_trace) -------
 #ifdef CCB_DEBUG
-constexpr int CCB_TRACE_SLOTS = 24, CCB_TRACE_WORDS = 48, CCB_TRACE_MAX = 1 << 14;
+constexpr int CCB_TRACE_SLOTS = 40, CCB_TRACE_WORDS = 64, CCB_TRACE_MAX = 1 << 14;
 __device__ long long g_trace_ts[CCB_TRACE_SLOTS];               // start of every kernel of the current round (globaltimer, ns)
 __device__ long long g_trace[CCB_TRACE_MAX][CCB_TRACE_WORDS];   // one record per round (k_bs_decide) / block (k_bs_finish)
 __device__ int g_trace_n;
@@ -75,9 +75,14 @@ __device__ __forceinline__ long long globaltimer_ns() {
     do {                                                                                \
         if (blockIdx.x == 0 && threadIdx.x == 0) g_trace_ts[slot] = globaltimer_ns();   \
     } while (0)
+#define CCB_TS_ANY(slot)                                                                \
+    do {                                                                                \
+        if (threadIdx.x == 0) atomicMax((unsigned long long *)&g_trace_ts[slot], (unsigned long long)globaltimer_ns()); \
+    } while (0)
 #else
 #define CCB_DBG(...)
 #define CCB_TS(slot)
+#define CCB_TS_ANY(slot)
 #endif
 
 // ---- small utilities ------------------------------------------------------------------------------

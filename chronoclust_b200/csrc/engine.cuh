@@ -31,7 +31,7 @@
 //                      prefix (induction: every earlier cell saw exact versions).  The recomputed decisions
 //                      become the next speculation; if they only move cells between outlier-side keys the next
 //                      round re-runs the outlier side alone (LIGHT round); an upgrade ends the block at that cell.
-//   and finally k_bs_commit_rows / k_bs_commit_cells / k_bs_finish write the exact prefix back.
+//   and finally k_bs_commit writes the exact prefix back (rows, per-cell results, then the block's bookkeeping).
 // All control flow lives in device memory (BsCtl): the whole loop of one ingest call is one CUDA graph with two
 // device-driven WHILE nodes (api.cu: build_graph), inside which   kernel 1 + S_o  ||  L + C_p   and then
 // D_p + V_p  ||  olist + C_o + D_o   run as parallel branches (disjoint data).
@@ -56,12 +56,15 @@ struct BsCtl {
     int32_t active, phase, it, itmax; // phase 0: iterating, 1: commit pending
     int32_t Mp, Mo0;
     int32_t nneed, tk_lo, tk_hi; // need-list length; range of entries whose top-K list is to be computed
+    int32_t nneed_raw;           // slots k_bs_spec asked for (more than BS_RMAX: k_bs_need re-does the list in cell order)
     int32_t nh, hnew0, no;       // hot outlier-side keys, index of the first created-in-block key, members
     int32_t npend;
     int32_t m_commit, upgrade;
     int32_t need_grow, done;
     int32_t ticket; // k_bs_pscan: CTAs finished (last one computes the key offsets)
     int32_t ticket_o; // k_bs_olist: likewise (the last one builds the key segments)
+    int32_t ticket_c; // k_bs_commit: likewise (the last one finishes the block)
+    int32_t o_big;    // outlier-side keys of this round with more members than a CTA of k_bs_chain_o derives itself
     int32_t m_exact;  // cells below this are exact since an earlier round of the block (first mismatch of the previous round)
     int32_t pclean; // refinement round whose pcore side (candidates, CONTESTED flags, accepts) is that of the round before
     int32_t m0, up0; // this round: first cell whose exact decision differs from the speculation / first upgrading cell
@@ -85,7 +88,7 @@ struct BsWs {
     int32_t *nrows, *ncell;          // [BS_RMAX] absolute row / block-relative cell of the need list
     double *tk_dist;
     int32_t *tk_idx; // [BS_RMAX][BS_TOPK]
-    int32_t *hkey, *hoff, *omem, *hrank; // hrank[q]: real creations before key hnew0 + q
+    int32_t *hkey, *hoff, *omem, *hrank; // hrank[h]: real creations before created-in-block key h (h >= hnew0; hrank[nh]: all)
     int32_t *hfirst;                     // [BS_RMAX + 1] first member of every outlier-side key
     unsigned long long *okeys;           // [BS_RMAX] (key, cell) of the pcore-rejected cells, sorted (k_bs_olist)
     int32_t *firstmember; // [O.cap], INT_MAX = unmodified in this block
@@ -262,6 +265,7 @@ __global__ void k_bs_begin(Eng e) {
         bc->Mp = Mp;
         bc->Mo0 = Mo0;
         bc->nneed = 0;
+        bc->nneed_raw = 0;
         bc->nh = bc->hnew0 = bc->no = 0;
         bc->npend = 0;
         bc->it = 0;
@@ -322,9 +326,9 @@ __global__ void __launch_bounds__(BS_THREADS, DP <= 16 ? 7 : 1) k_bs_spec(Eng e)
         }
     }
     group_argmin(bd, best);
-    if (part != 0 || !live) return;
-    int flag = 1;
-    if (best >= 0) {
+    const bool mine = part == 0 && live;
+    int flag = mine ? 1 : 0;
+    if (mine && best >= 0) {
         double wn;
         uint64_t nmask;
         const double r2s = tent_regs<DP>(e.P.cf1 + (size_t)best * D, e.P.cf2 + (size_t)best * D, e.P.w[best], x, nm, wn, nmask);
@@ -333,11 +337,30 @@ __global__ void __launch_bounds__(BS_THREADS, DP <= 16 ? 7 : 1) k_bs_spec(Eng e)
         // sending the cell through the serial chain for an exact test; k_bs_verify_p checks it like everything else
         else if (r2s > e.r2rej) best = -1;
     }
+    // need list: every cell that is not SAFE takes a top-K slot right here (one atomic per warp; the order of the slots
+    // is immaterial).  Should the block need more than BS_RMAX slots, k_bs_need hands them out again in cell order and
+    // truncates the block.
+    const unsigned fm = __ballot_sync(0xffffffffu, flag != 0);
+    int slot = -1;
+    if (fm) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == __ffs(fm) - 1) base = atomicAdd(&e.bc->nneed_raw, __popc(fm));
+        base = __shfl_sync(0xffffffffu, base, __ffs(fm) - 1);
+        if (flag) slot = base + __popc(fm & ((1u << lane) - 1u));
+    }
+    if (!mine) return;
     e.ws.pcand[i] = best;
     e.ws.pflag[i] = (uint8_t)flag;
     e.ws.prej[i] = best < 0;
     e.ws.ospec[i] = BS_KEY_NONE;
-    e.ws.tkpos[i] = -1;
+    if (slot >= 0 && slot < BS_RMAX) {
+        e.ws.tkpos[i] = slot;
+        e.ws.nrows[slot] = (int32_t)bc->pos + i;
+        e.ws.ncell[slot] = i;
+    } else {
+        e.ws.tkpos[i] = -1;
+    }
 }
 
 // ordered need list: every cell that is not SAFE gets a top-K slot, in cell order; the block is truncated at
@@ -380,6 +403,17 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
     __shared__ int s_cut;
     BsCtl *bc = e.bc;
     if (!bc->active) return;
+    if (bc->nneed_raw <= BS_RMAX) { // the usual case: k_bs_spec handed the slots out itself
+        if (threadIdx.x == 0) {
+            bc->Beff = bc->Bcur;
+            bc->nneed = bc->nneed_raw;
+            bc->tk_lo = 0;
+            bc->tk_hi = bc->nneed;
+            bc->rejects += bc->nneed;
+            bc->pairs += (int64_t)bc->nneed * bc->Mo0;
+        }
+        return;
+    }
     const int B = bc->Bcur, tid = threadIdx.x;
     const int per = (B + BS_CTA1 - 1) / BS_CTA1;
     const int lo = min(B, tid * per), hi = min(B, lo + per);
@@ -422,8 +456,9 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
             e.ws.tkpos[i] = base;
             e.ws.nrows[base] = row0 + i;
             e.ws.ncell[base] = i;
-        } else if (base == BS_RMAX) {
-            s_cut = i; // exactly one thread sees the first overflowing cell
+        } else {
+            e.ws.tkpos[i] = -1;
+            if (base == BS_RMAX) s_cut = i; // exactly one thread sees the first overflowing cell
         }
         ++base;
     }
@@ -618,6 +653,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
 // k_bs_chain_o: OUTLIER-SIDE keys (modified snapshot outlier MCs and MCs created in this block), one CTA per key;
 // members are few and scattered, so warps 1-3 gather the next batch with cp.async (index list first, then the
 // rows) while warp 0 replays the current one.
+__device__ __forceinline__ void derive_version(const Eng &e, const Num &nm, int i, const double *rec); // (section D)
+
 template <int DP>
 struct ChainCfg {
     static constexpr int NB = DP <= 16 ? 128 : (DP <= 32 ? 64 : 32);
@@ -770,7 +807,21 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_chain_o(Eng e) {
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     const int nh = bc->nh;
-    for (int key_idx = blockIdx.x; key_idx < nh; key_idx += gridDim.x) bs_chain_o_key<DP>(e, bc, key_idx, xs, mi);
+    for (int key_idx = blockIdx.x; key_idx < nh; key_idx += gridDim.x) {
+        bs_chain_o_key<DP>(e, bc, key_idx, xs, mi);
+        // D (derive) of this key's versions right here when the key is small -- the steady state: one to three members per
+        // key -- so that k_bs_derive_o has nothing left to do; a key with more members than the CTA has threads is left
+        // to that kernel, which spreads them over the whole GPU (the CTA is in step here: see bs_chain_o_key)
+        const int off = e.ws.hoff[key_idx], n = e.ws.hoff[key_idx + 1] - off;
+        if (n <= BS_THREADS) {
+            if ((int)threadIdx.x < n) {
+                const int i = e.ws.omem[off + threadIdx.x];
+                derive_version(e, e.nm, i, e.ws.ver + (size_t)i * e.ws.lsp);
+            }
+        } else if (threadIdx.x == 0) {
+            atomicAdd(&e.bc->o_big, 1);
+        }
+    }
 }
 
 // k_bs_chain_p: PCORE keys (CONTESTED members take the exact radius test in place).  The candidates of a key lie
@@ -978,6 +1029,7 @@ __device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint3
 #pragma unroll
     for (int h = 0; h < NH; ++h) st_ok[h] = lane + 32 * h < LSP;
     double R[GS][NH];
+    unsigned rej = 0u;
 #pragma unroll
     for (int q = 0; q < GS; ++q)
 #pragma unroll
@@ -997,11 +1049,7 @@ __device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint3
                 int r = (q == 0 && exact_first) ? 2 : bs_radius_fast<DP, NH>(nv[0], ra, lane, D, cf);
                 if (r == 2) r = bs_radius_test<DP, NH>(nv[0], ra, lane, D, delta2, eps2, div_mode, k, wsel) ? 1 : 0;
                 keep = r != 0;
-                if (lane == 0) {
-                    int raw;
-                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + q * 4));
-                    prej[raw & 0x7fffffff] = keep ? 0 : 1;
-                }
+                rej |= (keep ? 0u : 1u) << q;
             }
             if (keep) { // the record of a rejected cell is never read as a version
 #pragma unroll
@@ -1009,6 +1057,52 @@ __device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint3
             }
         }
     }
+    // the verdicts of the group's CONTESTED cells, lane q = cell q: one divergent region per group, not one per cell
+    if (lane < GS && ((cg >> lane) & 1u) && lane < ncell) {
+        int raw;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + lane * 4));
+        prej[raw & 0x7fffffff] = (uint8_t)((rej >> lane) & 1u);
+    }
+    return rec;
+}
+
+// 32 consecutive cells without a CONTESTED one inside a stage that holds one elsewhere: the straight-line schedule of the
+// clean stage (dependent add, store of the version before, load one batch ahead), out of line -- one copy, used rarely.
+template <int DP, int NH>
+__device__ __noinline__ ChainRec<NH> bs_chain_clean32(ChainRec<NH> rec, uint32_t xa, int lane) {
+    constexpr int LSP = 2 * DP + 2, GS = 8, NG = 4;
+    double(&v)[NH] = rec.v;
+    bool st_ok[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) st_ok[h] = lane + 32 * h < LSP;
+    double R[2][GS][NH];
+#pragma unroll
+    for (int q = 0; q < GS; ++q)
+#pragma unroll
+        for (int h = 0; h < NH; ++h) R[0][q][h] = lds_f64(xa + (q * LSP + 32 * h) * 8);
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+#pragma unroll
+        for (int q = 0; q < GS; ++q) {
+            double nv[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) nv[h] = dadd(v[h], R[k & 1][q][h]);
+            if (k + q > 0) {
+#pragma unroll
+                for (int h = 0; h < NH; ++h)
+                    if (st_ok[h]) sts_f64(xa + ((k * GS + q - 1) * LSP + 32 * h) * 8, v[h]);
+            }
+            if (k + 1 < NG) {
+#pragma unroll
+                for (int h = 0; h < NH; ++h) R[(k + 1) & 1][q][h] = lds_f64(xa + (((k + 1) * GS + q) * LSP + 32 * h) * 8);
+            }
+#pragma unroll
+            for (int h = 0; h < NH; ++h) v[h] = nv[h];
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+        if (st_ok[h]) sts_f64(xa + ((NG * GS - 1) * LSP + 32 * h) * 8, v[h]);
     return rec;
 }
 
@@ -1196,6 +1290,17 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
             const int ng = (cnt + GS - 1) / GS;
 #pragma unroll 1
             for (int g = 0; g < ng; ++g) {
+                if (NB == 64 && (g & 3) == 0 && cnt - g * GS >= 32 && (g ? c_hi : c_lo) == 0u) {
+                    // this half of the stage is clean: 32 cells of straight-line code
+                    ChainRec<NH> rec;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) rec.v[h] = v[h];
+                    rec = bs_chain_clean32<DP, NH>(rec, xa + g * (GS * LSP * 8), lane_o);
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) v[h] = rec.v[h];
+                    g += 3;
+                    continue;
+                }
                 uint32_t ga = xa + g * (GS * LSP * 8);
                 asm volatile("" : "+r"(ga));
                 const unsigned cg = ((g < 4 ? c_lo : c_hi) >> (8 * (g & 3))) & 0xffu;
@@ -1297,6 +1402,9 @@ __global__ void __launch_bounds__(BS_OL_THREADS, 1) k_bs_olist(Eng e) {
     const int tid = threadIdx.x;
     const int Mp = bc->Mp, KNEW = bc->Mp + bc->Mo0;
     const int nneed = bc->nneed, Beff = bc->Beff;
+    // only as many CTAs as the list can keep busy take part (a few hundred entries: a dozen CTAs); the rest leave at once
+    const int ncta = max(1, min((int)gridDim.x, (nneed + EPP - 1) / EPP));
+    if ((int)blockIdx.x >= ncta) return;
     // ---- every CTA: the entry list, in need-list order (the same in every CTA)
     constexpr int SPT = BS_RMAX / NT; // slots per thread
     unsigned long long mine[SPT];
@@ -1324,7 +1432,7 @@ __global__ void __launch_bounds__(BS_OL_THREADS, 1) k_bs_olist(Eng e) {
     __syncthreads();
     // ---- rank of this CTA's slice
     const int sub = tid % TPE, slot = tid / TPE;
-    for (int e0 = blockIdx.x * EPP; e0 < n; e0 += gridDim.x * EPP) { // (block-uniform bounds)
+    for (int e0 = blockIdx.x * EPP; e0 < n; e0 += ncta * EPP) { // (block-uniform bounds)
         const int en = e0 + slot;
         const unsigned long long my = en < n ? keys[en] : 0ull;
         int rank = 0;
@@ -1337,7 +1445,7 @@ __global__ void __launch_bounds__(BS_OL_THREADS, 1) k_bs_olist(Eng e) {
     // ---- the last CTA to get here builds the segments
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = atomicAdd(&bc->ticket_o, 1) == (int)gridDim.x - 1;
+    if (tid == 0) s_last = atomicAdd(&bc->ticket_o, 1) == ncta - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -1348,21 +1456,23 @@ __global__ void __launch_bounds__(BS_OL_THREADS, 1) k_bs_olist(Eng e) {
         if (key < KNEW) e.ws.firstmember[key - Mp] = INT_MAX;
     }
     __syncthreads();
-    // heads of the key segments, in key order (= list order: snapshot slots, then creations by creator)
+    // heads of the key segments, in key order (= list order: snapshot slots, then creations by creator), and the rank of
+    // every created-in-block key among the REAL creations, in key (= creator) order.  A key is real when its first member
+    // is its creator; a stale speculation can leave phantom keys (members, but the creator decided otherwise) -- those
+    // lie beyond the first mismatch and get no rank.  Both counts ride in one scan (heads | real creations << 16).
+    __shared__ int s_hnew0;
+    if (tid == 0) s_hnew0 = INT_MAX;
     const int per = (n + NT - 1) / NT;
     const int lo = min(n, tid * per), hi = min(n, lo + per);
     cnt = 0;
-    for (int t = lo; t < hi; ++t) cnt += (t == 0) || ((keys[t] >> 32) != (keys[t - 1] >> 32));
-    int total;
-    int h = block_exclusive_scan_t<NT>(cnt, s_warp, total);
-    if (tid == 0) {
-        bc->nh = total;
-        bc->no = n;
-        bc->hnew0 = total; // lowered below by the first created-in-block key
-        bc->ticket_o = 0;
-        e.ws.hoff[total] = n;
+    for (int t = lo; t < hi; ++t) {
+        const int key = (int)(keys[t] >> 32), i = (int)(keys[t] & 0xffffffffu);
+        if ((t == 0) || ((keys[t] >> 32) != (keys[t - 1] >> 32))) cnt += 1 + ((key >= KNEW && i == key - KNEW) ? (1 << 16) : 0);
     }
-    __syncthreads();
+    int total;
+    const int ex = block_exclusive_scan_t<NT>(cnt, s_warp, total);
+    int h = ex & 0xffff, rk = ex >> 16;
+    const int nh = total & 0xffff, nreal = total >> 16;
     for (int t = lo; t < hi; ++t) {
         const int key = (int)(keys[t] >> 32), i = (int)(keys[t] & 0xffffffffu);
         e.ws.omem[t] = i;
@@ -1370,28 +1480,28 @@ __global__ void __launch_bounds__(BS_OL_THREADS, 1) k_bs_olist(Eng e) {
             e.ws.hkey[h] = key;
             e.ws.hoff[h] = t;
             e.ws.hfirst[h] = i;
-            if (key < KNEW) e.ws.firstmember[key - Mp] = i;
-            else atomicMin(&bc->hnew0, h);
+            if (key < KNEW) {
+                e.ws.firstmember[key - Mp] = i;
+            } else {
+                atomicMin(&s_hnew0, h);
+                const bool real = i == key - KNEW;
+                e.ws.hrank[h] = rk; // real creations before this key
+                if (real) e.ws.newrank[i] = rk++;
+            }
             ++h;
         }
     }
     __syncthreads();
-    // rank of every created-in-block key among the creations, in key (= creator) order.  A key is REAL when
-    // its first member is its creator; a stale speculation can leave phantom keys (members, but the creator
-    // decided otherwise) -- those lie beyond the first mismatch and get no rank.
-    const int nh = bc->nh, hnew0 = bc->hnew0;
-    const int nk = nh - hnew0, per2 = (nk + NT - 1) / NT;
-    const int k0 = min(nk, tid * per2), k1 = min(nk, k0 + per2);
-    int creal = 0;
-    for (int q = k0; q < k1; ++q) creal += e.ws.omem[e.ws.hoff[hnew0 + q]] == e.ws.hkey[hnew0 + q] - KNEW;
-    int rtotal;
-    int rk = block_exclusive_scan_t<NT>(creal, s_warp, rtotal);
-    for (int q = k0; q < k1; ++q) {
-        const int creator = e.ws.hkey[hnew0 + q] - KNEW;
-        e.ws.hrank[q] = rk; // real creations before key hnew0 + q
-        if (e.ws.omem[e.ws.hoff[hnew0 + q]] == creator) e.ws.newrank[creator] = rk++;
+    const int hnew0 = min(s_hnew0, nh);
+    if (tid == 0) {
+        bc->nh = nh;
+        bc->no = n;
+        bc->hnew0 = hnew0;
+        bc->ticket_o = 0;
+        bc->o_big = 0;
+        e.ws.hoff[nh] = n;
+        e.ws.hrank[nh] = nreal;
     }
-    if (tid == 0) e.ws.hrank[nk] = rtotal;
 }
 
 // ---- D ----------------------------------------------------------------------------------------------
@@ -1446,6 +1556,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_o(Eng e) {
     CCB_TS(14);
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
+    if (!bc->o_big) return; // every key was small: k_bs_chain_o derived its versions itself
     const int no = bc->no;
     for (int t = blockIdx.x * BS_THREADS + threadIdx.x; t < no; t += gridDim.x * BS_THREADS) {
         const int i = e.ws.omem[t];
@@ -1794,6 +1905,7 @@ __device__ void bs_trace_round(const BsCtl *bc, int kind, int m0, int Beff_in, i
         t[17] = bc->Beff;
         t[18] = globaltimer_ns();
         for (int k = 0; k < CCB_TRACE_SLOTS; ++k) t[20 + k] = g_trace_ts[k];
+        t[19] = bc->Mo0;
     }
     for (int k = 3; k < CCB_TRACE_SLOTS; ++k) g_trace_ts[k] = 0;
 }
@@ -2040,53 +2152,56 @@ __device__ __forceinline__ void commit_row(const Eng &e, const BsCtl *bc, const 
     }
 }
 
-__global__ void __launch_bounds__(BS_THREADS) k_bs_commit_rows(Eng e) {
+// The three steps of the commit in ONE launch: the first `rows_ctas` CTAs write the rows back (one warp per key), the
+// others the per-cell results; the last CTA to finish (ticket) applies the upgrade (hddstream.py:397-430) and advances the
+// list lengths, id counters and the block cursor.
+__device__ __forceinline__ void bs_finish_block(const Eng &e, BsCtl *bc);
+
+__global__ void __launch_bounds__(BS_THREADS) k_bs_commit(Eng e, int rows_ctas) {
     e.fetch();
     CCB_TS(17);
-    const BsCtl *bc = e.bc;
+    __shared__ int s_last;
+    BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 1) return;
-    const Num nm = e.nm;
-    const int lane = threadIdx.x & 31;
     const int Mp = bc->Mp, Mo0 = bc->Mo0, KNEW = Mp + Mo0, m = bc->m_commit;
-    const int kidx = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
-    commit_row(e, bc, nm, kidx, lane, Mp, Mo0, KNEW, m);
-}
-
-__global__ void __launch_bounds__(BS_THREADS) k_bs_commit_cells(Eng e) {
-    e.fetch();
-    CCB_TS(18);
-    const BsCtl *bc = e.bc;
-    if (!bc->active || bc->phase != 1) return;
-    const int i = blockIdx.x * BS_THREADS + threadIdx.x;
-    const int m = bc->m_commit;
-    if (i >= m) return;
-    const int Mp = bc->Mp, KNEW = bc->Mp + bc->Mo0;
-    const int key = e.ws.eff[i];
-    int32_t uid;
-    uint8_t st;
-    if (key < Mp) {
-        uid = e.P.uid[key];
-        st = 0;
-    } else if (key < KNEW) {
-        uid = e.O.uid[key - Mp];
-        st = 1;
+    if ((int)blockIdx.x < rows_ctas) {
+        const Num nm = e.nm;
+        const int kidx = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
+        commit_row(e, bc, nm, kidx, threadIdx.x & 31, Mp, Mo0, KNEW, m);
     } else {
-        const int c = key - KNEW;
-        uid = (int32_t)(e.ctl->outlier_last_id + e.ws.newrank[c]);
-        st = c == i ? 3 : 1;
+        const int i = (blockIdx.x - rows_ctas) * BS_THREADS + threadIdx.x;
+        if (i < m) {
+            const int key = e.ws.eff[i];
+            int32_t uid;
+            uint8_t st;
+            if (key < Mp) {
+                uid = e.P.uid[key];
+                st = 0;
+            } else if (key < KNEW) {
+                uid = e.O.uid[key - Mp];
+                st = 1;
+            } else {
+                const int c = key - KNEW;
+                uid = (int32_t)(e.ctl->outlier_last_id + e.ws.newrank[c]);
+                st = c == i ? 3 : 1;
+            }
+            if (bc->upgrade && i == m - 1) st = 2;
+            e.assign[bc->pos + i] = uid;
+            if (e.stage) e.stage[bc->pos + i] = st;
+        }
     }
-    if (bc->upgrade && i == m - 1) st = 2;
-    e.assign[bc->pos + i] = uid;
-    if (e.stage) e.stage[bc->pos + i] = st;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&bc->ticket_c, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    bs_finish_block(e, bc);
 }
 
 // upgrade (hddstream.py:397-430), list lengths, id counters, next block length
-__global__ void __launch_bounds__(BS_THREADS) k_bs_finish(Eng e) {
-    e.fetch();
-    CCB_TS(19);
+__device__ __forceinline__ void bs_finish_block(const Eng &e, BsCtl *bc) {
     __shared__ int s_ncreated;
-    BsCtl *bc = e.bc;
-    if (!bc->active || bc->phase != 1) return;
     Ctl *ctl = e.ctl;
     const Num nm = e.nm;
     const int D = nm.D, DP = nm.DP, tid = threadIdx.x;
@@ -2099,7 +2214,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_finish(Eng e) {
             if (e.ws.hkey[mid] - KNEW < m) lo = mid + 1;
             else hi = mid;
         }
-        s_ncreated = e.ws.hrank[lo - hnew0];
+        s_ncreated = e.ws.hrank[lo];
     }
     for (int h = tid; h < nh; h += BS_THREADS) { // forget the modified-flags of this block
         const int key = e.ws.hkey[h];
@@ -2143,6 +2258,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_finish(Eng e) {
         else if (!bc->upgrade) bc->next_B = max(bc->next_B / 2, bc->Bmin);
         CCB_DBG(bs_trace_round(bc, 2, m, ncreated, bc->nneed);)
         bc->nh = 0;
+        bc->ticket_c = 0;
         bc->active = 0;
         if (bc->pos >= bc->N) bc->done = 1;
         if (e.h_outer) cudaGraphSetConditional(e.h_outer, bc->done ? 0u : 1u);

@@ -36,7 +36,15 @@ struct NearestCfg {
     // tile of TM microclusters, ~12-16 KB per buffer, TM a multiple of JU
     static constexpr int TM = ((1024 / DP) < 8 ? 8 : (1024 / DP)) / NEAREST_JU * NEAREST_JU;
     static constexpr int CELLS = NEAREST_THREADS * PPT;
+    // SPLIT layout (K > 1 and few rows: the steady state of the engine, a few hundred cells against 1e4 microclusters): a
+    // work item is 32 cells (lane = cell, the same cells in every warp) and the CTA's warps share the tile's microclusters
+    // -- four times the warps on the same work, each with a quarter of the instruction stream
+    static constexpr int TMS = (TM / (4 * (NEAREST_THREADS / 32))) * (4 * (NEAREST_THREADS / 32)) > 0
+                                   ? (TM / (4 * (NEAREST_THREADS / 32))) * (4 * (NEAREST_THREADS / 32))
+                                   : TM;
+    static constexpr bool CAN_SPLIT = K > 1 && TM >= 4 * (NEAREST_THREADS / 32);
 };
+constexpr int NEAREST_SPLIT_MAX_ROWS = 1024; // rows of one launch up to which the SPLIT layout is used
 
 // guards of the fused weight step (nearest_item): a non-zero magnitude below 2^-400, or a weight below 2^-64 / not a
 // power of two (never produced by k_pack_cw / the commit kernels, checked anyway), forces the unfused sequence
@@ -52,19 +60,27 @@ __device__ __forceinline__ bool small_weight(double w) {
 template <int K>
 __device__ __forceinline__ void topk_insert(double (&bd)[K], int (&bi)[K], double d, int j) {
     // strict <: an equal distance never displaces an earlier (smaller-index) entry
-    if (!(d < bd[K - 1])) return;
-    bd[K - 1] = d;
-    bi[K - 1] = j;
+    if constexpr (K == 1) {
+        if (!(d < bd[0])) return;
+        bd[0] = d;
+        bi[0] = j;
+        return;
+    } else {
+    // K > 1 (in-engine lists): BRANCH-FREE insertion into the ascending list.  lt[s] = d < bd[s] is monotone in s, so the
+    // new entry s is the old entry s - 1 where lt[s - 1], the candidate where only lt[s], itself otherwise.  A list that
+    // starts empty takes a candidate nearly every time in its first hundred microclusters, in some lane of the warp nearly
+    // always: with data-dependent branches the warp walked all K compare-and-swap steps divergently for every candidate
+    // (3 000 cycles per group of four, measured), with selects it is K compares + 3 K selects.
+    bool lt[K];
+#pragma unroll
+    for (int s = 0; s < K; ++s) lt[s] = d < bd[s];
 #pragma unroll
     for (int s = K - 1; s > 0; --s) {
-        if (bd[s] < bd[s - 1]) {
-            double td = bd[s];
-            bd[s] = bd[s - 1];
-            bd[s - 1] = td;
-            int ti = bi[s];
-            bi[s] = bi[s - 1];
-            bi[s - 1] = ti;
-        }
+        bd[s] = lt[s - 1] ? bd[s - 1] : (lt[s] ? d : bd[s]);
+        bi[s] = lt[s - 1] ? bi[s - 1] : (lt[s] ? j : bi[s]);
+    }
+    bd[0] = lt[0] ? d : bd[0];
+    bi[0] = lt[0] ? j : bi[0];
     }
 }
 
@@ -84,20 +100,22 @@ __device__ __forceinline__ void dyn_split(int R, int M, int target, int max_slab
 
 // One (row group, slab) work item: cells [cell0, cell0 + CELLS) of the row list against MCs [j0, j1).
 // seq counts the tiles this CTA has streamed so far (mbarrier buffer / parity bookkeeping across items).
-template <int DP, int K, bool DIV>
+template <int DP, int K, bool DIV, bool SPLIT = false>
 __device__ __forceinline__ void nearest_item(const double *__restrict__ X, const int32_t *__restrict__ rows, int64_t row_off,
                                              int64_t nrows, int64_t ld, int D, const double2 *__restrict__ cw, int64_t cell0,
                                              int j0, int j1, double *__restrict__ out_dist, int32_t *__restrict__ out_idx,
                                              int64_t out_off, int out_stride, int out_slab, double2 (*tile)[NearestCfg<DP, K>::TM * DP],
                                              uint64_t *bar, uint32_t &seq) {
     using Cfg = NearestCfg<DP, K>;
-    constexpr int PPT = Cfg::PPT, TM = Cfg::TM, JU = NEAREST_JU;
+    constexpr int PPT = Cfg::PPT, TM = SPLIT ? Cfg::TMS : Cfg::TM, JU = NEAREST_JU;
+    constexpr int NWARP = NEAREST_THREADS / 32, QS = TM / NWARP; // SPLIT: microclusters of a tile per warp
+    static_assert(!SPLIT || (PPT == 1 && QS % JU == 0 && QS > 0), "split layout");
     // ---- this thread's cells -> registers (row-contiguous 16-byte loads; every fetched sector is used)
     double p[PPT][DP];
     int64_t cell[PPT];
 #pragma unroll
     for (int u = 0; u < PPT; ++u) {
-        cell[u] = cell0 + threadIdx.x + u * NEAREST_THREADS;
+        cell[u] = cell0 + (SPLIT ? (threadIdx.x & 31) : threadIdx.x) + u * NEAREST_THREADS;
         const bool live = cell[u] < nrows;
         const int64_t r = live ? (rows ? (int64_t)rows[row_off + cell[u]] : row_off + cell[u]) : 0;
         const double *xr = X + r * ld;
@@ -118,6 +136,7 @@ __device__ __forceinline__ void nearest_item(const double *__restrict__ X, const
             for (int d = 0; d < DP; ++d) p[u][d] = (live && d < D) ? xr[d] : 0.0;
         }
     }
+    if (K > 1) { CCB_TS(24); }
     double bd[PPT][K];
     int bi[PPT][K];
 #pragma unroll
@@ -159,6 +178,7 @@ __device__ __forceinline__ void nearest_item(const double *__restrict__ X, const
         if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1); // that buffer was released by the barrier below
         const uint32_t q = seq + (uint32_t)t;
         mbar_wait(&bar[q & 1], (q >> 1) & 1);
+        if (K > 1 && t == 0) { CCB_TS(25); }
         const double2 *tl = tile[q & 1];
         const int jt = j0 + t * TM;
         const int n = min(TM, j1 - jt);
@@ -172,7 +192,8 @@ __device__ __forceinline__ void nearest_item(const double *__restrict__ X, const
             }
             fuse = !tiny_c;
         }
-        for (int jj = 0; jj < n; jj += JU) {
+        const int jlo = SPLIT ? (int)(threadIdx.x >> 5) * QS : 0, jhi = SPLIT ? min(n, jlo + QS) : n;
+        for (int jj = jlo; jj < jhi; jj += JU) {
             double acc[PPT][JU];
 #pragma unroll
             for (int u = 0; u < PPT; ++u)
@@ -210,24 +231,85 @@ __device__ __forceinline__ void nearest_item(const double *__restrict__ X, const
             }
 #pragma unroll
             for (int v = 0; v < JU; ++v) {
-                if (jj + v < n) {
+                if (jj + v < jhi) {
+                    if (K == 1) {
 #pragma unroll
-                    for (int u = 0; u < PPT; ++u) topk_insert<K>(bd[u], bi[u], acc[u][v], jt + jj + v);
+                        for (int u = 0; u < PPT; ++u) topk_insert<K>(bd[u], bi[u], acc[u][v], jt + jj + v);
+                    } else { // (warp-uniform branch: skipped once every lane's list has settled below the candidate)
+                        bool any = false;
+#pragma unroll
+                        for (int u = 0; u < PPT; ++u) any |= acc[u][v] < bd[u][K - 1];
+                        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                            for (int u = 0; u < PPT; ++u) topk_insert<K>(bd[u], bi[u], acc[u][v], jt + jj + v);
+                        }
+                    }
                 }
             }
         }
         __syncthreads();
     }
     seq += (uint32_t)ntiles;
+    if (K > 1) { CCB_TS(26); CCB_TS_ANY(27); }
 
+    if constexpr (SPLIT) {
+        // the warps' lists of the same 32 cells -> shared memory (the tile buffers are free: the loop above ended with a
+        // barrier), then warp 0 merges the four ascending lists of every cell.  The warps cover ascending index ranges of
+        // every tile, but tiles interleave them, so ties are broken by the index explicitly (better()).
+        double *sd = reinterpret_cast<double *>(&tile[0][0]);
+        int *si = reinterpret_cast<int *>(&tile[1][0]);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int u = 0; u < PPT; ++u) {
-        if (cell[u] < nrows) {
-            const size_t o = ((size_t)(out_off + cell[u]) * out_stride + out_slab) * K;
+        for (int s = 0; s < K; ++s) {
+            sd[(warp * 32 + lane) * K + s] = bd[0][s];
+            si[(warp * 32 + lane) * K + s] = bi[0][s];
+        }
+        __syncthreads();
+        if (warp == 0 && cell[0] < nrows) {
+            int pw[NWARP], hi_[NWARP];
+            double hd_[NWARP];
 #pragma unroll
+            for (int w = 0; w < NWARP; ++w) {
+                pw[w] = 0;
+                hd_[w] = sd[(w * 32 + lane) * K];
+                hi_[w] = si[(w * 32 + lane) * K];
+            }
+            const size_t o = ((size_t)(out_off + cell[0]) * out_stride + out_slab) * K;
             for (int s = 0; s < K; ++s) {
-                out_dist[o + s] = bd[u][s];
-                out_idx[o + s] = bi[u][s];
+                double bdv = 0.0;
+                int biv = -1, bw = 0;
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w)
+                    if (better(hd_[w], hi_[w], bdv, biv)) {
+                        bdv = hd_[w];
+                        biv = hi_[w];
+                        bw = w;
+                    }
+                out_dist[o + s] = biv >= 0 ? bdv : __longlong_as_double(0x7ff0000000000000LL);
+                out_idx[o + s] = biv;
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w)
+                    if (w == bw && biv >= 0) {
+                        pw[w] += 1;
+                        hi_[w] = -1;
+                        if (pw[w] < K) {
+                            hd_[w] = sd[(w * 32 + lane) * K + pw[w]];
+                            hi_[w] = si[(w * 32 + lane) * K + pw[w]];
+                        }
+                    }
+            }
+        }
+        __syncthreads(); // the next item's first tile lands in the same memory
+    } else {
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            if (cell[u] < nrows) {
+                const size_t o = ((size_t)(out_off + cell[u]) * out_stride + out_slab) * K;
+#pragma unroll
+                for (int s = 0; s < K; ++s) {
+                    out_dist[o + s] = bd[u][s];
+                    out_idx[o + s] = bi[u][s];
+                }
             }
         }
     }
@@ -272,6 +354,17 @@ __global__ void __launch_bounds__(NEAREST_THREADS)
     uint32_t seq = 0;
     if (range_dev) {
         int groups, smcs, nslab;
+        if (Cfg::CAN_SPLIT && nrows <= NEAREST_SPLIT_MAX_ROWS) {
+            dyn_split((int)nrows, M, gridDim.x, dyn_max_slabs, Cfg::TMS, 32, groups, smcs, nslab);
+            const int items = groups * nslab;
+            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+                const int g = it / nslab, sl = it - g * nslab;
+                const int j0 = sl * smcs;
+                nearest_item<DP, K, DIV, Cfg::CAN_SPLIT>(X, rows, row_off, nrows, ld, D, cw, (int64_t)g * 32, j0, min(M, j0 + smcs),
+                                                         out_dist, out_idx, row_off, dyn_max_slabs, sl, tile, bar, seq);
+            }
+            return;
+        }
         dyn_split((int)nrows, M, gridDim.x, dyn_max_slabs, Cfg::TM, Cfg::CELLS, groups, smcs, nslab);
         const int items = groups * nslab;
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -293,7 +386,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS)
 template <int K>
 __global__ void __launch_bounds__(128) k_topk_merge_dyn(const double *__restrict__ in_dist, const int32_t *__restrict__ in_idx,
                                                         const int32_t *__restrict__ range_dev, const int32_t *__restrict__ M_dev,
-                                                        int M, int target, int max_slabs, int tm, int cells,
+                                                        int M, int target, int max_slabs, int tm, int cells, int tm_split,
                                                         double *__restrict__ out_dist, int32_t *__restrict__ out_idx) {
     constexpr int QMAX = 8; // max_slabs <= 256
     CCB_TS(4);
@@ -301,28 +394,41 @@ __global__ void __launch_bounds__(128) k_topk_merge_dyn(const double *__restrict
     const int R = range_dev[1] - range_dev[0];
     if (M_dev) M = min(M, *M_dev);
     int groups, smcs, nslab;
-    dyn_split(R, M, target, max_slabs, tm, cells, groups, smcs, nslab);
+    if (tm_split > 0 && R <= NEAREST_SPLIT_MAX_ROWS) dyn_split(R, M, target, max_slabs, tm_split, 32, groups, smcs, nslab); // (as k_nearest)
+    else dyn_split(R, M, target, max_slabs, tm, cells, groups, smcs, nslab);
     const int nw = gridDim.x * (blockDim.x >> 5);
     for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < R; r += nw) {
         const size_t row = (size_t)range_dev[0] + r;
-        int hd[QMAX];
+        // every lane keeps the head of each of its lists AND the entry behind it in registers: a list that wins a round
+        // moves on to an entry that is already there, and the load of the one after that has a whole round (usually many)
+        // to arrive -- no dependent global load inside the K extraction rounds
+        int hd[QMAX], ci[QMAX], ni[QMAX];
+        double cd[QMAX], nd[QMAX];
 #pragma unroll
-        for (int q = 0; q < QMAX; ++q) hd[q] = 0;
+        for (int q = 0; q < QMAX; ++q) {
+            const int sl = lane + 32 * q;
+            hd[q] = 0;
+            ci[q] = ni[q] = -1;
+            cd[q] = nd[q] = 0.0;
+            if (sl < nslab) {
+                const size_t o = (row * max_slabs + sl) * K;
+                ci[q] = in_idx[o];
+                cd[q] = in_dist[o];
+                if (K > 1) {
+                    ni[q] = in_idx[o + 1];
+                    nd[q] = in_dist[o + 1];
+                }
+            }
+        }
         for (int s = 0; s < K; ++s) {
             double bdv = 0.0;
             int biv = -1, bq = 0;
 #pragma unroll
             for (int q = 0; q < QMAX; ++q) {
-                const int sl = lane + 32 * q;
-                if (sl < nslab && hd[q] < K) {
-                    const size_t o = (row * max_slabs + sl) * K + hd[q];
-                    const int j = in_idx[o];
-                    const double dv = in_dist[o];
-                    if (better(dv, j, bdv, biv)) {
-                        bdv = dv;
-                        biv = j;
-                        bq = q;
-                    }
+                if (better(cd[q], ci[q], bdv, biv)) { // (an exhausted or empty list carries index -1: never better)
+                    bdv = cd[q];
+                    biv = ci[q];
+                    bq = q;
                 }
             }
             double wd = bdv;
@@ -331,7 +437,17 @@ __global__ void __launch_bounds__(128) k_topk_merge_dyn(const double *__restrict
             if (wi >= 0 && wi == biv) {
 #pragma unroll
                 for (int q = 0; q < QMAX; ++q)
-                    if (q == bq) hd[q] += 1;
+                    if (q == bq) {
+                        hd[q] += 1;
+                        cd[q] = nd[q];
+                        ci[q] = ni[q];
+                        ni[q] = -1;
+                        if (hd[q] + 1 < K) {
+                            const size_t o = (row * max_slabs + lane + 32 * q) * K + hd[q] + 1;
+                            ni[q] = in_idx[o];
+                            nd[q] = in_dist[o];
+                        }
+                    }
             }
             if (lane == 0) {
                 out_dist[row * K + s] = wi >= 0 ? wd : __longlong_as_double(0x7ff0000000000000LL);

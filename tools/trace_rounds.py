@@ -55,7 +55,7 @@ fn.restype, fn.argtypes = C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]
 Xd = [torch.from_numpy(x).cuda() for x in Xs[:tps]]
 a = torch.empty(N, dtype=torch.int32, device="cuda")
 s = torch.empty(N, dtype=torch.uint8, device="cuda")
-buf = np.zeros((1 << 14, 48), dtype=np.int64)
+buf = np.zeros((1 << 14, 64), dtype=np.int64)
 saved = {}
 for rep in range(2):  # the second pass is the warm one
     h.reset()
@@ -78,7 +78,7 @@ for t in range(tps):
     rows = []
     for rec in r:
         kind = rec[0]
-        ts = rec[20:44]
+        ts = rec[20:60]
         if kind == 2:
             start = prev_end if prev_end is not None else ts[17]
             rows.append(("commit", rec, (rec[18] - start) / 1e3))
@@ -101,7 +101,7 @@ for t in range(tps):
         pe = None
         for rec in r:
             if rec[0] < 2 and sel(rec):
-                ts = rec[20:44]
+                ts = rec[20:60]
                 start = ts[0] if rec[4] == 0 else pe
                 if start:
                     cnt += 1
