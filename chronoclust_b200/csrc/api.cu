@@ -422,7 +422,7 @@ int ensure_bs_ws(ccb_handle *h) {
         BsWs &w = h->ws;
         w.bmax = B;
 #define WSA(field, n) if ((rc = ws_alloc(h, w.field, (n)))) return rc
-        WSA(pcand, B); WSA(ospec, B); WSA(tkpos, B); WSA(dec, B); WSA(eff, B); WSA(newrank, B); WSA(pend, B); WSA(vpos, B);
+        WSA(pcand, B); WSA(ospec, B); WSA(tkpos, B); WSA(dec, B); WSA(eff, B); WSA(newrank, B); WSA(pend, B); WSA(vpos, B); WSA(pbest, B);
         WSA(pflag, B); WSA(prej, B); WSA(upf, B);
         w.dp = h->DP;
         w.lsp = 2 * h->DP + 2;

@@ -76,6 +76,7 @@ struct BsCtl {
 
 struct BsWs {
     int32_t *pcand, *ospec, *tkpos, *dec, *eff, *newrank, *pend, *plist;
+    int32_t *pbest; // [bmax] nearest feasible pcore MC at the exact versions (k_bs_verify_p), for cells the pcore stage rejects
     uint8_t *pflag, *prej, *upf;
     double *ver;  // [bmax][lsp] VERSION records: CF1 at [0, D), CF2 at [dp, dp + D), W at [2 dp]; lsp = 2 dp + 2
     double *vcen, *vr2;
@@ -1673,6 +1674,7 @@ __global__ void __launch_bounds__(BS_VP_THREADS, DP <= 16 ? 5 : 1) k_bs_verify_p
         if (best != eff) mm = i;
     } else { // decided by k_bs_verify_o, which also reports its mismatch
         e.ws.dec[i] = BS_KEY_PENDING;
+        e.ws.pbest[i] = best;
         e.ws.pend[atomicAdd(&bc->npend, 1)] = i;
     }
     // first cell of the tile whose exact decision differs from the speculation -> one atomicMin per tile
@@ -1881,7 +1883,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
 // ---- M ----------------------------------------------------------------------------------------------
 #ifdef CCB_DEBUG
 // diagnostics build: one record per round / per block (see tools/trace_rounds.py for the layout)
-__device__ void bs_trace_round(const BsCtl *bc, int kind, int m0, int Beff_in, int nneed_in) {
+__device__ void bs_trace_round(const BsCtl *bc, int kind, int m0, int Beff_in, int nneed_in, const BsWs *ws = nullptr) {
     const int r = atomicAdd(&g_trace_n, 1);
     if (r < CCB_TRACE_MAX) {
         long long *t = g_trace[r];
@@ -1906,6 +1908,12 @@ __device__ void bs_trace_round(const BsCtl *bc, int kind, int m0, int Beff_in, i
         t[18] = globaltimer_ns();
         for (int k = 0; k < CCB_TRACE_SLOTS; ++k) t[20 + k] = g_trace_ts[k];
         t[19] = bc->Mo0;
+        if (ws && kind < 2 && m0 >= 0 && m0 < Beff_in) { // the first mismatching cell, as the round left it
+            t[60] = ws->dec[m0];
+            t[61] = ws->eff[m0];
+            t[62] = ws->pcand[m0];
+            t[63] = ws->pflag[m0] | (ws->prej[m0] << 1) | ((long long)(unsigned)ws->ospec[m0] << 8) | ((long long)ws->tkpos[m0] << 40);
+        }
     }
     for (int k = 3; k < CCB_TRACE_SLOTS; ++k) g_trace_ts[k] = 0;
 }
@@ -1976,10 +1984,16 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
             bc->phase = 1;
             bc->tk_lo = bc->tk_hi = 0;
             if (e.h_inner) cudaGraphSetConditional(e.h_inner, 0u);
-            CCB_DBG(bs_trace_round(bc, 1, m0, Beff, bc->nneed);)
+            CCB_DBG(bs_trace_round(bc, 1, m0, Beff, bc->nneed, &e.ws);)
         }
         return;
     }
+    CCB_DBG(__shared__ long long s_dbg[4]; if (tid == 0) {
+        s_dbg[0] = e.ws.dec[m0];
+        s_dbg[1] = e.ws.eff[m0];
+        s_dbg[2] = e.ws.pcand[m0];
+        s_dbg[3] = e.ws.pflag[m0] | (e.ws.prej[m0] << 1) | ((long long)(unsigned)e.ws.ospec[m0] << 8) | ((long long)e.ws.tkpos[m0] << 40);
+    })
     // ---- refinement: the recomputed decisions of [m0, Beff) become the next speculation
     int cut = Beff;
     for (int i0 = m0 + tid; i0 < Beff && cut == Beff; i0 += BS_CTA1 * SU) {
@@ -2028,6 +2042,14 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
             } else {
                 e.ws.ospec[i] = dc;
                 e.ws.pflag[i] = 1;
+                // speculated "absorbed by a pcore MC", exact "rejected by the pcore stage": the exact test was the one of the
+                // NEAREST pcore MC at its exact version, which need not be the speculated one -- the replay has to put the
+                // cell to the test in that chain (the chain it sat in may well accept it again, round after round)
+                if (ef < Mp) {
+                    const int pb = e.ws.pbest[i];
+                    e.ws.pcand[i] = pb;
+                    if (pb < 0) e.ws.prej[i] = 1; // no feasible pcore MC at all: straight to the outlier stage
+                }
             }
             if (ef >= Mp && dc >= Mp) e.ws.eff[i] = dc; // what k_bs_verify_p would record for this (rejected) cell
             else dirty = 1;
@@ -2088,7 +2110,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
             else bc->rounds_light += 1;
         }
         if (e.h_inner) cudaGraphSetConditional(e.h_inner, bc->phase == 0 ? 1u : 0u);
-        CCB_DBG(bs_trace_round(bc, 0, m0, Beff, nneed_old);)
+        CCB_DBG(bs_trace_round(bc, 0, m0, Beff, nneed_old, nullptr); if (g_trace_n - 1 < CCB_TRACE_MAX) for (int q = 0; q < 4; ++q) g_trace[g_trace_n - 1][60 + q] = s_dbg[q];)
     }
 }
 
