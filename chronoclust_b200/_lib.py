@@ -27,7 +27,7 @@ class Stats(C.Structure):
     _fields_ = [(n, i64) for n in (
         "points", "nearest_pairs", "upgrades", "created", "downgraded", "deleted", "kernel_launches", "borderline_pairs",
         "bsv_blocks", "bsv_rounds", "bsv_mismatches", "bsv_cuts_unknown", "bsv_cuts_rounds", "bsv_cuts_capacity",
-        "bsv_late_topk", "bsv_outlier_stage_cells", "bsv_replayed_cells", "bsv_light_rounds", "bsv_serial_cells")]
+        "bsv_late_topk", "bsv_outlier_stage_cells", "bsv_replayed_cells", "bsv_light_rounds", "bsv_serial_cells", "bsv_pdl")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -89,6 +89,9 @@ struct ccb_handle {
     // Two cached graphs: the double-buffered stores flip at every ccb_begin_timepoint with decay, so consecutive timepoints
     // alternate between two sets of (baked-in) pointers -- with one slot the graph was re-captured and re-instantiated at
     // every timepoint (~1 ms each).
+    // programmatic dependent launch between the engine's kernels: measured neutral on B200 (profiles/r2zc_pdl_experiment.md:
+    // the gaps between the kernels of a round are not launch latency), so it is off; the kernels keep CCB_PDL() (a no-op then)
+    bool pdl = false;
     cudaGraph_t bs_graph = nullptr, bs_graph_alt = nullptr;
     cudaGraphExec_t bs_exec = nullptr, bs_exec_alt = nullptr;
     Eng bs_graph_eng_alt{};
@@ -493,12 +496,29 @@ int sync_bc(ccb_handle *h) { // both control blocks -> pinned host mirrors
 // launched either on the handle's stream (bs_iters rounds enqueued per block; used when per-kernel timing is on) or
 // captured once into a CUDA graph whose block loop and round loop are WHILE conditional nodes driven from the
 // device (k_bs_begin / k_bs_decide / k_bs_commit call cudaGraphSetConditional): no idle launches, no host round trip.
+// Kernel launch with (pdl) or without the programmatic-stream-serialization attribute (see CCB_PDL in common.cuh)
+template <typename... KA, typename... A>
+cudaError_t launch_k(bool pdl, void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaStream_t s, A &&...a) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = g;
+    cfg.blockDim = b;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, KA(std::forward<A>(a))...);
+}
+
 int launch_prologue(ccb_handle *h, const Eng &e, cudaStream_t s) {
     const int g_cells = (h->bs_bmax + BS_THREADS - 1) / BS_THREADS;
     Timed tm(h, CCB_CAT_SPEC);
+    const bool pdl = h->pdl;
     k_bs_begin<<<1, 1, 0, s>>>(e);
-    CCB_DISPATCH_DP(h->DP, { k_bs_spec<kDP><<<g_cells * BS_SPLIT, BS_THREADS, 0, s>>>(e); })
-    k_bs_need<<<1, BS_CTA1, 0, s>>>(e);
+    CCB_DISPATCH_DP(h->DP, { launch_k(pdl, k_bs_spec<kDP>, g_cells * BS_SPLIT, BS_THREADS, 0, s, e); })
+    launch_k(pdl, k_bs_need, 1, BS_CTA1, 0, s, e);
     CKL(h);
     return CCB_OK;
 }
@@ -511,6 +531,7 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     const int g_cells = (B + BS_THREADS - 1) / BS_THREADS;
     const int g_tiles = (B / 32 + 1 + 3) / 4;
     int rc;
+    const bool pdl = h->pdl;
     cudaStream_t sa = side ? side : s;
     if (side) {
         CK(h, cudaEventRecord(h->ev_fork, s));
@@ -526,17 +547,17 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     }
     {
         Timed tm(h, CCB_CAT_SPEC);
-        k_bs_spec_o<<<BS_RMAX / BS_THREADS, BS_THREADS, 0, sa>>>(e);
+        launch_k(pdl, k_bs_spec_o, BS_RMAX / BS_THREADS, BS_THREADS, 0, sa, e);
     }
     {
         Timed tm(h, CCB_CAT_LISTS);
-        k_bs_tilecnt<<<g_tiles, BS_THREADS, 0, s>>>(e);
-        k_bs_pscan<<<std::max(mp_grid, 1), BS_CTA1, 0, s>>>(e);
-        k_bs_pscatter<<<B / 32 + 1, BS_THREADS, 0, s>>>(e);
+        launch_k(pdl, k_bs_tilecnt, g_tiles, BS_THREADS, 0, s, e);
+        launch_k(pdl, k_bs_pscan, std::max(mp_grid, 1), BS_CTA1, 0, s, e);
+        launch_k(pdl, k_bs_pscatter, B / 32 + 1, BS_THREADS, 0, s, e);
     }
     {
         Timed tm(h, CCB_CAT_PCORE);
-        CCB_DISPATCH_DP(h->DP, { k_bs_chain_p<kDP><<<std::max(mp_grid, 1), BS_CHAINP_THREADS, ChainPCfg<kDP>::SMEM, s>>>(e); })
+        CCB_DISPATCH_DP(h->DP, { launch_k(pdl, k_bs_chain_p<kDP>, std::max(mp_grid, 1), BS_CHAINP_THREADS, ChainPCfg<kDP>::SMEM, s, e); })
     }
     if (side) { // join: k_bs_olist needs the speculated outlier decisions, everything below the pcore replay
         CK(h, cudaEventRecord(h->ev_join, side));
@@ -547,23 +568,23 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     }
     {
         Timed tm(h, CCB_CAT_DERIVE);
-        k_bs_derive_p<<<g_cells, BS_THREADS, 0, sa>>>(e);
+        launch_k(pdl, k_bs_derive_p, g_cells, BS_THREADS, 0, sa, e);
     }
     {
         Timed tm(h, CCB_CAT_RESOLVE);
-        CCB_DISPATCH_DP(h->DP, { k_bs_verify_p<kDP><<<B / 32 + 1, BS_VP_THREADS, 0, sa>>>(e); })
+        CCB_DISPATCH_DP(h->DP, { launch_k(pdl, k_bs_verify_p<kDP>, B / 32 + 1, BS_VP_THREADS, 0, sa, e); })
     }
     {
         Timed tm(h, CCB_CAT_OLIST);
-        k_bs_olist<<<BS_OL_CTAS, BS_OL_THREADS, 0, s>>>(e);
+        launch_k(pdl, k_bs_olist, BS_OL_CTAS, BS_OL_THREADS, 0, s, e);
     }
     {
         Timed tm(h, CCB_CAT_CHAIN_O);
-        CCB_DISPATCH_DP(h->DP, { k_bs_chain_o<kDP><<<148 * 4, BS_THREADS, 0, s>>>(e); }) // CTAs loop over the keys
+        CCB_DISPATCH_DP(h->DP, { launch_k(pdl, k_bs_chain_o<kDP>, 148 * 4, BS_THREADS, 0, s, e); }) // CTAs loop over the keys
     }
     {
         Timed tm(h, CCB_CAT_DERIVE);
-        k_bs_derive_o<<<BS_RMAX / BS_THREADS, BS_THREADS, 0, s>>>(e);
+        launch_k(pdl, k_bs_derive_o, BS_RMAX / BS_THREADS, BS_THREADS, 0, s, e);
     }
     if (side) {
         CK(h, cudaEventRecord(h->ev_join, side));
@@ -571,11 +592,11 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     }
     {
         Timed tm(h, CCB_CAT_RESOLVE);
-        CCB_DISPATCH_DP(h->DP, { k_bs_verify_o<kDP><<<148 * 4, BS_THREADS, 0, s>>>(e); })
+        CCB_DISPATCH_DP(h->DP, { launch_k(pdl, k_bs_verify_o<kDP>, 148 * 4, BS_THREADS, 0, s, e); })
     }
     {
         Timed tm(h, CCB_CAT_DECIDE);
-        k_bs_decide<<<1, BS_CTA1, 0, s>>>(e);
+        launch_k(pdl, k_bs_decide, 1, BS_CTA1, 0, s, e);
     }
     CKL(h);
     return CCB_OK;
@@ -587,7 +608,7 @@ int launch_commit(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, cuda
     const int g_cells = (h->bs_bmax + BS_THREADS - 1) / BS_THREADS;
     const int rows_ctas = (mp_grid + BS_RMAX + 3) / 4;
     Timed tm(h, CCB_CAT_COMMIT);
-    k_bs_commit<<<rows_ctas + g_cells, BS_THREADS, 0, s>>>(e, rows_ctas); // rows | cells | (last CTA) finish
+    launch_k(h->pdl, k_bs_commit, rows_ctas + g_cells, BS_THREADS, 0, s, e, rows_ctas); // rows | cells | (last CTA) finish
     CKL(h);
     return CCB_OK;
 }
@@ -744,8 +765,19 @@ int ingest_core_bsv(ccb_handle *h, const double *dX, int64_t N, int64_t ld, int3
                 std::swap(h->bs_graph, h->bs_graph_alt);
                 std::swap(h->bs_exec, h->bs_exec_alt);
                 std::swap(h->bs_graph_eng, h->bs_graph_eng_alt);
-                if (!h->bs_exec || memcmp(&h->bs_graph_eng, &e, sizeof(Eng)) != 0)
-                    if ((rc = build_graph(h, e))) return rc;
+                if (!h->bs_exec || memcmp(&h->bs_graph_eng, &e, sizeof(Eng)) != 0) {
+                    rc = build_graph(h, e);
+                    if (rc && h->pdl) { // a driver that cannot take programmatic edges here: the same graph without them
+                        cudaGraph_t junk = nullptr;
+                        cudaStreamEndCapture(h->cap2, &junk);
+                        cudaStreamEndCapture(h->cap1, &junk);
+                        cudaGetLastError();
+                        drop_graph(h);
+                        h->pdl = false;
+                        rc = build_graph(h, e);
+                    }
+                    if (rc) return rc;
+                }
             }
             CK(h, cudaGraphLaunch(h->bs_exec, s));
         } else {
@@ -1169,6 +1201,7 @@ int ccb_get_stats(const ccb_handle *h, ccb_stats *out) {
         out->bsv_serial_cells = bb.serial_cells + b.serial_cells;
         out->nearest_pairs += bb.pairs + b.pairs;
     }
+    out->bsv_pdl = (h->bs_use_graph && h->pdl && (h->bs_exec || h->bs_exec_alt)) ? 1 : 0;
     return CCB_OK;
 }
 

@@ -85,6 +85,17 @@ __device__ __forceinline__ long long globaltimer_ns() {
 #define CCB_TS_ANY(slot)
 #endif
 
+// ---- programmatic dependent launch (sm_90+) -------------------------------------------------------
+// Every kernel of the engine starts with CCB_PDL(): it lets the NEXT kernel of the stream be scheduled right away
+// (launch_dependents) and then waits until the kernel BEFORE it has completed and flushed its writes (wait).  Launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization the launch latency of a kernel thus hides behind its predecessor; without
+// the attribute both instructions are no-ops.  Nothing but launch constants may be read before CCB_PDL().
+#define CCB_PDL()                                                      \
+    do {                                                               \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+        asm volatile("griddepcontrol.wait;" ::: "memory");             \
+    } while (0)
+
 // ---- small utilities ------------------------------------------------------------------------------
 __device__ __forceinline__ int popc64(uint64_t m) { return __popcll(m); }
 

@@ -241,6 +241,7 @@ __global__ void k_bs_init(BsCtl *bc, int64_t N, int32_t itmax, int32_t bmin, int
 __global__ void k_bs_begin(Eng e) {
     e.fetch();
     CCB_TS(0);
+    CCB_PDL();
     BsCtl *bc = e.bc;
     bc->active = 0;
     bc->tk_lo = bc->tk_hi = 0; // an idle block must not leave kernel 1 any work
@@ -306,6 +307,7 @@ template <int DP>
 __global__ void __launch_bounds__(BS_THREADS, DP <= 16 ? 7 : 1) k_bs_spec(Eng e) {
     e.fetch();
     CCB_TS(1);
+    CCB_PDL();
     const BsCtl *bc = e.bc;
     if (!bc->active) return;
     const int gt = blockIdx.x * BS_THREADS + threadIdx.x;
@@ -400,6 +402,7 @@ __device__ __forceinline__ int block_exclusive_scan_1024(int v, int *s_warp, int
 __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
     e.fetch();
     CCB_TS(2);
+    CCB_PDL();
     __shared__ int s_warp[33];
     __shared__ int s_cut;
     BsCtl *bc = e.bc;
@@ -478,6 +481,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
 __global__ void __launch_bounds__(BS_THREADS) k_bs_spec_o(Eng e) {
     e.fetch();
     CCB_TS(5);
+    CCB_PDL();
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->it != 0) return; // first round of a block only
     const int t = blockIdx.x * BS_THREADS + threadIdx.x;
@@ -510,6 +514,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_spec_o(Eng e) {
 __global__ void __launch_bounds__(BS_THREADS) k_bs_tilecnt(Eng e) {
     e.fetch();
     CCB_TS(6);
+    CCB_PDL();
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return;
     const int lane = threadIdx.x & 31;
@@ -536,6 +541,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_tilecnt(Eng e) {
 __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
     e.fetch();
     CCB_TS(7);
+    CCB_PDL();
     __shared__ int s_warp[33];
     __shared__ int s_last, s_max;
     BsCtl *bc = e.bc;
@@ -594,6 +600,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_pscan(Eng e) {
 __global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
     e.fetch();
     CCB_TS(8);
+    CCB_PDL();
     __shared__ int s_pos[32];
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return;
@@ -668,7 +675,6 @@ __device__ __forceinline__ void bs_chain_o_key(const Eng &e, const BsCtl *bc, in
                                                double (&xs)[2][ChainCfg<DP>::NB][DP], int (&mi)[2][ChainCfg<DP>::NB]) {
     constexpr int NB = ChainCfg<DP>::NB;
     constexpr int GS = 8;
-    constexpr int NH = DP > 32 ? 2 : 1;
     const Num nm = e.nm;
     const int D = nm.D;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -729,70 +735,78 @@ __device__ __forceinline__ void bs_chain_o_key(const Eng &e, const BsCtl *bc, in
         return;
     }
 
-    // ---- consumer (warp 0)
-    double cf1[NH], cf2[NH];
+    // ---- consumer (warp 0): lane = element of the VERSION record (CF1 | CF2 | W, the layout of ver), as in
+    // k_bs_chain_p: absorbing a cell is ONE dependent add for the lane that owns the element and one coalesced store of the
+    // record to ver[cell]; the addend of a CF2 lane is x * x (off the chain).  (Round 1 kept one dimension per lane: three
+    // adds, three scattered stores and their address arithmetic per member -- 40 us for the 2 000-member keys of the cold
+    // start, with 12 of 32 lanes busy.)
+    constexpr int LSP = 2 * DP + 2, NE = (2 * DP + 1 + 31) / 32; // elements per lane
+    double v[NE];
+    int src[NE];  // which coordinate of the cell feeds element e (-1: the weight lane, addend 1.0; -2: idle)
+    bool sq[NE];
 #pragma unroll
-    for (int h = 0; h < NH; ++h) {
-        const int d = lane + 32 * h;
-        // idle lanes carry 1.0 so that their (discarded) quotients stay on the fast path of the IEEE division
-        cf1[h] = d < D ? (s1 ? s1[d] : 0.0) : 1.0;
-        cf2[h] = d < D ? (s2 ? s2[d] : 0.0) : 1.0;
+    for (int h = 0; h < NE; ++h) {
+        const int el = lane + 32 * h;
+        src[h] = -2;
+        sq[h] = false;
+        v[h] = 0.0;
+        if (el < D) {
+            src[h] = el;
+            v[h] = s1 ? s1[el] : 0.0;
+        } else if (el >= DP && el < DP + D) {
+            src[h] = el - DP;
+            sq[h] = true;
+            v[h] = s2 ? s2[el - DP] : 0.0;
+        } else if (el == 2 * DP) {
+            src[h] = -1;
+            v[h] = w;
+        }
     }
+    // (the warp issues in order: addresses and addends are made before the dependent adds start, and the lane's base
+    // pointer is held in an opaque register so that it is not re-derived from special registers per member)
+    double *ver_lane = e.ws.ver + lane;
+    asm volatile("" : "+l"(ver_lane));
+    bool st[NE];
+#pragma unroll
+    for (int h = 0; h < NE; ++h) st[h] = src[h] != -2;
     __syncthreads(); // batch 0 staged
     for (int b = 0; b < nb; ++b) {
         const int cur = b & 1;
         const int cnt = min(NB, n - b * NB);
         for (int m0 = 0; m0 < cnt; m0 += GS) {
             const int g = min(GS, cnt - m0);
-            if (g == GS) {
-                int ii[GS];
-                double xv[GS][NH];
+            double *rec[GS];
+            double a[GS][NE];
 #pragma unroll
-                for (int s = 0; s < GS; ++s) {
-                    ii[s] = mi[cur][m0 + s];
+            for (int q = 0; q < GS; ++q) {
+                const int mq = min(m0 + q, cnt - 1); // (past the end of a ragged group: a valid slot, never stored)
+                rec[q] = ver_lane + (size_t)mi[cur][mq] * LSP;
 #pragma unroll
-                    for (int h = 0; h < NH; ++h) {
-                        const int d = lane + 32 * h;
-                        xv[s][h] = d < D ? xs[cur][m0 + s][d < DP ? d : 0] : 0.0;
-                    }
+                for (int h = 0; h < NE; ++h) {
+                    const double x = src[h] >= 0 ? xs[cur][mq][src[h]] : 1.0;
+                    a[q][h] = sq[h] ? dmul(x, x) : x;
+                    asm volatile("" : "+d"(a[q][h]));
                 }
+                asm volatile("" : "+l"(rec[q]));
+            }
+            if (g == GS) {
 #pragma unroll
-                for (int s = 0; s < GS; ++s) {
-                    w = dadd(w, 1.0);
+                for (int q = 0; q < GS; ++q)
 #pragma unroll
-                    for (int h = 0; h < NH; ++h) {
-                        const int d = lane + 32 * h;
-                        cf1[h] = dadd(cf1[h], xv[s][h]);
-                        cf2[h] = dadd(cf2[h], dmul(xv[s][h], xv[s][h]));
-                        if (d < D) {
-                            ver_cf1(e.ws, ii[s])[d] = cf1[h];
-                            ver_cf2(e.ws, ii[s])[d] = cf2[h];
+                    for (int h = 0; h < NE; ++h) {
+                        v[h] = dadd(v[h], a[q][h]);
+                        if (st[h]) rec[q][32 * h] = v[h];
+                    }
+            } else {
+#pragma unroll
+                for (int q = 0; q < GS - 1; ++q)
+                    if (q < g) { // warp-uniform
+#pragma unroll
+                        for (int h = 0; h < NE; ++h) {
+                            v[h] = dadd(v[h], a[q][h]);
+                            if (st[h]) rec[q][32 * h] = v[h];
                         }
                     }
-                    if (lane == 0) ver_w(e.ws, ii[s]) = w;
-                }
-                continue;
-            }
-            for (int m = m0; m < m0 + g; ++m) {
-                const int i = mi[cur][m];
-                double x[2];
-                x[0] = lane < D ? xs[cur][m][lane < DP ? lane : 0] : 0.0;
-                x[1] = (DP > 32 && lane + 32 < D) ? xs[cur][m][lane + 32 < DP ? lane + 32 : 0] : 0.0;
-                w = dadd(w, 1.0);
-#pragma unroll
-                for (int h = 0; h < NH; ++h) {
-                    cf1[h] = dadd(cf1[h], x[h]);
-                    cf2[h] = dadd(cf2[h], dmul(x[h], x[h]));
-                }
-#pragma unroll
-                for (int h = 0; h < NH; ++h) {
-                    const int d = lane + 32 * h;
-                    if (d < D) {
-                        ver_cf1(e.ws, i)[d] = cf1[h];
-                        ver_cf2(e.ws, i)[d] = cf2[h];
-                    }
-                }
-                if (lane == 0) ver_w(e.ws, i) = w;
             }
         }
         __syncthreads();
@@ -803,6 +817,7 @@ template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_chain_o(Eng e) {
     e.fetch();
     CCB_TS(13);
+    CCB_PDL();
     __shared__ __align__(16) double xs[2][ChainCfg<DP>::NB][DP];
     __shared__ int mi[2][ChainCfg<DP>::NB];
     const BsCtl *bc = e.bc;
@@ -1067,6 +1082,68 @@ __device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint3
     return rec;
 }
 
+// The same group when the record is one register per lane (NH == 1, D <= 15) and CONTESTED cells come in runs -- the cold
+// start and the saturated parameter corners, where whole chains are CONTESTED: TWO cells per step.  The verdict of cell q + 1
+// depends on that of cell q only through which state it is added to, so its test is evaluated for BOTH outcomes of cell q
+// next to cell q's own test (three independent instruction streams for the in-order warp instead of one dependent one)
+// and the right one is picked afterwards: ~1/2 of the latency per CONTESTED cell.  Anything the fast test cannot call
+// (and the first member of a chain) takes the one-by-one path with the exact test.  A rolled loop: the code stays small.
+template <int DP>
+__device__ __noinline__ ChainRec<1> bs_chain_slow_group_pairs(ChainRec<1> rec, uint32_t ga, uint32_t ma_g, unsigned cg, int ncell,
+                                                              int lane, int D, double delta2, double eps2, int div_mode, double k,
+                                                              double wsel, uint8_t *prej, const ChainFast cf, int exact_first) {
+    constexpr int LSP = 2 * DP + 2, GS = 8;
+    double v = rec.v[0];
+    const bool st_ok = lane < LSP;
+    unsigned rej = 0u;
+    double a0 = lds_f64(ga), a1 = lds_f64(ga + (ncell > 1 ? 1 : 0) * (LSP * 8));
+    int q = 0;
+#pragma unroll 1
+    while (q < ncell) {
+        const uint32_t ra = ga + q * (LSP * 8);
+        // the addends two and three cells ahead (clamped: never used past the group)
+        const double a2 = lds_f64(ga + min(q + 2, GS - 1) * (LSP * 8)), a3 = lds_f64(ga + min(q + 3, GS - 1) * (LSP * 8));
+        const bool cA = (cg >> q) & 1u, cB = q + 1 < ncell && ((cg >> (q + 1)) & 1u);
+        const double nvA = dadd(v, a0);
+        if (st_ok) sts_f64(ra, nvA);
+        if (cA && cB && !(q == 0 && exact_first)) {
+            const double nvB1 = dadd(nvA, a1), nvB0 = dadd(v, a1);
+            const int rA = bs_radius_fast<DP, 1>(nvA, ra, lane, D, cf);
+            const int rB1 = bs_radius_fast<DP, 1>(nvB1, ra, lane, D, cf);
+            const int rB0 = bs_radius_fast<DP, 1>(nvB0, ra, lane, D, cf);
+            const int rB = rA ? rB1 : rB0;
+            if (rA != 2 && rB != 2) {
+                const double nvB = rA ? nvB1 : nvB0;
+                if (st_ok) sts_f64(ra + LSP * 8, nvB);
+                v = rB ? nvB : (rA ? nvA : v);
+                rej |= ((rA ? 0u : 1u) << q) | ((rB ? 0u : 1u) << (q + 1));
+                q += 2;
+                a0 = a2;
+                a1 = a3;
+                continue;
+            }
+        }
+        bool keep = true;
+        if (cA) {
+            int r = (q == 0 && exact_first) ? 2 : bs_radius_fast<DP, 1>(nvA, ra, lane, D, cf);
+            if (r == 2) r = bs_radius_test<DP, 1>(nvA, ra, lane, D, delta2, eps2, div_mode, k, wsel) ? 1 : 0;
+            keep = r != 0;
+            rej |= (keep ? 0u : 1u) << q;
+        }
+        v = keep ? nvA : v;
+        q += 1;
+        a0 = a1;
+        a1 = a2;
+    }
+    if (lane < GS && ((cg >> lane) & 1u) && lane < ncell) {
+        int raw;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + lane * 4));
+        prej[raw & 0x7fffffff] = (uint8_t)((rej >> lane) & 1u);
+    }
+    rec.v[0] = v;
+    return rec;
+}
+
 // 32 consecutive cells without a CONTESTED one inside a stage that holds one elsewhere: the straight-line schedule of the
 // clean stage (dependent add, store of the version before, load one batch ahead), out of line -- one copy, used rarely.
 template <int DP, int NH>
@@ -1111,6 +1188,7 @@ template <int DP>
 __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
     e.fetch();
     CCB_TS(9);
+    CCB_PDL();
     using Cfg = ChainPCfg<DP>;
     constexpr int NB = Cfg::NB, S = Cfg::S, GS = 8, NH = Cfg::NH, LSP = Cfg::LSP, NG = NB / GS;
     static_assert(NB == 32 || NB == 64, "the CONTESTED flags of a stage are gathered by one or two ballots");
@@ -1323,8 +1401,17 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
                     ChainRec<NH> rec;
 #pragma unroll
                     for (int h = 0; h < NH; ++h) rec.v[h] = v[h];
-                    rec = bs_chain_slow_group<DP, NH>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
-                                                      nm.div_mode, nm.k, nm.wsel, e.ws.prej, cfast, (b | g) == 0);
+                    if constexpr (NH == 1) {
+                        if (__popc(cg) >= 2)
+                            rec = bs_chain_slow_group_pairs<DP>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
+                                                                nm.div_mode, nm.k, nm.wsel, e.ws.prej, cfast, (b | g) == 0);
+                        else
+                            rec = bs_chain_slow_group<DP, NH>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
+                                                              nm.div_mode, nm.k, nm.wsel, e.ws.prej, cfast, (b | g) == 0);
+                    } else {
+                        rec = bs_chain_slow_group<DP, NH>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
+                                                          nm.div_mode, nm.k, nm.wsel, e.ws.prej, cfast, (b | g) == 0);
+                    }
 #pragma unroll
                     for (int h = 0; h < NH; ++h) v[h] = rec.v[h];
                 }
@@ -1394,6 +1481,7 @@ __device__ __forceinline__ int block_exclusive_scan_t(int v, int *s_warp, int &t
 __global__ void __launch_bounds__(BS_OL_THREADS, 1) k_bs_olist(Eng e) {
     e.fetch();
     CCB_TS(12);
+    CCB_PDL();
     constexpr int NT = BS_OL_THREADS, TPE = BS_OL_TPE, EPP = NT / TPE; // entries ranked per pass
     __shared__ unsigned long long keys[BS_RMAX];
     __shared__ int s_warp[33];
@@ -1532,6 +1620,7 @@ __device__ __forceinline__ void derive_version(const Eng &e, const Num &nm, int 
 __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_p(Eng e) {
     e.fetch();
     CCB_TS(10);
+    CCB_PDL();
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return;
     const int i = blockIdx.x * BS_THREADS + threadIdx.x;
@@ -1555,6 +1644,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_p(Eng e) {
 __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_o(Eng e) {
     e.fetch();
     CCB_TS(14);
+    CCB_PDL();
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0) return;
     if (!bc->o_big) return; // every key was small: k_bs_chain_o derived its versions itself
@@ -1575,6 +1665,7 @@ template <int DP>
 __global__ void __launch_bounds__(BS_VP_THREADS, DP <= 16 ? 5 : 1) k_bs_verify_p(Eng e) {
     e.fetch();
     CCB_TS(11);
+    CCB_PDL();
     constexpr int NW = BS_VP_THREADS / 32, U = 1;
     __shared__ double s_bd[NW][32];
     __shared__ int s_best[NW][32], s_prev[NW][32];
@@ -1813,6 +1904,7 @@ template <int DP>
 __global__ void __launch_bounds__(BS_THREADS) k_bs_verify_o(Eng e) {
     e.fetch();
     CCB_TS(15);
+    CCB_PDL();
     constexpr int NW = BS_THREADS / 32;
     __shared__ double s_bd[NW];
     __shared__ int s_bkey[NW], s_bver[NW];
@@ -1933,6 +2025,7 @@ __device__ __forceinline__ int block_min_1024(int v, int *s_warp) {
 __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
     e.fetch();
     CCB_TS(16);
+    CCB_PDL();
     __shared__ int s_warp[33];
     __shared__ int s_act, s_cut;
     BsCtl *bc = e.bc;
@@ -2182,6 +2275,7 @@ __device__ __forceinline__ void bs_finish_block(const Eng &e, BsCtl *bc);
 __global__ void __launch_bounds__(BS_THREADS) k_bs_commit(Eng e, int rows_ctas) {
     e.fetch();
     CCB_TS(17);
+    CCB_PDL();
     __shared__ int s_last;
     BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 1) return;

@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS)
         ld = xref->ld;
     }
     CCB_TS(3);
+    CCB_PDL();
     if (nrows_dev) nrows = (int64_t)(*nrows_dev) - row_off;
     if (M_dev) M = min(M, *M_dev);
     if (range_dev) {
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(128) k_topk_merge_dyn(const double *__restrict
                                                         double *__restrict__ out_dist, int32_t *__restrict__ out_idx) {
     constexpr int QMAX = 8; // max_slabs <= 256
     CCB_TS(4);
+    CCB_PDL();
     const int lane = threadIdx.x & 31;
     const int R = range_dev[1] - range_dev[0];
     if (M_dev) M = min(M, *M_dev);

@@ -41,4 +41,4 @@ for rep in range(3):
                     f"cuts={st['bsv_cuts_unknown']-prev['bsv_cuts_unknown']}/{st['bsv_cuts_rounds']-prev['bsv_cuts_rounds']}/"
                     f"{st['bsv_cuts_capacity']-prev['bsv_cuts_capacity']} launches={st['kernel_launches']-prev['kernel_launches']}")
         prev = st
-    print(f"rep {rep}: " + " | ".join(line))
+    print(f"rep {rep}: " + " | ".join(line) + f" | pdl={h.stats()['bsv_pdl']}")
