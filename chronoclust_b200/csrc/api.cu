@@ -1227,6 +1227,17 @@ int64_t ccb_debug_trace(ccb_handle *h, int64_t *out, int64_t max_records) {
     return n;
 }
 
+int ccb_debug_counters(ccb_handle *h, int64_t *out16, int32_t reset) {
+    if (!h || !out16) return -1;
+    cudaStreamSynchronize(h->stream);
+    cudaMemcpyFromSymbol(out16, g_dbg_cnt, 16 * sizeof(long long));
+    if (reset) {
+        const long long z[16] = {0};
+        cudaMemcpyToSymbol(g_dbg_cnt, z, sizeof(z));
+    }
+    return 0;
+}
+
 int ccb_debug_chain(ccb_handle *h, int64_t *out, int32_t max_keys) {
     if (!h || !out) return fail(h, CCB_EINVAL, "null argument");
     if (!h->ws.dbg) { // first call switches the counters on

@@ -24,6 +24,8 @@ int ccb_debug_set(ccb_handle *h, int32_t mode);
  * tools/trace_rounds.py.  Returns the number of records written since the last call (at most max_records are copied) and
  * rewinds the ring. */
 int64_t ccb_debug_trace(ccb_handle *h, int64_t *out, int64_t max_records);
+/* 16 free-form event / cycle counters of the experiment at hand (see the CCB_DBG lines in csrc/engine.cuh). */
+int ccb_debug_counters(ccb_handle *h, int64_t *out16, int32_t reset);
 
 #ifdef __cplusplus
 }

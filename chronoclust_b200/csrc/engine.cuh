@@ -1096,44 +1096,49 @@ __device__ __noinline__ ChainRec<1> bs_chain_slow_group_pairs(ChainRec<1> rec, u
     double v = rec.v[0];
     const bool st_ok = lane < LSP;
     unsigned rej = 0u;
-    double a0 = lds_f64(ga), a1 = lds_f64(ga + (ncell > 1 ? 1 : 0) * (LSP * 8));
-    int q = 0;
+    double a0 = lds_f64(ga), a1 = lds_f64(ga + LSP * 8); // (a1 is stale when ncell == 1: never used)
 #pragma unroll 1
-    while (q < ncell) {
+    for (int q = 0; q < ncell; q += 2) { // two cells per trip
         const uint32_t ra = ga + q * (LSP * 8);
-        // the addends two and three cells ahead (clamped: never used past the group)
+        // the addends of the next trip (clamped: never used past the group)
         const double a2 = lds_f64(ga + min(q + 2, GS - 1) * (LSP * 8)), a3 = lds_f64(ga + min(q + 3, GS - 1) * (LSP * 8));
-        const bool cA = (cg >> q) & 1u, cB = q + 1 < ncell && ((cg >> (q + 1)) & 1u);
+        const bool hasB = q + 1 < ncell;
+        const bool cA = (cg >> q) & 1u, cB = hasB && ((cg >> (q + 1)) & 1u);
         const double nvA = dadd(v, a0);
         if (st_ok) sts_f64(ra, nvA);
+        int rA = 1, rB = 1;
+        double nvB;
+        bool done = false;
         if (cA && cB && !(q == 0 && exact_first)) {
             const double nvB1 = dadd(nvA, a1), nvB0 = dadd(v, a1);
-            const int rA = bs_radius_fast<DP, 1>(nvA, ra, lane, D, cf);
+            rA = bs_radius_fast<DP, 1>(nvA, ra, lane, D, cf);
             const int rB1 = bs_radius_fast<DP, 1>(nvB1, ra, lane, D, cf);
             const int rB0 = bs_radius_fast<DP, 1>(nvB0, ra, lane, D, cf);
-            const int rB = rA ? rB1 : rB0;
-            if (rA != 2 && rB != 2) {
-                const double nvB = rA ? nvB1 : nvB0;
-                if (st_ok) sts_f64(ra + LSP * 8, nvB);
-                v = rB ? nvB : (rA ? nvA : v);
-                rej |= ((rA ? 0u : 1u) << q) | ((rB ? 0u : 1u) << (q + 1));
-                q += 2;
-                a0 = a2;
-                a1 = a3;
-                continue;
+            rB = rA ? rB1 : rB0;
+            nvB = rA ? nvB1 : nvB0;
+            done = rA != 2 && rB != 2;
+        }
+        if (!done) { // one by one
+            if (cA) {
+                rA = (q == 0 && exact_first) ? 2 : bs_radius_fast<DP, 1>(nvA, ra, lane, D, cf);
+                if (rA == 2) rA = bs_radius_test<DP, 1>(nvA, ra, lane, D, delta2, eps2, div_mode, k, wsel) ? 1 : 0;
+            }
+            nvB = dadd(rA ? nvA : v, a1);
+            if (cB) {
+                rB = bs_radius_fast<DP, 1>(nvB, ra, lane, D, cf);
+                if (rB == 2) rB = bs_radius_test<DP, 1>(nvB, ra + LSP * 8, lane, D, delta2, eps2, div_mode, k, wsel) ? 1 : 0;
             }
         }
-        bool keep = true;
-        if (cA) {
-            int r = (q == 0 && exact_first) ? 2 : bs_radius_fast<DP, 1>(nvA, ra, lane, D, cf);
-            if (r == 2) r = bs_radius_test<DP, 1>(nvA, ra, lane, D, delta2, eps2, div_mode, k, wsel) ? 1 : 0;
-            keep = r != 0;
-            rej |= (keep ? 0u : 1u) << q;
+        if (hasB) {
+            if (st_ok) sts_f64(ra + LSP * 8, nvB);
+            v = rB ? nvB : (rA ? nvA : v);
+            rej |= ((cA && !rA) ? 1u : 0u) << q | ((cB && !rB) ? 1u : 0u) << (q + 1);
+        } else {
+            v = rA ? nvA : v;
+            rej |= ((cA && !rA) ? 1u : 0u) << q;
         }
-        v = keep ? nvA : v;
-        q += 1;
-        a0 = a1;
-        a1 = a2;
+        a0 = a2;
+        a1 = a3;
     }
     if (lane < GS && ((cg >> lane) & 1u) && lane < ncell) {
         int raw;

@@ -66,6 +66,11 @@ for rep in range(2):  # the second pass is the warm one
         n = fn(h._h, buf.ctypes.data_as(C.c_void_p), buf.shape[0])
         saved[f"t{t}"] = buf[:min(n, buf.shape[0])].copy()
 np.savez_compressed(out, **saved)
+cn = np.zeros(16, dtype=np.int64)
+fc = _l0.lib().ccb_debug_counters
+fc.restype, fc.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]
+fc(h._h, cn.ctypes.data_as(C.c_void_p), 1)
+print("debug counters:", cn.tolist())
 
 for t in range(tps):
     r = saved[f"t{t}"]
