@@ -518,7 +518,6 @@ int launch_prologue(ccb_handle *h, const Eng &e, cudaStream_t s) {
     const bool pdl = h->pdl;
     k_bs_begin<<<1, 1, 0, s>>>(e);
     CCB_DISPATCH_DP(h->DP, { launch_k(pdl, k_bs_spec<kDP>, g_cells * BS_SPLIT, BS_THREADS, 0, s, e); })
-    launch_k(pdl, k_bs_need, 1, BS_CTA1, 0, s, e);
     CKL(h);
     return CCB_OK;
 }
@@ -601,7 +600,7 @@ int launch_round(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, int m
     CKL(h);
     return CCB_OK;
 }
-constexpr int BS_LAUNCHES_PROLOGUE = 3, BS_LAUNCHES_ROUND = 14, BS_LAUNCHES_COMMIT = 1;
+constexpr int BS_LAUNCHES_PROLOGUE = 2, BS_LAUNCHES_ROUND = 14, BS_LAUNCHES_COMMIT = 1;
 
 int launch_commit(ccb_handle *h, const Eng &e, cudaStream_t s, int mp_grid, cudaStream_t side = nullptr) {
     (void)side;

@@ -64,6 +64,8 @@ struct BsCtl {
     int32_t ticket; // k_bs_pscan: CTAs finished (last one computes the key offsets)
     int32_t ticket_o; // k_bs_olist: likewise (the last one builds the key segments)
     int32_t ticket_c; // k_bs_commit: likewise (the last one finishes the block)
+    int32_t ticket_s; // k_bs_spec: likewise (the last one closes the need list)
+    int32_t tc_done;  // the per-(tile, key) candidate counts of round 1 were made by k_bs_spec (k_bs_tilecnt has nothing to do)
     int32_t o_big;    // outlier-side keys of this round with more members than a CTA of k_bs_chain_o derives itself
     int32_t m_exact;  // cells below this are exact since an earlier round of the block (first mismatch of the previous round)
     int32_t pclean; // refinement round whose pcore side (candidates, CONTESTED flags, accepts) is that of the round before
@@ -268,6 +270,7 @@ __global__ void k_bs_begin(Eng e) {
         bc->Mo0 = Mo0;
         bc->nneed = 0;
         bc->nneed_raw = 0;
+        bc->tc_done = 0;
         bc->nh = bc->hnew0 = bc->no = 0;
         bc->npend = 0;
         bc->it = 0;
@@ -303,71 +306,6 @@ __device__ __forceinline__ void group_argmin(double &d, int &j) { // over BS_SPL
     }
 }
 
-template <int DP>
-__global__ void __launch_bounds__(BS_THREADS, DP <= 16 ? 7 : 1) k_bs_spec(Eng e) {
-    e.fetch();
-    CCB_TS(1);
-    CCB_PDL();
-    const BsCtl *bc = e.bc;
-    if (!bc->active) return;
-    const int gt = blockIdx.x * BS_THREADS + threadIdx.x;
-    const int i = gt / BS_SPLIT, part = gt % BS_SPLIT;
-    if ((blockIdx.x * BS_THREADS + (threadIdx.x & ~31)) / BS_SPLIT >= bc->Bcur) return; // whole warps only (shuffles below)
-    const bool live = i < bc->Bcur;
-    const Num nm = e.nm;
-    const int D = nm.D, Mp = live ? bc->Mp : 0;
-    double x[DP];
-    load_row<DP>(e.X + (bc->pos + (live ? i : 0)) * e.ld, D, x);
-    int best = -1;
-    double bd = 0.0;
-    for (int j = part; j < Mp; j += BS_SPLIT) {
-        if (nm.pi_active && !feasible_regs<DP>(e.P.cf1 + (size_t)j * D, e.P.cf2 + (size_t)j * D, e.P.w[j], x, nm)) continue;
-        const double dv = dist_regs<DP>(x, e.P.cen + (size_t)j * D, e.P.mask[j], nm);
-        if (!(dv != dv) && (best < 0 || dv < bd)) {
-            best = j;
-            bd = dv;
-        }
-    }
-    group_argmin(bd, best);
-    const bool mine = part == 0 && live;
-    int flag = mine ? 1 : 0;
-    if (mine && best >= 0) {
-        double wn;
-        uint64_t nmask;
-        const double r2s = tent_regs<DP>(e.P.cf1 + (size_t)best * D, e.P.cf2 + (size_t)best * D, e.P.w[best], x, nm, wn, nmask);
-        if (bd <= e.theta && r2s <= e.r2safe) flag = 0;
-        // far beyond the radius limit on the snapshot: speculate "rejected by the pcore stage" right away instead of
-        // sending the cell through the serial chain for an exact test; k_bs_verify_p checks it like everything else
-        else if (r2s > e.r2rej) best = -1;
-    }
-    // need list: every cell that is not SAFE takes a top-K slot right here (one atomic per warp; the order of the slots
-    // is immaterial).  Should the block need more than BS_RMAX slots, k_bs_need hands them out again in cell order and
-    // truncates the block.
-    const unsigned fm = __ballot_sync(0xffffffffu, flag != 0);
-    int slot = -1;
-    if (fm) {
-        const int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == __ffs(fm) - 1) base = atomicAdd(&e.bc->nneed_raw, __popc(fm));
-        base = __shfl_sync(0xffffffffu, base, __ffs(fm) - 1);
-        if (flag) slot = base + __popc(fm & ((1u << lane) - 1u));
-    }
-    if (!mine) return;
-    e.ws.pcand[i] = best;
-    e.ws.pflag[i] = (uint8_t)flag;
-    e.ws.prej[i] = best < 0;
-    e.ws.ospec[i] = BS_KEY_NONE;
-    if (slot >= 0 && slot < BS_RMAX) {
-        e.ws.tkpos[i] = slot;
-        e.ws.nrows[slot] = (int32_t)bc->pos + i;
-        e.ws.ncell[slot] = i;
-    } else {
-        e.ws.tkpos[i] = -1;
-    }
-}
-
-// ordered need list: every cell that is not SAFE gets a top-K slot, in cell order; the block is truncated at
-// the first cell that does not fit (bounds the outlier-stage work of one block)
 constexpr int BS_CTA1 = 1024;
 
 __device__ __forceinline__ int block_exclusive_scan_1024(int v, int *s_warp, int &total) {
@@ -399,77 +337,189 @@ __device__ __forceinline__ int block_exclusive_scan_1024(int v, int *s_warp, int
     return r;
 }
 
-__global__ void __launch_bounds__(BS_CTA1, 1) k_bs_need(Eng e) {
-    e.fetch();
-    CCB_TS(2);
-    CCB_PDL();
-    __shared__ int s_warp[33];
-    __shared__ int s_cut;
-    BsCtl *bc = e.bc;
-    if (!bc->active) return;
-    if (bc->nneed_raw <= BS_RMAX) { // the usual case: k_bs_spec handed the slots out itself
-        if (threadIdx.x == 0) {
-            bc->Beff = bc->Bcur;
-            bc->nneed = bc->nneed_raw;
-            bc->tk_lo = 0;
-            bc->tk_hi = bc->nneed;
-            bc->rejects += bc->nneed;
-            bc->pairs += (int64_t)bc->nneed * bc->Mo0;
+template <int NT>
+__device__ __forceinline__ int block_exclusive_scan_t(int v, int *s_warp, int &total) { // NT threads, NT / 32 <= 32 warps
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = lane < NT / 32 ? s_warp[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
         }
-        return;
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
     }
+    __syncthreads();
+    total = s_warp[32];
+    const int r = s_warp[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+// Ordered need list (the rare case: more than BS_RMAX cells of the block are not SAFE): slots are handed out again in
+// cell order and the block is truncated at the first cell that does not fit (bounds the outlier-stage work of one block).
+// Runs in the last CTA of k_bs_spec (NT threads).
+template <int NT>
+__device__ __forceinline__ void bs_need_ordered(const Eng &e, BsCtl *bc, int *s_warp, int *s_cut) {
     const int B = bc->Bcur, tid = threadIdx.x;
-    const int per = (B + BS_CTA1 - 1) / BS_CTA1;
+    const int per = (B + NT - 1) / NT;
     const int lo = min(B, tid * per), hi = min(B, lo + per);
-    if (tid == 0) s_cut = B;
+    if (tid == 0) *s_cut = B;
     int cnt = 0;
-    // up to 32 cells per thread (blocks of <= 32 768 cells): their flags become one register mask, fetched with
-    // 16-byte loads; the slots are then handed out by walking the set bits
-    const bool small = per <= 32;
-    uint32_t fmask = 0u;
-    if (small) {
-        int i = lo;
-        if ((lo & 15) == 0)
-            for (; i + 16 <= hi; i += 16) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(e.ws.pflag + i);
-                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if ((w4[k4] >> (8 * b)) & 0xffu) fmask |= 1u << (i - lo + 4 * k4 + b);
-            }
-        for (; i < hi; ++i)
-            if (e.ws.pflag[i]) fmask |= 1u << (i - lo);
-        cnt = __popc(fmask);
-    } else {
-        for (int i = lo; i < hi; ++i) cnt += e.ws.pflag[i];
-    }
+    for (int i = lo; i < hi; ++i) cnt += e.ws.pflag[i] != 0;
     int total;
-    int base = block_exclusive_scan_1024(cnt, s_warp, total);
+    int base = block_exclusive_scan_t<NT>(cnt, s_warp, total);
     const int32_t row0 = (int32_t)bc->pos;
     for (int i = lo; i < hi; ++i) {
-        if (small) { // jump to the next flagged cell
-            if (!fmask) break;
-            i = lo + __ffs(fmask) - 1;
-            fmask &= fmask - 1;
-        } else if (!e.ws.pflag[i]) {
-            continue;
-        }
+        if (!e.ws.pflag[i]) continue;
         if (base < BS_RMAX) {
             e.ws.tkpos[i] = base;
             e.ws.nrows[base] = row0 + i;
             e.ws.ncell[base] = i;
         } else {
             e.ws.tkpos[i] = -1;
-            if (base == BS_RMAX) s_cut = i; // exactly one thread sees the first overflowing cell
+            if (base == BS_RMAX) *s_cut = i; // exactly one thread sees the first overflowing cell
         }
         ++base;
     }
     __syncthreads();
     if (tid == 0) {
-        bc->Beff = s_cut;
+        bc->Beff = *s_cut;
         bc->nneed = min(total, BS_RMAX);
+    }
+}
+
+// S: one CTA = one tile of 32 cells, BS_SPLIT lanes per cell.  Besides the speculation itself the kernel hands out the
+// top-K slots of the cells that are not SAFE, counts the tile's candidates per pcore key (k_bs_tilecnt's work in the first
+// round) and, in its last CTA, closes the need list -- three launches of round 1 folded into this one.
+template <int DP>
+__global__ void __launch_bounds__(BS_THREADS, DP <= 16 ? 7 : 1) k_bs_spec(Eng e) {
+    e.fetch();
+    CCB_TS(1);
+    CCB_PDL();
+    __shared__ int s_warp[33];
+    __shared__ int s_last, s_cut;
+    BsCtl *bc = e.bc;
+    if (!bc->active) return;
+    const int Bcur = bc->Bcur;
+    if ((int)blockIdx.x * (BS_THREADS / BS_SPLIT) >= Bcur) return; // (whole CTAs)
+    const int gt = blockIdx.x * BS_THREADS + threadIdx.x;
+    const int i = gt / BS_SPLIT, part = gt % BS_SPLIT;
+    const bool live = i < Bcur;
+    const Num nm = e.nm;
+    const int D = nm.D, Mp_all = bc->Mp, Mp = live ? Mp_all : 0;
+    // this tile's row of the per-(tile, key) candidate counts
+    int32_t *trow = e.ws.tilecnt + (size_t)blockIdx.x * e.ws.mp_stride;
+    for (int j = threadIdx.x; j < Mp_all; j += BS_THREADS) trow[j] = 0;
+    __syncthreads();
+    double x[DP];
+    load_row<DP>(e.X + (bc->pos + (live ? i : 0)) * e.ld, D, x);
+    int best = -1;
+    double bd = 0.0;
+    for (int j = part; j < Mp; j += BS_SPLIT) {
+        if (nm.pi_active && !feasible_regs<DP>(e.P.cf1 + (size_t)j * D, e.P.cf2 + (size_t)j * D, e.P.w[j], x, nm)) continue;
+        const double dv = dist_regs<DP>(x, e.P.cen + (size_t)j * D, e.P.mask[j], nm);
+        if (!(dv != dv) && (best < 0 || dv < bd)) {
+            best = j;
+            bd = dv;
+        }
+    }
+    group_argmin(bd, best); // (every lane of the group holds the result)
+    // radius^2 of the tentative MC (microcluster.py:213-233, mc_functions.py:45-56) on the snapshot: the group's lanes share
+    // the 2 D divisions (lane p: dimensions p, p + BS_SPLIT, ...), lane 0 sums the terms in index order
+    const int lane = threadIdx.x & 31, gbase = lane & ~(BS_SPLIT - 1);
+    constexpr int TPL = (DP + BS_SPLIT - 1) / BS_SPLIT;
+    double term[TPL];
+    {
+        const int b = best >= 0 ? best : 0;
+        const double *cf1 = e.P.cf1 + (size_t)b * D, *cf2 = e.P.cf2 + (size_t)b * D;
+        const double wn = dadd(best >= 0 ? e.P.w[b] : 0.0, 1.0);
+#pragma unroll
+        for (int u = 0; u < TPL; ++u) {
+            const int d = part + u * BS_SPLIT;
+            double t = 0.0;
+            if (d < D && best >= 0) {
+                // (x is a register array: select the coordinate without dynamic indexing)
+                double xv = 0.0;
+#pragma unroll
+                for (int dd = 0; dd < DP; ++dd)
+                    if (dd == d) xv = x[dd];
+                const double a = ddiv(dadd(cf2[d], dmul(xv, xv)), wn);
+                const double c = ddiv(dadd(cf1[d], xv), wn);
+                const double var = dsub(a, dmul(c, c));
+                t = (var <= nm.delta2) ? (nm.div_mode ? ddiv(var, nm.k) : dmul(var, nm.wsel)) : var;
+            }
+            term[u] = t;
+        }
+    }
+    double r2s = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+        const double t = __shfl_sync(0xffffffffu, term[d / BS_SPLIT], gbase + (d % BS_SPLIT));
+        if (d < D) r2s = dadd(r2s, t);
+    }
+    const bool mine = part == 0 && live;
+    int flag = mine ? 1 : 0;
+    if (mine && best >= 0) {
+        if (bd <= e.theta && r2s <= e.r2safe) flag = 0;
+        // far beyond the radius limit on the snapshot: speculate "rejected by the pcore stage" right away instead of
+        // sending the cell through the serial chain for an exact test; k_bs_verify_p checks it like everything else
+        else if (r2s > e.r2rej) best = -1;
+    }
+    // need list: every cell that is not SAFE takes a top-K slot right here (one atomic per warp; the order of the slots
+    // is immaterial).  Should the block need more than BS_RMAX slots, the last CTA hands them out again in cell order and
+    // truncates the block (bs_need_ordered).
+    const unsigned fm = __ballot_sync(0xffffffffu, flag != 0);
+    int slot = -1;
+    if (fm) {
+        int base = 0;
+        if (lane == __ffs(fm) - 1) base = atomicAdd(&bc->nneed_raw, __popc(fm));
+        base = __shfl_sync(0xffffffffu, base, __ffs(fm) - 1);
+        if (flag) slot = base + __popc(fm & ((1u << lane) - 1u));
+    }
+    if (mine) {
+        e.ws.pcand[i] = best;
+        e.ws.pflag[i] = (uint8_t)flag;
+        e.ws.prej[i] = best < 0;
+        e.ws.ospec[i] = BS_KEY_NONE;
+        if (slot >= 0 && slot < BS_RMAX) {
+            e.ws.tkpos[i] = slot;
+            e.ws.nrows[slot] = (int32_t)bc->pos + i;
+            e.ws.ncell[slot] = i;
+        } else {
+            e.ws.tkpos[i] = -1;
+        }
+        if (best >= 0) atomicAdd(&trow[best], 1);
+    }
+    // ---- the last CTA of the block closes the need list
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&bc->ticket_s, 1) == (Bcur + BS_THREADS / BS_SPLIT - 1) / (BS_THREADS / BS_SPLIT) - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int raw = *(volatile int32_t *)&bc->nneed_raw;
+    if (raw <= BS_RMAX) { // the usual case: the slots handed out above stand
+        if (threadIdx.x == 0) {
+            bc->Beff = Bcur;
+            bc->nneed = raw;
+            bc->tc_done = 1; // the tile counts above are those of the whole block
+        }
+    } else {
+        bs_need_ordered<BS_THREADS>(e, bc, s_warp, &s_cut);
+    }
+    if (threadIdx.x == 0) {
+        bc->ticket_s = 0;
         bc->tk_lo = 0;
         bc->tk_hi = bc->nneed;
         bc->rejects += bc->nneed;
@@ -517,6 +567,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_tilecnt(Eng e) {
     CCB_PDL();
     const BsCtl *bc = e.bc;
     if (!bc->active || bc->phase != 0 || bc->pclean) return;
+    if (bc->it == 0 && bc->tc_done) return; // round 1 of an untruncated block: k_bs_spec counted
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (BS_THREADS / 32) + (threadIdx.x >> 5);
     const int ntiles = (bc->Beff + 31) >> 5;
@@ -1453,35 +1504,6 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
 // (ticket) turns the sorted array into the key segments.  A single CTA spent 55 us in a bitonic sort of 4096 entries;
 // 148 CTAs need ~2 us for the 16.7 M comparisons.
 constexpr int BS_OL_THREADS = 512, BS_OL_TPE = 16, BS_OL_CTAS = 148;
-
-template <int NT>
-__device__ __forceinline__ int block_exclusive_scan_t(int v, int *s_warp, int &total) { // NT threads, NT / 32 <= 32 warps
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        const int w = lane < NT / 32 ? s_warp[lane] : 0;
-        int winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        s_warp[lane] = winc - w;
-        if (lane == 31) s_warp[32] = winc;
-    }
-    __syncthreads();
-    total = s_warp[32];
-    const int r = s_warp[warp] + inc - v;
-    __syncthreads();
-    return r;
-}
 
 __global__ void __launch_bounds__(BS_OL_THREADS, 1) k_bs_olist(Eng e) {
     e.fetch();
