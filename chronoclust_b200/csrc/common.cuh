@@ -63,7 +63,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 #ifdef CCB_DEBUG
 constexpr int CCB_TRACE_SLOTS = 40, CCB_TRACE_WORDS = 64, CCB_TRACE_MAX = 1 << 14;
 __device__ long long g_trace_ts[CCB_TRACE_SLOTS];               // start of every kernel of the current round (globaltimer, ns)
-__device__ long long g_trace[CCB_TRACE_MAX][CCB_TRACE_WORDS];   // one record per round (k_bs_decide) / block (k_bs_finish)
+__device__ long long g_trace[CCB_TRACE_MAX][CCB_TRACE_WORDS];   // one record per round (k_bs_decide) / block (k_bs_commit)
 __device__ int g_trace_n;
 __device__ unsigned long long g_dbg_cnt[16]; // free-form event / cycle counters of experiments (ccb_debug_counters)
 __device__ __forceinline__ long long globaltimer_ns() {

@@ -20,7 +20,7 @@ int ccb_debug_chain(ccb_handle *h, int64_t *out, int32_t max_keys);
  * proxy fence before handing a stage to the store thread (timing experiments).  0 restores normal operation. */
 int ccb_debug_set(ccb_handle *h, int32_t mode);
 /* Timeline of the engine: one record of 48 int64 per refinement round (kind 0 / 1, written by k_bs_decide) and per block
- * (kind 2, k_bs_finish): control-block fields and the start time (globaltimer, ns) of every kernel of the round; layout in
+ * (kind 2, k_bs_commit): control-block fields and the start time (globaltimer, ns) of every kernel of the round; layout in
  * tools/trace_rounds.py.  Returns the number of records written since the last call (at most max_records are copied) and
  * rewinds the ring. */
 int64_t ccb_debug_trace(ccb_handle *h, int64_t *out, int64_t max_records);

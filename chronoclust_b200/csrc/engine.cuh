@@ -13,7 +13,7 @@
 //                                                             creates (c == i: the cell itself creates it)
 // with KNEW = Mp + Mo0.  One block runs
 //   S   k_bs_spec      speculate from the snapshot: nearest feasible pcore MC (candidate), SAFE / CONTESTED,
-//       k_bs_need      ordered list of the cells that may reach the outlier stage, k_nearest top-K of the
+//                      (it also hands out the top-K slots of the cells that may reach the outlier stage), k_nearest top-K of the
 //       k_bs_spec_o    snapshot outlier list for them, speculated outlier decision
 //   then up to ITMAX rounds of
 //   L   k_bs_tilecnt / k_bs_pscan / k_bs_pscatter   ordered candidate list of every pcore MC
@@ -56,7 +56,7 @@ struct BsCtl {
     int32_t active, phase, it, itmax; // phase 0: iterating, 1: commit pending
     int32_t Mp, Mo0;
     int32_t nneed, tk_lo, tk_hi; // need-list length; range of entries whose top-K list is to be computed
-    int32_t nneed_raw;           // slots k_bs_spec asked for (more than BS_RMAX: k_bs_need re-does the list in cell order)
+    int32_t nneed_raw;           // slots k_bs_spec asked for (more than BS_RMAX: its last CTA re-does the list in cell order)
     int32_t nh, hnew0, no;       // hot outlier-side keys, index of the first created-in-block key, members
     int32_t npend;
     int32_t m_commit, upgrade;

@@ -126,7 +126,7 @@ int ccb_reset(ccb_handle *h);
 #define CCB_CAT_OLIST 10  /* kernel 2   outlier-side member lists (k_bs_olist) */
 #define CCB_CAT_DERIVE 11 /* kernel 2   centroid / preference mask / radius of every version (k_bs_derive) */
 #define CCB_CAT_DECIDE 12 /* kernel 2   exact-prefix decision / refinement (k_bs_decide) */
-#define CCB_CAT_COMMIT 13 /* kernel 2   write-back of the exact prefix (k_bs_commit_rows/cells, k_bs_finish) */
+#define CCB_CAT_COMMIT 13 /* kernel 2   write-back of the exact prefix (k_bs_commit) */
 #define CCB_NCAT 16
 int ccb_enable_timing(ccb_handle *h, int32_t on);
 int ccb_get_timing(ccb_handle *h, double ms[CCB_NCAT], int64_t launches[CCB_NCAT], int32_t reset);
