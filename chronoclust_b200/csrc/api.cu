@@ -98,6 +98,9 @@ struct ccb_handle {
     cudaStream_t cap1 = nullptr, cap2 = nullptr, cap3 = nullptr; // capture streams: block loop, round loop, side branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t copy_stream = nullptr; // host -> device segments of ccb_ingest, ahead of the engine
+    cudaStream_t res_stream = nullptr;  // device -> host copies of the per-cell results of a finished segment, behind the engine
+    unsigned char *h_res = nullptr;     // page-locked bounce buffer of those results ([n] int32 assignments, then [n] stages)
+    size_t res_cap = 0;                 // (rows)
     double *d_scale = nullptr;          // [2][CCB_MAX_D] scale_ / min_ of ccb_ingest_scaled
     cudaEvent_t ev_seg[8] = {nullptr};
     Eng bs_graph_eng{};         // the pointers / capacities the graph was captured with
@@ -1153,6 +1156,8 @@ void ccb_destroy(ccb_handle *h) {
     if (h->cap2) cudaStreamDestroy(h->cap2);
     if (h->cap3) cudaStreamDestroy(h->cap3);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->res_stream) cudaStreamDestroy(h->res_stream);
+    if (h->h_res) cudaFreeHost(h->h_res);
     cudaFree(h->d_scale);
     for (auto &ev : h->ev_seg)
         if (ev) cudaEventDestroy(ev);
@@ -1424,17 +1429,23 @@ static int ingest_host(ccb_handle *h, const double *X, int64_t N, int64_t ld, in
     };
     // segments of the input: one block's worth of rows first, then doubling, the last one takes the rest -- the engine
     // starts after a 3 MB copy instead of a 24 MB one and the copies (5x faster than the engine) stay ahead of it
+    // The per-cell results travel back the same way, one segment behind the engine: through a page-locked bounce buffer
+    // (the caller's arrays are ordinary pageable memory as a rule -- numpy -- and a device -> pageable copy runs at a
+    // fraction of the link rate), copied out by this thread while the engine works on the next segment.  A short last
+    // segment keeps the part that cannot overlap (its results) small.
     int64_t seg_end[8];
     int nseg = 1;
     seg_end[0] = N;
     if (!h->timing && N >= 262144) {
         int64_t len = h->bs_bmax, at = 0;
         nseg = 0;
-        while (nseg < 7 && at + len + len < N) {
+        while (nseg < 6 && at + len + len < N) {
             at += len;
             seg_end[nseg++] = at;
             len *= 2;
         }
+        const int64_t tail = 2 * (int64_t)h->bs_bmax;
+        if (N - at > 4 * tail) seg_end[nseg++] = N - tail;
         seg_end[nseg++] = N;
     }
     if (nseg == 1) {
@@ -1467,15 +1478,44 @@ static int ingest_host(ccb_handle *h, const double *X, int64_t N, int64_t ld, in
             CK(h, cudaEventRecord(h->ev_seg[k], h->copy_stream));
             return CCB_OK;
         };
+        if (!h->res_stream) CK(h, cudaStreamCreateWithFlags(&h->res_stream, cudaStreamNonBlocking));
+        if ((size_t)N > h->res_cap) {
+            if (h->h_res) cudaFreeHost(h->h_res);
+            h->h_res = nullptr;
+            h->res_cap = 0;
+            CK(h, cudaHostAlloc((void **)&h->h_res, (size_t)N * 5, cudaHostAllocDefault));
+            h->res_cap = (size_t)N;
+        }
+        int32_t *ba = reinterpret_cast<int32_t *>(h->h_res);
+        uint8_t *bs = h->h_res + (size_t)N * 4;
+        // results of segment k (its engine run is complete: ingest_core_bsv returns after a synchronisation) -> caller
+        auto results_seg = [&](int k) -> int {
+            int64_t r0, n;
+            seg_rows(k, r0, n);
+            if (n <= 0) return CCB_OK;
+            CK(h, cudaMemcpyAsync(ba + r0, h->d_assign + r0, (size_t)n * 4, cudaMemcpyDeviceToHost, h->res_stream));
+            if (stage) CK(h, cudaMemcpyAsync(bs + r0, h->d_stage + r0, (size_t)n, cudaMemcpyDeviceToHost, h->res_stream));
+            CK(h, cudaStreamSynchronize(h->res_stream));
+            memcpy(assign_uid + r0, ba + r0, (size_t)n * 4);
+            if (stage) memcpy(stage + r0, bs + r0, (size_t)n);
+            return CCB_OK;
+        };
         if ((rc = copy_seg(0))) return rc;
         for (int k = 0; k < nseg; ++k) {
             int64_t r0, n;
             seg_rows(k, r0, n);
             CK(h, cudaStreamWaitEvent(h->stream, h->ev_seg[k], 0));
             scale_rows(r0, n);
-            const std::function<int()> next = [&]() -> int { return k + 1 < nseg ? copy_seg(k + 1) : CCB_OK; };
+            // once the engine is running on segment k: queue the input of segment k + 1, fetch the results of segment k - 1
+            const std::function<int()> next = [&]() -> int {
+                int r = k + 1 < nseg ? copy_seg(k + 1) : CCB_OK;
+                if (!r && k > 0) r = results_seg(k - 1);
+                return r;
+            };
             if ((rc = ingest_core_bsv(h, h->d_X + r0 * ld, n, ld, h->d_assign + r0, h->d_stage + r0, &next))) return rc;
         }
+        if ((rc = results_seg(nseg - 1))) return rc;
+        return CCB_OK;
     }
     {
         Timed tm(h, CCB_CAT_COPY);

@@ -49,6 +49,9 @@ constexpr int BS_KEY_PENDING = -5; // rejected by the pcore stage in V, outlier 
 constexpr int BS_KEY_UNKNOWN = -1; // every listed snapshot candidate was modified earlier in the block
 constexpr int BS_RMAX = 4096;      // cells per block that may reach the outlier stage
 constexpr int BS_TOPK = 8;
+// plist entry = cell | flags: CONTESTED (exact radius test inside the chain) and, for a CONTESTED cell, the PREDICTED verdict
+// of that test (the snapshot's in round 1, the previous round's afterwards) -- a hint for the replay, never a result
+constexpr int BS_PL_CONT = (int)0x80000000, BS_PL_PREJ = 0x40000000, BS_PL_CELL = 0x3fffffff;
 
 struct BsCtl {
     int64_t N, pos;
@@ -471,10 +474,14 @@ __global__ void __launch_bounds__(BS_THREADS, DP <= 16 ? 7 : 1) k_bs_spec(Eng e)
     const bool mine = part == 0 && live;
     int flag = mine ? 1 : 0;
     if (mine && best >= 0) {
-        if (bd <= e.theta && r2s <= e.r2safe) flag = 0;
-        // far beyond the radius limit on the snapshot: speculate "rejected by the pcore stage" right away instead of
-        // sending the cell through the serial chain for an exact test; k_bs_verify_p checks it like everything else
-        else if (r2s > e.r2rej) best = -1;
+        if (bd <= e.theta && r2s <= e.r2safe) {
+            flag = 0;
+        } else {
+            if (r2s > nm.eps2) flag = 3; // CONTESTED, and the snapshot predicts "rejected" (bit 1: BS_PL_PREJ in plist)
+            // far beyond the radius limit on the snapshot: speculate "rejected by the pcore stage" right away instead of
+            // sending the cell through the serial chain for an exact test; k_bs_verify_p checks it like everything else
+            if (r2s > e.r2rej) best = -1;
+        }
     }
     // need list: every cell that is not SAFE takes a top-K slot right here (one atomic per warp; the order of the slots
     // is immaterial).  Should the block need more than BS_RMAX slots, the last CTA hands them out again in cell order and
@@ -667,7 +674,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_pscatter(Eng e) {
         if (c >= 0) {
             const int rank = __popc(peers & lanemask_lt());
             pos = e.ws.poff[c] + e.ws.tilecnt[(size_t)t * e.ws.mp_stride + c] + rank;
-            e.ws.plist[pos] = i | (e.ws.pflag[i] ? (int)0x80000000 : 0);
+            const int pf = e.ws.pflag[i];
+            e.ws.plist[pos] = i | (pf ? BS_PL_CONT : 0) | ((pf & 2) ? BS_PL_PREJ : 0);
             e.ws.vpos[i] = pos;
         }
         s_pos[lane] = pos;
@@ -1128,7 +1136,7 @@ __device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint3
     if (lane < GS && ((cg >> lane) & 1u) && lane < ncell) {
         int raw;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + lane * 4));
-        prej[raw & 0x7fffffff] = (uint8_t)((rej >> lane) & 1u);
+        prej[raw & BS_PL_CELL] = (uint8_t)((rej >> lane) & 1u);
     }
     return rec;
 }
@@ -1194,7 +1202,130 @@ __device__ __noinline__ ChainRec<1> bs_chain_slow_group_pairs(ChainRec<1> rec, u
     if (lane < GS && ((cg >> lane) & 1u) && lane < ncell) {
         int raw;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + lane * 4));
-        prej[raw & 0x7fffffff] = (uint8_t)((rej >> lane) & 1u);
+        prej[raw & BS_PL_CELL] = (uint8_t)((rej >> lane) & 1u);
+    }
+    rec.v[0] = v;
+    return rec;
+}
+
+// The same group, EIGHT cells per pass (NH == 1).  Every CONTESTED cell carries a predicted verdict (BS_PL_PREJ: the
+// snapshot's in round 1, its own verdict of the round before afterwards).  A pass lays the tentative records of the cells
+// q0 .. 7 along the predicted pattern (a predicted-rejected cell leaves the state alone, so runs of them are not even
+// chained), runs the fast tests of all of them side by side -- independent instruction streams, their integer sums through
+// back-to-back redux.sync, ONE redux for all "too close to call" flags -- and compares with the prediction: the cells in
+// front of the first deviation are final, the deviating cell itself is final too (its record was built on the right
+// state; an undecided one takes the exact test), and the next pass starts behind it.  With mostly right predictions that
+// is one pass of ~400 cycles per eight cells instead of eight dependent tests.  Nothing here can change a result: every
+// verdict is the fast test's (decision-exact by its clearance, re-checked by k_bs_verify_p) or the exact test's.
+template <int DP>
+__device__ __noinline__ ChainRec<1> bs_chain_slow_group_batch(ChainRec<1> rec, uint32_t ga, uint32_t ma_g, unsigned cg, unsigned pg,
+                                                              int ncell, int lane, int D, double delta2, double eps2, int div_mode,
+                                                              double k, double wsel, uint8_t *prej, uint8_t *pflag,
+                                                              const ChainFast cf, int exact_first) {
+    constexpr int LSP = 2 * DP + 2, GS = 8;
+    constexpr int CL = 1 << 26;
+    double v = rec.v[0];
+    const bool st_ok = lane < LSP, act = lane < D;
+    const unsigned live = (1u << ncell) - 1u;
+    cg &= live;
+    const unsigned pred = pg & cg; // predicted rejections
+    unsigned rej = 0u;             // verdicts
+    double a[GS];
+#pragma unroll
+    for (int q = 0; q < GS; ++q) a[q] = lds_f64(ga + q * (LSP * 8)); // (stale past ncell: never used)
+    int q0 = 0;
+    if (exact_first && (cg & 1u)) { // the first member of a chain takes the exact test: every block advances
+        const double nv = dadd(v, a[0]);
+        if (st_ok) sts_f64(ga, nv);
+        if (bs_radius_test<DP, 1>(nv, ga, lane, D, delta2, eps2, div_mode, k, wsel)) v = nv;
+        else rej |= 1u;
+        q0 = 1;
+    }
+#pragma unroll 1
+    while (q0 < ncell) {
+        const unsigned todo = live & ~((1u << q0) - 1u); // cells of this pass
+        const unsigned adv = todo & ~pred;               // ... that are predicted to join the chain
+        double nv[GS], sb[GS];                           // tentative record of cell q, state in front of it
+        {
+            // the state runs through a pure chain of adds: a cell that does not join adds -0.0, the exact identity of
+            // IEEE addition in round-to-nearest (x + -0.0 == x for every x, signed zeros included)
+            double ae[GS];
+#pragma unroll
+            for (int q = 0; q < GS; ++q) ae[q] = ((adv >> q) & 1u) ? a[q] : -0.0;
+            double st = v;
+#pragma unroll
+            for (int q = 0; q < GS; ++q) {
+                sb[q] = st;
+                nv[q] = dadd(st, a[q]);
+                st = dadd(st, ae[q]);
+            }
+        }
+        // fast tests of all eight records (bs_radius_fast, NT == 1, unsplit), reductions apart
+        int hs[GS], tlo[GS], thi[GS];
+        unsigned ambm = 0u;
+#pragma unroll
+        for (int q = 0; q < GS; ++q) {
+            const double wn = __shfl_sync(0xffffffffu, nv[q], 2 * DP);
+            const double c2 = __shfl_sync(0xffffffffu, nv[q], (lane + DP) & 31);
+            const double c1 = nv[q];
+            const double wn2 = dmul(wn, wn);
+            const double thr = dmul(wn2, cf.F);
+            const double d2w = dmul(cf.delta2, wn2);
+            const double tol = dmul(d2w, 0x1p-24);
+            tlo[q] = __double2int_rd(dsub(thr, cf.mg));
+            thi[q] = __double2int_ru(dadd(thr, cf.mg));
+            const double t = __fma_rn(-c1, c1, dmul(c2, wn));
+            const double diff = dsub(t, d2w);
+            if (act && !(fabs(diff) > tol)) ambm |= 1u << q;
+            const double tk = dmul(t, cf.invk);
+            const double vv = dmul(diff <= 0.0 ? tk : t, cf.fs);
+            int hi = __double2int_rn(vv); // saturates; NaN -> 0 (caught by ambm)
+            hi = max(min(hi, CL), -(1 << 20));
+            hs[q] = act ? hi : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < GS; ++q) hs[q] = __reduce_add_sync(0xffffffffu, hs[q]);
+        ambm = __reduce_or_sync(0xffffffffu, ambm);
+        unsigned accm = 0u, rejm = 0u;
+#pragma unroll
+        for (int q = 0; q < GS; ++q) {
+            accm |= (hs[q] < tlo[q] ? 1u : 0u) << q;
+            rejm |= (hs[q] > thi[q] ? 1u : 0u) << q;
+        }
+        accm &= ~ambm;
+        rejm &= ~ambm;
+        const unsigned und = ~(accm | rejm);
+        const unsigned dev = ((rejm & ~pred) | (accm & pred) | und) & cg & todo; // verdict != prediction, or none
+        const int qs = dev ? __ffs(dev) - 1 : ncell;                              // first deviating cell
+        const int qe = min(qs, ncell - 1);
+#pragma unroll
+        for (int q = 0; q < GS; ++q)
+            if (q >= q0 && q <= qe && st_ok) sts_f64(ga + q * (LSP * 8), nv[q]);
+        rej |= pred & todo & ((1u << qs) - 1u);
+        // state behind cell qe when the cells in front of it went as predicted and qe itself as `keep` says
+        double nq = nv[0], sq = sb[0];
+#pragma unroll
+        for (int q = 1; q < GS; ++q) {
+            nq = q == qe ? nv[q] : nq;
+            sq = q == qe ? sb[q] : sq;
+        }
+        bool keep;
+        if (dev) {
+            if ((und >> qs) & 1u) keep = bs_radius_test<DP, 1>(nq, ga + qs * (LSP * 8), lane, D, delta2, eps2, div_mode, k, wsel);
+            else keep = (accm >> qs) & 1u;
+            rej |= (keep ? 0u : 1u) << qs;
+        } else {
+            keep = !((pred >> qe) & 1u);
+        }
+        v = keep ? nq : sq;
+        q0 = qs + 1;
+    }
+    if (lane < GS && ((cg >> lane) & 1u)) { // verdicts of the CONTESTED cells (lane q = cell q) + next round's prediction
+        int raw;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + lane * 4));
+        const unsigned r = (rej >> lane) & 1u;
+        prej[raw & BS_PL_CELL] = (uint8_t)r;
+        pflag[raw & BS_PL_CELL] = (uint8_t)(1u | (r << 1));
     }
     rec.v[0] = v;
     return rec;
@@ -1376,13 +1507,17 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         uint32_t xa = xs_lane + s * (NB * LSP * 8), ma = ms_base + s * (NB * 4);
         asm volatile("" : "+r"(xa), "+r"(ma));
         // CONTESTED flags of the whole stage: lane l looks at cells l and l + 32
-        unsigned c_lo, c_hi = 0u;
+        unsigned c_lo, c_hi = 0u, p_lo = 0u, p_hi = 0u;
         {
             int f0, f1 = 0;
             asm volatile("ld.shared.s32 %0, [%1];" : "=r"(f0) : "r"(ma + lane_o * 4));
             if (NB > 32) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(f1) : "r"(ma + (lane_o + 32) * 4));
             c_lo = __ballot_sync(0xffffffffu, f0 < 0 && lane_o < cnt);
             if (NB > 32) c_hi = __ballot_sync(0xffffffffu, f1 < 0 && lane_o + 32 < cnt);
+            if (NH == 1 && (c_lo | c_hi)) { // predicted verdicts of the CONTESTED cells (bs_chain_slow_group_batch)
+                p_lo = __ballot_sync(0xffffffffu, (f0 & BS_PL_PREJ) != 0);
+                if (NB > 32) p_hi = __ballot_sync(0xffffffffu, (f1 & BS_PL_PREJ) != 0);
+            }
         }
         CCB_DBG(t_head += clock64() - t_h0;)
         if (cnt == NB && (c_lo | c_hi) == 0u) {
@@ -1458,10 +1593,17 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
 #pragma unroll
                     for (int h = 0; h < NH; ++h) rec.v[h] = v[h];
                     if constexpr (NH == 1) {
-                        if (__popc(cg) >= 2)
+                        if (__popc(cg) >= 2) {
+#ifdef CCB_CHAIN_PAIRS
                             rec = bs_chain_slow_group_pairs<DP>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
                                                                 nm.div_mode, nm.k, nm.wsel, e.ws.prej, cfast, (b | g) == 0);
-                        else
+#else
+                            const unsigned pgm = ((g < 4 ? p_lo : p_hi) >> (8 * (g & 3))) & 0xffu;
+                            rec = bs_chain_slow_group_batch<DP>(rec, ga, ma + g * (GS * 4), cg, pgm, ncell, lane_o, D, nm.delta2,
+                                                                nm.eps2, nm.div_mode, nm.k, nm.wsel, e.ws.prej, e.ws.pflag, cfast,
+                                                                (b | g) == 0);
+#endif
+                        } else
                             rec = bs_chain_slow_group<DP, NH>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
                                                               nm.div_mode, nm.k, nm.wsel, e.ws.prej, cfast, (b | g) == 0);
                     } else {
@@ -1659,8 +1801,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_bs_derive_p(Eng e) {
             const int t = idx / Mp, j = idx - t * Mp;
             const int lo = e.ws.poff[j];
             int pos = lo + (t < ntiles ? e.ws.tilecnt[(size_t)t * stride + j] : e.ws.pcnt[j]);
-            while (pos > lo && e.ws.prej[e.ws.plist[pos - 1] & 0x7fffffff]) --pos;
-            e.ws.tbase[(size_t)t * stride + j] = pos > lo ? (e.ws.plist[pos - 1] & 0x7fffffff) : -1;
+            while (pos > lo && e.ws.prej[e.ws.plist[pos - 1] & BS_PL_CELL]) --pos;
+            e.ws.tbase[(size_t)t * stride + j] = pos > lo ? (e.ws.plist[pos - 1] & BS_PL_CELL) : -1;
         }
     }
     if (i >= bc->Beff || e.ws.pcand[i] < 0 || e.ws.prej[i]) return; // not an accepted member of a pcore chain
@@ -2031,7 +2173,7 @@ __device__ void bs_trace_round(const BsCtl *bc, int kind, int m0, int Beff_in, i
             t[60] = ws->dec[m0];
             t[61] = ws->eff[m0];
             t[62] = ws->pcand[m0];
-            t[63] = ws->pflag[m0] | (ws->prej[m0] << 1) | ((long long)(unsigned)ws->ospec[m0] << 8) | ((long long)ws->tkpos[m0] << 40);
+            t[63] = (ws->pflag[m0] != 0) | (ws->prej[m0] << 1) | ((long long)(unsigned)ws->ospec[m0] << 8) | ((long long)ws->tkpos[m0] << 40);
         }
     }
     for (int k = 3; k < CCB_TRACE_SLOTS; ++k) g_trace_ts[k] = 0;
@@ -2112,7 +2254,7 @@ __global__ void __launch_bounds__(BS_CTA1, 1) k_bs_decide(Eng e) {
         s_dbg[0] = e.ws.dec[m0];
         s_dbg[1] = e.ws.eff[m0];
         s_dbg[2] = e.ws.pcand[m0];
-        s_dbg[3] = e.ws.pflag[m0] | (e.ws.prej[m0] << 1) | ((long long)(unsigned)e.ws.ospec[m0] << 8) | ((long long)e.ws.tkpos[m0] << 40);
+        s_dbg[3] = (e.ws.pflag[m0] != 0) | (e.ws.prej[m0] << 1) | ((long long)(unsigned)e.ws.ospec[m0] << 8) | ((long long)e.ws.tkpos[m0] << 40);
     })
     // ---- refinement: the recomputed decisions of [m0, Beff) become the next speculation
     int cut = Beff;

@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
-"""Fills the @PLACEHOLDER@ fields of DESIGN.md / README.md from the measured files under profiles/ (final passes of round 2),
-so that every number quoted in the documents is the one in the committed evidence.
+"""Generates DESIGN.md / README.md from tools/templates/*.in: the @PLACEHOLDER@ fields are filled from the measured files
+under profiles/ (final passes of round 2), so that every number quoted in the documents is the one in the committed
+evidence.  Edit the templates, then re-run.
 
-    python tools/fill_docs.py <1-GPU tag, e.g. r2z> <8-GPU tag, e.g. r2y>
+    python tools/fill_docs.py <1-GPU tag, e.g. r2z> <multi-GPU tag, e.g. r2y> [<tag of the 1-GPU line of the scaling tables>]
 """
 import json
 import re
@@ -14,8 +15,11 @@ b = json.load(open(f"{P}{one}_bench_c2.json"))
 app = json.load(open(f"{P}{one}_app_wall_c2.json"))["runs"]
 tp = open(f"{P}{one}_tp_wall_c2_graph.log").read().strip().splitlines()[-1]
 t = [float(x) for x in re.findall(r"t\d (\d+\.\d+)ms", tp)]
-bn = {N: json.load(open(f"{P}{multi}_bench_c2_{N}gpu.json")) for N in (1, 2, 4, 8)}
+one_multi = sys.argv[3] if len(sys.argv) > 3 else multi
+bn = {N: json.load(open(f"{P}{multi if N > 1 else one_multi}_bench_c2_{N}gpu.json")) for N in (1, 2, 4, 8)}
 sw = json.load(open(f"{P}{multi}_sweep64_8gpu.json"))
+if not bn[1].get("offline_c4"):  # (a quick 1-GPU line without the C4 leg: the final pass has it)
+    bn[1]["offline_c4"] = b["offline_c4"]
 
 M = lambda v: f"{v / 1e6:.1f}"
 sf, rd = b["serial_floor"], b["roofline_distance"]
@@ -54,7 +58,7 @@ vals = {
     "SWEEP": sweep, "SWEEPLINE": f"{sw['seconds']:.1f} s for 64 runs of 5e6 cells = {M(sw['value'])} M cells/s",
 }
 for path in ("DESIGN.md", "README.md"):
-    s = open(path).read()
+    s = open(f"tools/templates/{path}.in").read()  # the documents are GENERATED: edit the templates, not the outputs
     for k, v in vals.items():
         s = s.replace(f"@{k}@", v)
     left = re.findall(r"@[A-Z0-9_]+@", s)
