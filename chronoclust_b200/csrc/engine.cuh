@@ -49,6 +49,7 @@ constexpr int BS_KEY_PENDING = -5; // rejected by the pcore stage in V, outlier 
 constexpr int BS_KEY_UNKNOWN = -1; // every listed snapshot candidate was modified earlier in the block
 constexpr int BS_RMAX = 4096;      // cells per block that may reach the outlier stage
 constexpr int BS_TOPK = 8;
+constexpr int BS_COLD_B = 512;     // length of a block that starts without any microcluster
 // plist entry = cell | flags: CONTESTED (exact radius test inside the chain) and, for a CONTESTED cell, the PREDICTED verdict
 // of that test (the snapshot's in round 1, the previous round's afterwards) -- a hint for the replay, never a result
 constexpr int BS_PL_CONT = (int)0x80000000, BS_PL_PREJ = 0x40000000, BS_PL_CELL = 0x3fffffff;
@@ -267,7 +268,11 @@ __global__ void k_bs_begin(Eng e) {
             break;
         }
         const int64_t left = bc->N - bc->pos;
-        bc->Bcur = (int32_t)(left < bc->next_B ? left : bc->next_B);
+        // no microcluster at all (the first cells of a run): every cell of the block would be checked against every MC the
+        // cells in front of it may create -- quadratic in the block length -- while the exact prefix grows by a few hundred
+        // cells per block at best; a short block costs a quarter per round
+        const int32_t want = (Mp + Mo0 == 0) ? min(bc->next_B, BS_COLD_B) : bc->next_B;
+        bc->Bcur = (int32_t)(left < want ? left : want);
         bc->Beff = bc->Bcur;
         bc->Mp = Mp;
         bc->Mo0 = Mo0;
@@ -1147,12 +1152,17 @@ __device__ __noinline__ ChainRec<NH> bs_chain_slow_group(ChainRec<NH> rec, uint3
 // next to cell q's own test (three independent instruction streams for the in-order warp instead of one dependent one)
 // and the right one is picked afterwards: ~1/2 of the latency per CONTESTED cell.  Anything the fast test cannot call
 // (and the first member of a chain) takes the one-by-one path with the exact test.  A rolled loop: the code stays small.
+struct ChainRecD {
+    double v;
+    int dev; // CONTESTED cells of the group whose verdict differed from the prediction
+};
 template <int DP>
-__device__ __noinline__ ChainRec<1> bs_chain_slow_group_pairs(ChainRec<1> rec, uint32_t ga, uint32_t ma_g, unsigned cg, int ncell,
-                                                              int lane, int D, double delta2, double eps2, int div_mode, double k,
-                                                              double wsel, uint8_t *prej, const ChainFast cf, int exact_first) {
+__device__ __noinline__ ChainRecD bs_chain_slow_group_pairs(ChainRecD rec, uint32_t ga, uint32_t ma_g, unsigned cg, unsigned pg,
+                                                            int ncell, int lane, int D, double delta2, double eps2, int div_mode,
+                                                            double k, double wsel, uint8_t *prej, uint8_t *pflag,
+                                                            const ChainFast cf, int exact_first) {
     constexpr int LSP = 2 * DP + 2, GS = 8;
-    double v = rec.v[0];
+    double v = rec.v;
     const bool st_ok = lane < LSP;
     unsigned rej = 0u;
     double a0 = lds_f64(ga), a1 = lds_f64(ga + LSP * 8); // (a1 is stale when ncell == 1: never used)
@@ -1199,12 +1209,15 @@ __device__ __noinline__ ChainRec<1> bs_chain_slow_group_pairs(ChainRec<1> rec, u
         a0 = a2;
         a1 = a3;
     }
-    if (lane < GS && ((cg >> lane) & 1u) && lane < ncell) {
+    if (lane < GS && ((cg >> lane) & 1u) && lane < ncell) { // verdicts + next round's predictions
         int raw;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ma_g + lane * 4));
-        prej[raw & BS_PL_CELL] = (uint8_t)((rej >> lane) & 1u);
+        const unsigned r = (rej >> lane) & 1u;
+        prej[raw & BS_PL_CELL] = (uint8_t)r;
+        pflag[raw & BS_PL_CELL] = (uint8_t)(1u | (r << 1));
     }
-    rec.v[0] = v;
+    rec.v = v;
+    rec.dev = __popc((rej ^ pg) & cg & ((1u << ncell) - 1u));
     return rec;
 }
 
@@ -1218,13 +1231,14 @@ __device__ __noinline__ ChainRec<1> bs_chain_slow_group_pairs(ChainRec<1> rec, u
 // is one pass of ~400 cycles per eight cells instead of eight dependent tests.  Nothing here can change a result: every
 // verdict is the fast test's (decision-exact by its clearance, re-checked by k_bs_verify_p) or the exact test's.
 template <int DP>
-__device__ __noinline__ ChainRec<1> bs_chain_slow_group_batch(ChainRec<1> rec, uint32_t ga, uint32_t ma_g, unsigned cg, unsigned pg,
-                                                              int ncell, int lane, int D, double delta2, double eps2, int div_mode,
-                                                              double k, double wsel, uint8_t *prej, uint8_t *pflag,
-                                                              const ChainFast cf, int exact_first) {
+__device__ __noinline__ ChainRecD bs_chain_slow_group_batch(ChainRecD rec, uint32_t ga, uint32_t ma_g, unsigned cg, unsigned pg,
+                                                            int ncell, int lane, int D, double delta2, double eps2, int div_mode,
+                                                            double k, double wsel, uint8_t *prej, uint8_t *pflag,
+                                                            const ChainFast cf, int exact_first) {
     constexpr int LSP = 2 * DP + 2, GS = 8;
     constexpr int CL = 1 << 26;
-    double v = rec.v[0];
+    double v = rec.v;
+    int ndev = 0;
     const bool st_ok = lane < LSP, act = lane < D;
     const unsigned live = (1u << ncell) - 1u;
     cg &= live;
@@ -1311,6 +1325,7 @@ __device__ __noinline__ ChainRec<1> bs_chain_slow_group_batch(ChainRec<1> rec, u
         }
         bool keep;
         if (dev) {
+            ++ndev;
             if ((und >> qs) & 1u) keep = bs_radius_test<DP, 1>(nq, ga + qs * (LSP * 8), lane, D, delta2, eps2, div_mode, k, wsel);
             else keep = (accm >> qs) & 1u;
             rej |= (keep ? 0u : 1u) << qs;
@@ -1327,7 +1342,8 @@ __device__ __noinline__ ChainRec<1> bs_chain_slow_group_batch(ChainRec<1> rec, u
         prej[raw & BS_PL_CELL] = (uint8_t)r;
         pflag[raw & BS_PL_CELL] = (uint8_t)(1u | (r << 1));
     }
-    rec.v[0] = v;
+    rec.v = v;
+    rec.dev = ndev;
     return rec;
 }
 
@@ -1483,6 +1499,13 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
         cfast.delta2 = nm.delta2;
         cfast.mg = (double)(D + 8);
     }
+#if defined(CCB_CHAIN_PAIRS)
+    bool bmode = false;
+#elif defined(CCB_CHAIN_BATCH)
+    bool bmode = true;
+#else
+    bool bmode = bc->it > 0; // (see the CONTESTED groups below)
+#endif
     CCB_DBG(long long t_wait = 0, t_slow = 0, n_cont = 0, t_head = 0, t_tail = 0, n_clean = 0; const long long t_beg = clock64();
             const int dbgm = g_bs_dbg_mode;)
     // The replay warp issues in order and is alone on its scheduler: every dependent instruction costs its full latency.
@@ -1594,14 +1617,34 @@ __global__ void __launch_bounds__(BS_CHAINP_THREADS) k_bs_chain_p(Eng e) {
                     for (int h = 0; h < NH; ++h) rec.v[h] = v[h];
                     if constexpr (NH == 1) {
                         if (__popc(cg) >= 2) {
-#ifdef CCB_CHAIN_PAIRS
-                            rec = bs_chain_slow_group_pairs<DP>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
-                                                                nm.div_mode, nm.k, nm.wsel, e.ws.prej, cfast, (b | g) == 0);
-#else
+                            // runs of CONTESTED cells: eight per pass along the predicted verdicts while the predictions hold
+                            // (refinement rounds: a cell's verdict of the round before), two per step otherwise (round 1 on
+                            // a young MC: the snapshot's predictions are worth little) -- the last group's count decides
                             const unsigned pgm = ((g < 4 ? p_lo : p_hi) >> (8 * (g & 3))) & 0xffu;
-                            rec = bs_chain_slow_group_batch<DP>(rec, ga, ma + g * (GS * 4), cg, pgm, ncell, lane_o, D, nm.delta2,
-                                                                nm.eps2, nm.div_mode, nm.k, nm.wsel, e.ws.prej, e.ws.pflag, cfast,
-                                                                (b | g) == 0);
+                            ChainRecD rd;
+                            rd.v = v[0];
+                            rd.dev = 0;
+                            if (bmode)
+                                rd = bs_chain_slow_group_batch<DP>(rd, ga, ma + g * (GS * 4), cg, pgm, ncell, lane_o, D, nm.delta2,
+                                                                   nm.eps2, nm.div_mode, nm.k, nm.wsel, e.ws.prej, e.ws.pflag, cfast,
+                                                                   (b | g) == 0);
+                            else
+                                rd = bs_chain_slow_group_pairs<DP>(rd, ga, ma + g * (GS * 4), cg, pgm, ncell, lane_o, D, nm.delta2,
+                                                                   nm.eps2, nm.div_mode, nm.k, nm.wsel, e.ws.prej, e.ws.pflag, cfast,
+                                                                   (b | g) == 0);
+                            rec.v[0] = rd.v;
+                            CCB_DBG(if (lane_o == 0) {
+                                atomicAdd(&g_dbg_cnt[bmode ? 0 : 2], 1ull);             // groups taken eight / two at a time
+                                atomicAdd(&g_dbg_cnt[bmode ? 1 : 3], (unsigned long long)rd.dev); // ... and their deviations
+                                atomicAdd(&g_dbg_cnt[4], (unsigned long long)__popc(cg));
+                                atomicAdd(&g_dbg_cnt[5], (unsigned long long)__popc(pgm & cg)); // predicted rejections
+                            })
+#if defined(CCB_CHAIN_PAIRS)
+                            bmode = false;
+#elif defined(CCB_CHAIN_BATCH)
+                            bmode = true;
+#else
+                            bmode = rd.dev <= 1;
 #endif
                         } else
                             rec = bs_chain_slow_group<DP, NH>(rec, ga, ma + g * (GS * 4), cg, ncell, lane_o, D, nm.delta2, nm.eps2,
