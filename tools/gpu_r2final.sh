@@ -12,3 +12,4 @@ timeout 600 python tools/app_wall.py 1.0 > $out/${tag}_app_wall_c2.json 2> $out/
 timeout 300 python tools/tp_wall.py C2 1.0 > $out/${tag}_tp_wall_c2_graph.log 2>&1; tail -1 $out/${tag}_tp_wall_c2_graph.log
 timeout 300 python tools/fp64_latency.py > $out/${tag}_fp64_latency.log 2>&1; cat $out/${tag}_fp64_latency.log
 bash tools/gpu_profile_r2.sh $tag
+timeout 300 python tools/trace_rounds.py C2 1.0 --tps 5 --out $out/${tag}_trace_c2.npz --detail 0 > $out/${tag}_trace_c2.log 2>&1; grep "== t" $out/${tag}_trace_c2.log
