@@ -12,14 +12,18 @@
 //                                     KNEW + c (c <= i)       absorbed by the MC that cell c of this block
 //                                                             creates (c == i: the cell itself creates it)
 // with KNEW = Mp + Mo0.  One block runs
-//   S   k_bs_spec      speculate from the snapshot: nearest feasible pcore MC (candidate), SAFE / CONTESTED,
-//                      (it also hands out the top-K slots of the cells that may reach the outlier stage), k_nearest top-K of the
-//       k_bs_spec_o    snapshot outlier list for them, speculated outlier decision
+//   S   k_bs_spec      speculate from the snapshot: nearest feasible pcore MC (candidate), SAFE / CONTESTED (+ the
+//                      snapshot's verdict as a prediction for the replay); it also hands out the top-K slots of the cells
+//                      that may reach the outlier stage and counts the candidates per (tile, pcore MC) for round 1
+//       k_nearest      top-K of the snapshot outlier list for those cells (kernel 1, nearest.cuh)
+//       k_bs_spec_o    speculated outlier decision
 //   then up to ITMAX rounds of
 //   L   k_bs_tilecnt / k_bs_pscan / k_bs_pscatter   ordered candidate list of every pcore MC
 //   C   k_bs_chain_p   per pcore MC, its candidates in input order: CF1 += x, CF2 += x*x, W += 1 as dependent
 //                      fp64 adds (the only inherently serial work: ~1 DADD latency per cell); CONTESTED cells
-//                      take the exact radius test in place; the state after every absorb is kept (VERSION)
+//                      take the radius test in place (a division-free fast test, the exact one when that cannot
+//                      call it; runs of them two per step or eight per pass along predicted verdicts); the state
+//                      after every absorb is kept (VERSION)
 //       k_bs_olist     sort (key, cell) of the pcore-rejected cells -> outlier-side chains
 //       k_bs_chain_o   the same replay for modified snapshot outlier MCs and MCs created in this block
 //   D   k_bs_derive_p / k_bs_derive_o   centroid, preference mask, radius^2 of every version (cell-parallel)
