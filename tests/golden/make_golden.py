@@ -2,7 +2,7 @@
 """Generates the golden fixtures under tests/golden/ by running the LIVE reference.
 
 Run in the build container only (it imports /root/reference, which does not exist on the GPU
-box):   python tests/golden/make_golden.py
+box):   python tests/golden/make_golden.py [kat] [offline] [stress | stress:<name> ...] [c1]
 
 What it pins:
   c1.npz            config C1 = the reference's own synthetic_dataset d0-d4 with the integration
@@ -169,11 +169,22 @@ STRESS = {
     "c3like": (dict(N=4000, D=40, T=2, C=40, seed=1234),
                {"beta": 0.2, "delta": 0.05, "epsilon": 0.10, "lambda": 2, "k": 4, "mu": 0.01, "pi": 40,
                 "omicron": 4.35e-6, "upsilon": 6.5}, None),
+    # the saturated regime of the parameter sweep (config C5 at its smallest epsilon): the MCs sit at their radius limit,
+    # clusters split over several pcore MCs, > 20 % of the cells reach the outlier stage.  They pin the ORACLE there (the
+    # full-size C5 corner is compared with the oracle on the GPU); used by the CPU suites only (helpers.ORACLE_EXTRA_NAMES)
+    "saturated": (dict(N=6000, D=12, T=2, C=20, seed=4321),
+                  {"beta": 0.2, "delta": 0.05, "epsilon": 0.04, "lambda": 2, "k": 4, "mu": 0.01, "pi": 12,
+                   "omicron": 4.35e-6, "upsilon": 6.5}, None),
+    "saturated_k3": (dict(N=5000, D=6, T=3, C=6, seed=99),
+                     {"beta": 0.8, "delta": 0.03, "epsilon": 0.03, "lambda": 1, "k": 3, "mu": 0.01, "pi": 6,
+                      "omicron": 4.35e-6, "upsilon": 6.5}, None),
 }
 
 
-def make_stress():
+def make_stress(only=None):
     for name, (ga, cfg, ts) in STRESS.items():
+        if only and name not in only:
+            continue
         Xs = gen(**ga)
         out = run_reference(cfg, Xs, ts)
         out["gen"] = np.array(json.dumps(ga))
@@ -326,5 +337,8 @@ if __name__ == "__main__":
         make_offline_sets()
     if "stress" in which:
         make_stress()
+    only = [w.split(":", 1)[1] for w in which if w.startswith("stress:")]  # e.g. stress:saturated
+    if only:
+        make_stress(only)
     if "c1" in which:
         make_c1()

@@ -7,6 +7,9 @@ import numpy as np
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 STRESS_NAMES = ["downgrade", "feasibility", "churn", "tightdelta", "k1_gap", "c2like", "c3like"]
+# golden vectors of the live reference in the saturated regime (config C5's smallest epsilon): they pin the oracle -- and the
+# CPU model of the engine -- where the GPU suite compares the full-size C5 corner with the oracle (CPU suites only)
+ORACLE_EXTRA_NAMES = ["saturated", "saturated_k3"]
 
 
 def load(name):

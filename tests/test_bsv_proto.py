@@ -4,7 +4,7 @@ block length / refinement depth / top-K / reject cap."""
 import numpy as np
 import pytest
 
-from helpers import STRESS_NAMES, assert_list_equal, config_of, load, stress_inputs
+from helpers import ORACLE_EXTRA_NAMES, STRESS_NAMES, assert_list_equal, config_of, load, stress_inputs
 from proto.bsv import BsvHDDStream
 
 
@@ -26,7 +26,7 @@ def run_against(z, Xs, what, **kw):
                                 dict(bmin=1, bmax=7, itmax=1, topk=1, rmax=3),
                                 dict(bmin=512, bmax=512, itmax=8, topk=2, rmax=100000, contest=0.0),
                                 dict(bmin=64, bmax=2048, itmax=3, topk=4, rmax=256, contest=1e9)])
-@pytest.mark.parametrize("name", STRESS_NAMES)
+@pytest.mark.parametrize("name", STRESS_NAMES + ORACLE_EXTRA_NAMES)
 def test_bsv_model_matches_reference_on_stress(name, kw):
     z = load(f"stress_{name}.npz")
     o = run_against(z, stress_inputs(z), name, **kw)

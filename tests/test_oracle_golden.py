@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import (GOLDEN, STRESS_NAMES, assert_clusters_equal, assert_list_equal, bits_equal, config_of, load,
+from helpers import (GOLDEN, ORACLE_EXTRA_NAMES, STRESS_NAMES, assert_clusters_equal, assert_list_equal, bits_equal, config_of, load,
                      stress_inputs)
 from oracle.oracle import OracleHDDStream, lib as olib, _p
 
@@ -24,7 +24,7 @@ def run_oracle_against(z, Xs, what):
         assert_clusters_equal(o.clusters(), z, P, f"{what} t{i}")
 
 
-@pytest.mark.parametrize("name", STRESS_NAMES)
+@pytest.mark.parametrize("name", STRESS_NAMES + ORACLE_EXTRA_NAMES)
 def test_oracle_matches_reference_on_stress(name):
     z = load(f"stress_{name}.npz")
     run_oracle_against(z, stress_inputs(z), name)
